@@ -1,0 +1,171 @@
+/*
+ * include/oavif_ssimu2.h — C ABI of the B200 (sm_100a) SSIMULACRA2 scorer for oavif's
+ * target-quality search loop.
+ *
+ * What it replaces (all paths under /root/reference/):
+ *   src/tq.zig:37        fssimu2.computeSsimu2(allocator, e.rgb, decoded_rgb, e.w, e.h, 3, null)
+ *                        -> oavif_ssimu2_compute_rgb8()              (stateless, 1:1)
+ *                        -> oavif_ssimu2_set_source_rgb8() once per image (main.zig:86 e.rgb)
+ *                           + oavif_ssimu2_score_*() once per search pass (tq.zig:150)
+ *   src/io.zig:452-482   decodeAvifCommon: avifImageYUVToRGB at forced depth 8
+ *   src/io.zig:638-666   decodeAvifToRgb: per-pixel repack to tight RGB8
+ *                        -> oavif_ssimu2_score_yuv444(): takes decoder->image->yuvPlanes
+ *                           straight after avifDecoderNextImage (io.zig:463) and performs the
+ *                           same integer YUV->RGB8 arithmetic on the device
+ *                        -> oavif_ssimu2_yuv444_to_rgb8(): that conversion alone
+ *   tq.zig:135-181       (new, additive) batched probing: oavif_ssimu2_score_batch_*()
+ *
+ * Conventions: plain pointers and sizes only; every entry point returns 0 on success or a
+ * negative OAVIF_SSIMU2_E_* code (the Zig shim maps them onto an error set, as `try` at
+ * tq.zig:37 expects); oavif_ssimu2_last_error() gives the text.  A context is single-owner:
+ * one host thread at a time (the corpus driver creates one per GPU worker).  Calls are
+ * synchronous at this boundary — the callee has finished reading caller memory on return,
+ * which is what tq.zig:26-27 (`defer allocator.free(decoded_rgb)`) requires.
+ * There is NO CPU fallback: without a usable CUDA device every call fails with
+ * OAVIF_SSIMU2_E_CUDA.
+ */
+#ifndef OAVIF_SSIMU2_H
+#define OAVIF_SSIMU2_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OAVIF_SSIMU2_ABI_VERSION 1
+#define OAVIF_SSIMU2_MAX_SCALES 6
+
+enum {
+    OAVIF_SSIMU2_OK = 0,
+    OAVIF_SSIMU2_E_ARG = -1,      /* null pointer, zero size, stride too small, bad enum       */
+    OAVIF_SSIMU2_E_CUDA = -2,     /* CUDA runtime/driver error (no device, launch failure ...) */
+    OAVIF_SSIMU2_E_NOMEM = -3,    /* device or pinned allocation failed                        */
+    OAVIF_SSIMU2_E_STATE = -4,    /* score_* before set_source_*, or size beyond ctx capacity  */
+    OAVIF_SSIMU2_E_UNSUPPORTED = -5 /* matrix / depth / channel count outside the scored path  */
+};
+
+/* Gaussian-blur evaluation.  Both compute the sigma = 1.5 filter of SSIMULACRA2 v2.1.
+ *   RECURSIVE: the published 3-oscillator recursion in binary32, every row and column as one
+ *              serial chain (columns in parallel; rows through a shared-memory transpose).
+ *              Its round-off is part of the published result, so this is the default.
+ *   FIR:       the exactly equivalent 9-tap kernel in one tile-fused launch per scale set
+ *              (no intermediate planes); differs from RECURSIVE only by that round-off.      */
+enum { OAVIF_SSIMU2_BLUR_RECURSIVE = 0, OAVIF_SSIMU2_BLUR_FIR = 1 };
+
+enum { OAVIF_SSIMU2_OPT_BLUR = 1 };
+
+typedef struct oavif_ssimu2_ctx oavif_ssimu2_ctx;
+
+/* Pooled results of the last score call for one candidate (tests, trace tools). */
+typedef struct {
+    int32_t n_scales;
+    int32_t w[OAVIF_SSIMU2_MAX_SCALES];
+    int32_t h[OAVIF_SSIMU2_MAX_SCALES];
+    /* [scale][c*6 + {sum d, sum d^4, sum artifact, sum artifact^4, sum detail, sum detail^4}] */
+    double sums[OAVIF_SSIMU2_MAX_SCALES][18];
+    double score;
+} oavif_ssimu2_detail;
+
+/* Device-side milliseconds of the last call, from CUDA events on the context's stream. */
+typedef struct {
+    float h2d_ms;       /* host -> device copies of this call's pixels           */
+    float pyramid_ms;   /* YUV->RGB8, sRGB->linear, 2x pyramid, XYB              */
+    float blur_ms;      /* blur + error maps + pooling kernels                   */
+    float finalize_ms;  /* fixed-order reduction, weights, score, D2H of scores  */
+    float total_ms;     /* first event to last event                             */
+    uint32_t launches;  /* kernels of this library launched by the call          */
+} oavif_ssimu2_timing;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+
+int oavif_ssimu2_abi_version(void);
+
+/* device: CUDA ordinal.  max_w/max_h: largest image the context will see.  max_batch: most
+ * candidates scored per call (>= 1).  All device and pinned memory is allocated here; no
+ * allocation happens in score calls. */
+int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
+                            oavif_ssimu2_ctx **out);
+void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx);
+
+int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value);
+
+/* Launch on a caller-owned cudaStream_t (passed as void*) instead of the context's own. */
+int oavif_ssimu2_set_stream(oavif_ssimu2_ctx *ctx, void *cuda_stream);
+
+const char *oavif_ssimu2_last_error(const oavif_ssimu2_ctx *ctx); /* ctx may be NULL */
+
+/* Pinned host staging for src/io.zig's decode buffers (cudaHostAlloc / cudaFreeHost). */
+void *oavif_ssimu2_pinned_alloc(size_t bytes);
+void oavif_ssimu2_pinned_free(void *p);
+
+/* ---- source side: once per image (main.zig:86) ------------------------------------------ */
+
+/* rgb: interleaved 8-bit RGB, `stride` bytes per row (>= 3*w).  Uploads, builds and caches
+ * the source's six-scale XYB pyramid on the device. */
+int oavif_ssimu2_set_source_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w,
+                                 uint32_t h, size_t stride);
+
+/* ---- distorted side: once per search pass (tq.zig:150) ------------------------------------- */
+
+int oavif_ssimu2_score_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *dist, size_t stride,
+                            double *score);
+
+/* Decoded planes as libavif hands them over: depth 8 -> uint8_t samples, depth 10 -> uint16_t;
+ * strides in BYTES; full range; matrix = AV1 matrix_coefficients (1, 2, 5, 6, 9).
+ * rgba_path != 0 reproduces the conversion libavif runs when the decoded image has an alpha
+ * plane (io.zig:473); alpha itself is never scored (io.zig:654-663). */
+int oavif_ssimu2_score_yuv444(oavif_ssimu2_ctx *ctx, const void *y, const void *u, const void *v,
+                              size_t y_stride, size_t u_stride, size_t v_stride, int depth,
+                              int matrix, int rgba_path, double *score);
+
+/* n candidates (n <= max_batch) against the cached source in one pass over the device. */
+int oavif_ssimu2_score_batch_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *dists,
+                                  size_t stride, double *scores);
+int oavif_ssimu2_score_batch_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y,
+                                    const void *const *u, const void *const *v, size_t y_stride,
+                                    size_t u_stride, size_t v_stride, int depth, int matrix,
+                                    int rgba_path, double *scores);
+
+/* ---- device-resident inputs (pointers are CUDA device pointers on the context's device) -- */
+
+int oavif_ssimu2_set_source_rgb8_dev(oavif_ssimu2_ctx *ctx, const uint8_t *d_rgb, uint32_t w,
+                                     uint32_t h, size_t stride);
+int oavif_ssimu2_score_batch_rgb8_dev(oavif_ssimu2_ctx *ctx, uint32_t n,
+                                      const uint8_t *const *d_dists, size_t stride, double *scores);
+int oavif_ssimu2_score_batch_yuv444_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *d_y,
+                                        const void *const *d_u, const void *const *d_v,
+                                        size_t y_stride, size_t u_stride, size_t v_stride,
+                                        int depth, int matrix, int rgba_path, double *scores);
+
+/* ---- stateless forms ------------------------------------------------------------------------ */
+
+/* fssimu2.computeSsimu2(ref, dist, w, h, channels) — tq.zig:37.  channels must be 3 (the only
+ * value oavif passes); tight rows.  Creates and destroys a context internally on device 0. */
+int oavif_ssimu2_compute_rgb8(const uint8_t *ref, const uint8_t *dist, uint32_t w, uint32_t h,
+                              uint32_t channels, double *score);
+
+/* decodeAvifToRgb's pixel work (io.zig:470-478, 654-663) alone: planes -> tight RGB8. */
+int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void *u, const void *v,
+                                size_t y_stride, size_t u_stride, size_t v_stride, uint32_t w,
+                                uint32_t h, int depth, int matrix, int rgba_path, uint8_t *rgb_out);
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+
+int oavif_ssimu2_get_detail(oavif_ssimu2_ctx *ctx, uint32_t candidate, oavif_ssimu2_detail *out);
+int oavif_ssimu2_get_timing(oavif_ssimu2_ctx *ctx, oavif_ssimu2_timing *out);
+
+/* Copy one XYB plane of the cached pyramids to the host (tight w_s*h_s floats).
+ * which: 0 = source, 1 + k = candidate k of the last score call.  channel: 0 X, 1 Y, 2 B. */
+int oavif_ssimu2_debug_get_xyb(oavif_ssimu2_ctx *ctx, int which, int scale, int channel,
+                               float *out, uint32_t *w_out, uint32_t *h_out);
+
+/* Blur one host plane with the selected blur on the device (tests of the filter alone). */
+int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, uint32_t h,
+                            float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
