@@ -1,0 +1,823 @@
+// ssimu2_api.cu — the C ABI of include/oavif_ssimu2.h: context, HBM layout, launches.
+//
+// Product path only: no CPU fallback, nothing from oracle/.  Build (see oavif_b200/build.py):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+//
+// HBM layout per context (sized once in ctx_create for max_w x max_h x max_batch):
+//   in_src / in_dist[k]   staged input pixels (RGB8, or 3 YUV planes of u8/u16), tight rows
+//   src_pyr               source XYB pyramid: scales 0..5, 3 f32 planes each (Geom)
+//   dist_pyr[k]           one XYB pyramid per candidate
+//   hplanes[k]            RECURSIVE blur only: 5 row-filtered planes per channel and scale
+//   partials[k][cta][6]   per-CTA pooled sums (double), reduced in fixed order by k_finalize
+//   sums[k][6][18], scores[k]
+#include "../../include/oavif_ssimu2.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "ssimu2_common.cuh"
+#include "ssimu2_finalize.cuh"
+#include "ssimu2_fir.cuh"
+#include "ssimu2_iir.cuh"
+#include "ssimu2_pyramid.cuh"
+
+using namespace oavif;
+
+namespace {
+
+thread_local std::string t_last_error;
+
+struct HostPlanes {  // one candidate's input, host or device pointers
+    const void *p[3];
+};
+
+}  // namespace
+
+struct oavif_ssimu2_ctx {
+    int device = 0;
+    uint32_t max_w = 0, max_h = 0, max_batch = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
+
+    // capacities (computed from max_w x max_h)
+    long long cap_pyr_floats = 0, cap_in_bytes = 0, cap_ctas = 0, cap_hplane_floats = 0;
+
+    // current image
+    bool have_source = false;
+    Geom g{};
+    uint32_t last_n = 0;
+
+    uint8_t *d_in_src = nullptr, *d_in_dist = nullptr;
+    float *d_src_pyr = nullptr, *d_dist_pyr = nullptr, *d_hplanes = nullptr, *d_lut = nullptr;
+    const void **d_tbl = nullptr, **h_tbl = nullptr;
+    double *d_partials = nullptr, *d_sums = nullptr, *d_scores = nullptr;
+    double *h_sums = nullptr, *h_scores = nullptr;
+    float *d_dbg = nullptr;
+    long long dbg_floats = 0;
+    cudaEvent_t ev[5] = {};
+    oavif_ssimu2_timing timing{};
+    float taps[9] = {};
+    IirCoef iir{};
+    std::string err;
+};
+
+namespace {
+
+int fail(oavif_ssimu2_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? OAVIF_SSIMU2_E_NOMEM : OAVIF_SSIMU2_E_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int rup(int a, int b) { return cdiv(a, b) * b; }
+
+// Scale schedule of v2.1 §2: the size test looks at the previous scale's dimensions.
+void make_geom(int w, int h, Geom *g)
+{
+    memset(g, 0, sizeof *g);
+    const int tiles_x = cdiv(w, kPyrTile), tiles_y = cdiv(h, kPyrTile);
+    int cw = w, ch = h;
+    long long off = 0;
+    for (int s = 0; s < kMaxScales; ++s) {
+        if (cw < 8 || ch < 8) break;
+        if (s) {
+            cw = (cw + 1) / 2;
+            ch = (ch + 1) / 2;
+        }
+        g->w[s] = cw;
+        g->h[s] = ch;
+        g->pitch[s] = rup(tiles_x * (kPyrTile >> s), 32);
+        g->rows[s] = tiles_y * (kPyrTile >> s);
+        g->plane[s] = (long long)g->pitch[s] * g->rows[s];
+        g->off[s] = off;
+        off += 3 * g->plane[s];
+        g->n_scales = s + 1;
+    }
+    g->pyr_floats = off;
+}
+
+// Allocation never depends on the scale schedule: size for all six scales of max_w x max_h.
+long long pyr_capacity(int w, int h)
+{
+    const int tiles_x = cdiv(w, kPyrTile), tiles_y = cdiv(h, kPyrTile);
+    long long off = 0;
+    for (int s = 0; s < kMaxScales; ++s)
+        off += 3LL * rup(tiles_x * (kPyrTile >> s), 32) * (tiles_y * (kPyrTile >> s));
+    return off;
+}
+
+struct BlurPlan {
+    int first_cta[kMaxScales + 1];
+    int per_channel[kMaxScales];
+    int tiles_x[kMaxScales], tiles_y[kMaxScales];
+    int total;
+};
+
+void plan_fir(const Geom &g, BlurPlan *p)
+{
+    memset(p, 0, sizeof *p);
+    int acc = 0;
+    for (int s = 0; s < g.n_scales; ++s) {
+        p->tiles_x[s] = cdiv(g.w[s], kFirTW);
+        p->tiles_y[s] = cdiv(g.h[s], kFirTH);
+        p->per_channel[s] = p->tiles_x[s] * p->tiles_y[s];
+        p->first_cta[s] = acc;
+        acc += 3 * p->per_channel[s];
+    }
+    for (int s = g.n_scales; s <= kMaxScales; ++s) p->first_cta[s] = acc;
+    p->total = acc;
+}
+
+void plan_iir_v(const Geom &g, BlurPlan *p)
+{
+    memset(p, 0, sizeof *p);
+    int acc = 0;
+    for (int s = 0; s < g.n_scales; ++s) {
+        p->tiles_x[s] = cdiv(g.w[s], kIirVCols);
+        p->tiles_y[s] = 1;
+        p->per_channel[s] = p->tiles_x[s];
+        p->first_cta[s] = acc;
+        acc += 3 * p->per_channel[s];
+    }
+    for (int s = g.n_scales; s <= kMaxScales; ++s) p->first_cta[s] = acc;
+    p->total = acc;
+}
+
+long long cta_capacity(int w, int h)
+{
+    Geom g;
+    make_geom(w, h, &g);
+    BlurPlan a, b;
+    plan_fir(g, &a);
+    plan_iir_v(g, &b);
+    // smaller images inside the same bounding box never need more CTAs than the box itself,
+    // but a transposed image can: size for the larger of both orientations
+    Geom gt;
+    make_geom(h, w, &gt);
+    BlurPlan at, bt;
+    plan_fir(gt, &at);
+    plan_iir_v(gt, &bt);
+    int m = a.total;
+    if (b.total > m) m = b.total;
+    if (at.total > m) m = at.total;
+    if (bt.total > m) m = bt.total;
+    return m + 64;
+}
+
+// Closed form of the 9 taps: h[m] = sum_k beta_k cos(omega_k m), |m| <= N-1 (Charalampidis 2016,
+// truncated cosines k in {1,3,5}); also yields the recursion coefficients n2, d1.
+void solve_gaussian(double sigma, float taps[9], IirCoef *iir)
+{
+    const double kPi = 3.141592653589793238;
+    const double N = (double)std::lround(3.2795 * sigma + 0.2546);
+    const double om[3] = {kPi / (2.0 * N), 3.0 * kPi / (2.0 * N), 5.0 * kPi / (2.0 * N)};
+    const double p1 = 1.0 / std::tan(0.5 * om[0]), p3 = -1.0 / std::tan(0.5 * om[1]),
+                 p5 = 1.0 / std::tan(0.5 * om[2]);
+    const double r1 = p1 * p1 / std::sin(om[0]), r3 = -p3 * p3 / std::sin(om[1]),
+                 r5 = p5 * p5 / std::sin(om[2]);
+    double rho[3];
+    for (int i = 0; i < 3; ++i) rho[i] = std::exp(-0.5 * sigma * sigma * om[i] * om[i]) / N;
+    const double D13 = p1 * r3 - r1 * p3, D35 = p3 * r5 - r3 * p5, D51 = p5 * r1 - r5 * p1;
+    const double z15 = D35 / D13, z35 = D51 / D13;
+    // solve [p1 p3 p5; r1 r3 r5; z15 z35 1] beta = [1, N^2 - sigma^2, z15 rho1 + z35 rho3 + rho5]
+    double A[3][4] = {{p1, p3, p5, 1.0},
+                      {r1, r3, r5, N * N - sigma * sigma},
+                      {z15, z35, 1.0, z15 * rho[0] + z35 * rho[1] + rho[2]}};
+    for (int c = 0; c < 3; ++c) {  // Gauss-Jordan with partial pivoting
+        int piv = c;
+        for (int r = c + 1; r < 3; ++r)
+            if (std::fabs(A[r][c]) > std::fabs(A[piv][c])) piv = r;
+        for (int k = 0; k < 4; ++k) std::swap(A[c][k], A[piv][k]);
+        for (int r = 0; r < 3; ++r) {
+            if (r == c) continue;
+            const double f = A[r][c] / A[c][c];
+            for (int k = c; k < 4; ++k) A[r][k] -= f * A[c][k];
+        }
+    }
+    double beta[3];
+    for (int i = 0; i < 3; ++i) beta[i] = A[i][3] / A[i][i];
+    const int R = (int)N - 1;  // 4
+    for (int m = -R; m <= R; ++m) {
+        double hm = 0.0;
+        for (int i = 0; i < 3; ++i) hm += beta[i] * std::cos(om[i] * m);
+        taps[m + R] = (float)hm;
+    }
+    for (int i = 0; i < 3; ++i) {
+        iir->n2[i] = (float)(-beta[i] * std::cos(om[i] * (N + 1.0)));
+        iir->d1[i] = (float)(-2.0 * std::cos(om[i]));
+    }
+}
+
+int kind_of(int depth, int rgba_path)
+{
+    if (depth == 8) return IN_YUV8;
+    if (depth == 10) return rgba_path ? IN_YUV10_RGBA : IN_YUV10_RGB;
+    return -1;
+}
+
+bool yuv_consts(int matrix, YuvK *k)
+{
+    switch (matrix) {
+    case 2: case 5: case 6: *k = YuvK{16320, 32, 113, 22, 46, 90}; return true;
+    case 1: *k = YuvK{16320, 32, 119, 12, 30, 101}; return true;
+    case 9: *k = YuvK{16320, 32, 120, 11, 37, 94}; return true;
+    default: return false;
+    }
+}
+
+template <int KIND>
+void launch_pyr_kind(const PyrArgs &a, dim3 grid, cudaStream_t st)
+{
+    k_pyramid<KIND><<<grid, 256, 0, st>>>(a);
+}
+
+void launch_pyramid(int kind, const PyrArgs &a, int n, cudaStream_t st)
+{
+    const dim3 grid(cdiv(a.g.w[0], kPyrTile), cdiv(a.g.h[0], kPyrTile), n);
+    switch (kind) {
+    case IN_RGB8: launch_pyr_kind<IN_RGB8>(a, grid, st); break;
+    case IN_YUV8: launch_pyr_kind<IN_YUV8>(a, grid, st); break;
+    case IN_YUV10_RGB: launch_pyr_kind<IN_YUV10_RGB>(a, grid, st); break;
+    default: launch_pyr_kind<IN_YUV10_RGBA>(a, grid, st); break;
+    }
+}
+
+struct InputDesc {
+    int kind;            // InputKind
+    size_t stride[3];    // caller strides, bytes
+    int matrix;
+    bool on_device;      // caller pointers are device pointers
+};
+
+// Bytes per row actually holding pixels, per plane.
+size_t row_bytes(int kind, int w) { return kind == IN_RGB8 ? 3u * w : (kind == IN_YUV8 ? (size_t)w : 2u * w); }
+int nplanes(int kind) { return kind == IN_RGB8 ? 1 : 3; }
+
+// Stage (if host) `n` images and build their pyramids into `out`.  `slot0` selects the staging
+// buffer: the source uses in_src, candidates use in_dist.
+int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const HostPlanes *imgs,
+                   bool is_source, float *out, long long out_stride)
+{
+    const Geom &g = ctx->g;
+    const int w = g.w[0], h = g.h[0];
+    PyrArgs a{};
+    a.g = g;
+    a.out = out;
+    a.out_stride = out_stride;
+    a.lut = ctx->d_lut;
+    if (d.kind != IN_RGB8 && !yuv_consts(d.matrix, &a.k))
+        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "matrix_coefficients %d not on the scored path", d.matrix);
+    const size_t rb = row_bytes(d.kind, w);
+    const int np = nplanes(d.kind);
+    const int tbl0 = is_source ? 0 : 3;  // table rows: [0..2] source, [3..] candidates
+    if (d.on_device) {
+        for (uint32_t i = 0; i < n; ++i)
+            for (int p = 0; p < 3; ++p) ctx->h_tbl[tbl0 + 3 * i + p] = imgs[i].p[p < np ? p : 0];
+        for (int p = 0; p < 3; ++p) a.stride[p] = (long long)d.stride[p < np ? p : 0];
+    } else {
+        // tight rows on the device, each plane start 256-byte aligned
+        const size_t plane_bytes = (rb * h + 255) & ~(size_t)255;
+        uint8_t *base = is_source ? ctx->d_in_src : ctx->d_in_dist;
+        for (uint32_t i = 0; i < n; ++i)
+            for (int p = 0; p < np; ++p) {
+                uint8_t *dst = base + ((size_t)i * np + p) * plane_bytes;
+                CK(cudaMemcpy2DAsync(dst, rb, imgs[i].p[p], d.stride[p], rb, h, cudaMemcpyHostToDevice,
+                                     ctx->stream));
+                ctx->h_tbl[tbl0 + 3 * i + p] = dst;
+            }
+        if (np == 1)
+            for (uint32_t i = 0; i < n; ++i)
+                ctx->h_tbl[tbl0 + 3 * i + 1] = ctx->h_tbl[tbl0 + 3 * i + 2] = ctx->h_tbl[tbl0 + 3 * i];
+        for (int p = 0; p < 3; ++p) a.stride[p] = (long long)rb;
+    }
+    CK(cudaMemcpyAsync(ctx->d_tbl + tbl0, ctx->h_tbl + tbl0, sizeof(void *) * 3 * n, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    a.planes = ctx->d_tbl + tbl0;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    launch_pyramid(d.kind, a, (int)n, ctx->stream);
+    CK(cudaGetLastError());
+    ctx->timing.launches += 1;
+    return 0;
+}
+
+int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
+{
+    if (w == 0 || h == 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "zero image dimension");
+    if (w > (1u << 16) || h > (1u << 16)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "dimension above 65536");
+    if (pyr_capacity((int)w, (int)h) > ctx->cap_pyr_floats || (long long)w * h * 6 + 3 * 256 > ctx->cap_in_bytes)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "image %ux%u exceeds context capacity %ux%u", w, h, ctx->max_w,
+                    ctx->max_h);
+    return 0;
+}
+
+int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
+{
+    const Geom &g = ctx->g;
+    BlurPlan plan;
+    if (ctx->blur_mode == OAVIF_SSIMU2_BLUR_FIR) {
+        plan_fir(g, &plan);
+        BlurArgs b{};
+        b.g = g;
+        b.src = ctx->d_src_pyr;
+        b.dist = ctx->d_dist_pyr;
+        b.dist_stride = ctx->cap_pyr_floats;
+        b.partials = ctx->d_partials;
+        b.partials_stride = ctx->cap_ctas * 6;
+        for (int s = 0; s <= kMaxScales; ++s) b.first_cta[s] = plan.first_cta[s];
+        for (int s = 0; s < kMaxScales; ++s) {
+            b.tiles_x[s] = plan.tiles_x[s];
+            b.tiles_y[s] = plan.tiles_y[s];
+        }
+        memcpy(b.taps, ctx->taps, sizeof b.taps);
+        k_fir_fused<<<dim3(plan.total, n), kFirThreads, kFirSmemBytes, ctx->stream>>>(b);
+        CK(cudaGetLastError());
+        ctx->timing.launches += 1;
+    } else {
+        plan_iir_v(g, &plan);
+        int launches = 0;
+        const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats,
+                                              ctx->d_hplanes, ctx->cap_hplane_floats, ctx->d_partials,
+                                              ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, (int)n,
+                                              ctx->stream, &launches);
+        if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "recursive blur launch: %s", cudaGetErrorString(e));
+        ctx->timing.launches += launches;
+    }
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+
+    FinalArgs f{};
+    f.n_scales = g.n_scales;
+    for (int s = 0; s < kMaxScales; ++s) {
+        f.w[s] = g.w[s];
+        f.h[s] = g.h[s];
+        f.ctas_per_channel[s] = plan.per_channel[s];
+    }
+    for (int s = 0; s <= kMaxScales; ++s) f.first_cta[s] = plan.first_cta[s];
+    f.partials = ctx->d_partials;
+    f.partials_stride = ctx->cap_ctas * 6;
+    f.sums = ctx->d_sums;
+    f.scores = ctx->d_scores;
+    k_finalize<<<n, 1024, 0, ctx->stream>>>(f);
+    CK(cudaGetLastError());
+    ctx->timing.launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_scores, ctx->d_scores, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, sizeof(double) * n * kMaxScales * 18, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < n; ++i) scores[i] = ctx->h_scores[i];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing.pyramid_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.blur_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.finalize_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->timing.total_ms = ms;
+    return 0;
+}
+
+int score_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const HostPlanes *imgs, double *scores)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (!scores || !imgs || n == 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument or empty batch");
+    if (!ctx->have_source) return fail(ctx, OAVIF_SSIMU2_E_STATE, "score called before set_source");
+    if (n > ctx->max_batch) return fail(ctx, OAVIF_SSIMU2_E_STATE, "batch %u exceeds max_batch %u", n, ctx->max_batch);
+    const int w = ctx->g.w[0], h = ctx->g.h[0];
+    const int np = nplanes(d.kind);
+    for (uint32_t i = 0; i < n; ++i)
+        for (int p = 0; p < np; ++p)
+            if (!imgs[i].p[p]) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null plane pointer (candidate %u)", i);
+    for (int p = 0; p < np; ++p)
+        if (d.stride[p] < row_bytes(d.kind, w)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "stride smaller than a row");
+    (void)h;
+    CK(cudaSetDevice(ctx->device));
+    ctx->timing = oavif_ssimu2_timing{};
+    ctx->last_n = n;
+    if (ctx->g.n_scales == 0) {  // below 8x8 nothing is evaluated: the published result is 100
+        for (uint32_t i = 0; i < n; ++i) scores[i] = 100.0;
+        memset(ctx->h_sums, 0, sizeof(double) * n * kMaxScales * 18);
+        for (uint32_t i = 0; i < n; ++i) ctx->h_scores[i] = 100.0;
+        return 0;
+    }
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    const int rc = build_pyramids(ctx, d, n, imgs, false, ctx->d_dist_pyr, ctx->cap_pyr_floats);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    return run_blur_and_finalize(ctx, n, scores);
+}
+
+int set_source_common(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, size_t stride,
+                      bool on_device)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (!rgb) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null source pointer");
+    int rc = check_size(ctx, w, h);
+    if (rc) return rc;
+    if (stride < (size_t)3 * w) return fail(ctx, OAVIF_SSIMU2_E_ARG, "source stride smaller than a row");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_source = false;
+    make_geom((int)w, (int)h, &ctx->g);
+    if (ctx->g.n_scales == 0) {  // geometry still needed for argument checks in score_*
+        ctx->g.w[0] = (int)w;
+        ctx->g.h[0] = (int)h;
+        ctx->have_source = true;
+        return 0;
+    }
+    InputDesc d{};
+    d.kind = IN_RGB8;
+    d.stride[0] = stride;
+    d.on_device = on_device;
+    HostPlanes hp{{rgb, nullptr, nullptr}};
+    ctx->timing = oavif_ssimu2_timing{};
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = build_pyramids(ctx, d, 1, &hp, true, ctx->d_src_pyr, 0);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing.pyramid_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]); ctx->timing.total_ms = ms;
+    ctx->have_source = true;
+    return 0;
+}
+
+}  // namespace
+
+// ================================== C ABI ======================================================
+
+extern "C" {
+
+int oavif_ssimu2_abi_version(void) { return OAVIF_SSIMU2_ABI_VERSION; }
+
+const char *oavif_ssimu2_last_error(const oavif_ssimu2_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : t_last_error.c_str();
+}
+
+void *oavif_ssimu2_pinned_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        t_last_error = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+
+void oavif_ssimu2_pinned_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_in_src);
+    cudaFree(ctx->d_in_dist);
+    cudaFree(ctx->d_src_pyr);
+    cudaFree(ctx->d_dist_pyr);
+    cudaFree(ctx->d_hplanes);
+    cudaFree(ctx->d_lut);
+    cudaFree((void *)ctx->d_tbl);
+    cudaFree(ctx->d_partials);
+    cudaFree(ctx->d_sums);
+    cudaFree(ctx->d_scores);
+    cudaFree(ctx->d_dbg);
+    cudaFreeHost((void *)ctx->h_tbl);
+    cudaFreeHost(ctx->h_sums);
+    cudaFreeHost(ctx->h_scores);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch,
+                            oavif_ssimu2_ctx **out)
+{
+    if (!out) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null out pointer");
+    *out = nullptr;
+    if (max_w == 0 || max_h == 0 || max_batch == 0 || max_w > (1u << 16) || max_h > (1u << 16))
+        return fail(nullptr, OAVIF_SSIMU2_E_ARG, "bad context capacity %ux%ux%u", max_w, max_h, max_batch);
+    oavif_ssimu2_ctx *ctx = new (std::nothrow) oavif_ssimu2_ctx();
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->max_w = max_w;
+    ctx->max_h = max_h;
+    ctx->max_batch = max_batch;
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            const int rc_ = fail(nullptr, e_ == cudaErrorMemoryAllocation ? OAVIF_SSIMU2_E_NOMEM : OAVIF_SSIMU2_E_CUDA, \
+                                 "%s failed: %s", #call, cudaGetErrorString(e_));                  \
+            oavif_ssimu2_ctx_destroy(ctx);                                                         \
+            return rc_;                                                                            \
+        }                                                                                          \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (auto &e : ctx->ev) CKC(cudaEventCreate(&e));
+
+    const int mw = (int)max_w, mh = (int)max_h;
+    ctx->cap_pyr_floats = std::max(pyr_capacity(mw, mh), pyr_capacity(mh, mw));
+    ctx->cap_in_bytes = (long long)mw * mh * 6 + 3 * 256;
+    ctx->cap_ctas = cta_capacity(mw, mh);
+    ctx->cap_hplane_floats = iir_hplane_floats(ctx->cap_pyr_floats);
+
+    CKC(cudaMalloc(&ctx->d_in_src, (size_t)ctx->cap_in_bytes));
+    CKC(cudaMalloc(&ctx->d_in_dist, (size_t)ctx->cap_in_bytes * max_batch));
+    CKC(cudaMalloc(&ctx->d_src_pyr, sizeof(float) * ctx->cap_pyr_floats));
+    CKC(cudaMalloc(&ctx->d_dist_pyr, sizeof(float) * ctx->cap_pyr_floats * max_batch));
+    CKC(cudaMalloc(&ctx->d_hplanes, sizeof(float) * ctx->cap_hplane_floats * max_batch));
+    CKC(cudaMalloc(&ctx->d_lut, sizeof(float) * 256));
+    CKC(cudaMalloc((void **)&ctx->d_tbl, sizeof(void *) * 3 * (max_batch + 1)));
+    CKC(cudaHostAlloc((void **)&ctx->h_tbl, sizeof(void *) * 3 * (max_batch + 1), cudaHostAllocDefault));
+    CKC(cudaMalloc(&ctx->d_partials, sizeof(double) * 6 * ctx->cap_ctas * max_batch));
+    CKC(cudaMalloc(&ctx->d_sums, sizeof(double) * kMaxScales * 18 * max_batch));
+    CKC(cudaMalloc(&ctx->d_scores, sizeof(double) * max_batch));
+    CKC(cudaHostAlloc((void **)&ctx->h_sums, sizeof(double) * kMaxScales * 18 * max_batch, cudaHostAllocDefault));
+    CKC(cudaHostAlloc((void **)&ctx->h_scores, sizeof(double) * max_batch, cudaHostAllocDefault));
+
+    // sRGB -> linear table (v2.1 §1): double evaluation, one rounding to binary32
+    float lut[256];
+    for (int i = 0; i < 256; ++i) {
+        const double v = (double)i / 255.0;
+        lut[i] = (float)((v <= 0.04045) ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4));
+    }
+    CKC(cudaMemcpy(ctx->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
+    solve_gaussian(1.5, ctx->taps, &ctx->iir);
+
+    CKC(cudaFuncSetAttribute(k_fir_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirSmemBytes));
+    CKC(iir_configure());
+#undef CKC
+    *out = ctx;
+    return 0;
+}
+
+int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (option == OAVIF_SSIMU2_OPT_BLUR &&
+        (value == OAVIF_SSIMU2_BLUR_RECURSIVE || value == OAVIF_SSIMU2_BLUR_FIR)) {
+        ctx->blur_mode = value;
+        return 0;
+    }
+    return fail(ctx, OAVIF_SSIMU2_E_ARG, "unknown option %d / value %d", option, value);
+}
+
+int oavif_ssimu2_set_stream(oavif_ssimu2_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+int oavif_ssimu2_set_source_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, size_t stride)
+{
+    return set_source_common(ctx, rgb, w, h, stride, false);
+}
+
+int oavif_ssimu2_set_source_rgb8_dev(oavif_ssimu2_ctx *ctx, const uint8_t *d_rgb, uint32_t w, uint32_t h,
+                                     size_t stride)
+{
+    return set_source_common(ctx, d_rgb, w, h, stride, true);
+}
+
+int oavif_ssimu2_score_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *dist, size_t stride, double *score)
+{
+    InputDesc d{};
+    d.kind = IN_RGB8;
+    d.stride[0] = stride;
+    HostPlanes hp{{dist, nullptr, nullptr}};
+    return score_common(ctx, d, 1, &hp, score);
+}
+
+static int batch_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *dists, size_t stride,
+                      double *scores, bool dev)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (!dists || n == 0 || n > ctx->max_batch) return fail(ctx, OAVIF_SSIMU2_E_ARG, "bad batch (n=%u)", n);
+    InputDesc d{};
+    d.kind = IN_RGB8;
+    d.stride[0] = stride;
+    d.on_device = dev;
+    HostPlanes *hp = new (std::nothrow) HostPlanes[n];
+    if (!hp) return fail(ctx, OAVIF_SSIMU2_E_NOMEM, "out of host memory");
+    for (uint32_t i = 0; i < n; ++i) hp[i] = HostPlanes{{dists[i], nullptr, nullptr}};
+    const int rc = score_common(ctx, d, n, hp, scores);
+    delete[] hp;
+    return rc;
+}
+
+int oavif_ssimu2_score_batch_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *dists, size_t stride,
+                                  double *scores)
+{
+    return batch_rgb8(ctx, n, dists, stride, scores, false);
+}
+
+int oavif_ssimu2_score_batch_rgb8_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *d_dists,
+                                      size_t stride, double *scores)
+{
+    return batch_rgb8(ctx, n, d_dists, stride, scores, true);
+}
+
+static int batch_yuv(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y, const void *const *u,
+                     const void *const *v, size_t ys, size_t us, size_t vs, int depth, int matrix, int rgba_path,
+                     double *scores, bool dev)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (!y || !u || !v || n == 0 || n > ctx->max_batch) return fail(ctx, OAVIF_SSIMU2_E_ARG, "bad batch (n=%u)", n);
+    const int kind = kind_of(depth, rgba_path);
+    if (kind < 0) return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "depth %d not on the scored path (8 or 10)", depth);
+    YuvK k;
+    if (!yuv_consts(matrix, &k))
+        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "matrix_coefficients %d not on the scored path", matrix);
+    InputDesc d{};
+    d.kind = kind;
+    d.stride[0] = ys;
+    d.stride[1] = us;
+    d.stride[2] = vs;
+    d.matrix = matrix;
+    d.on_device = dev;
+    HostPlanes *hp = new (std::nothrow) HostPlanes[n];
+    if (!hp) return fail(ctx, OAVIF_SSIMU2_E_NOMEM, "out of host memory");
+    for (uint32_t i = 0; i < n; ++i) hp[i] = HostPlanes{{y[i], u[i], v[i]}};
+    const int rc = score_common(ctx, d, n, hp, scores);
+    delete[] hp;
+    return rc;
+}
+
+int oavif_ssimu2_score_yuv444(oavif_ssimu2_ctx *ctx, const void *y, const void *u, const void *v, size_t ys,
+                              size_t us, size_t vs, int depth, int matrix, int rgba_path, double *score)
+{
+    return batch_yuv(ctx, 1, &y, &u, &v, ys, us, vs, depth, matrix, rgba_path, score, false);
+}
+
+int oavif_ssimu2_score_batch_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y, const void *const *u,
+                                    const void *const *v, size_t ys, size_t us, size_t vs, int depth, int matrix,
+                                    int rgba_path, double *scores)
+{
+    return batch_yuv(ctx, n, y, u, v, ys, us, vs, depth, matrix, rgba_path, scores, false);
+}
+
+int oavif_ssimu2_score_batch_yuv444_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y,
+                                        const void *const *u, const void *const *v, size_t ys, size_t us,
+                                        size_t vs, int depth, int matrix, int rgba_path, double *scores)
+{
+    return batch_yuv(ctx, n, y, u, v, ys, us, vs, depth, matrix, rgba_path, scores, true);
+}
+
+int oavif_ssimu2_compute_rgb8(const uint8_t *ref, const uint8_t *dist, uint32_t w, uint32_t h, uint32_t channels,
+                              double *score)
+{
+    // The reference's stateless call (tq.zig:37).  One cached context per process, regrown on demand.
+    static std::mutex mu;
+    static oavif_ssimu2_ctx *cached = nullptr;
+    if (!ref || !dist || !score) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null argument");
+    if (channels != 3) return fail(nullptr, OAVIF_SSIMU2_E_UNSUPPORTED, "channels = %u (oavif always passes 3)", channels);
+    if (w == 0 || h == 0) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "zero image dimension");
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached && (pyr_capacity((int)w, (int)h) > cached->cap_pyr_floats ||
+                   (long long)w * h * 6 + 768 > cached->cap_in_bytes)) {
+        oavif_ssimu2_ctx_destroy(cached);
+        cached = nullptr;
+    }
+    if (!cached) {
+        const int rc = oavif_ssimu2_ctx_create(0, w, h, 1, &cached);
+        if (rc) return rc;
+    }
+    int rc = oavif_ssimu2_set_source_rgb8(cached, ref, w, h, (size_t)3 * w);
+    if (rc == 0) rc = oavif_ssimu2_score_rgb8(cached, dist, (size_t)3 * w, score);
+    if (rc) t_last_error = cached->err;
+    return rc;
+}
+
+int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void *u, const void *v, size_t ys,
+                                size_t us, size_t vs, uint32_t w, uint32_t h, int depth, int matrix, int rgba_path,
+                                uint8_t *rgb_out)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (!y || !u || !v || !rgb_out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    const int kind = kind_of(depth, rgba_path);
+    if (kind < 0) return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "depth %d not on the scored path (8 or 10)", depth);
+    Yuv2RgbArgs a{};
+    if (!yuv_consts(matrix, &a.k))
+        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "matrix_coefficients %d not on the scored path", matrix);
+    if (w == 0 || h == 0 || (long long)w * h * 6 + 768 > ctx->cap_in_bytes)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "image %ux%u exceeds context capacity", w, h);
+    const size_t rb = row_bytes(kind, (int)w);
+    if (ys < rb || us < rb || vs < rb) return fail(ctx, OAVIF_SSIMU2_E_ARG, "stride smaller than a row");
+    CK(cudaSetDevice(ctx->device));
+    const size_t plane_bytes = (rb * h + 255) & ~(size_t)255;
+    uint8_t *base = ctx->d_in_dist;
+    const void *src[3] = {y, u, v};
+    const size_t st[3] = {ys, us, vs};
+    for (int p = 0; p < 3; ++p)
+        CK(cudaMemcpy2DAsync(base + p * plane_bytes, rb, src[p], st[p], rb, h, cudaMemcpyHostToDevice, ctx->stream));
+    a.y = base;
+    a.u = base + plane_bytes;
+    a.v = base + 2 * plane_bytes;
+    a.stride[0] = a.stride[1] = a.stride[2] = (long long)rb;
+    a.w = (int)w;
+    a.h = (int)h;
+    a.out = ctx->d_in_src;  // 3 B/px fits the 6 B/px staging buffer
+    const dim3 grid(cdiv((int)w, 256), h);
+    if (kind == IN_YUV8) k_yuv_to_rgb8<IN_YUV8><<<grid, 256, 0, ctx->stream>>>(a);
+    else if (kind == IN_YUV10_RGB) k_yuv_to_rgb8<IN_YUV10_RGB><<<grid, 256, 0, ctx->stream>>>(a);
+    else k_yuv_to_rgb8<IN_YUV10_RGBA><<<grid, 256, 0, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgb_out, a.out, (size_t)w * h * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_source = false;  // the source staging buffer was reused
+    return 0;
+}
+
+int oavif_ssimu2_get_detail(oavif_ssimu2_ctx *ctx, uint32_t candidate, oavif_ssimu2_detail *out)
+{
+    if (!ctx || !out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    if (candidate >= ctx->last_n) return fail(ctx, OAVIF_SSIMU2_E_STATE, "candidate %u not in the last call", candidate);
+    memset(out, 0, sizeof *out);
+    out->n_scales = ctx->g.n_scales;
+    for (int s = 0; s < ctx->g.n_scales; ++s) {
+        out->w[s] = ctx->g.w[s];
+        out->h[s] = ctx->g.h[s];
+        for (int i = 0; i < 18; ++i) out->sums[s][i] = ctx->h_sums[((size_t)candidate * kMaxScales + s) * 18 + i];
+    }
+    out->score = ctx->h_scores[candidate];
+    return 0;
+}
+
+int oavif_ssimu2_get_timing(oavif_ssimu2_ctx *ctx, oavif_ssimu2_timing *out)
+{
+    if (!ctx || !out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    *out = ctx->timing;
+    return 0;
+}
+
+int oavif_ssimu2_debug_get_xyb(oavif_ssimu2_ctx *ctx, int which, int scale, int channel, float *out,
+                               uint32_t *w_out, uint32_t *h_out)
+{
+    if (!ctx || !out || !w_out || !h_out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    if (!ctx->have_source || scale < 0 || scale >= ctx->g.n_scales || channel < 0 || channel > 2 || which < 0 ||
+        which > (int)ctx->max_batch)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such plane");
+    CK(cudaSetDevice(ctx->device));
+    const Geom &g = ctx->g;
+    const float *base = which == 0 ? ctx->d_src_pyr : ctx->d_dist_pyr + (long long)(which - 1) * ctx->cap_pyr_floats;
+    const float *p = base + g.off[scale] + (long long)channel * g.plane[scale];
+    CK(cudaMemcpy2D(out, sizeof(float) * g.w[scale], p, sizeof(float) * g.pitch[scale], sizeof(float) * g.w[scale],
+                    g.h[scale], cudaMemcpyDeviceToHost));
+    *w_out = (uint32_t)g.w[scale];
+    *h_out = (uint32_t)g.h[scale];
+    return 0;
+}
+
+int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, uint32_t h, float *out)
+{
+    if (!ctx || !in || !out || w == 0 || h == 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const int pitch = rup((int)w, 32);
+    const long long need = 3LL * pitch * h;
+    if (need > ctx->dbg_floats) {
+        cudaFree(ctx->d_dbg);
+        ctx->d_dbg = nullptr;
+        ctx->dbg_floats = 0;
+        CK(cudaMalloc(&ctx->d_dbg, sizeof(float) * need));
+        ctx->dbg_floats = need;
+    }
+    float *d_in = ctx->d_dbg, *d_tmp = d_in + (long long)pitch * h, *d_out = d_tmp + (long long)pitch * h;
+    CK(cudaMemcpy2DAsync(d_in, sizeof(float) * pitch, in, sizeof(float) * w, sizeof(float) * w, h,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    const cudaError_t e = launch_debug_blur(ctx->blur_mode == OAVIF_SSIMU2_BLUR_FIR, ctx->taps, ctx->iir, d_in,
+                                            d_tmp, d_out, (int)w, (int)h, pitch, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "debug blur launch: %s", cudaGetErrorString(e));
+    CK(cudaMemcpy2DAsync(out, sizeof(float) * w, d_out, sizeof(float) * pitch, sizeof(float) * w, h,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+// ssimu2_pyramid.cuh — K0+K1+K2+K3 in one launch: decoded pixels -> six-scale XYB pyramid.
+//
+// Replaces, per image: avifImageYUVToRGB + repack (src/io.zig:470-478, 654-663), then the
+// scorer's sRGB->linear, 2x2 downsample chain and linear->XYB at every scale (SURVEY.md
+// Appendix A §1-§3).  One CTA owns a 64x64 scale-0 tile; because the 2x2 box pyramid of a
+// 64-aligned tile only ever looks inside the tile (edge clamping replicates the tile's own
+// last valid row/column), the CTA can walk all six scales without leaving registers/shared
+// memory: linear RGB is never written to HBM.  HBM traffic per scale-0 pixel: 3..6 B read,
+// 12 B * 1.333 written.
+#pragma once
+
+#include "ssimu2_common.cuh"
+
+namespace oavif {
+
+struct PyrArgs {
+    Geom g;
+    const void *const *planes;  // device table, 3 pointers per image (RGB8 uses the first)
+    long long stride[3];        // bytes per input row
+    float *out;                 // pyramid of image 0
+    long long out_stride;       // floats between consecutive images' pyramids
+    const float *lut;           // 256-entry sRGB->linear table
+    YuvK k;
+};
+
+// Load pixels x0..x0+3 of row y (coordinates clamped to the image) as 8-bit RGB.
+template <int KIND>
+__device__ __forceinline__ void load4_rgb8(const PyrArgs &a, const void *p0, const void *p1,
+                                           const void *p2, int x0, int y, int rgb[4][3])
+{
+    const int w = a.g.w[0];
+    const bool inside = (x0 + 3 < w);
+    if (KIND == IN_RGB8) {
+        const uint8_t *row = (const uint8_t *)p0 + (long long)y * a.stride[0];
+        const uint8_t *q = row + 3 * x0;
+        if (inside && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+            const uint32_t w0 = __ldg((const uint32_t *)q), w1 = __ldg((const uint32_t *)q + 1),
+                           w2 = __ldg((const uint32_t *)q + 2);
+            rgb[0][0] = w0 & 255; rgb[0][1] = (w0 >> 8) & 255; rgb[0][2] = (w0 >> 16) & 255;
+            rgb[1][0] = w0 >> 24; rgb[1][1] = w1 & 255; rgb[1][2] = (w1 >> 8) & 255;
+            rgb[2][0] = (w1 >> 16) & 255; rgb[2][1] = w1 >> 24; rgb[2][2] = w2 & 255;
+            rgb[3][0] = (w2 >> 8) & 255; rgb[3][1] = (w2 >> 16) & 255; rgb[3][2] = w2 >> 24;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int x = min(x0 + i, w - 1);
+                rgb[i][0] = __ldg(row + 3 * x);
+                rgb[i][1] = __ldg(row + 3 * x + 1);
+                rgb[i][2] = __ldg(row + 3 * x + 2);
+            }
+        }
+    } else if (KIND == IN_YUV8) {
+        const uint8_t *ry = (const uint8_t *)p0 + (long long)y * a.stride[0];
+        const uint8_t *ru = (const uint8_t *)p1 + (long long)y * a.stride[1];
+        const uint8_t *rv = (const uint8_t *)p2 + (long long)y * a.stride[2];
+        uint32_t Y[4], U[4], V[4];
+        const bool al = ((reinterpret_cast<uintptr_t>(ry + x0) | reinterpret_cast<uintptr_t>(ru + x0) |
+                          reinterpret_cast<uintptr_t>(rv + x0)) & 3) == 0;
+        if (inside && al) {
+            const uint32_t wy = __ldg((const uint32_t *)(ry + x0)), wu = __ldg((const uint32_t *)(ru + x0)),
+                           wv = __ldg((const uint32_t *)(rv + x0));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                Y[i] = (wy >> (8 * i)) & 255; U[i] = (wu >> (8 * i)) & 255; V[i] = (wv >> (8 * i)) & 255;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int x = min(x0 + i, w - 1);
+                Y[i] = __ldg(ry + x); U[i] = __ldg(ru + x); V[i] = __ldg(rv + x);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) yuv_to_rgb8<KIND>(Y[i], U[i], V[i], a.k, rgb[i][0], rgb[i][1], rgb[i][2]);
+    } else {
+        const uint16_t *ry = (const uint16_t *)((const uint8_t *)p0 + (long long)y * a.stride[0]);
+        const uint16_t *ru = (const uint16_t *)((const uint8_t *)p1 + (long long)y * a.stride[1]);
+        const uint16_t *rv = (const uint16_t *)((const uint8_t *)p2 + (long long)y * a.stride[2]);
+        uint32_t Y[4], U[4], V[4];
+        const bool al = ((reinterpret_cast<uintptr_t>(ry + x0) | reinterpret_cast<uintptr_t>(ru + x0) |
+                          reinterpret_cast<uintptr_t>(rv + x0)) & 7) == 0;
+        if (inside && al) {
+            const uint2 wy = __ldg((const uint2 *)(ry + x0)), wu = __ldg((const uint2 *)(ru + x0)),
+                        wv = __ldg((const uint2 *)(rv + x0));
+            Y[0] = wy.x & 0xffff; Y[1] = wy.x >> 16; Y[2] = wy.y & 0xffff; Y[3] = wy.y >> 16;
+            U[0] = wu.x & 0xffff; U[1] = wu.x >> 16; U[2] = wu.y & 0xffff; U[3] = wu.y >> 16;
+            V[0] = wv.x & 0xffff; V[1] = wv.x >> 16; V[2] = wv.y & 0xffff; V[3] = wv.y >> 16;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int x = min(x0 + i, w - 1);
+                Y[i] = __ldg(ry + x); U[i] = __ldg(ru + x); V[i] = __ldg(rv + x);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) yuv_to_rgb8<KIND>(Y[i], U[i], V[i], a.k, rgb[i][0], rgb[i][1], rgb[i][2]);
+    }
+}
+
+// grid = (tiles_x, tiles_y, n_images), block = 256 (16x16 threads, 4x4 scale-0 pixels each).
+template <int KIND>
+__global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ PyrArgs a)
+{
+    __shared__ float s_lut[256];
+    __shared__ float s_l2[3][16][17];  // scale-2 linear RGB of this tile
+    __shared__ float s_l3[3][8][9];
+    __shared__ float s_l4[3][4][5];
+
+    const int tid = threadIdx.x;
+    s_lut[tid] = a.lut[tid];
+    __syncthreads();
+
+    const Geom &g = a.g;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int bx = blockIdx.x, by = blockIdx.y, img = blockIdx.z;
+    const void *p0 = a.planes[3 * img + 0];
+    const void *p1 = a.planes[3 * img + 1];
+    const void *p2 = a.planes[3 * img + 2];
+    float *pyr = a.out + (long long)img * a.out_stride;
+    const XybConst kx = xyb_consts();
+
+    // ---- scale 0: 4x4 pixels per thread ------------------------------------------------
+    const int x0 = bx * 64 + tx * 4, y0 = by * 64 + ty * 4;
+    float lin[4][4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int y = min(y0 + j, g.h[0] - 1);
+        int rgb[4][3];
+        load4_rgb8<KIND>(a, p0, p1, p2, x0, y, rgb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            lin[j][i][0] = s_lut[rgb[i][0]];
+            lin[j][i][1] = s_lut[rgb[i][1]];
+            lin[j][i][2] = s_lut[rgb[i][2]];
+        }
+    }
+    {
+        float *X = pyr + g.off[0], *Y = X + g.plane[0], *B = Y + g.plane[0];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 vx, vy, vb;
+            linear_to_xyb(kx, lin[j][0][0], lin[j][0][1], lin[j][0][2], vx.x, vy.x, vb.x);
+            linear_to_xyb(kx, lin[j][1][0], lin[j][1][1], lin[j][1][2], vx.y, vy.y, vb.y);
+            linear_to_xyb(kx, lin[j][2][0], lin[j][2][1], lin[j][2][2], vx.z, vy.z, vb.z);
+            linear_to_xyb(kx, lin[j][3][0], lin[j][3][1], lin[j][3][2], vx.w, vy.w, vb.w);
+            const long long o = (long long)(y0 + j) * g.pitch[0] + x0;
+            *reinterpret_cast<float4 *>(X + o) = vx;
+            *reinterpret_cast<float4 *>(Y + o) = vy;
+            *reinterpret_cast<float4 *>(B + o) = vb;
+        }
+    }
+    if (g.n_scales < 2) return;
+
+    // ---- scale 1: 2x2 per thread, from registers -----------------------------------------
+    float l1[2][2][3];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                l1[j][i][c] = box4(lin[2 * j][2 * i][c], lin[2 * j][2 * i + 1][c], lin[2 * j + 1][2 * i][c],
+                                   lin[2 * j + 1][2 * i + 1][c]);
+    {
+        float *X = pyr + g.off[1], *Y = X + g.plane[1], *B = Y + g.plane[1];
+        const int x1 = bx * 32 + tx * 2, y1 = by * 32 + ty * 2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float2 vx, vy, vb;
+            linear_to_xyb(kx, l1[j][0][0], l1[j][0][1], l1[j][0][2], vx.x, vy.x, vb.x);
+            linear_to_xyb(kx, l1[j][1][0], l1[j][1][1], l1[j][1][2], vx.y, vy.y, vb.y);
+            const long long o = (long long)(y1 + j) * g.pitch[1] + x1;
+            *reinterpret_cast<float2 *>(X + o) = vx;
+            *reinterpret_cast<float2 *>(Y + o) = vy;
+            *reinterpret_cast<float2 *>(B + o) = vb;
+        }
+    }
+    if (g.n_scales < 3) return;
+
+    // ---- scale 2: 1 per thread; scale-1 coordinates clamp inside the thread's 2x2 --------
+    {
+        const int X2 = bx * 16 + tx, Y2 = by * 16 + ty;
+        const int ib = (2 * X2 + 1 < g.w[1]) ? 1 : 0;
+        const int jb = (2 * Y2 + 1 < g.h[1]) ? 1 : 0;
+        float l2[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float p00 = l1[0][0][c];
+            const float p01 = ib ? l1[0][1][c] : l1[0][0][c];
+            const float p10 = jb ? l1[1][0][c] : l1[0][0][c];
+            const float p11 = jb ? (ib ? l1[1][1][c] : l1[1][0][c]) : (ib ? l1[0][1][c] : l1[0][0][c]);
+            l2[c] = box4(p00, p01, p10, p11);
+            s_l2[c][ty][tx] = l2[c];
+        }
+        float vx, vy, vb;
+        linear_to_xyb(kx, l2[0], l2[1], l2[2], vx, vy, vb);
+        const long long o = (long long)Y2 * g.pitch[2] + X2;
+        float *X = pyr + g.off[2];
+        X[o] = vx;
+        X[o + g.plane[2]] = vy;
+        X[o + 2 * g.plane[2]] = vb;
+    }
+    if (g.n_scales < 4) return;
+    __syncthreads();
+
+    // ---- scale 3: 8x8 per tile, from shared memory; clamp to the tile-local last valid ---
+    if (tid < 64) {
+        const int cx = tid & 7, cy = tid >> 3;
+        const int lx = max(min(2 * cx + 1, g.w[2] - 1 - bx * 16), 0);
+        const int ly = max(min(2 * cy + 1, g.h[2] - 1 - by * 16), 0);
+        float l3[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            l3[c] = box4(s_l2[c][2 * cy][2 * cx], s_l2[c][2 * cy][lx], s_l2[c][ly][2 * cx], s_l2[c][ly][lx]);
+            s_l3[c][cy][cx] = l3[c];
+        }
+        float vx, vy, vb;
+        linear_to_xyb(kx, l3[0], l3[1], l3[2], vx, vy, vb);
+        const long long o = (long long)(by * 8 + cy) * g.pitch[3] + bx * 8 + cx;
+        float *X = pyr + g.off[3];
+        X[o] = vx;
+        X[o + g.plane[3]] = vy;
+        X[o + 2 * g.plane[3]] = vb;
+    }
+    if (g.n_scales < 5) return;
+    __syncthreads();
+
+    if (tid < 16) {
+        const int cx = tid & 3, cy = tid >> 2;
+        const int lx = max(min(2 * cx + 1, g.w[3] - 1 - bx * 8), 0);
+        const int ly = max(min(2 * cy + 1, g.h[3] - 1 - by * 8), 0);
+        float l4[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            l4[c] = box4(s_l3[c][2 * cy][2 * cx], s_l3[c][2 * cy][lx], s_l3[c][ly][2 * cx], s_l3[c][ly][lx]);
+            s_l4[c][cy][cx] = l4[c];
+        }
+        float vx, vy, vb;
+        linear_to_xyb(kx, l4[0], l4[1], l4[2], vx, vy, vb);
+        const long long o = (long long)(by * 4 + cy) * g.pitch[4] + bx * 4 + cx;
+        float *X = pyr + g.off[4];
+        X[o] = vx;
+        X[o + g.plane[4]] = vy;
+        X[o + 2 * g.plane[4]] = vb;
+    }
+    if (g.n_scales < 6) return;
+    __syncthreads();
+
+    if (tid < 4) {
+        const int cx = tid & 1, cy = tid >> 1;
+        const int lx = max(min(2 * cx + 1, g.w[4] - 1 - bx * 4), 0);
+        const int ly = max(min(2 * cy + 1, g.h[4] - 1 - by * 4), 0);
+        float l5[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            l5[c] = box4(s_l4[c][2 * cy][2 * cx], s_l4[c][2 * cy][lx], s_l4[c][ly][2 * cx], s_l4[c][ly][lx]);
+        float vx, vy, vb;
+        linear_to_xyb(kx, l5[0], l5[1], l5[2], vx, vy, vb);
+        const long long o = (long long)(by * 2 + cy) * g.pitch[5] + bx * 2 + cx;
+        float *X = pyr + g.off[5];
+        X[o] = vx;
+        X[o + g.plane[5]] = vy;
+        X[o + 2 * g.plane[5]] = vb;
+    }
+}
+
+// decodeAvifToRgb's pixel work alone (io.zig:470-478, 654-663): planes -> tight RGB8.
+struct Yuv2RgbArgs {
+    const void *y, *u, *v;
+    long long stride[3];
+    int w, h;
+    uint8_t *out;
+    YuvK k;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_yuv_to_rgb8(const __grid_constant__ Yuv2RgbArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= a.w || y >= a.h) return;
+    uint32_t Y, U, V;
+    if (KIND == IN_YUV8) {
+        Y = ((const uint8_t *)a.y + (long long)y * a.stride[0])[x];
+        U = ((const uint8_t *)a.u + (long long)y * a.stride[1])[x];
+        V = ((const uint8_t *)a.v + (long long)y * a.stride[2])[x];
+    } else {
+        Y = ((const uint16_t *)((const uint8_t *)a.y + (long long)y * a.stride[0]))[x];
+        U = ((const uint16_t *)((const uint8_t *)a.u + (long long)y * a.stride[1]))[x];
+        V = ((const uint16_t *)((const uint8_t *)a.v + (long long)y * a.stride[2]))[x];
+    }
+    int r, g, b;
+    yuv_to_rgb8<KIND>(Y, U, V, a.k, r, g, b);
+    uint8_t *o = a.out + ((long long)y * a.w + x) * 3;
+    o[0] = (uint8_t)r;
+    o[1] = (uint8_t)g;
+    o[2] = (uint8_t)b;
+}
+
+}  // namespace oavif
