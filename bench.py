@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — SSIMULACRA2 scoring throughput of the B200 path (BASELINE.json metric, config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--blur recursive|fir]
+
+Workload (config.workload): one full SSIMULACRA2 evaluation per step — 3840x2160 RGB8 source
+against a "decoded" 10-bit YUV444 frame, exactly what fssimu2.computeSsimu2 is asked at
+/root/reference/src/tq.zig:37 plus the decode-side YUV->RGB8 (io.zig:470-478).  Synthetic data
+(procedural gradients/edges/noise; the distorted frame is a synthetic degradation carried as 10-bit
+planes: the box's libaom cannot encode high bit depth).
+
+  value   Mpx/s, whole job (all ranks), inputs already resident in HBM, CUDA events, max over ranks
+  e2e     the same through the C ABI with PINNED HOST buffers: H2D of source + planes and the D2H
+          of the score are inside the timed region
+  roofline  the slowest kernel of a step against MEASURED_PEAKS.json's HBM copy bandwidth, with the
+          ALGORITHMIC bytes of SURVEY.md §8(d)
+  cpu_baseline  the CPU oracle (a port: the reference's own scorer, fssimu2, is not available) on
+          the box's host cores, bounded sample, rank 0 at N=1 only
+
+N > 1: one process per GPU (torchrun), images are independent => no collective on the data path;
+each rank scores its own pairs (weak scaling), barrier + max-over-ranks timing via NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 3840, 2160
+MPX = W * H / 1e6
+NSETS = 4  # distinct input pairs rotated so that a step's inputs are never L2-resident
+# SURVEY.md §8(d) algorithmic bytes per SOURCE pixel, S = sum of scale areas = 1.3330 at 4K
+S_SCALES = sum(((W + (1 << s) - 1) >> s) * ((H + (1 << s) - 1) >> s) for s in range(6)) / (W * H)
+ALG_BYTES_FULL = 27 + 6 + 120 * (S_SCALES - 1) + 216 * S_SCALES      # uncached pair, 10-bit YUV distorted
+ALG_BYTES_KERNEL = {"rows": 84 * S_SCALES, "cols": 84 * S_SCALES, "fir": 168 * S_SCALES}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_pairs(seed: int, n: int):
+    """n distinct 4K pairs: one procedural image + synthetic degradation, the others shifted copies
+    (distinct buffers are what keeps a step's inputs out of L2; the content class is the same)."""
+    from oavif_b200.host import synth
+    src = synth.synth(W, H, "mixture", seed)
+    dist = synth.distort(src, 0.25, seed=seed + 1000)
+    y, u, v = synth.rgb8_to_yuv444(dist, 10, 2)
+    out = [(src, (y, u, v))]
+    for i in range(1, n):
+        sh = 97 * i
+        out.append((np.ascontiguousarray(np.roll(src, sh, axis=1)),
+                    tuple(np.ascontiguousarray(np.roll(p, sh, axis=1)) for p in (y, u, v))))
+    return out
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows: list[list[str]] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+_cpu_data = None
+
+
+def cpu_oracle_rate(threads: int, seconds_budget: float, rows_hint: int | None = None):
+    """Mpx/s of the CPU oracle on `threads` host threads, each scoring its own horizontal band of
+    the 4K pair (bounded sample; input generation is outside the timed region).
+    Returns (mpx_per_s, rows_per_band, elapsed_s)."""
+    global _cpu_data
+    from concurrent.futures import ThreadPoolExecutor
+    from oavif_b200.host import synth
+    from oracle import oracle as O
+    if _cpu_data is None:
+        O.build()
+        src = synth.synth(W, 540, "mixture", 0)
+        _cpu_data = (src, synth.distort(src, 0.25, seed=1000))
+    src, dist_rgb = _cpu_data
+    if rows_hint is None:  # calibrate on one 3840x135 strip
+        t0 = time.perf_counter()
+        O.ssimu2_rgb8(src[:135], dist_rgb[:135], O.BLUR_IIR, fast=True)
+        per_row = (time.perf_counter() - t0) / 135
+        rows = int(max(64, min(540, seconds_budget / max(per_row, 1e-6))))
+    else:
+        rows = rows_hint
+
+    def work(i):
+        return O.ssimu2_rgb8(src[:rows], dist_rgb[:rows], O.BLUR_IIR, fast=True)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    dt = time.perf_counter() - t0
+    return threads * W * rows / 1e6 / dt, rows, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores.  fssimu2 0.1.1 (Zig)
+    is neither in /root/reference nor buildable here, so this is the oracle port (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    per_step = max(0.5, min(6.0, 150.0 / max(total, 1)))
+    rate0, rows, _ = cpu_oracle_rate(threads, per_step)
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_oracle_rate(threads, per_step, rows)
+    t0 = time.perf_counter()
+    px = 0.0
+    for _ in range(args.steps):
+        r, _, dt = cpu_oracle_rate(threads, per_step, rows)
+        px += threads * W * rows / 1e6
+    dt = time.perf_counter() - t0
+    value = px / dt
+    sample = f"{threads} threads x one {W}x{rows} band of the 4K pair per step (RGB8 pair; oracle -O3 x86-64-v3)"
+    line = {
+        "impl": "reference", "metric": "SSIMULACRA2 scorer throughput", "value": round(value, 3), "unit": "Mpx/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2 scoring-only {W}x{H} RGB8 source vs decoded frame, full SSIMULACRA2 eval",
+                   "sample": sample},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Mpx/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oavif_b200.host import ssimu2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the scored path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode = ssimu2.BLUR_FIR if args.blur == "fir" else ssimu2.BLUR_RECURSIVE
+    L = ssimu2.load()
+
+    # ---- inputs: NSETS pairs, device-resident (torch owns the memory) + pinned host copies ----
+    pairs = make_pairs(rank, NSETS)
+    dev = []
+    for src, (y, u, v) in pairs:
+        dev.append((torch.from_numpy(src).cuda(), tuple(torch.from_numpy(p.view(np.int16)).cuda() for p in (y, u, v))))
+    pin = []
+    for src, (y, u, v) in pairs[:2]:
+        bufs = []
+        for a in (src, y, u, v):
+            p = L.oavif_ssimu2_pinned_alloc(a.nbytes)
+            if not p:
+                raise SystemExit("pinned allocation failed")
+            view = np.ctypeslib.as_array((C.c_uint8 * a.nbytes).from_address(p)).view(a.dtype).reshape(a.shape)
+            view[...] = a
+            bufs.append(view)
+        pin.append(bufs)
+    torch.cuda.synchronize()
+
+    sc = ssimu2.Scorer(W, H, 1, device=local, blur=mode)
+    stream = torch.cuda.current_stream()
+    sc.set_stream(stream.cuda_stream)
+
+    def step_dev(i):
+        s, (y, u, v) = dev[i % NSETS]
+        sc.set_source_dev(s.data_ptr(), W, H, 3 * W)
+        return sc.score_batch_dev("yuv444", [[y.data_ptr(), u.data_ptr(), v.data_ptr()]], [2 * W] * 3, depth=10)[0]
+
+    def step_host(i):
+        s, y, u, v = pin[i % len(pin)]
+        sc.set_source(s)
+        return sc.score_yuv444(y, u, v, 10)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, collect=None):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+            if collect is not None:
+                collect(sc.timing())
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident (value) ----------------------------------------------------------------
+    ktimes = {"pyramid": [], "a": [], "b": [], "fin": [], "launches": 0}
+
+    def collect(t):
+        ktimes["pyramid"].append(t.pyramid_ms)
+        ktimes["a"].append(t.blur_a_ms)
+        ktimes["b"].append(t.blur_b_ms)
+        ktimes["fin"].append(t.finalize_ms)
+        ktimes["launches"] += t.launches + 1  # + the source-pyramid launch of set_source
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_dev, args.steps, args.warmup, collect)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_host = timed(step_host, args.steps, args.warmup)
+
+    # cached-source rate (what passes >= 2 of the search loop see) and the other blur, for context
+    s0, (y0, u0, v0) = dev[0]
+    sc.set_source_dev(s0.data_ptr(), W, H, 3 * W)
+
+    def step_cached(i):
+        _, (y, u, v) = dev[i % NSETS]
+        return sc.score_batch_dev("yuv444", [[y.data_ptr(), u.data_ptr(), v.data_ptr()]], [2 * W] * 3, depth=10)[0]
+
+    ms_cached = timed(step_cached, args.steps, args.warmup)
+    other = ssimu2.BLUR_RECURSIVE if mode == ssimu2.BLUR_FIR else ssimu2.BLUR_FIR
+    sc.set_blur(other)
+    ms_other = timed(step_dev, args.steps, args.warmup)
+    sc.set_blur(mode)
+    score = step_dev(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, peak_src = peaks()
+    value = world * MPX * args.steps / (ms_dev / 1e3)
+    e2e = world * MPX * args.steps / (ms_host / 1e3)
+    if mode == ssimu2.BLUR_FIR:
+        dom, dom_ms, alg = "k_fir_fused", float(np.mean(ktimes["a"])), ALG_BYTES_KERNEL["fir"]
+    else:
+        a_ms, b_ms = float(np.mean(ktimes["a"])), float(np.mean(ktimes["b"]))
+        if b_ms >= a_ms:
+            dom, dom_ms, alg = "k_iir_cols", b_ms, ALG_BYTES_KERNEL["cols"]
+        else:
+            dom, dom_ms, alg = "k_iir_rows", a_ms, ALG_BYTES_KERNEL["rows"]
+    achieved = alg * W * H / (dom_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom)
+    step_ms = ms_dev / args.steps
+    line = {
+        "metric": "SSIMULACRA2 scorer throughput", "value": round(value, 1), "unit": "Mpx/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2 scoring-only {W}x{H} RGB8 source vs decoded 10-bit YUV444, full SSIMULACRA2 eval per step",
+                   "blur": args.blur, "pairs_per_rank": NSETS,
+                   "l2": f"inputs rotate over {NSETS} pairs ({NSETS * (W * H * 9) / 1e6:.0f} MB) > 126 MB L2; "
+                         f"intermediates per step {(W * H * S_SCALES * 12 * 7) / 1e6:.0f} MB"},
+        "e2e": {"value": round(e2e, 1), "unit": "Mpx/s", "h2d_bytes_per_step": W * H * 9, "d2h_bytes_per_step": 8 + 864,
+                "ms_per_step": round(ms_host / args.steps, 4), "host_memory": "pinned (oavif_ssimu2_pinned_alloc)"},
+        "gpu_launches": int(ktimes["launches"]),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
+                     "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": peak_src,
+                     "alg_bytes_per_px": round(alg, 2), "kernel_ms": round(dom_ms, 4),
+                     "whole_step": {"alg_bytes_per_px": round(ALG_BYTES_FULL, 2),
+                                    "achieved": round(ALG_BYTES_FULL * W * H / (step_ms / 1e3) / 1e9, 1),
+                                    "frac": round(ALG_BYTES_FULL * W * H / (step_ms / 1e3) / 1e9 / hbm, 4),
+                                    "frac_of_nominal_8TBs": round(ALG_BYTES_FULL * W * H / (step_ms / 1e3) / 1e9 / 8000, 4)}},
+        "kernel_ms": {"pyramid_dist": round(float(np.mean(ktimes["pyramid"])), 4),
+                      "blur_a": round(float(np.mean(ktimes["a"])), 4), "blur_b": round(float(np.mean(ktimes["b"])), 4),
+                      "finalize+d2h": round(float(np.mean(ktimes["fin"])), 4)},
+        "cached_source": {"value": round(world * MPX * args.steps / (ms_cached / 1e3), 1), "unit": "Mpx/s",
+                          "ms_per_step": round(ms_cached / args.steps, 4)},
+        "other_blur": {"blur": "recursive" if args.blur == "fir" else "fir",
+                       "value": round(world * MPX * args.steps / (ms_other / 1e3), 1), "unit": "Mpx/s"},
+        "score_check": round(score, 6),
+        "parity": "scores match the in-repo CPU oracle (SSIMULACRA2 v2.1 restatement); parity vs fssimu2 0.1.1 unpinned",
+    }
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rate, rows, dt = cpu_oracle_rate(threads, 8.0)
+        rate1, rows1, dt1 = cpu_oracle_rate(1, 4.0)
+        line["cpu_baseline"] = {"value": round(rate, 3), "unit": "Mpx/s", "cores": threads, "kind": "port",
+                                "sample": f"{threads} threads x one {W}x{rows} band of the 4K pair, {dt:.1f} s",
+                                "single_thread": {"value": round(rate1, 3), "sample": f"{W}x{rows1} band, {dt1:.1f} s"}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blur", default="recursive", choices=["recursive", "fir"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

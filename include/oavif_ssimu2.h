@@ -72,7 +72,9 @@ typedef struct {
 typedef struct {
     float h2d_ms;       /* host -> device copies of this call's pixels           */
     float pyramid_ms;   /* YUV->RGB8, sRGB->linear, 2x pyramid, XYB              */
-    float blur_ms;      /* blur + error maps + pooling kernels                   */
+    float blur_ms;      /* blur + error maps + pooling kernels (a + b)           */
+    float blur_a_ms;    /* RECURSIVE: rows pass.  FIR: the fused kernel          */
+    float blur_b_ms;    /* RECURSIVE: columns pass + maps + pooling.  FIR: 0     */
     float finalize_ms;  /* fixed-order reduction, weights, score, D2H of scores  */
     float total_ms;     /* first event to last event                             */
     uint32_t launches;  /* kernels of this library launched by the call          */

@@ -59,7 +59,7 @@ struct oavif_ssimu2_ctx {
     double *h_sums = nullptr, *h_scores = nullptr;
     float *d_dbg = nullptr;
     long long dbg_floats = 0;
-    cudaEvent_t ev[5] = {};
+    cudaEvent_t ev[6] = {};  // start, h2d, pyramid, blur a, blur b, finalize
     oavif_ssimu2_timing timing{};
     float taps[9] = {};
     IirCoef iir{};
@@ -351,6 +351,7 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
         memcpy(b.taps, ctx->taps, sizeof b.taps);
         k_fir_fused<<<dim3(plan.total, n), kFirThreads, kFirSmemBytes, ctx->stream>>>(b);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[3], ctx->stream));
         ctx->timing.launches += 1;
     } else {
         plan_iir_v(g, &plan);
@@ -358,11 +359,11 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
         const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats,
                                               ctx->d_hplanes, ctx->cap_hplane_floats, ctx->d_partials,
                                               ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, (int)n,
-                                              ctx->stream, &launches);
+                                              ctx->stream, ctx->ev[3], &launches);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "recursive blur launch: %s", cudaGetErrorString(e));
         ctx->timing.launches += launches;
     }
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
 
     FinalArgs f{};
     f.n_scales = g.n_scales;
@@ -382,15 +383,17 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
     CK(cudaMemcpyAsync(ctx->h_scores, ctx->d_scores, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, sizeof(double) * n * kMaxScales * 18, cudaMemcpyDeviceToHost,
                        ctx->stream));
-    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (uint32_t i = 0; i < n; ++i) scores[i] = ctx->h_scores[i];
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing.pyramid_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.blur_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.finalize_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->timing.total_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[4]); ctx->timing.blur_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.blur_a_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.blur_b_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.finalize_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]); ctx->timing.total_ms = ms;
     return 0;
 }
 

@@ -47,17 +47,6 @@ __device__ __forceinline__ float iir_step(const IirCoef &k, IirState &s, float l
     return (o[0] + o[1]) + o[2];
 }
 
-__device__ __forceinline__ float quantity(int q, float a, float b)
-{
-    switch (q) {
-    case 0: return a;
-    case 1: return b;
-    case 2: return a * a;
-    case 3: return b * b;
-    default: return a * b;
-    }
-}
-
 __device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gmem_src, bool valid)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -357,7 +346,8 @@ inline cudaError_t iir_configure()
 inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float *src, const float *dist,
                                    long long pyr_stride, float *hplanes, long long hplanes_stride,
                                    double *partials, long long partials_stride, const int *first_cta_cols,
-                                   const int *col_blocks, int n, cudaStream_t st, int *launches)
+                                   const int *col_blocks, int n, cudaStream_t st, cudaEvent_t between,
+                                   int *launches)
 {
     IirArgs a{};
     a.g = g;
@@ -380,6 +370,7 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     k_iir_rows<<<dim3(acc, n), kIirThreads, sizeof(IirRowsSmem), st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (between) cudaEventRecord(between, st);
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
     k_iir_cols<<<dim3(first_cta_cols[kMaxScales], n), kIirThreads, 0, st>>>(a);

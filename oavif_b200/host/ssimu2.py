@@ -55,7 +55,7 @@ class Detail(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("pyramid_ms", C.c_float), ("blur_ms", C.c_float),
-                ("finalize_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32)]
+                ("blur_a_ms", C.c_float), ("blur_b_ms", C.c_float), ("finalize_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32)]
 
 
 _lib = None

@@ -1,0 +1,330 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Run with -m gpu on a B200.
+
+Bars (stated here, enforced below):
+  * integer / byte work (decoded YUV -> RGB8): bit-exact against libavif-generated fixtures;
+  * XYB pyramid planes and blurred planes: bit-identical binary32 against the oracle (both sides
+    execute one fixed sequence of IEEE operations);
+  * pooled sums: relative 1e-5 (the maps run in binary32 on the GPU where the published code widens
+    a few operations to double; sums are reduced in a different but fixed order);
+  * score: |delta| <= 1e-4 against the oracle in the same blur mode — 500x inside north_star's 0.05.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oavif_b200.host import ssimu2, synth
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-4
+SUM_RTOL = 1e-5
+MODES = [(ssimu2.BLUR_RECURSIVE, 0, "recursive"), (ssimu2.BLUR_FIR, 1, "fir")]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def scorer():
+    with ssimu2.Scorer(1100, 800, 4) as sc:
+        yield sc
+
+
+def test_cuda_extension_is_what_runs():
+    L = ssimu2.load()
+    assert L.oavif_ssimu2_abi_version() == 1
+    with open("/proc/self/maps") as f:
+        assert "liboavif_ssimu2.so" in f.read()
+
+
+# ---- K0: decoded YUV -> RGB8 --------------------------------------------------------------------
+def test_yuv_to_rgb8_bit_exact_vs_libavif_vectors(scorer, golden_dir):
+    g = np.load(os.path.join(golden_dir, "yuv2rgb_libavif.npz"))
+    for depth in (8, 10):
+        y, u, v = g[f"y{depth}"], g[f"u{depth}"], g[f"v{depth}"]
+        for m in (1, 2, 5, 6, 9):
+            for al in (0, 1):
+                got = scorer.yuv444_to_rgb8(y, u, v, depth, m, bool(al))
+                np.testing.assert_array_equal(got, g[f"rgb_d{depth}_m{m}_a{al}"], err_msg=f"d{depth} m{m} a{al}")
+
+
+def test_yuv_to_rgb8_exhaustive_luma_chroma_grid(scorer, oracle):
+    # every 10-bit luma against a chroma lattice that includes the extremes, both conversions
+    yy = np.arange(1024, dtype=np.uint16)
+    cc = np.array([0, 1, 2, 3, 255, 256, 511, 512, 513, 767, 1020, 1021, 1022, 1023], np.uint16)
+    Y = np.tile(yy, (len(cc) * len(cc), 1))
+    U = np.repeat(np.repeat(cc, len(cc)), 1024).reshape(-1, 1024)
+    V = np.repeat(np.tile(cc, len(cc)), 1024).reshape(-1, 1024)
+    for m in (2, 1, 9):
+        for al in (False, True):
+            np.testing.assert_array_equal(scorer.yuv444_to_rgb8(Y, U, V, 10, m, al),
+                                          oracle.yuv444_to_rgb8(Y, U, V, 10, m, al))
+    Y8, U8, V8 = (Y >> 2).astype(np.uint8), (U >> 2).astype(np.uint8), (V >> 2).astype(np.uint8)
+    np.testing.assert_array_equal(scorer.yuv444_to_rgb8(Y8, U8, V8, 8, 2), oracle.yuv444_to_rgb8(Y8, U8, V8, 8, 2))
+
+
+# ---- K1-K3: pyramid planes ------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [(64, 64), (65, 63), (100, 75), (257, 129), (333, 257), (1027, 771)])
+def test_xyb_pyramid_bit_identical(scorer, oracle, size):
+    w, h = size
+    src = synth.synth(w, h, "mixture", w)
+    dist = synth.distort(src, 0.3, seed=h)
+    scorer.set_blur(ssimu2.BLUR_FIR)
+    scorer.set_source(src)
+    scorer.score_rgb8(dist)
+    n = scorer.detail().n_scales
+    assert n >= 5
+    for s in range(n):
+        ws, wd = oracle.xyb_at_scale(src, s), oracle.xyb_at_scale(dist, s)
+        for c in range(3):
+            np.testing.assert_array_equal(bits(scorer.xyb(0, s, c)), bits(ws[c]), err_msg=f"src s{s} c{c}")
+            np.testing.assert_array_equal(bits(scorer.xyb(1, s, c)), bits(wd[c]), err_msg=f"dist s{s} c{c}")
+
+
+def test_all_input_forms_build_the_same_pyramid(scorer, oracle):
+    w, h = 203, 117
+    src = synth.synth(w, h, "noise", 8)
+    dist = synth.distort(src, 0.5)
+    scorer.set_blur(ssimu2.BLUR_FIR)
+    scorer.set_source(src)
+    for depth in (8, 10):
+        for rgba in (False, True):
+            y, u, v = synth.rgb8_to_yuv444(dist, depth, 1)
+            rgb = oracle.yuv444_to_rgb8(y, u, v, depth, 1, rgba)
+            a = scorer.score_yuv444(y, u, v, depth, 1, rgba)
+            planes = [scorer.xyb(1, 0, c) for c in range(3)]
+            b = scorer.score_rgb8(rgb)
+            assert a == b
+            for c in range(3):
+                np.testing.assert_array_equal(bits(planes[c]), bits(scorer.xyb(1, 0, c)))
+
+
+# ---- K4: the filter alone ----------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,omode,name", MODES)
+@pytest.mark.parametrize("size", [(9, 9), (40, 33), (131, 97), (640, 360)])
+def test_blur_bit_identical(scorer, oracle, mode, omode, name, size):
+    w, h = size
+    rng = np.random.default_rng(w * 1000 + h)
+    plane = rng.random((h, w), dtype=np.float32)
+    scorer.set_blur(mode)
+    np.testing.assert_array_equal(bits(scorer.blur(plane)), bits(oracle.blur(plane, omode)))
+
+
+# ---- whole path ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,omode,name", MODES)
+@pytest.mark.parametrize("case", [(64, 64, "mixture", 0.3), (100, 75, "noise", 0.1), (257, 129, "edges", 0.5),
+                                  (320, 240, "gradient", 0.05), (333, 257, "mixture", 1.0), (640, 360, "mixture", 0.2),
+                                  (1027, 771, "noise", 0.02), (31, 200, "noise", 0.4), (8, 8, "noise", 0.5)])
+def test_score_and_pooled_sums_vs_oracle(scorer, oracle, mode, omode, name, case):
+    w, h, kind, strength = case
+    src = synth.synth(w, h, kind, 21)
+    dist = synth.distort(src, strength, seed=5)
+    want, det = oracle.ssimu2_rgb8(src, dist, omode, detail=True)
+    scorer.set_blur(mode)
+    scorer.set_source(src)
+    got = scorer.score_rgb8(dist)
+    d = scorer.detail()
+    assert d.n_scales == det.n_scales
+    assert abs(got - want) <= SCORE_TOL, (got, want)
+    gs, ws = scorer.sums(), oracle.detail_sums(det)
+    np.testing.assert_allclose(gs, ws, rtol=SUM_RTOL, atol=1e-12)
+
+
+@pytest.mark.parametrize("mode,omode,name", MODES)
+def test_committed_oracle_scores(scorer, mode, omode, name, golden_dir):
+    with open(os.path.join(golden_dir, "oracle_scores.json")) as f:
+        cases = json.load(f)
+    key = "iir" if mode == ssimu2.BLUR_RECURSIVE else "fir"
+    scorer.set_blur(mode)
+    for c in cases:
+        src = synth.synth(c["w"], c["h"], c["kind"], c["seed"])
+        dist = synth.distort(src, c["strength"], seed=c["seed"] + 100)
+        scorer.set_source(src)
+        got = scorer.score_rgb8(dist)
+        assert abs(got - c[key]["score"]) <= SCORE_TOL, (c["w"], c["h"], got, c[key]["score"])
+        assert scorer.detail().n_scales == c[key]["n_scales"]
+
+
+@pytest.mark.parametrize("mode,omode,name", MODES)
+def test_real_decoder_output(scorer, oracle, mode, omode, name, golden_dir):
+    """Decoded planes of a real libavif/libaom round trip: scoring the planes directly equals scoring
+    the RGB8 libavif made from them (io.zig:470-478), and both equal the oracle."""
+    g = np.load(os.path.join(golden_dir, "avif_roundtrip.npz"))
+    src = g["src"]
+    scorer.set_blur(mode)
+    scorer.set_source(src)
+    for tag, depth, rgba in (("65", 8, False), ("40", 8, False), ("10", 10, False), ("10", 10, True)):
+        y, u, v = g[f"y{tag}"], g[f"u{tag}"], g[f"v{tag}"]
+        rgb = g["rgb10a"] if (tag == "10" and rgba) else g[f"rgb{tag}"]
+        a = scorer.score_yuv444(y, u, v, depth, 2, rgba)
+        b = scorer.score_rgb8(rgb)
+        assert a == b
+        assert abs(a - oracle.ssimu2_rgb8(src, rgb, omode)) <= SCORE_TOL
+    assert scorer.score_yuv444(g["y65"], g["u65"], g["v65"], 8) > scorer.score_yuv444(g["y40"], g["u40"], g["v40"], 8)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,omode,name", MODES)
+def test_identical_pair_is_exactly_100(scorer, mode, omode, name):
+    scorer.set_blur(mode)
+    for (w, h) in [(64, 64), (333, 257), (1027, 771)]:
+        src = synth.synth(w, h, "mixture", 3)
+        scorer.set_source(src)
+        assert scorer.score_rgb8(src) == 100.0
+        assert not scorer.sums().any()
+
+
+def test_below_8_pixels_scores_100_like_the_published_loop(scorer, oracle):
+    src = synth.synth(7, 64, "noise", 6)
+    dist = synth.distort(src, 0.4)
+    assert oracle.ssimu2_rgb8(src, dist) == 100.0
+    scorer.set_source(src)
+    assert scorer.score_rgb8(dist) == 100.0
+    assert scorer.detail().n_scales == 0
+
+
+@pytest.mark.parametrize("mode,omode,name", MODES)
+def test_strided_rows(scorer, mode, omode, name):
+    w, h = 150, 90
+    src = synth.synth(w, h, "mixture", 1)
+    dist = synth.distort(src, 0.3)
+    scorer.set_blur(mode)
+    scorer.set_source(src)
+    tight = scorer.score_rgb8(dist)
+    pad = np.zeros((h, w + 9, 3), np.uint8)
+    pad[:, :w] = dist
+    assert scorer.score_rgb8(pad[:, :w]) == tight          # row stride 3*(w+9)
+    spad = np.full((h, w + 5, 3), 77, np.uint8)
+    spad[:, :w] = src
+    scorer.set_source(spad[:, :w])
+    assert scorer.score_rgb8(dist) == tight
+    y, u, v = synth.rgb8_to_yuv444(dist, 10)
+    t2 = scorer.score_yuv444(y, u, v, 10)
+    big = np.zeros((3, h, w + 6), np.uint16)
+    big[0, :, :w], big[1, :, :w], big[2, :, :w] = y, u, v
+    assert scorer.score_yuv444(big[0, :, :w], big[1, :, :w], big[2, :, :w], 10) == t2
+
+
+@pytest.mark.parametrize("mode,omode,name", MODES)
+def test_batch_equals_single_and_is_deterministic(scorer, mode, omode, name):
+    w, h = 400, 300
+    src = synth.synth(w, h, "mixture", 9)
+    cands = [synth.distort(src, s, seed=i) for i, s in enumerate((0.1, 0.3, 0.6, 1.0))]
+    scorer.set_blur(mode)
+    scorer.set_source(src)
+    single = [scorer.score_rgb8(c) for c in cands]
+    batch = scorer.score_batch_rgb8(cands)
+    assert batch == single                                   # bit-identical doubles
+    sums0 = scorer.sums(2).copy()
+    again = scorer.score_batch_rgb8(cands)
+    assert again == batch and (scorer.sums(2) == sums0).all()
+    yuv = [synth.rgb8_to_yuv444(c, 10) for c in cands]
+    by = scorer.score_batch_yuv444(yuv, 10)
+    assert by == [scorer.score_yuv444(*p, 10) for p in yuv]
+    assert all(a > b for a, b in zip(batch, batch[1:]))
+
+
+def test_modes_differ_only_by_recursion_roundoff(scorer):
+    src = synth.synth(640, 360, "mixture", 4)
+    dist = synth.distort(src, 0.6)
+    scorer.set_source(src)
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    a = scorer.score_rgb8(dist)
+    scorer.set_blur(ssimu2.BLUR_FIR)
+    b = scorer.score_rgb8(dist)
+    assert a != b and abs(a - b) < 0.5
+
+
+def test_error_behaviour(oracle):
+    src = synth.synth(64, 48, "noise", 0)
+    with ssimu2.Scorer(64, 48, 2) as sc:
+        with pytest.raises(ssimu2.Ssimu2Error) as e:
+            sc.score_rgb8(src)
+        assert e.value.code == ssimu2.E_ARG or e.value.code == ssimu2.E_STATE
+        L = ssimu2.load()
+        out = C.c_double()
+        assert L.oavif_ssimu2_score_rgb8(sc._ctx, src.ctypes.data, 192, C.byref(out)) == ssimu2.E_STATE
+        with pytest.raises(ssimu2.Ssimu2Error) as e:
+            sc.set_source(synth.synth(512, 512, "noise", 0))
+        assert e.value.code == ssimu2.E_STATE
+        sc.set_source(src)
+        assert L.oavif_ssimu2_score_rgb8(sc._ctx, src.ctypes.data, 100, C.byref(out)) == ssimu2.E_ARG
+        assert L.oavif_ssimu2_score_rgb8(sc._ctx, None, 192, C.byref(out)) == ssimu2.E_ARG
+        y = np.zeros((48, 64), np.uint8)
+        with pytest.raises(ssimu2.Ssimu2Error) as e:
+            sc.score_yuv444(y, y, y, 8, matrix=0)
+        assert e.value.code == ssimu2.E_UNSUPPORTED
+        with pytest.raises(ssimu2.Ssimu2Error) as e:
+            sc.score_yuv444(y.astype(np.uint16), y.astype(np.uint16), y.astype(np.uint16), 12)
+        assert e.value.code == ssimu2.E_UNSUPPORTED
+        with pytest.raises(ssimu2.Ssimu2Error):
+            sc.score_batch_rgb8([src, src, src])             # beyond max_batch
+        assert sc.score_rgb8(src) == 100.0                   # context still usable after errors
+    with pytest.raises(ssimu2.Ssimu2Error):
+        ssimu2.Scorer(64, 64, device=99)
+
+
+def test_stateless_call_mirrors_the_reference_signature(oracle):
+    src = synth.synth(320, 200, "mixture", 12)
+    dist = synth.distort(src, 0.4)
+    want = oracle.ssimu2_rgb8(src, dist, oracle.BLUR_IIR)
+    got = ssimu2.compute_ssimu2(src.reshape(-1), dist.reshape(-1), 320, 200, 3)
+    assert abs(got - want) <= SCORE_TOL
+    assert ssimu2.compute_ssimu2(src, src) == 100.0
+    big = synth.synth(500, 400, "edges", 1)                  # cached context regrows
+    assert ssimu2.compute_ssimu2(big, big) == 100.0
+    with pytest.raises(ssimu2.Ssimu2Error):
+        ssimu2.compute_ssimu2(np.zeros((4, 4, 4), np.uint8), np.zeros((4, 4, 4), np.uint8))
+
+
+def test_device_resident_inputs_and_external_stream(oracle):
+    import torch
+    w, h = 256, 192
+    src = synth.synth(w, h, "mixture", 2)
+    dist = synth.distort(src, 0.3)
+    y, u, v = synth.rgb8_to_yuv444(dist, 10)
+    with ssimu2.Scorer(w, h, 2) as sc:
+        sc.set_source(src)
+        host = sc.score_yuv444(y, u, v, 10)
+        st = torch.cuda.Stream()
+        sc.set_stream(st.cuda_stream)
+        dsrc = torch.from_numpy(src).cuda()
+        dy, du, dv = (torch.from_numpy(p.view(np.int16)).cuda() for p in (y, u, v))
+        drgb = torch.from_numpy(dist).cuda()
+        torch.cuda.synchronize()
+        sc.set_source_dev(dsrc.data_ptr(), w, h, 3 * w)
+        a = sc.score_batch_dev("yuv444", [[dy.data_ptr(), du.data_ptr(), dv.data_ptr()]] * 2, [2 * w] * 3, depth=10)
+        assert a == [host, host]
+        b = sc.score_batch_dev("rgb8", [[drgb.data_ptr()]], [3 * w])
+        assert abs(b[0] - oracle.ssimu2_rgb8(src, dist)) <= SCORE_TOL
+        sc.set_stream(None)
+
+
+# ---- BASELINE.json full sizes: properties that do not need the oracle's minutes ----------------------------
+@pytest.mark.parametrize("mode,omode,name", MODES)
+def test_full_size_4k_properties(oracle, mode, omode, name):
+    w, h = 3840, 2160
+    src = synth.synth(w, h, "mixture", 0)
+    d1, d2 = synth.distort(src, 0.2, seed=1), synth.distort(src, 0.6, seed=2)
+    with ssimu2.Scorer(w, h, 3, blur=mode) as sc:
+        sc.set_source(src)
+        assert sc.score_rgb8(src) == 100.0
+        s = sc.score_batch_rgb8([d1, d2, d1])
+        assert s[0] == s[2] and s[0] > s[1]
+        y, u, v = synth.rgb8_to_yuv444(d1, 10)
+        rgb = oracle.yuv444_to_rgb8(y, u, v, 10)
+        assert sc.score_yuv444(y, u, v, 10) == sc.score_rgb8(rgb)
+        # swapping which image is the source changes artifact <-> detail_lost sums only
+        sums_ab = sc.sums(0).copy()
+        sc.set_source(d1)
+        sc.score_rgb8(src)
+        sums_ba = sc.sums(0)
+        np.testing.assert_allclose(sums_ab[:, 0::6], sums_ba[:, 0::6], rtol=1e-6)   # SSIM term is symmetric
+        if mode == ssimu2.BLUR_RECURSIVE:                                           # one oracle run at full size
+            sc.set_source(src)
+            got = sc.score_rgb8(d2)
+            assert abs(got - oracle.ssimu2_rgb8(src, d2, omode, fast=True)) <= SCORE_TOL
