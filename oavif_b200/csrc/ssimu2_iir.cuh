@@ -56,9 +56,9 @@ __device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gmem_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-constexpr int kIirRows = 32;    // rows per CTA in the rows pass
+constexpr int kIirRows = 64;    // rows per CTA in the rows pass (two per lane: 6 independent chains)
 constexpr int kIirChunk = 32;   // columns per staged tile
-constexpr int kIirSlots = 4;    // tile ring: k-1, k, k+1 in use while k+2 lands
+constexpr int kIirSlots = 4;    // tile ring: t-1, t in use while t+1, t+2 land
 constexpr int kIirThreads = 160;
 constexpr int kIirVCols = 32;   // columns per CTA in the columns pass
 constexpr int kIirVBatch = 20;  // rows between two map phases (20*32 px = 4 per thread)
@@ -90,41 +90,27 @@ __device__ __forceinline__ void decode_cta(const IirArgs &a, int cta, int &s, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// rows pass.  grid = (sum over scales of 3 * ceil(h/32), n_candidates), block = 160, dynamic smem.
+// rows pass.  grid = (sum over scales of 3 * ceil(h/64), n_candidates), block = 160, dynamic smem.
+//
+// Chunk t emits outputs n = 32t-4 .. 32t+27, so its right taps (n+4) are exactly tile t and its left
+// taps (n-6) fall in tiles t-1 and t: two tiles are in use while tiles t+1 and t+2 are in flight
+// (cp.async, two chunks of slack).  Chunk 0's first four outputs are the recursion's warm-up steps
+// n = -4..-1 and are dropped.
 struct IirRowsSmem {
     float ta[kIirSlots][kIirRows][kIirChunk + 1];  // source channel tiles, ring
     float tb[kIirSlots][kIirRows][kIirChunk + 1];  // distorted channel tiles, ring
-    float to[5][kIirRows][kIirChunk + 1];          // per-warp output staging
+    float to[5][kIirRows][kIirChunk + 1];          // per-warp output staging (transposed write-out)
 };
 
-template <int Q>
-__device__ __forceinline__ float tile_quantity(const IirRowsSmem &sm, int slot, int lane, int col)
+// quantity q of {a, b, a*a, b*b, a*b} = x * (y*m + o) with warp-uniform tile pointers for x, y and
+// (m, o) = (0, 1) for the two plain planes, (1, 0) for the products.  y*0+1 and x*1 are exact, so
+// every quantity is bit-identical to the direct expression, with no divergent code.
+__device__ __forceinline__ float pick_quantity(const float *px, const float *py, int j, float m, float o)
 {
-    if (Q == 0) return sm.ta[slot][lane][col];
-    if (Q == 1) return sm.tb[slot][lane][col];
-    if (Q == 2) { const float v = sm.ta[slot][lane][col]; return v * v; }
-    if (Q == 3) { const float v = sm.tb[slot][lane][col]; return v * v; }
-    return sm.ta[slot][lane][col] * sm.tb[slot][lane][col];
+    return px[j] * fmaf(py[j], m, o);
 }
 
-// 32 consecutive outputs n = 32t .. 32t+31 of this lane's row; taps at n+4 and n-6 come from the
-// ring slots holding tiles t-1 (prev), t (cur), t+1 (next).  Fully unrolled: all columns static.
-template <int Q>
-__device__ __forceinline__ void rows_chunk(IirRowsSmem &sm, const IirCoef &k, IirState &st, int t, int lane)
-{
-    const int prev = (t + kIirSlots - 1) & (kIirSlots - 1), cur = t & (kIirSlots - 1),
-              next = (t + 1) & (kIirSlots - 1);
-#pragma unroll
-    for (int j = 0; j < kIirChunk; ++j) {
-        const float r = (j + 4 < kIirChunk) ? tile_quantity<Q>(sm, cur, lane, j + 4)
-                                            : tile_quantity<Q>(sm, next, lane, j + 4 - kIirChunk);
-        const float l = (j >= 6) ? tile_quantity<Q>(sm, cur, lane, j - 6)
-                                 : tile_quantity<Q>(sm, prev, lane, j - 6 + kIirChunk);
-        sm.to[Q][lane][j] = iir_step(k, st, l, r);
-    }
-}
-
-__global__ void __launch_bounds__(kIirThreads) k_iir_rows(const __grid_constant__ IirArgs a)
+__global__ void __launch_bounds__(kIirThreads, 2) k_iir_rows(const __grid_constant__ IirArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IirRowsSmem &sm = *reinterpret_cast<IirRowsSmem *>(smem_raw);
@@ -139,76 +125,94 @@ __global__ void __launch_bounds__(kIirThreads) k_iir_rows(const __grid_constant_
     const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
     const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
     float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff;
-    const int nch = (w + kIirChunk - 1) / kIirChunk;
+    const int nch = (w + kIirChunk - 1) / kIirChunk;          // input tiles
+    const int nout = (w + 4 + kIirChunk - 1) / kIirChunk;     // output chunks
     const IirCoef k = a.k;
+    const bool x_is_b = (q == 1) || (q == 3);   // x: b for {b, b*b}, a otherwise
+    const bool y_is_a = (q == 2);                 // y: a for a*a, b for {b*b, a*b}; unused for q < 2
+    const float ym = q < 2 ? 0.0f : 1.0f, yo = q < 2 ? 1.0f : 0.0f;
 
-    // tile t of both planes -> ring slot t % 4; the 64 row segments are shared by the 5 warps.
+    // tile t of both planes -> ring slot t & 3.  Warp q stages rows q, q+5, ... of both planes.
     // Anything outside the image (t < 0, t >= nch, row >= h, column >= w) lands as zeros: that IS
     // the filter's zero padding.
+    const int rows_here = min(kIirRows, h - y0);
     auto issue_tile = [&](int t) {
         const int slot = t & (kIirSlots - 1);
         const int gx = t * kIirChunk + lane;
-        for (int it = q; it < 2 * kIirRows; it += 5) {
-            const int row = it & (kIirRows - 1);
-            const bool second = it >= kIirRows;
-            const int gy = y0 + row;
-            const bool valid = (t >= 0) && (t < nch) && (gy < h) && (gx < w);
-            const float *src = (second ? pb : pa) + (valid ? (long long)gy * pitch + gx : 0);
-            cp_async_f32(second ? &sm.tb[slot][row][lane] : &sm.ta[slot][row][lane], src, valid);
+        const bool col_ok = (t >= 0) && (gx < w);
+        const long long o0 = (long long)y0 * pitch + gx;
+#pragma unroll 1
+        for (int row = q; row < kIirRows; row += 5) {
+            const bool valid = col_ok && (row < rows_here);
+            const long long o = valid ? o0 + (long long)row * pitch : 0;
+            cp_async_f32(&sm.ta[slot][row][lane], pa + o, valid);
+            cp_async_f32(&sm.tb[slot][row][lane], pb + o, valid);
         }
         cp_async_commit();
     };
 
-    issue_tile(-1);
-    issue_tile(0);
-    issue_tile(1);
+#pragma unroll 1
+    for (int t = -1; t <= 1; ++t) issue_tile(t);
     cp_async_wait_all();
     __syncthreads();
 
-    IirState st;
+    IirState st0, st1;  // rows lane and lane + 32
 #pragma unroll
-    for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
-    // n = -N+1 .. -1: right taps are columns 0..3, left taps are padding, nothing is emitted
-#pragma unroll
-    for (int n = -4; n < 0; ++n) {
-        float r;
-        switch (q) {
-        case 0: r = tile_quantity<0>(sm, 0, lane, n + 4); break;
-        case 1: r = tile_quantity<1>(sm, 0, lane, n + 4); break;
-        case 2: r = tile_quantity<2>(sm, 0, lane, n + 4); break;
-        case 3: r = tile_quantity<3>(sm, 0, lane, n + 4); break;
-        default: r = tile_quantity<4>(sm, 0, lane, n + 4); break;
-        }
-        (void)iir_step(k, st, 0.0f, r);
-    }
+    for (int i = 0; i < 3; ++i) st0.p[i] = st0.p2[i] = st1.p[i] = st1.p2[i] = 0.0f;
 
-    for (int t = 0; t < nch; ++t) {
+    for (int t = 0; t < nout; ++t) {
         issue_tile(t + 2);
-        switch (q) {  // warp-uniform
-        case 0: rows_chunk<0>(sm, k, st, t, lane); break;
-        case 1: rows_chunk<1>(sm, k, st, t, lane); break;
-        case 2: rows_chunk<2>(sm, k, st, t, lane); break;
-        case 3: rows_chunk<3>(sm, k, st, t, lane); break;
-        default: rows_chunk<4>(sm, k, st, t, lane); break;
+        const int cur = t & (kIirSlots - 1), prev = (t + kIirSlots - 1) & (kIirSlots - 1);
+        const float(*tx)[kIirRows][kIirChunk + 1] = x_is_b ? sm.tb : sm.ta;
+        const float(*ty)[kIirRows][kIirChunk + 1] = y_is_a ? sm.ta : sm.tb;
+        const float *x0 = &tx[cur][lane][0], *y0p = &ty[cur][lane][0];
+        const float *x1 = &tx[cur][lane + 32][0], *y1p = &ty[cur][lane + 32][0];
+        const float *px0 = &tx[prev][lane][0], *py0 = &ty[prev][lane][0];
+        const float *px1 = &tx[prev][lane + 32][0], *py1 = &ty[prev][lane + 32][0];
+        float *o0 = &sm.to[q][lane][0], *o1 = &sm.to[q][lane + 32][0];
+        float r0[kIirChunk], r1[kIirChunk];
+#pragma unroll
+        for (int j = 0; j < kIirChunk; ++j) {
+            r0[j] = pick_quantity(x0, y0p, j, ym, yo);
+            r1[j] = pick_quantity(x1, y1p, j, ym, yo);
+        }
+#pragma unroll
+        for (int j = 0; j < kIirChunk; ++j) {
+            float l0, l1;
+            if (j >= 10) {
+                l0 = r0[j - 10];
+                l1 = r1[j - 10];
+            } else {
+                l0 = pick_quantity(px0, py0, j + 22, ym, yo);
+                l1 = pick_quantity(px1, py1, j + 22, ym, yo);
+            }
+            o0[j] = iir_step(k, st0, l0, r0[j]);
+            o1[j] = iir_step(k, st1, l1, r1[j]);
         }
         __syncwarp();
-        // transposed write-out: this warp's 32x32 tile, one 128-byte row segment per store
-        const int nb = t * kIirChunk;
+        // transposed write-out: 64 row segments of 32 floats starting at column 32t - 4
+        const int n = t * kIirChunk - 4 + lane;
+        if (n >= 0 && n < nch * kIirChunk) {
+            float *dst = ph + (long long)y0 * pitch + n;
+            const float *srcp = &sm.to[q][0][lane];
 #pragma unroll 4
-        for (int rr = 0; rr < kIirRows; ++rr) {
-            const int gy = y0 + rr;
-            if (gy < h) ph[(long long)gy * pitch + nb + lane] = sm.to[q][rr][lane];
+            for (int rr = 0; rr < rows_here; ++rr) dst[(long long)rr * pitch] = srcp[rr * (kIirChunk + 1)];
         }
-        cp_async_wait_all();
-        __syncthreads();  // tile t+2 visible; every warp is past its reads of tile t-1
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();  // tile t+1 visible to all; every warp is past its reads of tile t-1
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 160.
+//
+// Each warp streams its quantity's row-filtered plane down the image, 20 rows per batch; the next
+// batch's 20 loads and this batch's a/b samples are issued before the current batch is computed, so
+// DRAM latency is covered by a full batch of arithmetic.  The exchange buffer is double-buffered:
+// one barrier per batch.
 __global__ void __launch_bounds__(kIirThreads) k_iir_cols(const __grid_constant__ IirArgs a)
 {
-    __shared__ float ex[5][kIirVBatch][kIirVCols];
+    __shared__ float ex[2][5][kIirVBatch][kIirVCols];
     __shared__ double sred[5 * 6];
 
     int s, c, cb;
@@ -222,57 +226,73 @@ __global__ void __launch_bounds__(kIirThreads) k_iir_cols(const __grid_constant_
     const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff +
                       cb * kIirVCols + lane;
     const IirCoef k = a.k;
+    constexpr int kPx = (kIirVBatch * kIirVCols) / kIirThreads;  // 4 map pixels per thread and batch
 
     IirState st;
 #pragma unroll
     for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
-    // n = -4..-1: right taps are rows 0..3
+    // n = -4..-1: right taps are rows 0..3, nothing emitted
 #pragma unroll
     for (int n = -4; n < 0; ++n) {
         const int rr = n + 4;
         (void)iir_step(k, st, 0.0f, rr < h ? __ldg(ph + (long long)rr * pitch) : 0.0f);
     }
     // carry[j] = input row (n0 + j - 6) for j < 10, i.e. the previous batch's R[j + 10].
-    // Before the first batch those are rows -6..3: zero for j < 6, rows 0..3 for j = 6..9.
     float carry[10];
 #pragma unroll
     for (int j = 0; j < 10; ++j) {
         const int rr = j - 6;
         carry[j] = (rr >= 0 && rr < h) ? __ldg(ph + (long long)rr * pitch) : 0.0f;
     }
+    float R[kIirVBatch], Rn[kIirVBatch];
+#pragma unroll
+    for (int j = 0; j < kIirVBatch; ++j) {
+        const int rr = j + 4;
+        R[j] = rr < h ? __ldg(ph + (long long)rr * pitch) : 0.0f;
+    }
 
     double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int n0 = 0; n0 < h; n0 += kIirVBatch) {
-        float R[kIirVBatch];
+    int buf = 0;
+    for (int n0 = 0; n0 < h; n0 += kIirVBatch, buf ^= 1) {
+        // prefetch: next batch's right taps, and this batch's a/b samples for the maps
 #pragma unroll
         for (int j = 0; j < kIirVBatch; ++j) {
-            const int rr = n0 + j + 4;
-            R[j] = rr < h ? __ldg(ph + (long long)rr * pitch) : 0.0f;
+            const int rr = n0 + kIirVBatch + j + 4;
+            Rn[j] = rr < h ? __ldg(ph + (long long)rr * pitch) : 0.0f;
+        }
+        float av[kPx], bv[kPx];
+#pragma unroll
+        for (int i = 0; i < kPx; ++i) {
+            const int idx = threadIdx.x + i * kIirThreads;
+            const int gy = n0 + (idx >> 5), gx = cb * kIirVCols + (idx & 31);
+            const bool ok = gy < h && gx < w;
+            const long long o = ok ? (long long)gy * pitch + gx : 0;
+            av[i] = __ldg(pa + o);
+            bv[i] = __ldg(pb + o);
         }
 #pragma unroll
         for (int j = 0; j < kIirVBatch; ++j) {
             const float l = (j < 10) ? carry[j] : R[j - 10];
-            ex[q][j][lane] = iir_step(k, st, l, R[j]);
+            ex[buf][q][j][lane] = iir_step(k, st, l, R[j]);
         }
 #pragma unroll
         for (int j = 0; j < 10; ++j) carry[j] = R[j + 10];
+#pragma unroll
+        for (int j = 0; j < kIirVBatch; ++j) R[j] = Rn[j];
         __syncthreads();
 
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < (kIirVBatch * kIirVCols) / kIirThreads; ++i) {
+        for (int i = 0; i < kPx; ++i) {
             const int idx = threadIdx.x + i * kIirThreads;
             const int row = idx >> 5, col = idx & 31;
-            const int gy = n0 + row, gx = cb * kIirVCols + col;
-            if (gy < h && gx < w) {
-                const long long o = (long long)gy * pitch + gx;
-                error_maps(__ldg(pa + o), __ldg(pb + o), ex[0][row][col], ex[1][row][col], ex[2][row][col],
-                           ex[3][row][col], ex[4][row][col], acc);
-            }
+            if (n0 + row < h && cb * kIirVCols + col < w)
+                error_maps(av[i], bv[i], ex[buf][0][row][col], ex[buf][1][row][col], ex[buf][2][row][col],
+                           ex[buf][3][row][col], ex[buf][4][row][col], acc);
         }
 #pragma unroll
         for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
-        __syncthreads();
+        // no second barrier: the next batch writes the other half of ex
     }
     block_reduce6<kIirThreads / 32>(dacc, sred,
                                     a.partials + (long long)cand * a.partials_stride + (long long)blockIdx.x * 6);
