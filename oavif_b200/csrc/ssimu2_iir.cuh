@@ -47,21 +47,18 @@ __device__ __forceinline__ float iir_step(const IirCoef &k, IirState &s, float l
     return (o[0] + o[1]) + o[2];
 }
 
-__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gmem_src, bool valid)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int bytes = valid ? 4 : 0;  // src-size 0 => the 4 destination bytes are zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes));
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-constexpr int kIirRows = 64;    // rows per CTA in the rows pass (two per lane: 6 independent chains)
-constexpr int kIirChunk = 32;   // columns per staged tile
-constexpr int kIirSlots = 4;    // tile ring: t-1, t in use while t+1, t+2 land
-constexpr int kIirThreads = 160;
-constexpr int kIirVCols = 32;   // columns per CTA in the columns pass
-constexpr int kIirVBatch = 20;  // rows between two map phases (20*32 px = 4 per thread)
+// Work decomposition (v3): every warp is an independent task — no block barrier anywhere, so the
+// hardware scheduler balances tasks over the 4 x 148 sub-partitions by itself.
+//   rows pass   : task = (32 rows, 1 channel, 1 quantity), CTA = 1 warp, lane = row
+//   columns pass: task = (32 columns, 1 channel, all 5 quantities), CTA = 1 warp, lane = column
+constexpr int kIirRows = 32;     // rows per rows-pass task
+constexpr int kIirChunk = 32;    // columns per staged tile
+constexpr int kIirPitch = 36;    // smem tile pitch in floats: 16-byte rows, conflict-free 128-bit access
+constexpr int kIirSlots = 4;     // tile ring: t-1, t in use while t+1, t+2 land
+constexpr int kIirVCols = 32;    // columns per columns-pass task
 
 struct IirArgs {
     Geom g;
@@ -75,7 +72,7 @@ struct IirArgs {
     double *partials;
     long long partials_stride;
     int first_cta[kMaxScales + 1];
-    int blocks[kMaxScales];     // row blocks (rows pass) or column blocks (columns pass) per channel
+    int blocks[kMaxScales];     // tasks per channel: 5 * ceil(h/32) (rows pass) or ceil(w/32) (columns pass)
 };
 
 __device__ __forceinline__ void decode_cta(const IirArgs &a, int cta, int &s, int &c, int &blk)
@@ -89,64 +86,67 @@ __device__ __forceinline__ void decode_cta(const IirArgs &a, int cta, int &s, in
     blk = local - c * a.blocks[s];
 }
 
+__device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gmem_src, int src_bytes)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    // bytes beyond src_bytes (0, 4, 8, 12 or 16) are zero-filled: the filter's zero padding
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+
 // ------------------------------------------------------------------------------------------------
-// rows pass.  grid = (sum over scales of 3 * ceil(h/64), n_candidates), block = 160, dynamic smem.
+// rows pass.  grid = (sum over scales of 3 * 5 * ceil(h/32), n_candidates), block = 32, dynamic smem.
 //
 // Chunk t emits outputs n = 32t-4 .. 32t+27, so its right taps (n+4) are exactly tile t and its left
 // taps (n-6) fall in tiles t-1 and t: two tiles are in use while tiles t+1 and t+2 are in flight
-// (cp.async, two chunks of slack).  Chunk 0's first four outputs are the recursion's warm-up steps
-// n = -4..-1 and are dropped.
+// (cp.async, 16 bytes per lane, two chunks of slack).  Chunk 0's first four outputs are the
+// recursion's warm-up steps n = -4..-1 and are dropped.
+// Quantity q of {a, b, a*a, b*b, a*b} = x * (y*m + o) with warp-uniform tile pointers for x, y and
+// (m, o) = (0, 1) for the two plain planes, (1, 0) for the products: y*0+1 and x*1 are exact, so every
+// quantity is bit-identical to the direct expression, with one code path.
 struct IirRowsSmem {
-    float ta[kIirSlots][kIirRows][kIirChunk + 1];  // source channel tiles, ring
-    float tb[kIirSlots][kIirRows][kIirChunk + 1];  // distorted channel tiles, ring
-    float to[5][kIirRows][kIirChunk + 1];          // per-warp output staging (transposed write-out)
+    float tile[2][kIirSlots][kIirRows][kIirPitch];  // [plane a|b][ring slot][row][column]
+    float out[kIirRows][kIirPitch];                 // output staging (transposed write-out)
 };
 
-// quantity q of {a, b, a*a, b*b, a*b} = x * (y*m + o) with warp-uniform tile pointers for x, y and
-// (m, o) = (0, 1) for the two plain planes, (1, 0) for the products.  y*0+1 and x*1 are exact, so
-// every quantity is bit-identical to the direct expression, with no divergent code.
-__device__ __forceinline__ float pick_quantity(const float *px, const float *py, int j, float m, float o)
-{
-    return px[j] * fmaf(py[j], m, o);
-}
-
-__global__ void __launch_bounds__(kIirThreads, 2) k_iir_rows(const __grid_constant__ IirArgs a)
+__global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IirRowsSmem &sm = *reinterpret_cast<IirRowsSmem *>(smem_raw);
 
-    int s, c, rb;
-    decode_cta(a, blockIdx.x, s, c, rb);
+    int s, c, blk;
+    decode_cta(a, blockIdx.x, s, c, blk);
+    const int q = blk % 5, rb = blk / 5;
     const int cand = blockIdx.y;
     const int w = a.g.w[s], h = a.g.h[s], pitch = a.g.pitch[s];
     const int y0 = rb * kIirRows;
-    const long long poff = a.g.off[s] + (long long)c * a.g.plane[s];
+    const int rows_here = min(kIirRows, h - y0);
+    const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + (long long)y0 * pitch;
     const float *pa = a.src + poff;
     const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
-    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int lane = threadIdx.x;
     float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff;
     const int nch = (w + kIirChunk - 1) / kIirChunk;          // input tiles
     const int nout = (w + 4 + kIirChunk - 1) / kIirChunk;     // output chunks
     const IirCoef k = a.k;
-    const bool x_is_b = (q == 1) || (q == 3);   // x: b for {b, b*b}, a otherwise
-    const bool y_is_a = (q == 2);                 // y: a for a*a, b for {b*b, a*b}; unused for q < 2
+    const bool need_a = (q != 1) && (q != 3), need_b = (q != 0) && (q != 2);
+    const int xp = (q == 1 || q == 3) ? 1 : 0;    // x: b for {b, b*b}, a otherwise
+    const int yp = (q == 0 || q == 2) ? 0 : 1;    // y: a for a*a, b for {b*b, a*b}; for q < 2 any LOADED plane (y*0+1)
     const float ym = q < 2 ? 0.0f : 1.0f, yo = q < 2 ? 1.0f : 0.0f;
 
-    // tile t of both planes -> ring slot t & 3.  Warp q stages rows q, q+5, ... of both planes.
-    // Anything outside the image (t < 0, t >= nch, row >= h, column >= w) lands as zeros: that IS
-    // the filter's zero padding.
-    const int rows_here = min(kIirRows, h - y0);
+    // Stage tile t: lane l copies 16 bytes = columns 4*(l&7)..+3 of rows (l>>3) + 4i, i = 0..7.
+    const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
     auto issue_tile = [&](int t) {
         const int slot = t & (kIirSlots - 1);
-        const int gx = t * kIirChunk + lane;
-        const bool col_ok = (t >= 0) && (gx < w);
-        const long long o0 = (long long)y0 * pitch + gx;
-#pragma unroll 1
-        for (int row = q; row < kIirRows; row += 5) {
-            const bool valid = col_ok && (row < rows_here);
-            const long long o = valid ? o0 + (long long)row * pitch : 0;
-            cp_async_f32(&sm.ta[slot][row][lane], pa + o, valid);
-            cp_async_f32(&sm.tb[slot][row][lane], pb + o, valid);
+        const int gx = t * kIirChunk + sub_col;
+        int bytes = 0;
+        if (t >= 0 && gx < w) bytes = min(4, w - gx) * 4;
+#pragma unroll
+        for (int i = 0; i < kIirRows / 4; ++i) {
+            const int row = sub_row + 4 * i;
+            const int nb = row < rows_here ? bytes : 0;
+            const long long o = nb ? (long long)row * pitch + gx : 0;
+            if (need_a) cp_async_16(&sm.tile[0][slot][row][sub_col], pa + o, nb);
+            if (need_b) cp_async_16(&sm.tile[1][slot][row][sub_col], pb + o, nb);
         }
         cp_async_commit();
     };
@@ -154,148 +154,186 @@ __global__ void __launch_bounds__(kIirThreads, 2) k_iir_rows(const __grid_consta
 #pragma unroll 1
     for (int t = -1; t <= 1; ++t) issue_tile(t);
     cp_async_wait_all();
-    __syncthreads();
-
-    IirState st0, st1;  // rows lane and lane + 32
-#pragma unroll
-    for (int i = 0; i < 3; ++i) st0.p[i] = st0.p2[i] = st1.p[i] = st1.p2[i] = 0.0f;
-
-    for (int t = 0; t < nout; ++t) {
-        issue_tile(t + 2);
-        const int cur = t & (kIirSlots - 1), prev = (t + kIirSlots - 1) & (kIirSlots - 1);
-        const float(*tx)[kIirRows][kIirChunk + 1] = x_is_b ? sm.tb : sm.ta;
-        const float(*ty)[kIirRows][kIirChunk + 1] = y_is_a ? sm.ta : sm.tb;
-        const float *x0 = &tx[cur][lane][0], *y0p = &ty[cur][lane][0];
-        const float *x1 = &tx[cur][lane + 32][0], *y1p = &ty[cur][lane + 32][0];
-        const float *px0 = &tx[prev][lane][0], *py0 = &ty[prev][lane][0];
-        const float *px1 = &tx[prev][lane + 32][0], *py1 = &ty[prev][lane + 32][0];
-        float *o0 = &sm.to[q][lane][0], *o1 = &sm.to[q][lane + 32][0];
-        float r0[kIirChunk], r1[kIirChunk];
-#pragma unroll
-        for (int j = 0; j < kIirChunk; ++j) {
-            r0[j] = pick_quantity(x0, y0p, j, ym, yo);
-            r1[j] = pick_quantity(x1, y1p, j, ym, yo);
-        }
-#pragma unroll
-        for (int j = 0; j < kIirChunk; ++j) {
-            float l0, l1;
-            if (j >= 10) {
-                l0 = r0[j - 10];
-                l1 = r1[j - 10];
-            } else {
-                l0 = pick_quantity(px0, py0, j + 22, ym, yo);
-                l1 = pick_quantity(px1, py1, j + 22, ym, yo);
-            }
-            o0[j] = iir_step(k, st0, l0, r0[j]);
-            o1[j] = iir_step(k, st1, l1, r1[j]);
-        }
-        __syncwarp();
-        // transposed write-out: 64 row segments of 32 floats starting at column 32t - 4
-        const int n = t * kIirChunk - 4 + lane;
-        if (n >= 0 && n < nch * kIirChunk) {
-            float *dst = ph + (long long)y0 * pitch + n;
-            const float *srcp = &sm.to[q][0][lane];
-#pragma unroll 4
-            for (int rr = 0; rr < rows_here; ++rr) dst[(long long)rr * pitch] = srcp[rr * (kIirChunk + 1)];
-        }
-        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        __syncthreads();  // tile t+1 visible to all; every warp is past its reads of tile t-1
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 160.
-//
-// Each warp streams its quantity's row-filtered plane down the image, 20 rows per batch; the next
-// batch's 20 loads and this batch's a/b samples are issued before the current batch is computed, so
-// DRAM latency is covered by a full batch of arithmetic.  The exchange buffer is double-buffered:
-// one barrier per batch.
-__global__ void __launch_bounds__(kIirThreads) k_iir_cols(const __grid_constant__ IirArgs a)
-{
-    __shared__ float ex[2][5][kIirVBatch][kIirVCols];
-    __shared__ double sred[5 * 6];
-
-    int s, c, cb;
-    decode_cta(a, blockIdx.x, s, c, cb);
-    const int cand = blockIdx.y;
-    const int w = a.g.w[s], h = a.g.h[s], pitch = a.g.pitch[s];
-    const long long poff = a.g.off[s] + (long long)c * a.g.plane[s];
-    const float *pa = a.src + poff;
-    const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
-    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
-    const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff +
-                      cb * kIirVCols + lane;
-    const IirCoef k = a.k;
-    constexpr int kPx = (kIirVBatch * kIirVCols) / kIirThreads;  // 4 map pixels per thread and batch
+    __syncwarp();
 
     IirState st;
 #pragma unroll
     for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
-    // n = -4..-1: right taps are rows 0..3, nothing emitted
+
+#pragma unroll 1
+    for (int t = 0; t < nout; ++t) {
+        issue_tile(t + 2);
+        const int cur = t & (kIirSlots - 1), prev = (t + kIirSlots - 1) & (kIirSlots - 1);
+        const float4 *x4 = reinterpret_cast<const float4 *>(&sm.tile[xp][cur][lane][0]);
+        const float4 *y4 = reinterpret_cast<const float4 *>(&sm.tile[yp][cur][lane][0]);
+        const float4 *px4 = reinterpret_cast<const float4 *>(&sm.tile[xp][prev][lane][0]);
+        const float4 *py4 = reinterpret_cast<const float4 *>(&sm.tile[yp][prev][lane][0]);
+        float r[kIirChunk], lp[12];
+#pragma unroll
+        for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
+            const float4 xv = x4[j4], yv = y4[j4];
+            r[4 * j4 + 0] = xv.x * fmaf(yv.x, ym, yo);
+            r[4 * j4 + 1] = xv.y * fmaf(yv.y, ym, yo);
+            r[4 * j4 + 2] = xv.z * fmaf(yv.z, ym, yo);
+            r[4 * j4 + 3] = xv.w * fmaf(yv.w, ym, yo);
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 3; ++j4) {  // previous tile's columns 20..31 (22..31 are the left taps)
+            const float4 xv = px4[5 + j4], yv = py4[5 + j4];
+            lp[4 * j4 + 0] = xv.x * fmaf(yv.x, ym, yo);
+            lp[4 * j4 + 1] = xv.y * fmaf(yv.y, ym, yo);
+            lp[4 * j4 + 2] = xv.z * fmaf(yv.z, ym, yo);
+            lp[4 * j4 + 3] = xv.w * fmaf(yv.w, ym, yo);
+        }
+        float4 *o4 = reinterpret_cast<float4 *>(&sm.out[lane][0]);
+#pragma unroll
+        for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
+            float o[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * j4 + jj;
+                const float l = (j >= 10) ? r[j - 10] : lp[j + 2];  // column j+22 of the previous tile
+                o[jj] = iir_step(k, st, l, r[j]);
+            }
+            o4[j4] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        __syncwarp();
+        // transposed write-out: 16 bytes per lane, 4 rows per instruction, starting at column 32t - 4
+        {
+            const int n = t * kIirChunk - 4 + sub_col;
+            if (n >= 0 && n < nch * kIirChunk) {
+#pragma unroll
+                for (int i = 0; i < kIirRows / 4; ++i) {
+                    const int row = sub_row + 4 * i;
+                    if (row < rows_here)
+                        *reinterpret_cast<float4 *>(ph + (long long)row * pitch + n) =
+                            *reinterpret_cast<const float4 *>(&sm.out[row][sub_col]);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncwarp();  // tile t+1 landed for every lane; staging and tile t-1 are free again
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 32.
+//
+// One warp streams all five row-filtered planes of its 32 columns down the image: 15 independent
+// recursions per lane (ample ILP), the left taps in a 10-deep circular register delay line per
+// quantity, loads issued one 5-row batch ahead of their use.  The five filtered values of a pixel
+// are in the lane's registers when the last one is produced, so the SSIM / edge-diff maps are
+// evaluated on the spot: no shared memory, no barrier, nothing written but six sums per task.
+struct ColsBatch {
+    float r[5][5];     // [quantity][row in batch]: right taps = row-filtered input rows
+    float a[5], b[5];  // the pixel's own XYB samples (for the edge-diff map)
+};
+
+__device__ __forceinline__ void cols_load(ColsBatch &B, const float *ph, long long q_stride, const float *pa,
+                                          const float *pb, int pitch, int h, int n_first)
+{
+    // right taps of outputs n_first..n_first+4 are input rows n_first+4..n_first+8
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int rr = n_first + j + 4;
+        const bool ok = rr < h;
+        const long long o = ok ? (long long)rr * pitch : 0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float v = __ldg(ph + q * q_stride + o);
+            B.r[q][j] = ok ? v : 0.0f;
+        }
+        const int n = n_first + j;
+        const long long on = n < h ? (long long)n * pitch : 0;
+        B.a[j] = __ldg(pa + on);
+        B.b[j] = __ldg(pb + on);
+    }
+}
+
+// five outputs n_first .. n_first+4; PHASE (0 or 5) is n_first mod 10: it makes every delay-line
+// index a compile-time constant.
+template <int PHASE>
+__device__ __forceinline__ void cols_compute(const ColsBatch &B, const IirCoef &k, IirState st[5], float d[5][10],
+                                             int n_first, int h, bool col_ok, float acc[6])
+{
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int slot = (PHASE + j + 4) % 10;  // row (n+4) mod 10 == row (n-6) mod 10
+        float o[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float l = d[q][slot];
+            o[q] = iir_step(k, st[q], l, B.r[q][j]);
+            d[q][slot] = B.r[q][j];
+        }
+        if (col_ok && n_first + j < h) error_maps(B.a[j], B.b[j], o[0], o[1], o[2], o[3], o[4], acc);
+    }
+}
+
+__global__ void __launch_bounds__(32) k_iir_cols(const __grid_constant__ IirArgs a)
+{
+    int s, c, cb;
+    decode_cta(a, blockIdx.x, s, c, cb);
+    const int cand = blockIdx.y;
+    const int w = a.g.w[s], h = a.g.h[s], pitch = a.g.pitch[s];
+    const int lane = threadIdx.x;
+    const int gx = cb * kIirVCols + lane;
+    const bool col_ok = gx < w;
+    const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + gx;
+    const float *pa = a.src + poff;
+    const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
+    const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + poff;
+    const long long qs = a.q_stride;
+    const IirCoef k = a.k;
+
+    IirState st[5];
+    float d[5][10];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) st[q].p[i] = st[q].p2[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) d[q][i] = 0.0f;
+    }
+    // n = -4..-1: right taps are rows 0..3 (kept at delay slots 0..3), left taps are padding
 #pragma unroll
     for (int n = -4; n < 0; ++n) {
         const int rr = n + 4;
-        (void)iir_step(k, st, 0.0f, rr < h ? __ldg(ph + (long long)rr * pitch) : 0.0f);
-    }
-    // carry[j] = input row (n0 + j - 6) for j < 10, i.e. the previous batch's R[j + 10].
-    float carry[10];
+        const bool ok = rr < h;
 #pragma unroll
-    for (int j = 0; j < 10; ++j) {
-        const int rr = j - 6;
-        carry[j] = (rr >= 0 && rr < h) ? __ldg(ph + (long long)rr * pitch) : 0.0f;
-    }
-    float R[kIirVBatch], Rn[kIirVBatch];
-#pragma unroll
-    for (int j = 0; j < kIirVBatch; ++j) {
-        const int rr = j + 4;
-        R[j] = rr < h ? __ldg(ph + (long long)rr * pitch) : 0.0f;
+        for (int q = 0; q < 5; ++q) {
+            const float v = ok ? __ldg(ph + q * qs + (long long)rr * pitch) : 0.0f;
+            (void)iir_step(k, st[q], 0.0f, v);
+            d[q][rr] = v;
+        }
     }
 
     double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    int buf = 0;
-    for (int n0 = 0; n0 < h; n0 += kIirVBatch, buf ^= 1) {
-        // prefetch: next batch's right taps, and this batch's a/b samples for the maps
-#pragma unroll
-        for (int j = 0; j < kIirVBatch; ++j) {
-            const int rr = n0 + kIirVBatch + j + 4;
-            Rn[j] = rr < h ? __ldg(ph + (long long)rr * pitch) : 0.0f;
-        }
-        float av[kPx], bv[kPx];
-#pragma unroll
-        for (int i = 0; i < kPx; ++i) {
-            const int idx = threadIdx.x + i * kIirThreads;
-            const int gy = n0 + (idx >> 5), gx = cb * kIirVCols + (idx & 31);
-            const bool ok = gy < h && gx < w;
-            const long long o = ok ? (long long)gy * pitch + gx : 0;
-            av[i] = __ldg(pa + o);
-            bv[i] = __ldg(pb + o);
-        }
-#pragma unroll
-        for (int j = 0; j < kIirVBatch; ++j) {
-            const float l = (j < 10) ? carry[j] : R[j - 10];
-            ex[buf][q][j][lane] = iir_step(k, st, l, R[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 10; ++j) carry[j] = R[j + 10];
-#pragma unroll
-        for (int j = 0; j < kIirVBatch; ++j) R[j] = Rn[j];
-        __syncthreads();
-
+    ColsBatch B0, B1;
+    cols_load(B0, ph, qs, pa, pb, pitch, h, 0);
+#pragma unroll 1
+    for (int n0 = 0; n0 < h; n0 += 10) {
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < kPx; ++i) {
-            const int idx = threadIdx.x + i * kIirThreads;
-            const int row = idx >> 5, col = idx & 31;
-            if (n0 + row < h && cb * kIirVCols + col < w)
-                error_maps(av[i], bv[i], ex[buf][0][row][col], ex[buf][1][row][col], ex[buf][2][row][col],
-                           ex[buf][3][row][col], ex[buf][4][row][col], acc);
-        }
+        cols_load(B1, ph, qs, pa, pb, pitch, h, n0 + 5);
+        cols_compute<0>(B0, k, st, d, n0, h, col_ok, acc);
+        cols_load(B0, ph, qs, pa, pb, pitch, h, n0 + 10);
+        cols_compute<5>(B1, k, st, d, n0 + 5, h, col_ok, acc);
 #pragma unroll
         for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
-        // no second barrier: the next batch writes the other half of ex
     }
-    block_reduce6<kIirThreads / 32>(dacc, sred,
-                                    a.partials + (long long)cand * a.partials_stride + (long long)blockIdx.x * 6);
+    // fixed shuffle tree over the 32 columns, lane 0 writes the task's six sums
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double x = dacc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        dacc[j] = x;
+    }
+    if (lane == 0) {
+        double *out = a.partials + (long long)cand * a.partials_stride + (long long)blockIdx.x * 6;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) out[j] = dacc[j];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -382,18 +420,18 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     a.partials_stride = partials_stride;
     int acc = 0;
     for (int s = 0; s < g.n_scales; ++s) {
-        a.blocks[s] = (g.h[s] + kIirRows - 1) / kIirRows;
+        a.blocks[s] = 5 * ((g.h[s] + kIirRows - 1) / kIirRows);
         a.first_cta[s] = acc;
         acc += 3 * a.blocks[s];
     }
     for (int s = g.n_scales; s <= kMaxScales; ++s) a.first_cta[s] = acc;
-    k_iir_rows<<<dim3(acc, n), kIirThreads, sizeof(IirRowsSmem), st>>>(a);
+    k_iir_rows<<<dim3(acc, n), 32, sizeof(IirRowsSmem), st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (between) cudaEventRecord(between, st);
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
-    k_iir_cols<<<dim3(first_cta_cols[kMaxScales], n), kIirThreads, 0, st>>>(a);
+    k_iir_cols<<<dim3(first_cta_cols[kMaxScales], n), 32, 0, st>>>(a);
     *launches = 2;
     return cudaGetLastError();
 }
