@@ -50,15 +50,18 @@ __device__ __forceinline__ float iir_step(const IirCoef &k, IirState &s, float l
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// Work decomposition (v3): every warp is an independent task — no block barrier anywhere, so the
-// hardware scheduler balances tasks over the 4 x 148 sub-partitions by itself.
-//   rows pass   : task = (32 rows, 1 channel, 1 quantity), CTA = 1 warp, lane = row
-//   columns pass: task = (32 columns, 1 channel, all 5 quantities), CTA = 1 warp, lane = column
+// Work decomposition (v4): small independent tasks so that the hardware scheduler balances the
+// 4 x 148 sub-partitions by itself, and explicit software pipelining inside each task because a
+// sub-partition only ever hosts one or two of these warps (latency must be hidden by ILP, not TLP).
+//   rows pass   : task = (32 rows, 1 channel, 1 quantity); CTA = 1 warp; lane = row
+//   columns pass: task = (32 columns, 1 channel); CTA = 2 warps: warp 0 runs the five recursions,
+//                 warp 1 evaluates the maps one 5-row batch behind it; lane = column
 constexpr int kIirRows = 32;     // rows per rows-pass task
 constexpr int kIirChunk = 32;    // columns per staged tile
 constexpr int kIirPitch = 36;    // smem tile pitch in floats: 16-byte rows, conflict-free 128-bit access
-constexpr int kIirSlots = 4;     // tile ring: t-1, t in use while t+1, t+2 land
+constexpr int kIirSlots = 3;     // tile ring: t-1, t in use while t+1 lands (L2-prefetched 3 tiles ahead)
 constexpr int kIirVCols = 32;    // columns per columns-pass task
+constexpr int kIirVBatch = 5;    // rows per exchange batch in the columns pass
 
 struct IirArgs {
     Geom g;
@@ -93,19 +96,66 @@ __device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gmem_s
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
+// The recursion, software-pipelined by hand.  iir_step() above is the definition; this form performs
+// the SAME operations on the SAME values (sum*n2, minus prev2, fma(-d1, prev, .), (o1+o3)+o5) but
+// issues "sum*n2 - prev2" of step n+1 — which only needs the output of step n-1 — next to the fused
+// multiply-add of step n, so the dependent chain per step is one FFMA instead of five operations.
+struct IirPipe {
+    float p1[3];  // outputs of the previous step, per oscillator
+    float u[3];   // sum*n2 - prev2 of the CURRENT step, already evaluated
+};
+
+__device__ __forceinline__ void pipe_begin(const IirCoef &k, IirPipe &P, const IirState &st, float sum0)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        P.p1[i] = st.p[i];
+        P.u[i] = sum0 * k.n2[i] - st.p2[i];
+    }
+}
+
+// finishes the current step (returns its output) and pre-evaluates the next one from `sum_next`
+__device__ __forceinline__ float pipe_step(const IirCoef &k, IirPipe &P, float sum_next)
+{
+    float nw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) nw[i] = fmaf(-k.d1[i], P.p1[i], P.u[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        P.u[i] = sum_next * k.n2[i] - P.p1[i];
+        P.p1[i] = nw[i];
+    }
+    return (nw[0] + nw[1]) + nw[2];
+}
+
+// last step of a run: also hands (prev, prev2) back as an IirState
+__device__ __forceinline__ float pipe_end(const IirCoef &k, IirPipe &P, IirState &st)
+{
+    float nw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        nw[i] = fmaf(-k.d1[i], P.p1[i], P.u[i]);
+        st.p2[i] = P.p1[i];
+        st.p[i] = nw[i];
+    }
+    return (nw[0] + nw[1]) + nw[2];
+}
+
 // ------------------------------------------------------------------------------------------------
 // rows pass.  grid = (sum over scales of 3 * 5 * ceil(h/32), n_candidates), block = 32, dynamic smem.
 //
 // Chunk t emits outputs n = 32t-4 .. 32t+27, so its right taps (n+4) are exactly tile t and its left
-// taps (n-6) fall in tiles t-1 and t: two tiles are in use while tiles t+1 and t+2 are in flight
-// (cp.async, 16 bytes per lane, two chunks of slack).  Chunk 0's first four outputs are the
-// recursion's warm-up steps n = -4..-1 and are dropped.
+// taps (n-6) fall in tiles t-1 and t.  Tiles arrive by cp.async (16 bytes per lane) one chunk ahead of
+// use and are pulled into L2 four chunks ahead; results leave as 16-byte row segments through a
+// staging tile that reuses the slot of tile t-1 (dead once the chunk's samples are in registers).
+// Chunk 0's first four outputs are the recursion's warm-up steps n = -4..-1 and are dropped.
 // Quantity q of {a, b, a*a, b*b, a*b} = x * (y*m + o) with warp-uniform tile pointers for x, y and
 // (m, o) = (0, 1) for the two plain planes, (1, 0) for the products: y*0+1 and x*1 are exact, so every
 // quantity is bit-identical to the direct expression, with one code path.
 struct IirRowsSmem {
     float tile[2][kIirSlots][kIirRows][kIirPitch];  // [plane a|b][ring slot][row][column]
-    float out[kIirRows][kIirPitch];                 // output staging (transposed write-out)
 };
 
 __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs a)
@@ -136,7 +186,7 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
     // Stage tile t: lane l copies 16 bytes = columns 4*(l&7)..+3 of rows (l>>3) + 4i, i = 0..7.
     const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
     auto issue_tile = [&](int t) {
-        const int slot = t & (kIirSlots - 1);
+        const int slot = (t + kIirSlots) % kIirSlots;
         const int gx = t * kIirChunk + sub_col;
         int bytes = 0;
         if (t >= 0 && gx < w) bytes = min(4, w - gx) * 4;
@@ -150,7 +200,17 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
         }
         cp_async_commit();
     };
+    // Pull tile t into L2: lane = row, one 128-byte line per plane.
+    auto prefetch_tile = [&](int t) {
+        if (t < nch && lane < rows_here) {
+            const long long o = (long long)lane * pitch + t * kIirChunk;
+            if (need_a) prefetch_l2(pa + o);
+            if (need_b) prefetch_l2(pb + o);
+        }
+    };
 
+#pragma unroll 1
+    for (int t = 2; t <= 4; ++t) prefetch_tile(t);
 #pragma unroll 1
     for (int t = -1; t <= 1; ++t) issue_tile(t);
     cp_async_wait_all();
@@ -162,21 +222,12 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
 
 #pragma unroll 1
     for (int t = 0; t < nout; ++t) {
-        issue_tile(t + 2);
-        const int cur = t & (kIirSlots - 1), prev = (t + kIirSlots - 1) & (kIirSlots - 1);
+        const int cur = t % kIirSlots, prev = (t + kIirSlots - 1) % kIirSlots;
         const float4 *x4 = reinterpret_cast<const float4 *>(&sm.tile[xp][cur][lane][0]);
         const float4 *y4 = reinterpret_cast<const float4 *>(&sm.tile[yp][cur][lane][0]);
         const float4 *px4 = reinterpret_cast<const float4 *>(&sm.tile[xp][prev][lane][0]);
         const float4 *py4 = reinterpret_cast<const float4 *>(&sm.tile[yp][prev][lane][0]);
         float r[kIirChunk], lp[12];
-#pragma unroll
-        for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
-            const float4 xv = x4[j4], yv = y4[j4];
-            r[4 * j4 + 0] = xv.x * fmaf(yv.x, ym, yo);
-            r[4 * j4 + 1] = xv.y * fmaf(yv.y, ym, yo);
-            r[4 * j4 + 2] = xv.z * fmaf(yv.z, ym, yo);
-            r[4 * j4 + 3] = xv.w * fmaf(yv.w, ym, yo);
-        }
 #pragma unroll
         for (int j4 = 0; j4 < 3; ++j4) {  // previous tile's columns 20..31 (22..31 are the left taps)
             const float4 xv = px4[5 + j4], yv = py4[5 + j4];
@@ -185,15 +236,29 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
             lp[4 * j4 + 2] = xv.z * fmaf(yv.z, ym, yo);
             lp[4 * j4 + 3] = xv.w * fmaf(yv.w, ym, yo);
         }
-        float4 *o4 = reinterpret_cast<float4 *>(&sm.out[lane][0]);
+#pragma unroll
+        for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
+            const float4 xv = x4[j4], yv = y4[j4];
+            r[4 * j4 + 0] = xv.x * fmaf(yv.x, ym, yo);
+            r[4 * j4 + 1] = xv.y * fmaf(yv.y, ym, yo);
+            r[4 * j4 + 2] = xv.z * fmaf(yv.z, ym, yo);
+            r[4 * j4 + 3] = xv.w * fmaf(yv.w, ym, yo);
+        }
+        // sums l + r of the 32 steps (left tap of step j: column j+22 of the previous tile, or r[j-10])
+        float sum[kIirChunk];
+#pragma unroll
+        for (int j = 0; j < kIirChunk; ++j) sum[j] = ((j >= 10) ? r[j - 10] : lp[j + 2]) + r[j];
+        // tile t-1 is dead from here on (its samples are in registers): its slot is the staging tile
+        float4 *o4 = reinterpret_cast<float4 *>(&sm.tile[xp][prev][lane][0]);
+        IirPipe P;
+        pipe_begin(k, P, st, sum[0]);
 #pragma unroll
         for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
             float o[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int j = 4 * j4 + jj;
-                const float l = (j >= 10) ? r[j - 10] : lp[j + 2];  // column j+22 of the previous tile
-                o[jj] = iir_step(k, st, l, r[j]);
+                o[jj] = (j + 1 < kIirChunk) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
             }
             o4[j4] = make_float4(o[0], o[1], o[2], o[3]);
         }
@@ -207,132 +272,175 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
                     const int row = sub_row + 4 * i;
                     if (row < rows_here)
                         *reinterpret_cast<float4 *>(ph + (long long)row * pitch + n) =
-                            *reinterpret_cast<const float4 *>(&sm.out[row][sub_col]);
+                            *reinterpret_cast<const float4 *>(&sm.tile[xp][prev][row][sub_col]);
                 }
             }
         }
+        __syncwarp();            // staging consumed: the slot may be overwritten
+        issue_tile(t + 2);       // lands in the slot tile t-1 / the staging tile just vacated
+        prefetch_tile(t + 5);
         asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        __syncwarp();  // tile t+1 landed for every lane; staging and tile t-1 are free again
+        __syncwarp();            // tile t+1 (issued one chunk ago) is visible to every lane
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 32.
+// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 64.
 //
-// One warp streams all five row-filtered planes of its 32 columns down the image: 15 independent
-// recursions per lane (ample ILP), the left taps in a 10-deep circular register delay line per
-// quantity, loads issued one 5-row batch ahead of their use.  The five filtered values of a pixel
-// are in the lane's registers when the last one is produced, so the SSIM / edge-diff maps are
-// evaluated on the spot: no shared memory, no barrier, nothing written but six sums per task.
+// Warp 0 streams all five row-filtered planes of its 32 columns down the image: 15 recursions per lane,
+// left taps in a 10-deep circular register delay line per quantity, loads issued one 5-row batch ahead.
+// It drops the five filtered values of each pixel into a double-buffered shared-memory batch; warp 1,
+// one batch behind, loads the pixel's own XYB samples and evaluates the SSIM / edge-diff maps and the
+// six pooled sums.  One block barrier per 5 rows; the two warps sit on different sub-partitions.
 struct ColsBatch {
-    float r[5][5];     // [quantity][row in batch]: right taps = row-filtered input rows
-    float a[5], b[5];  // the pixel's own XYB samples (for the edge-diff map)
+    float r[5][kIirVBatch];  // [quantity][row in batch]: right taps = row-filtered input rows
 };
 
-__device__ __forceinline__ void cols_load(ColsBatch &B, const float *ph, long long q_stride, const float *pa,
-                                          const float *pb, int pitch, int h, int n_first)
+__device__ __forceinline__ void cols_load(ColsBatch &B, const float *ph, long long q_stride, int pitch, int h,
+                                          int n_first)
 {
     // right taps of outputs n_first..n_first+4 are input rows n_first+4..n_first+8
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
+    for (int j = 0; j < kIirVBatch; ++j) {
         const int rr = n_first + j + 4;
         const bool ok = rr < h;
-        const long long o = ok ? (long long)rr * pitch : 0;
+        const long long o = (long long)rr * pitch;
+        // predicated loads (no select on the loaded value: nothing may depend on it until it is used)
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-            const float v = __ldg(ph + q * q_stride + o);
-            B.r[q][j] = ok ? v : 0.0f;
+            B.r[q][j] = 0.0f;
+            if (ok) B.r[q][j] = __ldg(ph + q * q_stride + o);
         }
-        const int n = n_first + j;
-        const long long on = n < h ? (long long)n * pitch : 0;
-        B.a[j] = __ldg(pa + on);
-        B.b[j] = __ldg(pb + on);
     }
 }
 
-// five outputs n_first .. n_first+4; PHASE (0 or 5) is n_first mod 10: it makes every delay-line
-// index a compile-time constant.
+// five outputs n_first .. n_first+4 of every quantity into ex[q][j][lane]; PHASE (0 or 5) is
+// n_first mod 10: it makes every delay-line index a compile-time constant.
 template <int PHASE>
 __device__ __forceinline__ void cols_compute(const ColsBatch &B, const IirCoef &k, IirState st[5], float d[5][10],
-                                             int n_first, int h, bool col_ok, float acc[6])
+                                             float (*ex)[kIirVBatch][kIirVCols], int lane)
 {
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const int slot = (PHASE + j + 4) % 10;  // row (n+4) mod 10 == row (n-6) mod 10
-        float o[5];
+    for (int q = 0; q < 5; ++q) {
+        float sum[kIirVBatch];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            const float l = d[q][slot];
-            o[q] = iir_step(k, st[q], l, B.r[q][j]);
+        for (int j = 0; j < kIirVBatch; ++j) {
+            const int slot = (PHASE + j + 4) % 10;  // row (n+4) mod 10 == row (n-6) mod 10
+            sum[j] = d[q][slot] + B.r[q][j];
             d[q][slot] = B.r[q][j];
         }
-        if (col_ok && n_first + j < h) error_maps(B.a[j], B.b[j], o[0], o[1], o[2], o[3], o[4], acc);
+        IirPipe P;
+        pipe_begin(k, P, st[q], sum[0]);
+#pragma unroll
+        for (int j = 0; j < kIirVBatch; ++j)
+            ex[q][j][lane] = (j + 1 < kIirVBatch) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st[q]);
     }
 }
 
-__global__ void __launch_bounds__(32) k_iir_cols(const __grid_constant__ IirArgs a)
+__global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs a)
 {
+    __shared__ float ex[2][5][kIirVBatch][kIirVCols];
+
     int s, c, cb;
     decode_cta(a, blockIdx.x, s, c, cb);
     const int cand = blockIdx.y;
     const int w = a.g.w[s], h = a.g.h[s], pitch = a.g.pitch[s];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     const int gx = cb * kIirVCols + lane;
     const bool col_ok = gx < w;
     const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + gx;
-    const float *pa = a.src + poff;
-    const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
-    const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + poff;
-    const long long qs = a.q_stride;
-    const IirCoef k = a.k;
+    const int nbatch = (h + kIirVBatch - 1) / kIirVBatch;  // producer runs batches 0..nbatch-1, consumer one behind
 
-    IirState st[5];
-    float d[5][10];
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) st[q].p[i] = st[q].p2[i] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) d[q][i] = 0.0f;
-    }
-    // n = -4..-1: right taps are rows 0..3 (kept at delay slots 0..3), left taps are padding
-#pragma unroll
-    for (int n = -4; n < 0; ++n) {
-        const int rr = n + 4;
-        const bool ok = rr < h;
+    if (role == 0) {
+        // ---------------- producer: the five column recursions ----------------
+        const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + poff;
+        const long long qs = a.q_stride;
+        const IirCoef k = a.k;
+        IirState st[5];
+        float d[5][10];
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-            const float v = ok ? __ldg(ph + q * qs + (long long)rr * pitch) : 0.0f;
-            (void)iir_step(k, st[q], 0.0f, v);
-            d[q][rr] = v;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) st[q].p[i] = st[q].p2[i] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) d[q][i] = 0.0f;
         }
-    }
-
-    double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    ColsBatch B0, B1;
-    cols_load(B0, ph, qs, pa, pb, pitch, h, 0);
+        // n = -4..-1: right taps are rows 0..3 (kept at delay slots 0..3), left taps are padding
+#pragma unroll
+        for (int n = -4; n < 0; ++n) {
+            const int rr = n + 4;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                float v = 0.0f;
+                if (rr < h) v = __ldg(ph + q * qs + (long long)rr * pitch);
+                (void)iir_step(k, st[q], 0.0f, v);
+                d[q][rr] = v;
+            }
+        }
+        ColsBatch B0, B1;
+        cols_load(B0, ph, qs, pitch, h, 0);
 #pragma unroll 1
-    for (int n0 = 0; n0 < h; n0 += 10) {
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        cols_load(B1, ph, qs, pa, pb, pitch, h, n0 + 5);
-        cols_compute<0>(B0, k, st, d, n0, h, col_ok, acc);
-        cols_load(B0, ph, qs, pa, pb, pitch, h, n0 + 10);
-        cols_compute<5>(B1, k, st, d, n0 + 5, h, col_ok, acc);
+        for (int b = 0; b < nbatch; b += 2) {
+            cols_load(B1, ph, qs, pitch, h, (b + 1) * kIirVBatch);
+            cols_compute<0>(B0, k, st, d, ex[0], lane);
+            __syncthreads();  // batch b published; consumer finished batch b-1 (other buffer)
+            cols_load(B0, ph, qs, pitch, h, (b + 2) * kIirVBatch);
+            cols_compute<5>(B1, k, st, d, ex[1], lane);
+            __syncthreads();  // batch b+1 published
+        }
+        __syncthreads();      // consumer's last batch
+    } else {
+        // ---------------- consumer: maps + pooling, one batch behind ----------------
+        const float *pa = a.src + poff;
+        const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
+        double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        float av[kIirVBatch], bv[kIirVBatch], an[kIirVBatch], bn[kIirVBatch];
+        auto load_ab = [&](float *A, float *Bv, int n_first) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
-    }
-    // fixed shuffle tree over the 32 columns, lane 0 writes the task's six sums
+            for (int j = 0; j < kIirVBatch; ++j) {
+                const int n = n_first + j;
+                A[j] = 0.0f;
+                Bv[j] = 0.0f;
+                if (n < h) {
+                    A[j] = __ldg(pa + (long long)n * pitch);
+                    Bv[j] = __ldg(pb + (long long)n * pitch);
+                }
+            }
+        };
+        auto maps = [&](const float *A, const float *Bv, int buf, int n_first) {
+            float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        double x = dacc[j];
+            for (int j = 0; j < kIirVBatch; ++j)
+                if (col_ok && n_first + j < h)
+                    error_maps(A[j], Bv[j], ex[buf][0][j][lane], ex[buf][1][j][lane], ex[buf][2][j][lane],
+                               ex[buf][3][j][lane], ex[buf][4][j][lane], acc);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        dacc[j] = x;
-    }
-    if (lane == 0) {
-        double *out = a.partials + (long long)cand * a.partials_stride + (long long)blockIdx.x * 6;
+            for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
+        };
+        load_ab(av, bv, 0);
+#pragma unroll 1
+        for (int b = 0; b < nbatch; b += 2) {
+            load_ab(an, bn, (b + 1) * kIirVBatch);
+            __syncthreads();                                   // batch b is in ex[0]
+            maps(av, bv, 0, b * kIirVBatch);
+            load_ab(av, bv, (b + 2) * kIirVBatch);
+            __syncthreads();                                   // batch b+1 is in ex[1]
+            maps(an, bn, 1, (b + 1) * kIirVBatch);
+        }
+        __syncthreads();
+        // fixed shuffle tree over the 32 columns, lane 0 writes the task's six sums
 #pragma unroll
-        for (int j = 0; j < 6; ++j) out[j] = dacc[j];
+        for (int j = 0; j < 6; ++j) {
+            double x = dacc[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            dacc[j] = x;
+        }
+        if (lane == 0) {
+            double *out = a.partials + (long long)cand * a.partials_stride + (long long)blockIdx.x * 6;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) out[j] = dacc[j];
+        }
     }
 }
 
@@ -431,7 +539,7 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     if (between) cudaEventRecord(between, st);
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
-    k_iir_cols<<<dim3(first_cta_cols[kMaxScales], n), 32, 0, st>>>(a);
+    k_iir_cols<<<dim3(first_cta_cols[kMaxScales], n), 64, 0, st>>>(a);
     *launches = 2;
     return cudaGetLastError();
 }
