@@ -167,6 +167,11 @@ int oavif_ssimu2_debug_get_xyb(oavif_ssimu2_ctx *ctx, int which, int scale, int 
 int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, uint32_t h,
                             float *out);
 
+/* Profiling aid: re-run only the RECURSIVE rows pass on the pyramids of the last score call,
+ * `iters` times, and report its mean device time.  variant 0 is the product kernel; bit 0 drops
+ * its stores, bit 1 its tile loads (to attribute time; the row-filtered planes are then garbage). */
+int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,7 @@ struct oavif_ssimu2_ctx {
     int device = 0;
     uint32_t max_w = 0, max_h = 0, max_batch = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    IirStreams iir_streams{};
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
 
     // capacities (computed from max_w x max_h)
@@ -359,7 +360,7 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
         const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats,
                                               ctx->d_hplanes, ctx->cap_hplane_floats, ctx->d_partials,
                                               ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, (int)n,
-                                              ctx->stream, ctx->ev[3], &launches);
+                                              ctx->stream, ctx->iir_streams, ctx->ev[3], &launches);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "recursive blur launch: %s", cudaGetErrorString(e));
         ctx->timing.launches += launches;
     }
@@ -512,6 +513,9 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     cudaFreeHost(ctx->h_scores);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->iir_streams.fork) cudaEventDestroy(ctx->iir_streams.fork);
+    if (ctx->iir_streams.join) cudaEventDestroy(ctx->iir_streams.join);
+    if (ctx->iir_streams.side) cudaStreamDestroy(ctx->iir_streams.side);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -543,6 +547,9 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     for (auto &e : ctx->ev) CKC(cudaEventCreate(&e));
+    CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.side, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->iir_streams.fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->iir_streams.join, cudaEventDisableTiming));
 
     const int mw = (int)max_w, mh = (int)max_h;
     ctx->cap_pyr_floats = std::max(pyr_capacity(mw, mh), pyr_capacity(mh, mw));
@@ -820,6 +827,31 @@ int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, 
     CK(cudaMemcpy2DAsync(out, sizeof(float) * w, d_out, sizeof(float) * pitch, sizeof(float) * w, h,
                          cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms)
+{
+    if (!ctx || !mean_ms || iters <= 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "bad argument");
+    if (!ctx->have_source || ctx->last_n == 0 || ctx->g.n_scales == 0)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "needs a previous score call");
+    CK(cudaSetDevice(ctx->device));
+    BlurPlan plan;
+    plan_iir_v(ctx->g, &plan);
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (int i = 0; i < iters; ++i) {
+        int launches = 0;
+        const cudaError_t e = launch_iir_blur(ctx->g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats,
+                                              ctx->d_hplanes, ctx->cap_hplane_floats, ctx->d_partials,
+                                              ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, 1, ctx->stream,
+                                              ctx->iir_streams, nullptr, &launches, variant, true);
+        if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
+    }
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    *mean_ms = ms / iters;
     return 0;
 }
 

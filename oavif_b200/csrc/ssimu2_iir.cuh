@@ -50,7 +50,7 @@ __device__ __forceinline__ float iir_step(const IirCoef &k, IirState &s, float l
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// Work decomposition (v4): small independent tasks so that the hardware scheduler balances the
+// Work decomposition (v5): small independent tasks so that the hardware scheduler balances the
 // 4 x 148 sub-partitions by itself, and explicit software pipelining inside each task because a
 // sub-partition only ever hosts one or two of these warps (latency must be hidden by ILP, not TLP).
 //   rows pass   : task = (32 rows, 1 channel, 1 quantity); CTA = 1 warp; lane = row
@@ -59,7 +59,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 constexpr int kIirRows = 32;     // rows per rows-pass task
 constexpr int kIirChunk = 32;    // columns per staged tile
 constexpr int kIirPitch = 36;    // smem tile pitch in floats: 16-byte rows, conflict-free 128-bit access
-constexpr int kIirSlots = 3;     // tile ring: t-1, t in use while t+1 lands (L2-prefetched 3 tiles ahead)
+constexpr int kIirSlots = 4;     // tile ring: t-1, t, t+1 in use while t+2 lands
 constexpr int kIirVCols = 32;    // columns per columns-pass task
 constexpr int kIirVBatch = 5;    // rows per exchange batch in the columns pass
 
@@ -75,7 +75,7 @@ struct IirArgs {
     double *partials;
     long long partials_stride;
     int first_cta[kMaxScales + 1];
-    int blocks[kMaxScales];     // tasks per channel: 5 * ceil(h/32) (rows pass) or ceil(w/32) (columns pass)
+    int blocks[kMaxScales];     // tasks per channel and scale
 };
 
 __device__ __forceinline__ void decode_cta(const IirArgs &a, int cta, int &s, int &c, int &blk)
@@ -96,7 +96,18 @@ __device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gmem_s
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+__device__ __forceinline__ void cp_async_4(float *smem_dst, const float *gmem_src, bool valid)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 4 : 0;  // src-size 0 => the destination is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes));
+}
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 // The recursion, software-pipelined by hand.  iir_step() above is the definition; this form performs
 // the SAME operations on the SAME values (sum*n2, minus prev2, fma(-d1, prev, .), (o1+o3)+o5) but
@@ -144,28 +155,33 @@ __device__ __forceinline__ float pipe_end(const IirCoef &k, IirPipe &P, IirState
 }
 
 // ------------------------------------------------------------------------------------------------
-// rows pass.  grid = (sum over scales of 3 * 5 * ceil(h/32), n_candidates), block = 32, dynamic smem.
+// rows pass.  Two task classes, launched side by side on two streams because they need different
+// amounts of shared memory: NPLANES = 1 for the quantities made from one plane {a, b, a*a, b*b}
+// (grid = sum over scales of 3 * 4 * ceil(h/32)), NPLANES = 2 for a*b (3 * ceil(h/32)).  block = 32.
 //
-// Chunk t emits outputs n = 32t-4 .. 32t+27, so its right taps (n+4) are exactly tile t and its left
-// taps (n-6) fall in tiles t-1 and t.  Tiles arrive by cp.async (16 bytes per lane) one chunk ahead of
-// use and are pulled into L2 four chunks ahead; results leave as 16-byte row segments through a
-// staging tile that reuses the slot of tile t-1 (dead once the chunk's samples are in registers).
-// Chunk 0's first four outputs are the recursion's warm-up steps n = -4..-1 and are dropped.
-// Quantity q of {a, b, a*a, b*b, a*b} = x * (y*m + o) with warp-uniform tile pointers for x, y and
-// (m, o) = (0, 1) for the two plain planes, (1, 0) for the products: y*0+1 and x*1 are exact, so every
-// quantity is bit-identical to the direct expression, with one code path.
+// Chunk t emits the 128-byte-aligned outputs n = 32t .. 32t+31: right taps (n+4) come from tiles t and
+// t+1, left taps (n-6) from tiles t-1 and t.  Tiles arrive by cp.async (16 bytes per lane) two chunks
+// ahead of use; results leave as whole 128-byte lines (streaming stores) through a staging tile that
+// reuses the slot of tile t-1, dead once the chunk's samples are in registers.
+// A quantity is x * (y*m + o) with (m, o) = (0, 1) for the plain planes and (1, 0) for the products:
+// y*0+1 and x*1 are exact, so every quantity is bit-identical to the direct expression, one code path.
+// VARIANT is a profiling aid (oavif_ssimu2_debug_time_rows): bit 0 drops the stores, bit 1 the tile
+// loads after the first ones.  0 is the product kernel.
+template <int NPLANES>
 struct IirRowsSmem {
-    float tile[2][kIirSlots][kIirRows][kIirPitch];  // [plane a|b][ring slot][row][column]
+    float tile[NPLANES][kIirSlots][kIirRows][kIirPitch];  // [plane][ring slot][row][column]
 };
 
+template <int NPLANES, int VARIANT>
 __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    IirRowsSmem &sm = *reinterpret_cast<IirRowsSmem *>(smem_raw);
+    IirRowsSmem<NPLANES> &sm = *reinterpret_cast<IirRowsSmem<NPLANES> *>(smem_raw);
 
     int s, c, blk;
     decode_cta(a, blockIdx.x, s, c, blk);
-    const int q = blk % 5, rb = blk / 5;
+    const int q = NPLANES == 2 ? 4 : (blk & 3);
+    const int rb = NPLANES == 2 ? blk : (blk >> 2);
     const int cand = blockIdx.y;
     const int w = a.g.w[s], h = a.g.h[s], pitch = a.g.pitch[s];
     const int y0 = rb * kIirRows;
@@ -175,18 +191,18 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
     const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
     const int lane = threadIdx.x;
     float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff;
-    const int nch = (w + kIirChunk - 1) / kIirChunk;          // input tiles
-    const int nout = (w + 4 + kIirChunk - 1) / kIirChunk;     // output chunks
+    const int nch = (w + kIirChunk - 1) / kIirChunk;
     const IirCoef k = a.k;
-    const bool need_a = (q != 1) && (q != 3), need_b = (q != 0) && (q != 2);
-    const int xp = (q == 1 || q == 3) ? 1 : 0;    // x: b for {b, b*b}, a otherwise
-    const int yp = (q == 0 || q == 2) ? 0 : 1;    // y: a for a*a, b for {b*b, a*b}; for q < 2 any LOADED plane (y*0+1)
+    // plane 0 of the ring holds a for {a, a*a, a*b} and b for {b, b*b}; plane 1 (a*b only) holds b
+    const float *p0 = (NPLANES == 1 && (q & 1)) ? pb : pa;
+    const float *p1 = pb;
+    constexpr int yp = NPLANES - 1;  // y operand: the same plane for squares, plane 1 for a*b
     const float ym = q < 2 ? 0.0f : 1.0f, yo = q < 2 ? 1.0f : 0.0f;
 
     // Stage tile t: lane l copies 16 bytes = columns 4*(l&7)..+3 of rows (l>>3) + 4i, i = 0..7.
     const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
     auto issue_tile = [&](int t) {
-        const int slot = (t + kIirSlots) % kIirSlots;
+        const int slot = (t + kIirSlots) & (kIirSlots - 1);
         const int gx = t * kIirChunk + sub_col;
         int bytes = 0;
         if (t >= 0 && gx < w) bytes = min(4, w - gx) * 4;
@@ -195,61 +211,53 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
             const int row = sub_row + 4 * i;
             const int nb = row < rows_here ? bytes : 0;
             const long long o = nb ? (long long)row * pitch + gx : 0;
-            if (need_a) cp_async_16(&sm.tile[0][slot][row][sub_col], pa + o, nb);
-            if (need_b) cp_async_16(&sm.tile[1][slot][row][sub_col], pb + o, nb);
+            cp_async_16(&sm.tile[0][slot][row][sub_col], p0 + o, nb);
+            if (NPLANES == 2) cp_async_16(&sm.tile[NPLANES - 1][slot][row][sub_col], p1 + o, nb);
         }
         cp_async_commit();
     };
-    // Pull tile t into L2: lane = row, one 128-byte line per plane.
-    auto prefetch_tile = [&](int t) {
-        if (t < nch && lane < rows_here) {
-            const long long o = (long long)lane * pitch + t * kIirChunk;
-            if (need_a) prefetch_l2(pa + o);
-            if (need_b) prefetch_l2(pb + o);
-        }
+    auto sample4 = [&](int slot, int j4, float *out) {
+        const float4 xv = *reinterpret_cast<const float4 *>(&sm.tile[0][slot][lane][4 * j4]);
+        const float4 yv = *reinterpret_cast<const float4 *>(&sm.tile[yp][slot][lane][4 * j4]);
+        out[0] = xv.x * fmaf(yv.x, ym, yo);
+        out[1] = xv.y * fmaf(yv.y, ym, yo);
+        out[2] = xv.z * fmaf(yv.z, ym, yo);
+        out[3] = xv.w * fmaf(yv.w, ym, yo);
     };
 
 #pragma unroll 1
-    for (int t = 2; t <= 4; ++t) prefetch_tile(t);
-#pragma unroll 1
     for (int t = -1; t <= 1; ++t) issue_tile(t);
-    cp_async_wait_all();
+    issue_tile(2);
+    cp_async_wait<1>();
     __syncwarp();
 
     IirState st;
 #pragma unroll
     for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
+    {   // n = -4 .. -1: right taps are columns 0..3 of tile 0, left taps are padding, nothing emitted
+        float w4[4];
+        sample4(0, 0, w4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) (void)iir_step(k, st, 0.0f, w4[i]);
+    }
 
 #pragma unroll 1
-    for (int t = 0; t < nout; ++t) {
-        const int cur = t % kIirSlots, prev = (t + kIirSlots - 1) % kIirSlots;
-        const float4 *x4 = reinterpret_cast<const float4 *>(&sm.tile[xp][cur][lane][0]);
-        const float4 *y4 = reinterpret_cast<const float4 *>(&sm.tile[yp][cur][lane][0]);
-        const float4 *px4 = reinterpret_cast<const float4 *>(&sm.tile[xp][prev][lane][0]);
-        const float4 *py4 = reinterpret_cast<const float4 *>(&sm.tile[yp][prev][lane][0]);
-        float r[kIirChunk], lp[12];
+    for (int t = 0; t < nch; ++t) {
+        const int cur = t & (kIirSlots - 1), prev = (t + kIirSlots - 1) & (kIirSlots - 1),
+                  next = (t + 1) & (kIirSlots - 1);
+        // samples v[i] = quantity at column 32t - 8 + i, i = 0..43 (columns 32t-8 .. 32t+35)
+        float v[44];
+        sample4(prev, 6, v);
+        sample4(prev, 7, v + 4);
 #pragma unroll
-        for (int j4 = 0; j4 < 3; ++j4) {  // previous tile's columns 20..31 (22..31 are the left taps)
-            const float4 xv = px4[5 + j4], yv = py4[5 + j4];
-            lp[4 * j4 + 0] = xv.x * fmaf(yv.x, ym, yo);
-            lp[4 * j4 + 1] = xv.y * fmaf(yv.y, ym, yo);
-            lp[4 * j4 + 2] = xv.z * fmaf(yv.z, ym, yo);
-            lp[4 * j4 + 3] = xv.w * fmaf(yv.w, ym, yo);
-        }
-#pragma unroll
-        for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
-            const float4 xv = x4[j4], yv = y4[j4];
-            r[4 * j4 + 0] = xv.x * fmaf(yv.x, ym, yo);
-            r[4 * j4 + 1] = xv.y * fmaf(yv.y, ym, yo);
-            r[4 * j4 + 2] = xv.z * fmaf(yv.z, ym, yo);
-            r[4 * j4 + 3] = xv.w * fmaf(yv.w, ym, yo);
-        }
-        // sums l + r of the 32 steps (left tap of step j: column j+22 of the previous tile, or r[j-10])
+        for (int j4 = 0; j4 < kIirChunk / 4; ++j4) sample4(cur, j4, v + 8 + 4 * j4);
+        sample4(next, 0, v + 40);
+        // step j (output column 32t + j): left tap column 32t + j - 6 = v[j+2], right tap 32t + j + 4 = v[j+12]
         float sum[kIirChunk];
 #pragma unroll
-        for (int j = 0; j < kIirChunk; ++j) sum[j] = ((j >= 10) ? r[j - 10] : lp[j + 2]) + r[j];
+        for (int j = 0; j < kIirChunk; ++j) sum[j] = v[j + 2] + v[j + 12];
         // tile t-1 is dead from here on (its samples are in registers): its slot is the staging tile
-        float4 *o4 = reinterpret_cast<float4 *>(&sm.tile[xp][prev][lane][0]);
+        float4 *o4 = reinterpret_cast<float4 *>(&sm.tile[0][prev][lane][0]);
         IirPipe P;
         pipe_begin(k, P, st, sum[0]);
 #pragma unroll
@@ -263,83 +271,49 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
             o4[j4] = make_float4(o[0], o[1], o[2], o[3]);
         }
         __syncwarp();
-        // transposed write-out: 16 bytes per lane, 4 rows per instruction, starting at column 32t - 4
-        {
-            const int n = t * kIirChunk - 4 + sub_col;
-            if (n >= 0 && n < nch * kIirChunk) {
+        // transposed write-out of output tile t: whole 128-byte lines, 4 rows per instruction
+        if (!(VARIANT & 1) || t == nch - 1) {
+            float *dst = ph + t * kIirChunk + sub_col;
 #pragma unroll
-                for (int i = 0; i < kIirRows / 4; ++i) {
-                    const int row = sub_row + 4 * i;
-                    if (row < rows_here)
-                        *reinterpret_cast<float4 *>(ph + (long long)row * pitch + n) =
-                            *reinterpret_cast<const float4 *>(&sm.tile[xp][prev][row][sub_col]);
-                }
+            for (int i = 0; i < kIirRows / 4; ++i) {
+                const int row = sub_row + 4 * i;
+                if (row < rows_here)
+                    __stcs(reinterpret_cast<float4 *>(dst + (long long)row * pitch),
+                           *reinterpret_cast<const float4 *>(&sm.tile[0][prev][row][sub_col]));
             }
         }
-        __syncwarp();            // staging consumed: the slot may be overwritten
-        issue_tile(t + 2);       // lands in the slot tile t-1 / the staging tile just vacated
-        prefetch_tile(t + 5);
-        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        __syncwarp();            // tile t+1 (issued one chunk ago) is visible to every lane
+        __syncwarp();                 // staging consumed: the slot may be overwritten
+        if (!(VARIANT & 2)) issue_tile(t + 3);  // lands in the slot of tile t-1 / the staging tile
+        else cp_async_commit();
+        cp_async_wait<1>();           // tile t+2 (issued one chunk ago) has landed
+        __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 64.
 //
-// Warp 0 streams all five row-filtered planes of its 32 columns down the image: 15 recursions per lane,
-// left taps in a 10-deep circular register delay line per quantity, loads issued one 5-row batch ahead.
-// It drops the five filtered values of each pixel into a double-buffered shared-memory batch; warp 1,
-// one batch behind, loads the pixel's own XYB samples and evaluates the SSIM / edge-diff maps and the
-// six pooled sums.  One block barrier per 5 rows; the two warps sit on different sub-partitions.
-struct ColsBatch {
-    float r[5][kIirVBatch];  // [quantity][row in batch]: right taps = row-filtered input rows
+// Warp 0 (producer) streams all five row-filtered planes of its 32 columns down the image through a
+// shared-memory ring fed by cp.async RCAP-16 rows ahead of use (both taps of the recursion are read
+// from the ring, so there is no register delay line), runs the 15 recursions per lane and drops the
+// five filtered values of each pixel into a double-buffered batch.  Warp 1 (consumer), one 5-row
+// batch behind, streams the pixel's own XYB samples through its own ring and evaluates the
+// SSIM / edge-diff maps and the six pooled sums.  One block barrier per 5 rows.
+template <int RCAP>
+struct IirColsSmem {
+    float ring[5][RCAP][kIirVCols];            // producer input rows, row r at [r & (RCAP-1)]
+    float ab[2][32][kIirVCols];                // consumer rows of the two XYB planes
+    float ex[2][5][kIirVBatch][kIirVCols];     // filtered values, double-buffered
 };
 
-__device__ __forceinline__ void cols_load(ColsBatch &B, const float *ph, long long q_stride, int pitch, int h,
-                                          int n_first)
-{
-    // right taps of outputs n_first..n_first+4 are input rows n_first+4..n_first+8
-#pragma unroll
-    for (int j = 0; j < kIirVBatch; ++j) {
-        const int rr = n_first + j + 4;
-        const bool ok = rr < h;
-        const long long o = (long long)rr * pitch;
-        // predicated loads (no select on the loaded value: nothing may depend on it until it is used)
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            B.r[q][j] = 0.0f;
-            if (ok) B.r[q][j] = __ldg(ph + q * q_stride + o);
-        }
-    }
-}
-
-// five outputs n_first .. n_first+4 of every quantity into ex[q][j][lane]; PHASE (0 or 5) is
-// n_first mod 10: it makes every delay-line index a compile-time constant.
-template <int PHASE>
-__device__ __forceinline__ void cols_compute(const ColsBatch &B, const IirCoef &k, IirState st[5], float d[5][10],
-                                             float (*ex)[kIirVBatch][kIirVCols], int lane)
-{
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        float sum[kIirVBatch];
-#pragma unroll
-        for (int j = 0; j < kIirVBatch; ++j) {
-            const int slot = (PHASE + j + 4) % 10;  // row (n+4) mod 10 == row (n-6) mod 10
-            sum[j] = d[q][slot] + B.r[q][j];
-            d[q][slot] = B.r[q][j];
-        }
-        IirPipe P;
-        pipe_begin(k, P, st[q], sum[0]);
-#pragma unroll
-        for (int j = 0; j < kIirVBatch; ++j)
-            ex[q][j][lane] = (j + 1 < kIirVBatch) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st[q]);
-    }
-}
-
+template <int RCAP>
 __global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs a)
 {
-    __shared__ float ex[2][5][kIirVBatch][kIirVCols];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IirColsSmem<RCAP> &sm = *reinterpret_cast<IirColsSmem<RCAP> *>(smem_raw);
+    constexpr int D = ((RCAP - 15) / 5) * 5;   // rows of look-ahead; D + 15 <= RCAP, D % 5 == 0
+    static_assert(D % kIirVBatch == 0 && D + 15 <= RCAP, "ring geometry");
+    constexpr int DA = 20;                     // consumer look-ahead (ring of 32 rows)
 
     int s, c, cb;
     decode_cta(a, blockIdx.x, s, c, cb);
@@ -349,44 +323,68 @@ __global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs
     const int gx = cb * kIirVCols + lane;
     const bool col_ok = gx < w;
     const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + gx;
-    const int nbatch = (h + kIirVBatch - 1) / kIirVBatch;  // producer runs batches 0..nbatch-1, consumer one behind
+    const int nbatch = (h + kIirVBatch - 1) / kIirVBatch;
 
     if (role == 0) {
         // ---------------- producer: the five column recursions ----------------
         const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + poff;
         const long long qs = a.q_stride;
         const IirCoef k = a.k;
-        IirState st[5];
-        float d[5][10];
+        auto issue_rows = [&](int r0, int n) {  // rows r0 .. r0+n-1 of all five planes (zeros beyond h)
+            for (int j = 0; j < n; ++j) {
+                const int rr = r0 + j;
+                const bool ok = rr < h;
+                const long long o = ok ? (long long)rr * pitch : 0;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
+                for (int q = 0; q < 5; ++q) cp_async_4(&sm.ring[q][rr & (RCAP - 1)][lane], ph + q * qs + o, ok);
+            }
+        };
+        // rows -6..-1 are padding: their ring slots hold zeros until real rows wrap around to them
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int j = 1; j <= 6; ++j) sm.ring[q][RCAP - j][lane] = 0.0f;
+        issue_rows(0, 4 + D);                   // everything before the first batch's own request
+        cp_async_commit();
+        IirState st[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
 #pragma unroll
             for (int i = 0; i < 3; ++i) st[q].p[i] = st[q].p2[i] = 0.0f;
+        cp_async_wait<0>();
+        // n = -4..-1: right taps are rows 0..3, left taps are padding, nothing emitted
 #pragma unroll
-            for (int i = 0; i < 10; ++i) d[q][i] = 0.0f;
-        }
-        // n = -4..-1: right taps are rows 0..3 (kept at delay slots 0..3), left taps are padding
+        for (int n = -4; n < 0; ++n)
 #pragma unroll
-        for (int n = -4; n < 0; ++n) {
-            const int rr = n + 4;
+            for (int q = 0; q < 5; ++q) (void)iir_step(k, st[q], 0.0f, sm.ring[q][n + 4][lane]);
+
+#pragma unroll 1
+        for (int b = 0; b < nbatch; ++b) {
+            const int n0 = b * kIirVBatch;
+#pragma unroll
+            for (int j = 0; j < kIirVBatch; ++j) {   // request rows n0+4+D .. n0+8+D
+                const int rr = n0 + 4 + D + j;
+                const bool ok = rr < h;
+                const long long o = ok ? (long long)rr * pitch : 0;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) cp_async_4(&sm.ring[q][rr & (RCAP - 1)][lane], ph + q * qs + o, ok);
+            }
+            cp_async_commit();
+            cp_async_wait<D / kIirVBatch>();          // rows up to n0+8 have landed
+            float (*ex)[kIirVBatch][kIirVCols] = sm.ex[b & 1];
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
-                float v = 0.0f;
-                if (rr < h) v = __ldg(ph + q * qs + (long long)rr * pitch);
-                (void)iir_step(k, st[q], 0.0f, v);
-                d[q][rr] = v;
+                float sum[kIirVBatch];
+#pragma unroll
+                for (int j = 0; j < kIirVBatch; ++j)
+                    sum[j] = sm.ring[q][(n0 + j - 6) & (RCAP - 1)][lane] + sm.ring[q][(n0 + j + 4) & (RCAP - 1)][lane];
+                IirPipe P;
+                pipe_begin(k, P, st[q], sum[0]);
+#pragma unroll
+                for (int j = 0; j < kIirVBatch; ++j)
+                    ex[q][j][lane] = (j + 1 < kIirVBatch) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st[q]);
             }
-        }
-        ColsBatch B0, B1;
-        cols_load(B0, ph, qs, pitch, h, 0);
-#pragma unroll 1
-        for (int b = 0; b < nbatch; b += 2) {
-            cols_load(B1, ph, qs, pitch, h, (b + 1) * kIirVBatch);
-            cols_compute<0>(B0, k, st, d, ex[0], lane);
-            __syncthreads();  // batch b published; consumer finished batch b-1 (other buffer)
-            cols_load(B0, ph, qs, pitch, h, (b + 2) * kIirVBatch);
-            cols_compute<5>(B1, k, st, d, ex[1], lane);
-            __syncthreads();  // batch b+1 published
+            __syncthreads();  // batch b published; the consumer is done with the other buffer
         }
         __syncthreads();      // consumer's last batch
     } else {
@@ -394,38 +392,33 @@ __global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs
         const float *pa = a.src + poff;
         const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
         double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        float av[kIirVBatch], bv[kIirVBatch], an[kIirVBatch], bn[kIirVBatch];
-        auto load_ab = [&](float *A, float *Bv, int n_first) {
-#pragma unroll
-            for (int j = 0; j < kIirVBatch; ++j) {
-                const int n = n_first + j;
-                A[j] = 0.0f;
-                Bv[j] = 0.0f;
-                if (n < h) {
-                    A[j] = __ldg(pa + (long long)n * pitch);
-                    Bv[j] = __ldg(pb + (long long)n * pitch);
-                }
+        auto issue_ab = [&](int r0, int n) {
+            for (int j = 0; j < n; ++j) {
+                const int rr = r0 + j;
+                const bool ok = rr < h;
+                const long long o = ok ? (long long)rr * pitch : 0;
+                cp_async_4(&sm.ab[0][rr & 31][lane], pa + o, ok);
+                cp_async_4(&sm.ab[1][rr & 31][lane], pb + o, ok);
             }
         };
-        auto maps = [&](const float *A, const float *Bv, int buf, int n_first) {
+        issue_ab(0, DA);
+        cp_async_commit();
+#pragma unroll 1
+        for (int b = 0; b < nbatch; ++b) {
+            const int n0 = b * kIirVBatch;
+            issue_ab(n0 + DA, kIirVBatch);
+            cp_async_commit();
+            cp_async_wait<DA / kIirVBatch>();         // rows up to n0+4 have landed
+            __syncthreads();                          // batch b is in ex[b & 1]
             float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float (*ex)[kIirVBatch][kIirVCols] = sm.ex[b & 1];
 #pragma unroll
             for (int j = 0; j < kIirVBatch; ++j)
-                if (col_ok && n_first + j < h)
-                    error_maps(A[j], Bv[j], ex[buf][0][j][lane], ex[buf][1][j][lane], ex[buf][2][j][lane],
-                               ex[buf][3][j][lane], ex[buf][4][j][lane], acc);
+                if (col_ok && n0 + j < h)
+                    error_maps(sm.ab[0][(n0 + j) & 31][lane], sm.ab[1][(n0 + j) & 31][lane], ex[0][j][lane],
+                               ex[1][j][lane], ex[2][j][lane], ex[3][j][lane], ex[4][j][lane], acc);
 #pragma unroll
             for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
-        };
-        load_ab(av, bv, 0);
-#pragma unroll 1
-        for (int b = 0; b < nbatch; b += 2) {
-            load_ab(an, bn, (b + 1) * kIirVBatch);
-            __syncthreads();                                   // batch b is in ex[0]
-            maps(av, bv, 0, b * kIirVBatch);
-            load_ab(av, bv, (b + 2) * kIirVBatch);
-            __syncthreads();                                   // batch b+1 is in ex[1]
-            maps(an, bn, 1, (b + 1) * kIirVBatch);
         }
         __syncthreads();
         // fixed shuffle tree over the 32 columns, lane 0 writes the task's six sums
@@ -506,14 +499,29 @@ inline long long iir_hplane_floats(long long pyr_floats) { return 5 * pyr_floats
 
 inline cudaError_t iir_configure()
 {
-    return cudaFuncSetAttribute(k_iir_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem));
+    cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(IirColsSmem<64>));
+    return e;
+}
+
+struct IirStreams {
+    cudaStream_t side;       // runs the a*b rows tasks next to the single-plane ones
+    cudaEvent_t fork, join;
+};
+
+template <int VARIANT>
+inline void launch_rows_variant(const IirArgs &a1, int n1, const IirArgs &a2, int n2, int ncand, cudaStream_t st,
+                                cudaStream_t side)
+{
+    k_iir_rows<1, VARIANT><<<dim3(n1, ncand), 32, sizeof(IirRowsSmem<1>), st>>>(a1);
+    k_iir_rows<2, VARIANT><<<dim3(n2, ncand), 32, sizeof(IirRowsSmem<2>), side>>>(a2);
 }
 
 inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float *src, const float *dist,
                                    long long pyr_stride, float *hplanes, long long hplanes_stride,
                                    double *partials, long long partials_stride, const int *first_cta_cols,
-                                   const int *col_blocks, int n, cudaStream_t st, cudaEvent_t between,
-                                   int *launches)
+                                   const int *col_blocks, int n, cudaStream_t st, const IirStreams &ss,
+                                   cudaEvent_t between, int *launches, int variant = 0, bool rows_only = false)
 {
     IirArgs a{};
     a.g = g;
@@ -526,21 +534,45 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     a.q_stride = pyr_stride;
     a.partials = partials;
     a.partials_stride = partials_stride;
-    int acc = 0;
+    IirArgs a1 = a, a2 = a;   // single-plane quantities | a*b
+    int n1 = 0, n2 = 0;
     for (int s = 0; s < g.n_scales; ++s) {
-        a.blocks[s] = 5 * ((g.h[s] + kIirRows - 1) / kIirRows);
-        a.first_cta[s] = acc;
-        acc += 3 * a.blocks[s];
+        const int nrb = (g.h[s] + kIirRows - 1) / kIirRows;
+        a1.blocks[s] = 4 * nrb;
+        a1.first_cta[s] = n1;
+        n1 += 3 * 4 * nrb;
+        a2.blocks[s] = nrb;
+        a2.first_cta[s] = n2;
+        n2 += 3 * nrb;
     }
-    for (int s = g.n_scales; s <= kMaxScales; ++s) a.first_cta[s] = acc;
-    k_iir_rows<<<dim3(acc, n), 32, sizeof(IirRowsSmem), st>>>(a);
+    for (int s = g.n_scales; s <= kMaxScales; ++s) {
+        a1.first_cta[s] = n1;
+        a2.first_cta[s] = n2;
+    }
+    cudaEventRecord(ss.fork, st);
+    cudaStreamWaitEvent(ss.side, ss.fork, 0);
+    switch (variant) {
+    case 0: launch_rows_variant<0>(a1, n1, a2, n2, n, st, ss.side); break;
+    case 1: launch_rows_variant<1>(a1, n1, a2, n2, n, st, ss.side); break;
+    case 2: launch_rows_variant<2>(a1, n1, a2, n2, n, st, ss.side); break;
+    default: launch_rows_variant<3>(a1, n1, a2, n2, n, st, ss.side); break;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    cudaEventRecord(ss.join, ss.side);
+    cudaStreamWaitEvent(st, ss.join, 0);
     if (between) cudaEventRecord(between, st);
+    *launches = 2;
+    if (rows_only) return cudaSuccess;
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
-    k_iir_cols<<<dim3(first_cta_cols[kMaxScales], n), 64, 0, st>>>(a);
-    *launches = 2;
+    // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
+    const int scale0_tasks = 3 * col_blocks[0] * n;
+    if (scale0_tasks <= 148 * 4)
+        k_iir_cols<64><<<dim3(first_cta_cols[kMaxScales], n), 64, sizeof(IirColsSmem<64>), st>>>(a);
+    else
+        k_iir_cols<32><<<dim3(first_cta_cols[kMaxScales], n), 64, sizeof(IirColsSmem<32>), st>>>(a);
+    *launches = 3;
     return cudaGetLastError();
 }
 

@@ -39,6 +39,7 @@ SYMBOLS = (
     "oavif_ssimu2_score_batch_rgb8_dev", "oavif_ssimu2_score_batch_yuv444_dev",
     "oavif_ssimu2_compute_rgb8", "oavif_ssimu2_yuv444_to_rgb8", "oavif_ssimu2_get_detail",
     "oavif_ssimu2_get_timing", "oavif_ssimu2_debug_get_xyb", "oavif_ssimu2_debug_blur",
+    "oavif_ssimu2_debug_time_rows",
 )
 
 
@@ -99,6 +100,7 @@ def load() -> C.CDLL:
     L.oavif_ssimu2_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.oavif_ssimu2_debug_get_xyb.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32), C.POINTER(u32)]
     L.oavif_ssimu2_debug_blur.argtypes = [vp, vp, u32, u32, vp]
+    L.oavif_ssimu2_debug_time_rows.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -294,6 +296,11 @@ class Scorer:
         _check(self._L.oavif_ssimu2_debug_get_xyb(self._ctx, which, scale, channel, buf.ctypes.data, C.byref(w),
                                                   C.byref(h)), self._ctx)
         return buf[: w.value * h.value].reshape(h.value, w.value).copy()
+
+    def time_rows(self, variant: int = 0, iters: int = 10) -> float:
+        ms = C.c_float()
+        _check(self._L.oavif_ssimu2_debug_time_rows(self._ctx, variant, iters, C.byref(ms)), self._ctx)
+        return ms.value
 
     def blur(self, plane: np.ndarray) -> np.ndarray:
         p = np.ascontiguousarray(plane, np.float32)

@@ -1,0 +1,16 @@
+#!/usr/bin/env python
+"""Attribute the rows pass's time: product kernel vs. no stores / no loads / no prefetch (GPU only)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from oavif_b200.host import ssimu2
+import torch
+(src, yuv), = bench.make_pairs(0, 1)
+with ssimu2.Scorer(bench.W, bench.H, 1) as sc:
+    sc.set_source(src)
+    sc.score_yuv444(*yuv, 10)
+    names = {0: "product", 1: "no stores", 2: "no loads", 3: "no stores, no loads"}
+    for v, nm in names.items():
+        sc.time_rows(v, 3)
+        print(f"variant {v} ({nm}): {sc.time_rows(v, 20):.4f} ms")
