@@ -130,7 +130,9 @@ int oavif_ssimu2_score_batch_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const voi
                                     size_t u_stride, size_t v_stride, int depth, int matrix,
                                     int rgba_path, double *scores);
 
-/* ---- device-resident inputs (pointers are CUDA device pointers on the context's device) -- */
+/* ---- device-resident inputs (pointers are CUDA device pointers on the context's device) --
+ * set_source_rgb8_dev only enqueues work: the buffer must stay unmodified until the next score call
+ * on this context has returned. */
 
 int oavif_ssimu2_set_source_rgb8_dev(oavif_ssimu2_ctx *ctx, const uint8_t *d_rgb, uint32_t w,
                                      uint32_t h, size_t stride);

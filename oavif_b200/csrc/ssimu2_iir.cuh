@@ -372,18 +372,25 @@ __global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs
             cp_async_commit();
             cp_async_wait<D / kIirVBatch>();          // rows up to n0+8 have landed
             float (*ex)[kIirVBatch][kIirVCols] = sm.ex[b & 1];
+            // ring rows of the taps: left tap row n-6, right tap row n+4, advancing one row per step
+            int il = (n0 - 6) & (RCAP - 1), ir = (n0 + 4) & (RCAP - 1);
+            float sum[kIirVBatch][5];
 #pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                float sum[kIirVBatch];
+            for (int j = 0; j < kIirVBatch; ++j) {
 #pragma unroll
-                for (int j = 0; j < kIirVBatch; ++j)
-                    sum[j] = sm.ring[q][(n0 + j - 6) & (RCAP - 1)][lane] + sm.ring[q][(n0 + j + 4) & (RCAP - 1)][lane];
-                IirPipe P;
-                pipe_begin(k, P, st[q], sum[0]);
-#pragma unroll
-                for (int j = 0; j < kIirVBatch; ++j)
-                    ex[q][j][lane] = (j + 1 < kIirVBatch) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st[q]);
+                for (int q = 0; q < 5; ++q) sum[j][q] = sm.ring[q][il][lane] + sm.ring[q][ir][lane];
+                il = (il + 1) & (RCAP - 1);
+                ir = (ir + 1) & (RCAP - 1);
             }
+            // all 15 recursions advance together: step j of every quantity before step j+1 of any
+            IirPipe P[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) pipe_begin(k, P[q], st[q], sum[0][q]);
+#pragma unroll
+            for (int j = 0; j < kIirVBatch; ++j)
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    ex[q][j][lane] = (j + 1 < kIirVBatch) ? pipe_step(k, P[q], sum[j + 1][q]) : pipe_end(k, P[q], st[q]);
             __syncthreads();  // batch b published; the consumer is done with the other buffer
         }
         __syncthreads();      // consumer's last batch

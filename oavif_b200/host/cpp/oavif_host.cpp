@@ -1,0 +1,573 @@
+// oavif_host.cpp — see oavif_host.hpp.  Links against liboavif_ssimu2.so (the CUDA scorer) and
+// dlopens libavif.  Nothing here computes a score on the CPU.
+#include "oavif_host.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <thread>
+#include <cstdarg>
+
+#include "../../../include/oavif_ssimu2.h"
+
+namespace oavif_host {
+
+namespace {
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+std::string fmt(const char *f, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// images
+
+HostImage load_pnm(const std::string &path)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::string magic;
+    f >> magic;
+    HostImage img;
+    img.name = path.substr(path.find_last_of('/') + 1);
+    uint32_t maxval = 0;
+    if (magic == "P6") {
+        auto next = [&]() {
+            std::string t;
+            while (f >> t) {
+                if (t[0] == '#') {
+                    std::string rest;
+                    std::getline(f, rest);
+                    continue;
+                }
+                return (uint32_t)std::stoul(t);
+            }
+            throw std::runtime_error("truncated PPM header");
+        };
+        img.w = next();
+        img.h = next();
+        maxval = next();
+        img.channels = 3;
+        f.get();
+    } else if (magic == "P7") {  // io.zig:309-406
+        std::string key, tupl;
+        uint32_t depth = 0;
+        while (f >> key) {
+            if (key == "ENDHDR") break;
+            if (key == "WIDTH") f >> img.w;
+            else if (key == "HEIGHT") f >> img.h;
+            else if (key == "DEPTH") f >> depth;
+            else if (key == "MAXVAL") f >> maxval;
+            else if (key == "TUPLTYPE") f >> tupl;
+            else if (key[0] == '#') std::getline(f, key);
+        }
+        f.get();
+        if (depth != 3 && depth != 4) throw std::runtime_error("PAM: only RGB / RGB_ALPHA supported by the harness");
+        img.channels = depth;
+    } else {
+        throw std::runtime_error("unsupported image format (harness reads P6/P7 only): " + path);
+    }
+    if (maxval != 255 || img.w == 0 || img.h == 0) throw std::runtime_error("PNM: need MAXVAL 255");
+    img.data.resize((size_t)img.w * img.h * img.channels);
+    f.read(reinterpret_cast<char *>(img.data.data()), (std::streamsize)img.data.size());
+    if ((size_t)f.gcount() != img.data.size()) throw std::runtime_error("PNM: short pixel data");
+    f.clear();
+    f.seekg(0, std::ios::end);
+    img.file_bytes = (size_t)f.tellg();
+    return img;
+}
+
+static inline uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// Procedural corpus image (gradients / edges / textured noise / mixture): the harness's own
+// deterministic definition — a pure function of (w, h, kind, seed, x, y).
+HostImage synth_image(uint32_t w, uint32_t h, uint32_t kind, uint64_t seed, bool alpha)
+{
+    HostImage img;
+    img.w = w;
+    img.h = h;
+    img.channels = alpha ? 4 : 3;
+    img.data.resize((size_t)w * h * img.channels);
+    img.name = fmt("synth_%05llu_k%u_%ux%u", (unsigned long long)seed, kind & 3, w, h);
+    double p[12];
+    for (int i = 0; i < 12; ++i) p[i] = (double)(splitmix64(seed * 1315423911ull + i) >> 11) / 9007199254740992.0;
+    const int per[3] = {8 << (int)(p[0] * 4.999), 8 << (int)(p[1] * 4.999), 8 << (int)(p[2] * 4.999)};
+    std::vector<float> noise((size_t)w * h * 3);
+    for (size_t i = 0; i < noise.size(); ++i) {
+        const uint64_t r = splitmix64(seed * 0x100000001B3ull + i);
+        float g = 0.f;
+        for (int k = 0; k < 4; ++k) g += (float)((r >> (16 * k)) & 0xffff) / 65536.0f;
+        noise[i] = (g - 2.0f) * 20.0f;
+    }
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const double u = (double)x / std::max(1u, w - 1), v = (double)y / std::max(1u, h - 1);
+            double px[3];
+            for (int c = 0; c < 3; ++c) {
+                const double grad = 255.0 * (p[3 + c] * (1 - u) * (1 - v) + p[6 + c] * u * (1 - v) + p[9 + c] * (1 - u) * v +
+                                             (1.0 - p[3 + c]) * u * v);
+                const bool on = c == 0 ? (((x / per[0]) + (y / per[0])) & 1) : c == 1 ? ((x / per[1]) & 1) : ((y / per[2]) & 1);
+                const double edge = on ? 220.0 - 60.0 * p[c] : 30.0 + 60.0 * p[c + 1];
+                // 3x3 box of the white noise = band-limited texture
+                double nz = 0;
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const uint32_t yy = std::min<int64_t>(std::max<int64_t>((int64_t)y + dy, 0), h - 1);
+                        const uint32_t xx = std::min<int64_t>(std::max<int64_t>((int64_t)x + dx, 0), w - 1);
+                        nz += noise[((size_t)yy * w + xx) * 3 + c];
+                    }
+                nz /= 3.0;
+                const double tex = 0.6 * grad + 50.0 + nz;
+                double val;
+                switch (kind & 3) {
+                case 0: val = grad; break;
+                case 1: val = edge; break;
+                case 2: val = tex; break;
+                default: val = (u + v < 0.7) ? grad : (u - v > 0.1 ? edge : tex); val = 0.85 * val + 0.15 * tex; break;
+                }
+                px[c] = val;
+            }
+            uint8_t *o = &img.data[((size_t)y * w + x) * img.channels];
+            for (int c = 0; c < 3; ++c) o[c] = (uint8_t)std::min(255.0, std::max(0.0, std::floor(px[c] + 0.5)));
+            if (alpha) {
+                const double dx = (x - w / 2.0) / (w / 2.0), dy = (y - h / 2.0) / (h / 2.0);
+                o[3] = (uint8_t)std::min(255.0, std::max(0.0, 255.0 * (1.2 - std::sqrt(dx * dx + dy * dy))));
+            }
+        }
+    img.file_bytes = img.data.size();
+    return img;
+}
+
+std::vector<uint8_t> to_rgb8(const HostImage &img)
+{  // io.zig:57-133, 8-bit branches (main.zig:86 aliases the data when channels == 3)
+    if (img.channels == 3) return img.data;
+    std::vector<uint8_t> rgb((size_t)img.w * img.h * 3);
+    for (size_t i = 0, n = (size_t)img.w * img.h; i < n; ++i) {
+        rgb[3 * i + 0] = img.data[4 * i + 0];
+        rgb[3 * i + 1] = img.data[4 * i + 1];
+        rgb[3 * i + 2] = img.data[4 * i + 2];
+    }
+    return rgb;
+}
+
+// ------------------------------------------------------------------------------------------------
+// libavif glue
+
+Decoded::~Decoded()
+{
+    if (decoder && lib) lib->avifDecoderDestroy(decoder);
+}
+
+std::vector<uint8_t> Codec::encode(const HostImage &src, uint32_t q, const EncOptions &o) const
+{
+    const uint32_t depth = o.tenbit ? 10 : 8;  // io.zig:546 with an 8-bit source
+    void *image = L.avifImageCreate(src.w, src.h, depth, 1 /* AVIF_PIXEL_FORMAT_YUV444 */);
+    if (!image) throw std::runtime_error("avifImageCreate failed");
+    struct ImgGuard {
+        const LibAvif &L;
+        void *p;
+        ~ImgGuard() { L.avifImageDestroy(p); }
+    } ig{L, image};
+    AvifImageView v{static_cast<uint8_t *>(image)};
+    v.colorPrimaries() = (uint16_t)o.color_primaries;
+    v.transferCharacteristics() = (uint16_t)o.transfer_characteristics;
+    v.matrixCoefficients() = (uint16_t)o.matrix_coefficients;
+
+    AvifRGBImage rgb{};
+    L.avifRGBImageSetDefaults(&rgb, image);
+    rgb.format = src.channels == 4 ? 1 : 0;
+    std::vector<uint16_t> scaled;
+    if (depth == 10) {  // io.zig:566-579
+        scaled.resize(src.data.size());
+        for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = (uint16_t)(((size_t)src.data[i] * 1023 + 127) / 255);
+        rgb.pixels = reinterpret_cast<uint8_t *>(scaled.data());
+        rgb.rowBytes = src.w * src.channels * 2;
+        rgb.depth = 10;
+    } else {  // io.zig:611-617
+        rgb.pixels = const_cast<uint8_t *>(src.data.data());
+        rgb.rowBytes = src.w * src.channels;
+        rgb.depth = 8;
+    }
+    if (L.avifImageRGBToYUV(image, &rgb) != 0) throw std::runtime_error("ConvertFailed");
+
+    uint8_t *enc = static_cast<uint8_t *>(L.avifEncoderCreate());
+    if (!enc) throw std::runtime_error("avifEncoderCreate failed");
+    struct EncGuard {
+        const LibAvif &L;
+        void *p;
+        ~EncGuard() { L.avifEncoderDestroy(p); }
+    } eg{L, enc};
+    auto i32 = [&](size_t off) -> int32_t & { return *reinterpret_cast<int32_t *>(enc + off); };
+    // copyToEncoder, parse_args.zig:65-74
+    i32(kEncQualityAlpha) = (int32_t)o.quality_alpha;
+    i32(kEncSpeed) = (int32_t)o.speed;
+    i32(kEncMaxThreads) = (int32_t)o.max_threads;
+    i32(kEncTileRowsLog2) = (int32_t)o.tile_rows_log2;
+    i32(kEncTileColsLog2) = (int32_t)o.tile_cols_log2;
+    i32(kEncAutoTiling) = o.auto_tiling ? 1 : 0;
+    if (L.avifEncoderSetCodecSpecificOption(enc, "tune", o.tune.c_str()) != 0) throw std::runtime_error("InvalidCodecOption");
+    i32(kEncQuality) = (int32_t)q;  // io.zig:625-626
+    i32(kEncQualityAlpha) = (int32_t)o.quality_alpha;
+    AvifRWData out{nullptr, 0};
+    int rc = L.avifEncoderAddImage(enc, image, 1, 2 /* AVIF_ADD_IMAGE_FLAG_SINGLE */);
+    if (rc != 0) throw std::runtime_error(std::string("AddImageFailed: ") + L.avifResultToString(rc));
+    rc = L.avifEncoderFinish(enc, &out);
+    if (rc != 0) throw std::runtime_error(std::string("FinishFailed: ") + L.avifResultToString(rc));
+    std::vector<uint8_t> bytes(out.data, out.data + out.size);
+    L.avifRWDataFree(&out);
+    return bytes;
+}
+
+Decoded Codec::decode(const std::vector<uint8_t> &avif) const
+{
+    Decoded d;
+    d.lib = &L;
+    d.decoder = L.avifDecoderCreate();
+    if (!d.decoder) throw std::runtime_error("avifDecoderCreate failed");
+    if (L.avifDecoderSetIOMemory(d.decoder, avif.data(), avif.size()) != 0) throw std::runtime_error("SetIOFailed");
+    if (L.avifDecoderParse(d.decoder) != 0) throw std::runtime_error("ParseFailed");
+    if (L.avifDecoderNextImage(d.decoder) != 0) throw std::runtime_error("DecodeImageFailed");
+    d.img = AvifImageView{*reinterpret_cast<uint8_t **>(static_cast<uint8_t *>(d.decoder) + kDecImage)};
+    if (!d.img.p || d.img.yuvFormat() != 1) throw std::runtime_error("decoder->image is not YUV444");
+    return d;
+}
+
+std::vector<uint8_t> Codec::decode_to_rgb8(const std::vector<uint8_t> &avif) const
+{  // the reference's own decode path (io.zig:468-481, 638-666), kept for comparisons
+    Decoded d = decode(avif);
+    AvifRGBImage rgb{};
+    L.avifRGBImageSetDefaults(&rgb, d.img.p);
+    rgb.depth = 8;
+    rgb.format = d.img.alphaPlane() ? 1 : 0;
+    if (L.avifRGBImageAllocatePixels(&rgb) != 0) throw std::runtime_error("AllocatePixelsFailed");
+    if (L.avifImageYUVToRGB(d.img.p, &rgb) != 0) {
+        L.avifRGBImageFreePixels(&rgb);
+        throw std::runtime_error("ConvertToRGBFailed");
+    }
+    const uint32_t w = d.img.width(), h = d.img.height(), ch = rgb.format == 1 ? 4 : 3;
+    std::vector<uint8_t> out((size_t)w * h * 3);
+    for (uint32_t y = 0; y < h; ++y) {
+        const uint8_t *row = rgb.pixels + (size_t)y * rgb.rowBytes;
+        for (uint32_t x = 0; x < w; ++x)
+            for (int c = 0; c < 3; ++c) out[((size_t)y * w + x) * 3 + c] = row[x * ch + c];
+    }
+    L.avifRGBImageFreePixels(&rgb);
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scorer
+
+GpuScorer::GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode)
+    : max_batch_(max_batch)
+{
+    if (oavif_ssimu2_ctx_create(device, max_w, max_h, max_batch, &ctx_) != 0)
+        throw std::runtime_error(std::string("oavif_ssimu2_ctx_create: ") + oavif_ssimu2_last_error(nullptr));
+    oavif_ssimu2_set_option(ctx_, OAVIF_SSIMU2_OPT_BLUR, blur_mode);
+}
+
+GpuScorer::~GpuScorer() { oavif_ssimu2_ctx_destroy(ctx_); }
+
+void GpuScorer::set_source(const uint8_t *rgb, uint32_t w, uint32_t h)
+{
+    if (oavif_ssimu2_set_source_rgb8(ctx_, rgb, w, h, (size_t)w * 3) != 0)
+        throw std::runtime_error(std::string("set_source: ") + oavif_ssimu2_last_error(ctx_));
+}
+
+std::vector<double> GpuScorer::score(const std::vector<const Decoded *> &cands)
+{
+    std::vector<double> out(cands.size());
+    for (size_t base = 0; base < cands.size(); base += max_batch_) {
+        const size_t n = std::min<size_t>(max_batch_, cands.size() - base);
+        std::vector<const void *> y(n), u(n), v(n);
+        const AvifImageView &i0 = cands[base]->img;
+        for (size_t i = 0; i < n; ++i) {
+            const AvifImageView &im = cands[base + i]->img;
+            if (im.depth() != i0.depth() || im.rowBytes(0) != i0.rowBytes(0) || im.rowBytes(1) != i0.rowBytes(1) ||
+                im.rowBytes(2) != i0.rowBytes(2))
+                throw std::runtime_error("batched candidates differ in layout");
+            y[i] = im.plane(0);
+            u[i] = im.plane(1);
+            v[i] = im.plane(2);
+        }
+        const int rc = oavif_ssimu2_score_batch_yuv444(ctx_, (uint32_t)n, y.data(), u.data(), v.data(), i0.rowBytes(0),
+                                                       i0.rowBytes(1), i0.rowBytes(2), (int)i0.depth(),
+                                                       (int)i0.matrixCoefficients(), i0.alphaPlane() != nullptr,
+                                                       out.data() + base);
+        if (rc != 0) throw std::runtime_error(std::string("score: ") + oavif_ssimu2_last_error(ctx_));
+        oavif_ssimu2_timing t;
+        oavif_ssimu2_get_timing(ctx_, &t);
+        device_ms += t.total_ms;
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one image: main.zig:86-116
+
+SearchResult search_image(const Codec &codec, ScorerIface &scorer, const HostImage &img, const EncOptions &o,
+                          uint32_t batch_width, uint32_t host_threads)
+{
+    SearchResult R;
+    const double t_start = now_ms();
+    R.out_depth = o.tenbit ? 10 : 8;
+    if (o.quality >= 0) {  // main.zig:93-100
+        R.log += fmt("Encoding [q%d, speed %u, %u-bit]\n", o.quality, o.speed, R.out_depth);
+        R.avif = codec.encode(img, (uint32_t)o.quality, o);
+        R.size = R.avif.size();
+        R.tq.q = (uint32_t)o.quality;
+        R.log += fmt("Compressed to %zu bytes (%.3f bpp)\n", R.size, (double)(R.size * 8) / ((double)img.w * img.h));
+        R.total_ms = now_ms() - t_start;
+        return R;
+    }
+    R.log += fmt("Searching [tgt %g±%.1f, speed %u, %u-bit]\n", o.score_tgt, o.tolerance, o.speed, R.out_depth);
+    const std::vector<uint8_t> rgb = to_rgb8(img);
+    scorer.set_source(rgb.data(), img.w, img.h);
+
+    TQOptions topt;
+    topt.score_tgt = o.score_tgt;
+    topt.tolerance = o.tolerance;
+    topt.max_pass = o.max_pass;
+
+    // EncBuffer (main.zig:11-23): the bytes of the LAST pass the policy consumed
+    uint32_t buf_q = 0;
+    std::vector<uint8_t> buf;
+    std::vector<std::pair<uint32_t, std::vector<uint8_t>>> spec_bytes;  // speculative encodes kept by q
+    std::mutex mu;
+
+    auto probe_many = [&](const std::vector<uint32_t> &qs) {
+        std::vector<std::vector<uint8_t>> bytes(qs.size());
+        std::vector<Decoded> dec(qs.size());
+        std::vector<std::string> errs(qs.size());
+        double enc_ms = 0, dec_ms = 0;
+        auto work = [&](size_t i) {
+            try {
+                const double t0 = now_ms();
+                bytes[i] = codec.encode(img, qs[i], o);
+                const double t1 = now_ms();
+                dec[i] = codec.decode(bytes[i]);
+                const double t2 = now_ms();
+                std::lock_guard<std::mutex> lk(mu);
+                enc_ms += t1 - t0;
+                dec_ms += t2 - t1;
+            } catch (const std::exception &e) {
+                errs[i] = e.what();
+            }
+        };
+        if (qs.size() == 1 || host_threads <= 1) {
+            for (size_t i = 0; i < qs.size(); ++i) work(i);
+        } else {
+            std::vector<std::thread> th;
+            std::atomic<size_t> next{0};
+            const size_t nt = std::min<size_t>(host_threads, qs.size());
+            for (size_t t = 0; t < nt; ++t)
+                th.emplace_back([&] {
+                    for (size_t i; (i = next.fetch_add(1)) < qs.size();) work(i);
+                });
+            for (auto &t : th) t.join();
+        }
+        for (const auto &e : errs)
+            if (!e.empty()) throw std::runtime_error(e);
+        R.encode_ms += enc_ms;
+        R.decode_ms += dec_ms;
+        std::vector<const Decoded *> ptrs;
+        for (auto &d : dec) ptrs.push_back(&d);
+        const double t0 = now_ms();
+        std::vector<double> sc = scorer.score(ptrs);
+        R.score_ms += now_ms() - t0;
+        for (size_t i = 0; i < qs.size(); ++i) spec_bytes.emplace_back(qs[i], std::move(bytes[i]));
+        return sc;
+    };
+    auto take_bytes = [&](uint32_t q) {  // tq.zig:31-35: the consumed pass becomes the cached buffer
+        for (auto &p : spec_bytes)
+            if (p.first == q) {
+                buf = p.second;
+                buf_q = q;
+                return;
+            }
+    };
+
+    if (batch_width <= 1) {
+        R.tq = findTargetQuality(topt, [&](uint32_t q) {
+            const double s = probe_many({q})[0];
+            take_bytes(q);
+            return s;
+        });
+    } else {
+        R.tq = findTargetQualityBatched(topt, batch_width, probe_many, &R.batched);
+        // the reference's cache holds the last pass of the sequential procedure
+        if (!R.tq.history.empty()) take_bytes(R.tq.history.back().q);
+    }
+    R.log += fmt("Found q%u (score %.2f, %u passes)\n", R.tq.q, R.tq.score, R.tq.num_pass);
+    if (buf_q == R.tq.q && !buf.empty()) {  // main.zig:109-112
+        R.avif = buf;
+        R.size = buf.size();
+    } else {  // main.zig:113 -> encodeAvifToFile: one more encode, not counted in num_pass
+        bool have = false;
+        if (batch_width > 1)
+            for (auto &p : spec_bytes)
+                if (p.first == R.tq.q) {  // deterministic encoder: the speculative bytes ARE that encode
+                    R.avif = p.second;
+                    have = true;
+                }
+        if (!have) R.avif = codec.encode(img, R.tq.q, o);
+        R.size = R.avif.size();
+        R.reencoded = true;
+    }
+    R.log += fmt("Compressed to %zu bytes (%.3f bpp)\n", R.size, (double)(R.size * 8) / ((double)img.w * img.h));
+    R.total_ms = now_ms() - t_start;
+    return R;
+}
+
+// ------------------------------------------------------------------------------------------------
+// corpus driver: scripts/measure.py
+
+std::vector<CorpusRow> run_corpus(const std::string &libavif_path, const CorpusSpec &spec, const EncOptions &o,
+                                  double *wall_s)
+{
+    const size_t n = spec.files.empty() ? spec.synth_count : spec.files.size();
+    std::vector<CorpusRow> rows(n);
+    LibAvif lib(libavif_path);
+    Codec codec(lib);
+    const int G = std::max(1, spec.n_gpus);
+    const uint32_t W = std::max(1u, spec.workers_per_gpu);
+    const double t0 = now_ms();
+    std::vector<std::thread> workers;
+    std::vector<std::string> fatal((size_t)G * W);
+    for (int g = 0; g < G; ++g)
+        for (uint32_t wk = 0; wk < W; ++wk)
+            workers.emplace_back([&, g, wk] {
+                std::unique_ptr<GpuScorer> scorer;  // one context per worker, sized on first use
+                uint32_t cap_w = 0, cap_h = 0;
+                // image i belongs to GPU (i mod G); within a GPU, to worker ((i div G) mod W)
+                for (size_t i = (size_t)g + (size_t)G * wk; i < n; i += (size_t)G * W) {
+                    CorpusRow &r = rows[i];
+                    r.gpu = spec.first_gpu + g;
+                    const double ti = now_ms();
+                    try {
+                        HostImage img = spec.files.empty()
+                                            ? synth_image(spec.synth_w, spec.synth_h, (uint32_t)(i & 3), i)
+                                            : load_pnm(spec.files[i]);
+                        r.image = img.name;
+                        r.orig_bytes = img.file_bytes;
+                        if (!scorer || img.w > cap_w || img.h > cap_h) {
+                            cap_w = std::max(cap_w, img.w);
+                            cap_h = std::max(cap_h, img.h);
+                            scorer.reset();
+                            scorer.reset(new GpuScorer(spec.first_gpu + g, cap_w, cap_h, std::max(1u, spec.batch_width),
+                                                       spec.blur_mode));
+                        }
+                        const double te = now_ms();  // measure.py times the oavif process: load excluded is closest
+                        SearchResult sr = search_image(codec, *scorer, img, o, spec.batch_width, spec.batch_width);
+                        r.encoding_time_ms = now_ms() - te;
+                        r.final_bytes = sr.size;
+                        r.passes = sr.tq.num_pass;
+                        r.q = sr.tq.q;
+                        r.score = sr.tq.score;
+                        r.status = "ok";
+                    } catch (const std::exception &e) {  // one bad image must not kill the sweep
+                        r.status = "error";
+                        r.error = e.what();
+                        if (r.image.empty()) r.image = spec.files.empty() ? fmt("synth_%05zu", i) : spec.files[i];
+                        (void)ti;
+                    }
+                }
+            });
+    for (auto &t : workers) t.join();
+    if (wall_s) *wall_s = (now_ms() - t0) / 1e3;
+    return rows;
+}
+
+std::string corpus_csv(const std::vector<CorpusRow> &rows)
+{  // header and column formats of measure.py:180-206
+    std::ostringstream s;
+    s << "Image,Original Bytes,Final Bytes,Savings Bytes,Savings %,Encoding Time (ms),Passes,Status,Error\r\n";
+    for (const auto &r : rows) {
+        if (r.status == "ok") {
+            const size_t sav = r.orig_bytes > r.final_bytes ? r.orig_bytes - r.final_bytes : 0;
+            const double pct = r.orig_bytes ? 100.0 * (double)sav / (double)r.orig_bytes : 0.0;
+            s << r.image << ',' << r.orig_bytes << ',' << r.final_bytes << ',' << sav << ',' << fmt("%.2f", pct) << ','
+              << fmt("%.2f", r.encoding_time_ms) << ',' << r.passes << ",ok,\r\n";
+        } else {
+            std::string e = r.error;
+            std::replace(e.begin(), e.end(), ',', ';');
+            s << r.image << ',' << r.orig_bytes << ",,,,,," << r.status << ',' << e << "\r\n";
+        }
+    }
+    return s.str();
+}
+
+std::string corpus_summary(const std::vector<CorpusRow> &rows, double wall_s)
+{  // measure.py:208-269
+    std::vector<double> t;
+    std::vector<double> p;
+    size_t ok = 0, err = 0, orig = 0, fin = 0;
+    for (const auto &r : rows) {
+        if (r.status == "ok") {
+            ++ok;
+            t.push_back(r.encoding_time_ms);
+            p.push_back(r.passes);
+            orig += r.orig_bytes;
+            fin += r.final_bytes;
+        } else {
+            ++err;
+        }
+    }
+    auto mean = [](const std::vector<double> &v) {
+        double s = 0;
+        for (double x : v) s += x;
+        return v.empty() ? 0.0 : s / v.size();
+    };
+    auto stdev = [&](const std::vector<double> &v) {
+        if (v.size() < 2) return 0.0;
+        const double m = mean(v);
+        double s = 0;
+        for (double x : v) s += (x - m) * (x - m);
+        return std::sqrt(s / (v.size() - 1));
+    };
+    auto median = [](std::vector<double> v) {
+        if (v.empty()) return 0.0;
+        std::sort(v.begin(), v.end());
+        return v.size() % 2 ? v[v.size() / 2] : 0.5 * (v[v.size() / 2 - 1] + v[v.size() / 2]);
+    };
+    std::ostringstream s;
+    s << "Run Summary\n";
+    s << fmt("Images: %zu ok, 0 no-output, %zu errors\n", ok, err);
+    s << fmt("Total wall time: %.2f s\n", wall_s);
+    s << fmt("Throughput: %.2f images/s\n", wall_s > 0 ? ok / wall_s : 0.0);
+    s << fmt("Input bytes throughput: %.2f MiB/s\n", wall_s > 0 ? orig / wall_s / 1048576.0 : 0.0);
+    s << fmt("Output bytes throughput: %.2f MiB/s\n", wall_s > 0 ? fin / wall_s / 1048576.0 : 0.0);
+    s << fmt("Original total bytes: %zu\nFinal total bytes:    %zu\n", orig, fin);
+    s << fmt("%% saved (overall):    %.2f%%\n", orig ? 100.0 * (double)(orig > fin ? orig - fin : 0) / orig : 0.0);
+    s << fmt("Average encoding time: %.2f ms ± %.2f\n", mean(t), stdev(t));
+    s << fmt("Median encoding time:  %.2f ms\n", median(t));
+    const double mx = p.empty() ? 0 : *std::max_element(p.begin(), p.end());
+    const double mn = p.empty() ? 0 : *std::min_element(p.begin(), p.end());
+    s << fmt("Average passes:        %.2f ± %.2f (max: %.0f, min: %.0f)\n", mean(p), stdev(p), mx, mn);
+    return s.str();
+}
+
+}  // namespace oavif_host

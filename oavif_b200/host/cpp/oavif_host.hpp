@@ -1,0 +1,140 @@
+// oavif_host.hpp — C++ host harness above the C ABI of include/oavif_ssimu2.h.
+//
+// The reference's host side is Zig and cannot be compiled in this image, so the parts of it that sit
+// on either side of the scored path are restated here in C++, function for function:
+//   AvifEncOptions / copyToEncoder      src/parse_args.zig:48-74      -> EncOptions, Codec::encode
+//   encodeAvifToBuffer                  src/io.zig:544-636            -> Codec::encode
+//   decodeAvifCommon (up to NextImage)  src/io.zig:452-466            -> Codec::decode (planes handed over,
+//                                                                         no avifImageYUVToRGB, no repack)
+//   computeScoreAtQuality               src/tq.zig:21-38              -> ImageJob::probe / probe_batch
+//   findTargetQuality                   src/tq.zig:124-210            -> tq.hpp
+//   main(): "Found q.." / re-encode     src/main.zig:103-116          -> search_image
+//   scripts/measure.py                  CSV schema lines 178-206      -> run_corpus
+// The loaders (PNG/JPEG/WebP, src/io.zig:136-445) are out of scope: the harness reads PAM/PPM (the
+// one raw format the reference also reads, io.zig:309-406) or generates procedural images.
+#pragma once
+
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "avif_dl.hpp"
+#include "tq.hpp"
+
+struct oavif_ssimu2_ctx;
+
+namespace oavif_host {
+
+struct EncOptions {  // parse_args.zig:48-63, same defaults
+    uint32_t quality_alpha = 0, speed = 9, max_threads = 1, tile_rows_log2 = 0, tile_cols_log2 = 0;
+    bool auto_tiling = true;
+    double score_tgt = 80.0;
+    bool tenbit = true;
+    std::string tune = "iq";
+    double tolerance = 2.0;
+    uint32_t max_pass = 6;
+    int quality = -1;  // -q bypass when >= 0
+    uint32_t color_primaries = 2, transfer_characteristics = 2, matrix_coefficients = 2;
+};
+
+struct HostImage {  // the subset of io.zig's Image the harness produces: 8-bit, 3 or 4 channels
+    uint32_t w = 0, h = 0, channels = 3;
+    std::vector<uint8_t> data;  // interleaved, tight rows
+    size_t file_bytes = 0;      // "Original Bytes" of the measure.py CSV
+    std::string name;
+};
+
+HostImage load_pnm(const std::string &path);                       // P6 / P7 (RGB, RGB_ALPHA), MAXVAL 255
+HostImage synth_image(uint32_t w, uint32_t h, uint32_t kind, uint64_t seed, bool alpha = false);
+std::vector<uint8_t> to_rgb8(const HostImage &img);                // Image.toRGB8, io.zig:57-133 (8-bit cases)
+
+struct Decoded {  // a decoder kept alive so that its planes can be handed to the scorer in place
+    const LibAvif *lib = nullptr;
+    void *decoder = nullptr;
+    AvifImageView img{nullptr};
+    Decoded() = default;
+    Decoded(const Decoded &) = delete;
+    Decoded &operator=(const Decoded &) = delete;
+    Decoded(Decoded &&o) noexcept { *this = std::move(o); }
+    Decoded &operator=(Decoded &&o) noexcept
+    {
+        std::swap(lib, o.lib);
+        std::swap(decoder, o.decoder);
+        std::swap(img, o.img);
+        return *this;
+    }
+    ~Decoded();
+};
+
+class Codec {
+  public:
+    explicit Codec(const LibAvif &lib) : L(lib) {}
+    std::vector<uint8_t> encode(const HostImage &img, uint32_t q, const EncOptions &o) const;  // io.zig:544-636
+    Decoded decode(const std::vector<uint8_t> &avif) const;                                       // io.zig:452-466
+    std::vector<uint8_t> decode_to_rgb8(const std::vector<uint8_t> &avif) const;                 // io.zig:638-666
+    const LibAvif &L;
+};
+
+// How one decoded candidate is scored.  The product path is the CUDA library; tests may inject
+// another scorer (the CPU oracle) through this interface to compare search traces.
+struct ScorerIface {
+    virtual ~ScorerIface() = default;
+    virtual void set_source(const uint8_t *rgb, uint32_t w, uint32_t h) = 0;
+    virtual std::vector<double> score(const std::vector<const Decoded *> &cands) = 0;
+};
+
+class GpuScorer : public ScorerIface {  // include/oavif_ssimu2.h
+  public:
+    GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode);
+    ~GpuScorer() override;
+    void set_source(const uint8_t *rgb, uint32_t w, uint32_t h) override;
+    std::vector<double> score(const std::vector<const Decoded *> &cands) override;
+    double device_ms = 0.0;  // accumulated total_ms of the calls
+  private:
+    oavif_ssimu2_ctx *ctx_ = nullptr;
+    uint32_t max_batch_;
+};
+
+struct SearchResult {
+    TQResult tq;
+    BatchedStats batched;
+    std::vector<uint8_t> avif;   // the bytes oavif would write
+    size_t size = 0;             // e.buf.size as printed by main.zig:116
+    bool reencoded = false;      // main.zig:113 path (extra encode, not counted in num_pass)
+    uint32_t out_depth = 8;
+    double encode_ms = 0, decode_ms = 0, score_ms = 0, total_ms = 0;
+    std::string log;             // the stderr lines of main.zig:78-116
+};
+
+// main.zig:86-116 for one image: toRGB8, (bypass | search), write/re-encode.  batch_width <= 1 is the
+// reference's sequential loop; > 1 scores speculative candidates together (same decisions, tq.hpp).
+SearchResult search_image(const Codec &codec, ScorerIface &scorer, const HostImage &img, const EncOptions &o,
+                          uint32_t batch_width, uint32_t host_threads);
+
+struct CorpusRow {  // measure.py:178-206
+    std::string image, status, error;
+    size_t orig_bytes = 0, final_bytes = 0;
+    double encoding_time_ms = 0;
+    uint32_t passes = 0, q = 0;
+    double score = 0;
+    int gpu = -1;
+};
+
+struct CorpusSpec {
+    std::vector<std::string> files;       // PAM/PPM inputs, or
+    uint32_t synth_count = 0, synth_w = 1920, synth_h = 1080;  // procedural: seed = index, kind = seed mod 4
+    int first_gpu = 0, n_gpus = 1;
+    uint32_t workers_per_gpu = 1, batch_width = 1;
+    int blur_mode = 0;
+};
+
+// scripts/measure.py as a library call: images sharded over GPUs by index (i mod G), one scorer
+// context per worker, no collective; rows come back in image order.
+std::vector<CorpusRow> run_corpus(const std::string &libavif_path, const CorpusSpec &spec, const EncOptions &o,
+                                  double *wall_s);
+std::string corpus_csv(const std::vector<CorpusRow> &rows);
+std::string corpus_summary(const std::vector<CorpusRow> &rows, double wall_s);
+
+}  // namespace oavif_host
