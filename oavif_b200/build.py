@@ -38,5 +38,35 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+HOST_SRC = [os.path.join(ROOT, "host", "cpp", f) for f in ("oavif_host.cpp", "host_capi.cpp")]
+HOST_OUT = os.path.join(ROOT, "lib", "liboavif_host.so")
+HOST_CLI = os.path.join(ROOT, "lib", "oavif-b200")
+
+
+def build_host(force: bool = False) -> str:
+    """The C++ harness above the C ABI (g++ only; links the CUDA library by rpath)."""
+    build()
+    deps = [os.path.join(ROOT, "host", "cpp", f) for f in os.listdir(os.path.join(ROOT, "host", "cpp"))]
+    deps += [OUT, os.path.join(ROOT, "..", "include", "oavif_host.h")]
+    cli_src = os.path.join(ROOT, "host", "cpp", "main.cpp")
+    stale = force or not os.path.exists(HOST_OUT) or any(os.path.getmtime(HOST_OUT) < os.path.getmtime(d) for d in deps)
+    if stale:
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", HOST_OUT,
+               *HOST_SRC, "-L" + os.path.dirname(OUT), "-loavif_ssimu2", "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("g++ failed: " + " ".join(cmd))
+    if os.path.exists(cli_src) and (stale or not os.path.exists(HOST_CLI)):
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", HOST_CLI, cli_src,
+               "-L" + os.path.dirname(OUT), "-loavif_host", "-loavif_ssimu2", "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("g++ failed: " + " ".join(cmd))
+    return HOST_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

@@ -200,19 +200,30 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
     const float ym = q < 2 ? 0.0f : 1.0f, yo = q < 2 ? 1.0f : 0.0f;
 
     // Stage tile t: lane l copies 16 bytes = columns 4*(l&7)..+3 of rows (l>>3) + 4i, i = 0..7.
+    // All addresses are base + 32-bit element offsets (one IMAD.WIDE each); rows beyond the image are
+    // clamped to a valid address and zero-filled through the copy's source size.
     const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
+    const float *g0 = p0 + sub_col, *g1 = p1 + sub_col;
+    unsigned row_off[kIirRows / 4];
+    bool row_ok[kIirRows / 4];
+#pragma unroll
+    for (int i = 0; i < kIirRows / 4; ++i) {
+        const int row = sub_row + 4 * i;
+        row_ok[i] = row < rows_here;
+        row_off[i] = (unsigned)(min(row, rows_here - 1) * pitch);
+    }
     auto issue_tile = [&](int t) {
         const int slot = (t + kIirSlots) & (kIirSlots - 1);
         const int gx = t * kIirChunk + sub_col;
         int bytes = 0;
         if (t >= 0 && gx < w) bytes = min(4, w - gx) * 4;
+        const unsigned col_off = bytes ? (unsigned)(t * kIirChunk) : 0u;
 #pragma unroll
         for (int i = 0; i < kIirRows / 4; ++i) {
-            const int row = sub_row + 4 * i;
-            const int nb = row < rows_here ? bytes : 0;
-            const long long o = nb ? (long long)row * pitch + gx : 0;
-            cp_async_16(&sm.tile[0][slot][row][sub_col], p0 + o, nb);
-            if (NPLANES == 2) cp_async_16(&sm.tile[NPLANES - 1][slot][row][sub_col], p1 + o, nb);
+            const int nb = row_ok[i] ? bytes : 0;
+            cp_async_16(&sm.tile[0][slot][sub_row + 4 * i][sub_col], g0 + (row_off[i] + col_off), nb);
+            if (NPLANES == 2)
+                cp_async_16(&sm.tile[NPLANES - 1][slot][sub_row + 4 * i][sub_col], g1 + (row_off[i] + col_off), nb);
         }
         cp_async_commit();
     };
@@ -273,14 +284,13 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
         __syncwarp();
         // transposed write-out of output tile t: whole 128-byte lines, 4 rows per instruction
         if (!(VARIANT & 1) || t == nch - 1) {
-            float *dst = ph + t * kIirChunk + sub_col;
+            float *dst = ph + sub_col;
+            const unsigned col_off = (unsigned)(t * kIirChunk);
 #pragma unroll
-            for (int i = 0; i < kIirRows / 4; ++i) {
-                const int row = sub_row + 4 * i;
-                if (row < rows_here)
-                    __stcs(reinterpret_cast<float4 *>(dst + (long long)row * pitch),
-                           *reinterpret_cast<const float4 *>(&sm.tile[0][prev][row][sub_col]));
-            }
+            for (int i = 0; i < kIirRows / 4; ++i)
+                if (row_ok[i])
+                    __stcs(reinterpret_cast<float4 *>(dst + (row_off[i] + col_off)),
+                           *reinterpret_cast<const float4 *>(&sm.tile[0][prev][sub_row + 4 * i][sub_col]));
         }
         __syncwarp();                 // staging consumed: the slot may be overwritten
         if (!(VARIANT & 2)) issue_tile(t + 3);  // lands in the slot of tile t-1 / the staging tile
@@ -328,16 +338,20 @@ __global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs
     if (role == 0) {
         // ---------------- producer: the five column recursions ----------------
         const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + poff;
-        const long long qs = a.q_stride;
-        const IirCoef k = a.k;
-        auto issue_rows = [&](int r0, int n) {  // rows r0 .. r0+n-1 of all five planes (zeros beyond h)
-            for (int j = 0; j < n; ++j) {
-                const int rr = r0 + j;
-                const bool ok = rr < h;
-                const long long o = ok ? (long long)rr * pitch : 0;
+        const float *phq[5];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) cp_async_4(&sm.ring[q][rr & (RCAP - 1)][lane], ph + q * qs + o, ok);
-            }
+        for (int q = 0; q < 5; ++q) phq[q] = ph + q * a.q_stride;
+        const IirCoef k = a.k;
+        // one row of all five planes into the ring (zeros beyond h): base pointer + 32-bit row offset
+        auto issue_row = [&](int rr) {
+            const bool ok = rr < h;
+            const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
+            float *dst = &sm.ring[0][rr & (RCAP - 1)][lane];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) cp_async_4(dst + q * (RCAP * kIirVCols), phq[q] + o, ok);
+        };
+        auto issue_rows = [&](int r0, int n) {
+            for (int j = 0; j < n; ++j) issue_row(r0 + j);
         };
         // rows -6..-1 are padding: their ring slots hold zeros until real rows wrap around to them
 #pragma unroll
@@ -362,13 +376,7 @@ __global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs
         for (int b = 0; b < nbatch; ++b) {
             const int n0 = b * kIirVBatch;
 #pragma unroll
-            for (int j = 0; j < kIirVBatch; ++j) {   // request rows n0+4+D .. n0+8+D
-                const int rr = n0 + 4 + D + j;
-                const bool ok = rr < h;
-                const long long o = ok ? (long long)rr * pitch : 0;
-#pragma unroll
-                for (int q = 0; q < 5; ++q) cp_async_4(&sm.ring[q][rr & (RCAP - 1)][lane], ph + q * qs + o, ok);
-            }
+            for (int j = 0; j < kIirVBatch; ++j) issue_row(n0 + 4 + D + j);   // rows n0+4+D .. n0+8+D
             cp_async_commit();
             cp_async_wait<D / kIirVBatch>();          // rows up to n0+8 have landed
             float (*ex)[kIirVBatch][kIirVCols] = sm.ex[b & 1];
@@ -403,7 +411,7 @@ __global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs
             for (int j = 0; j < n; ++j) {
                 const int rr = r0 + j;
                 const bool ok = rr < h;
-                const long long o = ok ? (long long)rr * pitch : 0;
+                const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
                 cp_async_4(&sm.ab[0][rr & 31][lane], pa + o, ok);
                 cp_async_4(&sm.ab[1][rr & 31][lane], pb + o, ok);
             }
@@ -413,7 +421,14 @@ __global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             const int n0 = b * kIirVBatch;
-            issue_ab(n0 + DA, kIirVBatch);
+#pragma unroll
+            for (int j = 0; j < kIirVBatch; ++j) {
+                const int rr = n0 + DA + j;
+                const bool ok = rr < h;
+                const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
+                cp_async_4(&sm.ab[0][rr & 31][lane], pa + o, ok);
+                cp_async_4(&sm.ab[1][rr & 31][lane], pb + o, ok);
+            }
             cp_async_commit();
             cp_async_wait<DA / kIirVBatch>();         // rows up to n0+4 have landed
             __syncthreads();                          // batch b is in ex[b & 1]
