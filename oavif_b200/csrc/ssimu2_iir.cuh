@@ -61,7 +61,6 @@ constexpr int kIirChunk = 32;    // columns per staged tile
 constexpr int kIirPitch = 36;    // smem tile pitch in floats: 16-byte rows, conflict-free 128-bit access
 constexpr int kIirSlots = 4;     // tile ring: t-1, t, t+1 in use while t+2 lands
 constexpr int kIirVCols = 32;    // columns per columns-pass task
-constexpr int kIirVBatch = 5;    // rows per exchange batch in the columns pass
 
 struct IirArgs {
     Geom g;
@@ -301,161 +300,143 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
 }
 
 // ------------------------------------------------------------------------------------------------
-// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 64.
+// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 224.
 //
-// Warp 0 (producer) streams all five row-filtered planes of its 32 columns down the image through a
+// One CTA owns 32 columns of one channel; lane = column, so every global access is a 128-byte row
+// segment.  Warps 0..4 (producers) each stream ONE row-filtered plane down the image through a private
 // shared-memory ring fed by cp.async RCAP-16 rows ahead of use (both taps of the recursion are read
-// from the ring, so there is no register delay line), runs the 15 recursions per lane and drops the
-// five filtered values of each pixel into a double-buffered batch.  Warp 1 (consumer), one 5-row
-// batch behind, streams the pixel's own XYB samples through its own ring and evaluates the
-// SSIM / edge-diff maps and the six pooled sums.  One block barrier per 5 rows.
+// from the ring: no register delay line) and drop the filtered values into a double-buffered 6-row
+// batch.  Warps 5..6 (consumers), one batch behind, stream the pixel's own XYB samples through their
+// own ring and evaluate the SSIM / edge-diff maps and the six pooled sums for alternate rows.
+// Seven warps per task is what gives a sub-partition enough independent work to hide latencies when a
+// single 4K pair is all the GPU has.  One block barrier per 6 rows.
+constexpr int kIirVBatch = 6;    // rows per exchange batch in the columns pass
+constexpr int kIirVThreads = 224;
+
 template <int RCAP>
 struct IirColsSmem {
     float ring[5][RCAP][kIirVCols];            // producer input rows, row r at [r & (RCAP-1)]
     float ab[2][32][kIirVCols];                // consumer rows of the two XYB planes
     float ex[2][5][kIirVBatch][kIirVCols];     // filtered values, double-buffered
+    double red[2][6];
 };
 
 template <int RCAP>
-__global__ void __launch_bounds__(64) k_iir_cols(const __grid_constant__ IirArgs a)
+__global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IirColsSmem<RCAP> &sm = *reinterpret_cast<IirColsSmem<RCAP> *>(smem_raw);
-    constexpr int D = ((RCAP - 15) / 5) * 5;   // rows of look-ahead; D + 15 <= RCAP, D % 5 == 0
-    static_assert(D % kIirVBatch == 0 && D + 15 <= RCAP, "ring geometry");
-    constexpr int DA = 20;                     // consumer look-ahead (ring of 32 rows)
+    constexpr int B = kIirVBatch;
+    constexpr int D = ((RCAP - B - 10) / B) * B;   // rows of look-ahead: D + B + 10 <= RCAP, D % B == 0
+    constexpr int DA = 18;                         // consumer look-ahead (ring of 32 rows)
+    static_assert(D >= B && DA % B == 0 && DA + B <= 32, "ring geometry");
 
     int s, c, cb;
     decode_cta(a, blockIdx.x, s, c, cb);
     const int cand = blockIdx.y;
     const int w = a.g.w[s], h = a.g.h[s], pitch = a.g.pitch[s];
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gx = cb * kIirVCols + lane;
     const bool col_ok = gx < w;
     const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + gx;
-    const int nbatch = (h + kIirVBatch - 1) / kIirVBatch;
+    const int nbatch = (h + B - 1) / B;
 
-    if (role == 0) {
-        // ---------------- producer: the five column recursions ----------------
-        const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + poff;
-        const float *phq[5];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) phq[q] = ph + q * a.q_stride;
+    if (warp < 5) {
+        // ---------------- producer: the column recursion of quantity `warp` ----------------
+        const int q = warp;
+        const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff;
         const IirCoef k = a.k;
-        // one row of all five planes into the ring (zeros beyond h): base pointer + 32-bit row offset
-        auto issue_row = [&](int rr) {
-            const bool ok = rr < h;
-            const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
-            float *dst = &sm.ring[0][rr & (RCAP - 1)][lane];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) cp_async_4(dst + q * (RCAP * kIirVCols), phq[q] + o, ok);
-        };
-        auto issue_rows = [&](int r0, int n) {
-            for (int j = 0; j < n; ++j) issue_row(r0 + j);
+        float *ring = &sm.ring[q][0][lane];
+        auto issue_row = [&](int rr) {   // zeros beyond h; base pointer + 32-bit row offset
+            cp_async_4(ring + (rr & (RCAP - 1)) * kIirVCols, ph + (unsigned)(min(rr, h - 1) * pitch), rr < h);
         };
         // rows -6..-1 are padding: their ring slots hold zeros until real rows wrap around to them
 #pragma unroll
-        for (int q = 0; q < 5; ++q)
-#pragma unroll
-            for (int j = 1; j <= 6; ++j) sm.ring[q][RCAP - j][lane] = 0.0f;
-        issue_rows(0, 4 + D);                   // everything before the first batch's own request
+        for (int j = 1; j <= 6; ++j) ring[(RCAP - j) * kIirVCols] = 0.0f;
+        for (int rr = 0; rr < 4 + D; ++rr) issue_row(rr);   // everything before the first batch's request
         cp_async_commit();
-        IirState st[5];
+        IirState st;
 #pragma unroll
-        for (int q = 0; q < 5; ++q)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) st[q].p[i] = st[q].p2[i] = 0.0f;
+        for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
         cp_async_wait<0>();
         // n = -4..-1: right taps are rows 0..3, left taps are padding, nothing emitted
 #pragma unroll
-        for (int n = -4; n < 0; ++n)
-#pragma unroll
-            for (int q = 0; q < 5; ++q) (void)iir_step(k, st[q], 0.0f, sm.ring[q][n + 4][lane]);
+        for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, ring[(n + 4) * kIirVCols]);
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
-            const int n0 = b * kIirVBatch;
+            const int n0 = b * B;
 #pragma unroll
-            for (int j = 0; j < kIirVBatch; ++j) issue_row(n0 + 4 + D + j);   // rows n0+4+D .. n0+8+D
+            for (int j = 0; j < B; ++j) issue_row(n0 + 4 + D + j);
             cp_async_commit();
-            cp_async_wait<D / kIirVBatch>();          // rows up to n0+8 have landed
-            float (*ex)[kIirVBatch][kIirVCols] = sm.ex[b & 1];
-            // ring rows of the taps: left tap row n-6, right tap row n+4, advancing one row per step
+            cp_async_wait<D / B>();                    // rows up to n0 + B + 3 have landed
+            float sum[B];
             int il = (n0 - 6) & (RCAP - 1), ir = (n0 + 4) & (RCAP - 1);
-            float sum[kIirVBatch][5];
 #pragma unroll
-            for (int j = 0; j < kIirVBatch; ++j) {
-#pragma unroll
-                for (int q = 0; q < 5; ++q) sum[j][q] = sm.ring[q][il][lane] + sm.ring[q][ir][lane];
+            for (int j = 0; j < B; ++j) {
+                sum[j] = ring[il * kIirVCols] + ring[ir * kIirVCols];
                 il = (il + 1) & (RCAP - 1);
                 ir = (ir + 1) & (RCAP - 1);
             }
-            // all 15 recursions advance together: step j of every quantity before step j+1 of any
-            IirPipe P[5];
+            float *ex = &sm.ex[b & 1][q][0][lane];
+            IirPipe P;
+            pipe_begin(k, P, st, sum[0]);
 #pragma unroll
-            for (int q = 0; q < 5; ++q) pipe_begin(k, P[q], st[q], sum[0][q]);
-#pragma unroll
-            for (int j = 0; j < kIirVBatch; ++j)
-#pragma unroll
-                for (int q = 0; q < 5; ++q)
-                    ex[q][j][lane] = (j + 1 < kIirVBatch) ? pipe_step(k, P[q], sum[j + 1][q]) : pipe_end(k, P[q], st[q]);
-            __syncthreads();  // batch b published; the consumer is done with the other buffer
+            for (int j = 0; j < B; ++j)
+                ex[j * kIirVCols] = (j + 1 < B) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
+            __syncthreads();  // batch b published; the consumers are done with the other buffer
         }
-        __syncthreads();      // consumer's last batch
+        __syncthreads();      // consumers' last batch
+        __syncthreads();      // final reduction
     } else {
-        // ---------------- consumer: maps + pooling, one batch behind ----------------
+        // ---------------- consumers: maps + pooling for rows j = cw, cw+2, cw+4 of each batch ----------------
+        const int cw = warp - 5;
         const float *pa = a.src + poff;
         const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
         double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        auto issue_ab = [&](int r0, int n) {
-            for (int j = 0; j < n; ++j) {
-                const int rr = r0 + j;
-                const bool ok = rr < h;
-                const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
-                cp_async_4(&sm.ab[0][rr & 31][lane], pa + o, ok);
-                cp_async_4(&sm.ab[1][rr & 31][lane], pb + o, ok);
-            }
+        auto issue_ab = [&](int rr) {
+            const bool ok = rr < h;
+            const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
+            cp_async_4(&sm.ab[0][rr & 31][lane], pa + o, ok);
+            cp_async_4(&sm.ab[1][rr & 31][lane], pb + o, ok);
         };
-        issue_ab(0, DA);
+        for (int rr = cw; rr < DA; rr += 2) issue_ab(rr);
         cp_async_commit();
+        cp_async_wait<0>();   // the in-loop wait only covers groups committed inside the loop
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
-            const int n0 = b * kIirVBatch;
+            const int n0 = b * B;
 #pragma unroll
-            for (int j = 0; j < kIirVBatch; ++j) {
-                const int rr = n0 + DA + j;
-                const bool ok = rr < h;
-                const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
-                cp_async_4(&sm.ab[0][rr & 31][lane], pa + o, ok);
-                cp_async_4(&sm.ab[1][rr & 31][lane], pb + o, ok);
-            }
+            for (int j = 0; j < B; j += 2) issue_ab(n0 + DA + cw + j);
             cp_async_commit();
-            cp_async_wait<DA / kIirVBatch>();         // rows up to n0+4 have landed
-            __syncthreads();                          // batch b is in ex[b & 1]
+            cp_async_wait<DA / B>();                   // this warp's rows up to n0 + B - 1 have landed
+            __syncthreads();                           // batch b is in ex[b & 1]
             float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float (*ex)[kIirVBatch][kIirVCols] = sm.ex[b & 1];
+            const float *ex = &sm.ex[b & 1][0][0][lane];
 #pragma unroll
-            for (int j = 0; j < kIirVBatch; ++j)
-                if (col_ok && n0 + j < h)
-                    error_maps(sm.ab[0][(n0 + j) & 31][lane], sm.ab[1][(n0 + j) & 31][lane], ex[0][j][lane],
-                               ex[1][j][lane], ex[2][j][lane], ex[3][j][lane], ex[4][j][lane], acc);
+            for (int j = 0; j < B; j += 2) {
+                const int jj = j + cw, n = n0 + jj;
+                if (col_ok && n < h)
+                    error_maps(sm.ab[0][n & 31][lane], sm.ab[1][n & 31][lane], ex[(0 * B + jj) * kIirVCols],
+                               ex[(1 * B + jj) * kIirVCols], ex[(2 * B + jj) * kIirVCols],
+                               ex[(3 * B + jj) * kIirVCols], ex[(4 * B + jj) * kIirVCols], acc);
+            }
 #pragma unroll
             for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
         }
         __syncthreads();
-        // fixed shuffle tree over the 32 columns, lane 0 writes the task's six sums
+        // fixed shuffle tree over the 32 columns, then the two consumers in fixed order
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             double x = dacc[j];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-            dacc[j] = x;
+            if (lane == 0) sm.red[cw][j] = x;
         }
-        if (lane == 0) {
-            double *out = a.partials + (long long)cand * a.partials_stride + (long long)blockIdx.x * 6;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) out[j] = dacc[j];
-        }
+        __syncthreads();
+        if (cw == 0 && lane < 6)
+            a.partials[(long long)cand * a.partials_stride + (long long)blockIdx.x * 6 + lane] =
+                sm.red[0][lane] + sm.red[1][lane];
     }
 }
 
@@ -591,9 +572,9 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
     const int scale0_tasks = 3 * col_blocks[0] * n;
     if (scale0_tasks <= 148 * 4)
-        k_iir_cols<64><<<dim3(first_cta_cols[kMaxScales], n), 64, sizeof(IirColsSmem<64>), st>>>(a);
+        k_iir_cols<64><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<64>), st>>>(a);
     else
-        k_iir_cols<32><<<dim3(first_cta_cols[kMaxScales], n), 64, sizeof(IirColsSmem<32>), st>>>(a);
+        k_iir_cols<32><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<32>), st>>>(a);
     *launches = 3;
     return cudaGetLastError();
 }

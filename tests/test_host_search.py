@@ -1,0 +1,135 @@
+"""The C++ host harness around the scored path: libavif glue (src/io.zig), one-image search
+(src/main.zig:86-116) and the corpus loop (scripts/measure.py).
+
+CPU part: the harness with the CPU oracle INJECTED as scorer must walk exactly the trace that a
+plain Python loop (transcribed policy + libavif + oracle) walks, and write the bytes a direct encode
+at the chosen q produces.  GPU part: with the CUDA scorer it must choose the same quantizer, take the
+same passes and emit byte-identical AVIF (north_star), sequentially and in batched mode.
+
+The bundled libaom cannot ENCODE 10-bit, so every real encode here runs with --tenbit 0."""
+import csv
+import os
+
+import numpy as np
+import pytest
+
+from oavif_b200.host import harness as H
+from oavif_b200.host import synth
+from test_tq_policy import z_search
+
+pytestmark = pytest.mark.skipif(H.find_libavif() is None, reason="no libavif in this image")
+
+
+class OracleScorer:
+    def __init__(self, oracle, mode=0):
+        self.O, self.mode, self.n = oracle, mode, 0
+
+    def set_source(self, rgb):
+        self.src = rgb
+
+    def score(self, y, u, v, depth, matrix, rgba):
+        self.n += 1
+        return self.O.ssimu2_rgb8(self.src, self.O.yuv444_to_rgb8(y, u, v, depth, matrix, rgba), self.mode)
+
+
+def opts(**kw):
+    return H.default_opts(tenbit=0, **kw)
+
+
+def test_default_options_are_the_reference_defaults():
+    o = H.default_opts()
+    assert (o.quality_alpha, o.speed, o.max_threads, o.auto_tiling, o.score_tgt, o.tenbit, o.tune, o.tolerance, o.max_pass,
+            o.quality, o.color_primaries, o.transfer_characteristics, o.matrix_coefficients) == \
+           (0, 9, 1, 1, 80.0, 1, b"iq", 2.0, 6, -1, 2, 2, 2)          # parse_args.zig:49-63
+
+
+def test_encode_is_deterministic_and_decode_matches_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "avif_roundtrip.npz"))
+    src = g["src"]
+    a = H.encode(src, 65, opts())
+    assert a == H.encode(src, 65, opts()) and len(a) == int(g["avif_bytes65"])
+    np.testing.assert_array_equal(H.decode_rgb8(a, src.shape[1], src.shape[0]), g["rgb65"])
+    assert len(H.encode(src, 40, opts())) == int(g["avif_bytes40"])
+
+
+def test_ten_bit_encode_fails_loudly_with_this_libaom():
+    src = synth.synth(64, 48, "mixture", 1)
+    with pytest.raises(RuntimeError, match="AddImageFailed"):
+        H.encode(src, 50, H.default_opts())                          # tenbit = 1 (the reference default)
+
+
+def test_search_with_injected_oracle_equals_a_plain_python_loop(oracle):
+    src = synth.synth(160, 120, "mixture", 3)
+    o = opts(score_tgt=80.0, max_pass=6)
+    sc = OracleScorer(oracle)
+    r, avif = H.search_image(src, o, scorer=sc)
+
+    def probe(q):
+        rgb = H.decode_rgb8(H.encode(src, q, o), 160, 120)
+        return oracle.ssimu2_rgb8(src, rgb)
+
+    want = z_search(probe, 80.0, 2.0, 6)
+    assert (r.q, r.score, r.history()) == (want[0], want[1], want[2])
+    assert r.num_pass == len(want[2]) == sc.n
+    assert avif == H.encode(src, r.q, o) and r.size == len(avif)
+    log = r.log.decode()
+    assert f"Found q{r.q} (score {r.score:.2f}, {r.num_pass} passes)" in log      # measure.py parses "N passes"
+    assert "Searching [tgt 80±2.0, speed 9, 8-bit]" in log and f"Compressed to {len(avif)} bytes" in log
+
+
+def test_quality_bypass_and_alpha_input(oracle):
+    rgba = synth.synth_rgba(96, 64, "noise", 2)
+    r, avif = H.search_image(rgba, opts(quality=55), scorer=OracleScorer(oracle))
+    assert r.num_pass == 0 and r.q == 55 and avif == H.encode(rgba, 55, opts())
+    assert "Encoding [q55, speed 9, 8-bit]" in r.log.decode()
+    # search on RGBA: alpha is encoded but never scored (io.zig:106-111, 654-663)
+    sc = OracleScorer(oracle)
+    r2, _ = H.search_image(rgba, opts(max_pass=3), scorer=sc)
+    np.testing.assert_array_equal(sc.src, rgba[..., :3])
+    assert r2.num_pass == sc.n >= 1
+
+
+def test_batched_search_same_result_with_injected_oracle(oracle):
+    src = synth.synth(128, 96, "edges", 5)
+    o = opts(score_tgt=85.0, tolerance=1.0, max_pass=6)
+    r1, a1 = H.search_image(src, o, scorer=OracleScorer(oracle))
+    r4, a4 = H.search_image(src, o, batch_width=4, scorer=OracleScorer(oracle))
+    assert (r4.q, r4.score, r4.history(), r4.num_pass) == (r1.q, r1.score, r1.history(), r1.num_pass)
+    assert a4 == a1 and r4.device_passes <= r1.num_pass
+
+
+# ---- GPU ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(256, 192, "mixture", 80.0, 2.0), (320, 200, "noise", 70.0, 1.0),
+                                  (200, 300, "edges", 90.0, 2.0), (512, 384, "gradient", 85.0, 1.0)])
+def test_gpu_scored_search_equals_oracle_scored_search(oracle, case):
+    w, h, kind, tgt, tol = case
+    src = synth.synth(w, h, kind, 11)
+    o = opts(score_tgt=tgt, tolerance=tol, max_pass=6)
+    want, bytes_cpu = H.search_image(src, o, scorer=OracleScorer(oracle))
+    got, bytes_gpu = H.search_image(src, o, device=0)
+    assert (got.q, got.num_pass, [q for q, _ in got.history()]) == (want.q, want.num_pass, [q for q, _ in want.history()])
+    assert bytes_gpu == bytes_cpu
+    for (_, a), (_, b) in zip(got.history(), want.history()):
+        assert abs(a - b) <= 1e-4
+    bat, bytes_bat = H.search_image(src, o, batch_width=4, device=0)
+    assert (bat.q, bat.num_pass, bat.history()) == (got.q, got.num_pass, got.history()) and bytes_bat == bytes_gpu
+
+
+@pytest.mark.gpu
+def test_corpus_driver_csv_and_sharding(tmp_path):
+    o = opts(max_pass=3, speed=10)
+    csv1 = str(tmp_path / "one.csv")
+    r1 = H.corpus_synth(6, 192, 128, n_gpus=1, workers_per_gpu=1, opts=o, csv_path=csv1)
+    assert r1["ok"] == 6, r1
+    rows = list(csv.reader(open(csv1, newline="")))
+    assert rows[0] == ["Image", "Original Bytes", "Final Bytes", "Savings Bytes", "Savings %", "Encoding Time (ms)",
+                       "Passes", "Status", "Error"]                                   # measure.py:180-192
+    assert len(rows) == 7 and all(r[7] == "ok" for r in rows[1:])
+    assert [r[0] for r in rows[1:]] == [f"synth_{i:05d}_k{i % 4}_192x128" for i in range(6)]
+    assert "Throughput:" in r1["summary"] and "Average passes:" in r1["summary"]
+    # more workers: same per-image results (only the timings differ)
+    csv3 = str(tmp_path / "three.csv")
+    r3 = H.corpus_synth(6, 192, 128, n_gpus=1, workers_per_gpu=3, opts=o, csv_path=csv3)
+    rows3 = list(csv.reader(open(csv3, newline="")))
+    assert r3["ok"] == 6 and [(r[0], r[2], r[6]) for r in rows3] == [(r[0], r[2], r[6]) for r in rows]
