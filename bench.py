@@ -183,17 +183,12 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
-    import torch.distributed as dist
-    from oavif_b200.host import ssimu2
+    from oavif_b200.host import dist, ssimu2
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the scored path has no CPU fallback")
+    rank, world, local = dist.init("nccl")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mode = ssimu2.BLUR_FIR if args.blur == "fir" else ssimu2.BLUR_RECURSIVE
     L = ssimu2.load()
 
@@ -229,10 +224,7 @@ def run_ours(args):
         sc.set_source(s)
         return sc.score_yuv444(y, u, v, 10)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = dist.barrier
 
     def timed(fn, steps, warmup, collect=None):
         for i in range(warmup):
@@ -246,12 +238,7 @@ def run_ours(args):
                 collect(sc.timing())
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return dist.max_over_ranks(e0.elapsed_time(e1))
 
     # ---- device-resident (value) ----------------------------------------------------------------
     ktimes = {"pyramid": [], "a": [], "b": [], "fin": [], "launches": 0}
@@ -286,8 +273,7 @@ def run_ours(args):
     score = step_dev(0)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        dist.finalize()
         return
 
     hbm, peak_src = peaks()
@@ -346,8 +332,7 @@ def run_ours(args):
                                 "sample": f"{reps} x ({threads} threads x one {W}x{rows} band of the 4K pair), {dt:.1f} s",
                                 "single_thread": {"value": round(rate1, 3), "sample": f"{W}x{rows1} band, {dt1:.1f} s"}}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    dist.finalize()
 
 
 def main():

@@ -302,15 +302,16 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
 // ------------------------------------------------------------------------------------------------
 // columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 224.
 //
-// One CTA owns 32 columns of one channel; lane = column, so every global access is a 128-byte row
-// segment.  Warps 0..4 (producers) each stream ONE row-filtered plane down the image through a private
-// shared-memory ring fed by cp.async RCAP-16 rows ahead of use (both taps of the recursion are read
-// from the ring: no register delay line) and drop the filtered values into a double-buffered 6-row
-// batch.  Warps 5..6 (consumers), one batch behind, stream the pixel's own XYB samples through their
-// own ring and evaluate the SSIM / edge-diff maps and the six pooled sums for alternate rows.
-// Seven warps per task is what gives a sub-partition enough independent work to hide latencies when a
-// single 4K pair is all the GPU has.  One block barrier per 6 rows.
-constexpr int kIirVBatch = 6;    // rows per exchange batch in the columns pass
+// One CTA owns 32 columns of one channel; lane = column in the arithmetic, so the recursions of a warp
+// are 32 independent columns.  Warps 0..4 (producers) each stream ONE row-filtered plane down the image
+// through a private shared-memory ring.  The ring is fed by 16-byte cp.async: one instruction moves
+// four whole 128-byte row segments (8 lanes per row), RCAP-18 rows ahead of use; both taps of the
+// recursion are read back from the ring (no register delay line).  Each producer drops its filtered
+// values into a double-buffered 8-row batch.  Warps 5..6 (consumers), one batch behind, stream the
+// pixel's own XYB samples the same way and evaluate the SSIM / edge-diff maps and the six pooled sums
+// for rows 0..3 and 4..7 of the batch.  Seven warps per task give a sub-partition enough independent
+// work to hide latencies when a single 4K pair is all the GPU has.  One block barrier per 8 rows.
+constexpr int kIirVBatch = 8;    // rows per exchange batch in the columns pass
 constexpr int kIirVThreads = 224;
 
 template <int RCAP>
@@ -328,8 +329,8 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     IirColsSmem<RCAP> &sm = *reinterpret_cast<IirColsSmem<RCAP> *>(smem_raw);
     constexpr int B = kIirVBatch;
     constexpr int D = ((RCAP - B - 10) / B) * B;   // rows of look-ahead: D + B + 10 <= RCAP, D % B == 0
-    constexpr int DA = 18;                         // consumer look-ahead (ring of 32 rows)
-    static_assert(D >= B && DA % B == 0 && DA + B <= 32, "ring geometry");
+    constexpr int DA = 16;                         // consumer look-ahead (ring of 32 rows)
+    static_assert(D >= B && DA % B == 0 && DA + B <= 32 && B % 4 == 0, "ring geometry");
 
     int s, c, cb;
     decode_cta(a, blockIdx.x, s, c, cb);
@@ -338,43 +339,50 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gx = cb * kIirVCols + lane;
     const bool col_ok = gx < w;
-    const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + gx;
+    // copy role of a lane: row (lane >> 3) of a 4-row group, columns 4*(lane & 7)..+3 of the 32
+    const int crow = lane >> 3, ccol = (lane & 7) * 4;
+    const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + cb * kIirVCols;
     const int nbatch = (h + B - 1) / B;
 
     if (warp < 5) {
         // ---------------- producer: the column recursion of quantity `warp` ----------------
         const int q = warp;
-        const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff;
+        const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff + ccol;
         const IirCoef k = a.k;
-        float *ring = &sm.ring[q][0][lane];
-        auto issue_row = [&](int rr) {   // zeros beyond h; base pointer + 32-bit row offset
-            cp_async_4(ring + (rr & (RCAP - 1)) * kIirVCols, ph + (unsigned)(min(rr, h - 1) * pitch), rr < h);
+        float *ring = &sm.ring[q][0][0];
+        auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h): one 16-byte copy per lane
+            const int rr = r0 + crow;
+            cp_async_16(ring + (rr & (RCAP - 1)) * kIirVCols + ccol, ph + (unsigned)(min(rr, h - 1) * pitch),
+                        rr < h ? 16 : 0);
         };
         // rows -6..-1 are padding: their ring slots hold zeros until real rows wrap around to them
 #pragma unroll
-        for (int j = 1; j <= 6; ++j) ring[(RCAP - j) * kIirVCols] = 0.0f;
-        for (int rr = 0; rr < 4 + D; ++rr) issue_row(rr);   // everything before the first batch's request
+        for (int j = 1; j <= 6; ++j) ring[(RCAP - j) * kIirVCols + lane] = 0.0f;
+        for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0);   // everything before the first batch's request
         cp_async_commit();
         IirState st;
 #pragma unroll
         for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
         cp_async_wait<0>();
+        __syncwarp();
+        const float *col = ring + lane;
         // n = -4..-1: right taps are rows 0..3, left taps are padding, nothing emitted
 #pragma unroll
-        for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, ring[(n + 4) * kIirVCols]);
+        for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, col[(n + 4) * kIirVCols]);
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             const int n0 = b * B;
 #pragma unroll
-            for (int j = 0; j < B; ++j) issue_row(n0 + 4 + D + j);
+            for (int j = 0; j < B; j += 4) issue_rows4(n0 + 4 + D + j);
             cp_async_commit();
-            cp_async_wait<D / B>();                    // rows up to n0 + B + 3 have landed
+            cp_async_wait<D / B>();                    // rows up to n0 + B + 3 have landed (this lane's copies)
+            __syncwarp();                              // ... and every other lane's
             float sum[B];
             int il = (n0 - 6) & (RCAP - 1), ir = (n0 + 4) & (RCAP - 1);
 #pragma unroll
             for (int j = 0; j < B; ++j) {
-                sum[j] = ring[il * kIirVCols] + ring[ir * kIirVCols];
+                sum[j] = col[il * kIirVCols] + col[ir * kIirVCols];
                 il = (il + 1) & (RCAP - 1);
                 ir = (ir + 1) & (RCAP - 1);
             }
@@ -389,37 +397,38 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();      // consumers' last batch
         __syncthreads();      // final reduction
     } else {
-        // ---------------- consumers: maps + pooling for rows j = cw, cw+2, cw+4 of each batch ----------------
+        // ---------------- consumers: maps + pooling for rows 4*cw .. 4*cw+3 of each batch ----------------
         const int cw = warp - 5;
-        const float *pa = a.src + poff;
-        const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
+        const float *pa = a.src + poff + ccol;
+        const float *pb = a.dist + (long long)cand * a.dist_stride + poff + ccol;
         double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        auto issue_ab = [&](int rr) {
-            const bool ok = rr < h;
+        auto issue_ab4 = [&](int r0) {   // rows r0..r0+3 of both planes
+            const int rr = r0 + crow;
             const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
-            cp_async_4(&sm.ab[0][rr & 31][lane], pa + o, ok);
-            cp_async_4(&sm.ab[1][rr & 31][lane], pb + o, ok);
+            const int nb = rr < h ? 16 : 0;
+            cp_async_16(&sm.ab[0][rr & 31][ccol], pa + o, nb);
+            cp_async_16(&sm.ab[1][rr & 31][ccol], pb + o, nb);
         };
-        for (int rr = cw; rr < DA; rr += 2) issue_ab(rr);
+        for (int r0 = 4 * cw; r0 < DA; r0 += B) issue_ab4(r0);
         cp_async_commit();
         cp_async_wait<0>();   // the in-loop wait only covers groups committed inside the loop
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
-            const int n0 = b * B;
-#pragma unroll
-            for (int j = 0; j < B; j += 2) issue_ab(n0 + DA + cw + j);
+            const int n0 = b * B + 4 * cw;             // this warp's four rows of the batch
+            issue_ab4(n0 + DA);
             cp_async_commit();
-            cp_async_wait<DA / B>();                   // this warp's rows up to n0 + B - 1 have landed
+            cp_async_wait<DA / B>();                   // this warp's rows up to n0 + 3 have landed
+            __syncwarp();
             __syncthreads();                           // batch b is in ex[b & 1]
             float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            const float *ex = &sm.ex[b & 1][0][0][lane];
+            const float *ex = &sm.ex[b & 1][0][4 * cw][lane];
 #pragma unroll
-            for (int j = 0; j < B; j += 2) {
-                const int jj = j + cw, n = n0 + jj;
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + j;
                 if (col_ok && n < h)
-                    error_maps(sm.ab[0][n & 31][lane], sm.ab[1][n & 31][lane], ex[(0 * B + jj) * kIirVCols],
-                               ex[(1 * B + jj) * kIirVCols], ex[(2 * B + jj) * kIirVCols],
-                               ex[(3 * B + jj) * kIirVCols], ex[(4 * B + jj) * kIirVCols], acc);
+                    error_maps(sm.ab[0][n & 31][lane], sm.ab[1][n & 31][lane], ex[(0 * B + j) * kIirVCols],
+                               ex[(1 * B + j) * kIirVCols], ex[(2 * B + j) * kIirVCols],
+                               ex[(3 * B + j) * kIirVCols], ex[(4 * B + j) * kIirVCols], acc);
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
@@ -571,7 +580,7 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
     // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
     const int scale0_tasks = 3 * col_blocks[0] * n;
-    if (scale0_tasks <= 148 * 4)
+    if (scale0_tasks <= 148 * 3)
         k_iir_cols<64><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<64>), st>>>(a);
     else
         k_iir_cols<32><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<32>), st>>>(a);

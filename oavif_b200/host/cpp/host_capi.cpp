@@ -1,6 +1,7 @@
 // host_capi.cpp — extern "C" face of the harness (include/oavif_host.h).
 #include <cstring>
-#include <fstream>
+#include <cstdio>
+#include <stdexcept>
 #include <string>
 
 #include "../../../include/oavif_host.h"
@@ -210,8 +211,11 @@ int oavif_host_corpus_synth(const char *libavif_path, uint32_t count, uint32_t w
         double wall = 0;
         const auto rows = run_corpus(libavif_path, spec, to_cpp(opts), &wall);
         if (csv_path) {
-            std::ofstream f(csv_path, std::ios::binary);
-            f << corpus_csv(rows);
+            const std::string csv = corpus_csv(rows);
+            FILE *f = fopen(csv_path, "wb");
+            if (!f) throw std::runtime_error(std::string("cannot write ") + csv_path);
+            fwrite(csv.data(), 1, csv.size(), f);
+            fclose(f);
         }
         if (summary && summary_cap) {
             const std::string s = corpus_summary(rows, wall);

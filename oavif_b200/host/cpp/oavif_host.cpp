@@ -8,9 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
-#include <fstream>
 #include <mutex>
-#include <sstream>
 #include <stdexcept>
 #include <thread>
 #include <cstdarg>
@@ -39,46 +37,55 @@ std::string fmt(const char *f, ...)
 // ------------------------------------------------------------------------------------------------
 // images
 
+// NB: no <iostream>/<fstream>/<sstream> anywhere in the harness: the toolchain links libstdc++
+// statically into this shared object, and a second copy of the iostream locale machinery inside a
+// host process that already has one (CPython + ctypes) is not initialised reliably.
 HostImage load_pnm(const std::string &path)
 {
-    std::ifstream f(path, std::ios::binary);
+    FILE *f = fopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("cannot open " + path);
-    std::string magic;
-    f >> magic;
+    struct Closer {
+        FILE *f;
+        ~Closer() { fclose(f); }
+    } closer{f};
     HostImage img;
     img.name = path.substr(path.find_last_of('/') + 1);
+    auto token = [&]() -> std::string {  // whitespace-separated token, '#' comments skipped
+        std::string t;
+        int ch;
+        for (;;) {
+            ch = fgetc(f);
+            if (ch == EOF) return t;
+            if (ch == '#' && t.empty()) {
+                while (ch != '\n' && ch != EOF) ch = fgetc(f);
+                continue;
+            }
+            if (ch == ' ' || ch == '\t' || ch == '\n' || ch == '\r') {
+                if (!t.empty()) return t;
+                continue;
+            }
+            t.push_back((char)ch);
+        }
+    };
+    const std::string magic = token();
     uint32_t maxval = 0;
     if (magic == "P6") {
-        auto next = [&]() {
-            std::string t;
-            while (f >> t) {
-                if (t[0] == '#') {
-                    std::string rest;
-                    std::getline(f, rest);
-                    continue;
-                }
-                return (uint32_t)std::stoul(t);
-            }
-            throw std::runtime_error("truncated PPM header");
-        };
-        img.w = next();
-        img.h = next();
-        maxval = next();
+        img.w = (uint32_t)std::stoul(token());
+        img.h = (uint32_t)std::stoul(token());
+        maxval = (uint32_t)std::stoul(token());  // token() consumed the single whitespace after MAXVAL
         img.channels = 3;
-        f.get();
     } else if (magic == "P7") {  // io.zig:309-406
-        std::string key, tupl;
         uint32_t depth = 0;
-        while (f >> key) {
+        for (;;) {
+            const std::string key = token();
+            if (key.empty()) throw std::runtime_error("PAM: truncated header");
             if (key == "ENDHDR") break;
-            if (key == "WIDTH") f >> img.w;
-            else if (key == "HEIGHT") f >> img.h;
-            else if (key == "DEPTH") f >> depth;
-            else if (key == "MAXVAL") f >> maxval;
-            else if (key == "TUPLTYPE") f >> tupl;
-            else if (key[0] == '#') std::getline(f, key);
+            if (key == "WIDTH") img.w = (uint32_t)std::stoul(token());
+            else if (key == "HEIGHT") img.h = (uint32_t)std::stoul(token());
+            else if (key == "DEPTH") depth = (uint32_t)std::stoul(token());
+            else if (key == "MAXVAL") maxval = (uint32_t)std::stoul(token());
+            else if (key == "TUPLTYPE") (void)token();
         }
-        f.get();
         if (depth != 3 && depth != 4) throw std::runtime_error("PAM: only RGB / RGB_ALPHA supported by the harness");
         img.channels = depth;
     } else {
@@ -86,11 +93,9 @@ HostImage load_pnm(const std::string &path)
     }
     if (maxval != 255 || img.w == 0 || img.h == 0) throw std::runtime_error("PNM: need MAXVAL 255");
     img.data.resize((size_t)img.w * img.h * img.channels);
-    f.read(reinterpret_cast<char *>(img.data.data()), (std::streamsize)img.data.size());
-    if ((size_t)f.gcount() != img.data.size()) throw std::runtime_error("PNM: short pixel data");
-    f.clear();
-    f.seekg(0, std::ios::end);
-    img.file_bytes = (size_t)f.tellg();
+    if (fread(img.data.data(), 1, img.data.size(), f) != img.data.size()) throw std::runtime_error("PNM: short pixel data");
+    fseek(f, 0, SEEK_END);
+    img.file_bytes = (size_t)ftell(f);
     return img;
 }
 
@@ -503,21 +508,20 @@ std::vector<CorpusRow> run_corpus(const std::string &libavif_path, const CorpusS
 
 std::string corpus_csv(const std::vector<CorpusRow> &rows)
 {  // header and column formats of measure.py:180-206
-    std::ostringstream s;
-    s << "Image,Original Bytes,Final Bytes,Savings Bytes,Savings %,Encoding Time (ms),Passes,Status,Error\r\n";
+    std::string s = "Image,Original Bytes,Final Bytes,Savings Bytes,Savings %,Encoding Time (ms),Passes,Status,Error\r\n";
     for (const auto &r : rows) {
         if (r.status == "ok") {
             const size_t sav = r.orig_bytes > r.final_bytes ? r.orig_bytes - r.final_bytes : 0;
             const double pct = r.orig_bytes ? 100.0 * (double)sav / (double)r.orig_bytes : 0.0;
-            s << r.image << ',' << r.orig_bytes << ',' << r.final_bytes << ',' << sav << ',' << fmt("%.2f", pct) << ','
-              << fmt("%.2f", r.encoding_time_ms) << ',' << r.passes << ",ok,\r\n";
+            s += r.image + fmt(",%zu,%zu,%zu,%.2f,%.2f,%u,ok,\r\n", r.orig_bytes, r.final_bytes, sav, pct,
+                               r.encoding_time_ms, r.passes);
         } else {
             std::string e = r.error;
             std::replace(e.begin(), e.end(), ',', ';');
-            s << r.image << ',' << r.orig_bytes << ",,,,,," << r.status << ',' << e << "\r\n";
+            s += r.image + fmt(",%zu,,,,,,", r.orig_bytes) + r.status + "," + e + "\r\n";
         }
     }
-    return s.str();
+    return s;
 }
 
 std::string corpus_summary(const std::vector<CorpusRow> &rows, double wall_s)
@@ -553,21 +557,20 @@ std::string corpus_summary(const std::vector<CorpusRow> &rows, double wall_s)
         std::sort(v.begin(), v.end());
         return v.size() % 2 ? v[v.size() / 2] : 0.5 * (v[v.size() / 2 - 1] + v[v.size() / 2]);
     };
-    std::ostringstream s;
-    s << "Run Summary\n";
-    s << fmt("Images: %zu ok, 0 no-output, %zu errors\n", ok, err);
-    s << fmt("Total wall time: %.2f s\n", wall_s);
-    s << fmt("Throughput: %.2f images/s\n", wall_s > 0 ? ok / wall_s : 0.0);
-    s << fmt("Input bytes throughput: %.2f MiB/s\n", wall_s > 0 ? orig / wall_s / 1048576.0 : 0.0);
-    s << fmt("Output bytes throughput: %.2f MiB/s\n", wall_s > 0 ? fin / wall_s / 1048576.0 : 0.0);
-    s << fmt("Original total bytes: %zu\nFinal total bytes:    %zu\n", orig, fin);
-    s << fmt("%% saved (overall):    %.2f%%\n", orig ? 100.0 * (double)(orig > fin ? orig - fin : 0) / orig : 0.0);
-    s << fmt("Average encoding time: %.2f ms ± %.2f\n", mean(t), stdev(t));
-    s << fmt("Median encoding time:  %.2f ms\n", median(t));
+    std::string s = "Run Summary\n";
+    s += fmt("Images: %zu ok, 0 no-output, %zu errors\n", ok, err);
+    s += fmt("Total wall time: %.2f s\n", wall_s);
+    s += fmt("Throughput: %.2f images/s\n", wall_s > 0 ? ok / wall_s : 0.0);
+    s += fmt("Input bytes throughput: %.2f MiB/s\n", wall_s > 0 ? orig / wall_s / 1048576.0 : 0.0);
+    s += fmt("Output bytes throughput: %.2f MiB/s\n", wall_s > 0 ? fin / wall_s / 1048576.0 : 0.0);
+    s += fmt("Original total bytes: %zu\nFinal total bytes:    %zu\n", orig, fin);
+    s += fmt("%% saved (overall):    %.2f%%\n", orig ? 100.0 * (double)(orig > fin ? orig - fin : 0) / orig : 0.0);
+    s += fmt("Average encoding time: %.2f ms ± %.2f\n", mean(t), stdev(t));
+    s += fmt("Median encoding time:  %.2f ms\n", median(t));
     const double mx = p.empty() ? 0 : *std::max_element(p.begin(), p.end());
     const double mn = p.empty() ? 0 : *std::min_element(p.begin(), p.end());
-    s << fmt("Average passes:        %.2f ± %.2f (max: %.0f, min: %.0f)\n", mean(p), stdev(p), mx, mn);
-    return s.str();
+    s += fmt("Average passes:        %.2f ± %.2f (max: %.0f, min: %.0f)\n", mean(p), stdev(p), mx, mn);
+    return s;
 }
 
 }  // namespace oavif_host

@@ -98,6 +98,40 @@ def test_batched_search_same_result_with_injected_oracle(oracle):
     assert a4 == a1 and r4.device_passes <= r1.num_pass
 
 
+def test_corpus_driver_without_a_gpu_records_errors_and_keeps_going(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    path = str(tmp_path / "c.csv")
+    r = H.corpus_synth(3, 96, 64, opts=opts(max_pass=2), csv_path=path)
+    assert r["ok"] == 0 and "Images: 0 ok, 0 no-output, 3 errors" in r["summary"]
+    rows = list(csv.reader(open(path, newline="")))
+    assert len(rows) == 4 and all(x[7] == "error" and "oavif_ssimu2_ctx_create" in x[8] for x in rows[1:])  # no CPU fallback
+
+
+def test_cli_reads_pam_and_ppm_and_reports_like_the_reference(tmp_path):
+    import subprocess
+    cli = os.path.join(os.path.dirname(H.LIB_PATH), "oavif-b200")
+    img = synth.synth_rgba(40, 30, "noise", 1)
+    pam = tmp_path / "a.pam"
+    pam.write_bytes(b"P7\nWIDTH 40\nHEIGHT 30\nDEPTH 4\nMAXVAL 255\nTUPLTYPE RGB_ALPHA\nENDHDR\n" + img.tobytes())
+    ppm = tmp_path / "a.ppm"
+    ppm.write_bytes(b"P6\n# comment\n40 30\n255\n" + img[..., :3].tobytes())
+    env = dict(os.environ, OAVIF_LIBAVIF=H.find_libavif())
+    for f, kind in ((pam, "RGBA"), (ppm, "RGB")):
+        out = tmp_path / (f.name + ".avif")
+        p = subprocess.run([cli, "--tenbit", "0", "-q", "60", str(f), str(out)], capture_output=True, text=True, env=env)
+        assert p.returncode == 0, p.stderr
+        assert f"Read 40x30, {kind}, 8-bit, {f.stat().st_size} bytes" in p.stderr
+        assert "Encoding [q60, speed 9, 8-bit]" in p.stderr and f"Compressed to {out.stat().st_size} bytes" in p.stderr
+        px = img if kind == "RGBA" else np.ascontiguousarray(img[..., :3])
+        assert out.read_bytes() == H.encode(px, 60, opts())
+    bad = subprocess.run([cli, "--speed", "11", str(ppm), "x.avif"], capture_output=True, text=True, env=env)
+    assert bad.returncode != 0 and "--speed must be between 0 and 10" in bad.stderr           # parse_args.zig:84
+    miss = subprocess.run([cli, "--tolerance", "-3", str(ppm), "x.avif"], capture_output=True, text=True, env=env)
+    assert miss.returncode != 0 and "Missing value" in miss.stderr                             # parse_args.zig:126
+
+
 # ---- GPU ------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [(256, 192, "mixture", 80.0, 2.0), (320, 200, "noise", 70.0, 1.0),
