@@ -300,26 +300,27 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
 }
 
 // ------------------------------------------------------------------------------------------------
-// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 224.
+// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 288.
 //
 // One CTA owns 32 columns of one channel; lane = column in the arithmetic, so the recursions of a warp
 // are 32 independent columns.  Warps 0..4 (producers) each stream ONE row-filtered plane down the image
 // through a private shared-memory ring.  The ring is fed by 16-byte cp.async: one instruction moves
 // four whole 128-byte row segments (8 lanes per row), RCAP-18 rows ahead of use; both taps of the
 // recursion are read back from the ring (no register delay line).  Each producer drops its filtered
-// values into a double-buffered 8-row batch.  Warps 5..6 (consumers), one batch behind, stream the
+// values into a double-buffered 8-row batch.  Warps 5..8 (consumers), one batch behind, stream the
 // pixel's own XYB samples the same way and evaluate the SSIM / edge-diff maps and the six pooled sums
-// for rows 0..3 and 4..7 of the batch.  Seven warps per task give a sub-partition enough independent
-// work to hide latencies when a single 4K pair is all the GPU has.  One block barrier per 8 rows.
+// for two rows of the batch each (a producer step costs ~17 instructions, a map pixel ~70, so 5 + 4
+// warps are balanced).  Nine warps per task give a sub-partition enough independent work to hide
+// latencies when a single 4K pair is all the GPU has.  One block barrier per 8 rows.
 constexpr int kIirVBatch = 8;    // rows per exchange batch in the columns pass
-constexpr int kIirVThreads = 224;
+constexpr int kIirVThreads = 288;   // 5 producer warps + 4 consumer warps
 
 template <int RCAP>
 struct IirColsSmem {
     float ring[5][RCAP][kIirVCols];            // producer input rows, row r at [r & (RCAP-1)]
     float ab[2][32][kIirVCols];                // consumer rows of the two XYB planes
     float ex[2][5][kIirVBatch][kIirVCols];     // filtered values, double-buffered
-    double red[2][6];
+    double red[4][6];
 };
 
 template <int RCAP>
@@ -378,14 +379,15 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             cp_async_commit();
             cp_async_wait<D / B>();                    // rows up to n0 + B + 3 have landed (this lane's copies)
             __syncwarp();                              // ... and every other lane's
+            // n0 is a multiple of 8 and so is RCAP: the left taps (rows n0-6+j) can only wrap at j = 6,
+            // the right taps (rows n0+4+j) only at j = 4 -> two bases each, static offsets otherwise
             float sum[B];
-            int il = (n0 - 6) & (RCAP - 1), ir = (n0 + 4) & (RCAP - 1);
+            const float *l0 = col + ((n0 - 6) & (RCAP - 1)) * kIirVCols, *l1 = col + (n0 & (RCAP - 1)) * kIirVCols;
+            const float *r0 = col + ((n0 + 4) & (RCAP - 1)) * kIirVCols, *r1 = col + ((n0 + 8) & (RCAP - 1)) * kIirVCols;
 #pragma unroll
-            for (int j = 0; j < B; ++j) {
-                sum[j] = col[il * kIirVCols] + col[ir * kIirVCols];
-                il = (il + 1) & (RCAP - 1);
-                ir = (ir + 1) & (RCAP - 1);
-            }
+            for (int j = 0; j < B; ++j)
+                sum[j] = (j < 6 ? l0[j * kIirVCols] : l1[(j - 6) * kIirVCols]) +
+                         (j < 4 ? r0[j * kIirVCols] : r1[(j - 4) * kIirVCols]);
             float *ex = &sm.ex[b & 1][q][0][lane];
             IirPipe P;
             pipe_begin(k, P, st, sum[0]);
@@ -397,8 +399,10 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();      // consumers' last batch
         __syncthreads();      // final reduction
     } else {
-        // ---------------- consumers: maps + pooling for rows 4*cw .. 4*cw+3 of each batch ----------------
-        const int cw = warp - 5;
+        // ---------------- consumers: maps + pooling for rows 2*cw, 2*cw+1 of each batch ----------------
+        const int cw = warp - 5;                       // 0..3
+        const int grp = cw >> 1;                       // rows 4*grp .. 4*grp+3 are staged by the even warp of a pair
+        const bool loader = (cw & 1) == 0;
         const float *pa = a.src + poff + ccol;
         const float *pb = a.dist + (long long)cand * a.dist_stride + poff + ccol;
         double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -409,21 +413,21 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             cp_async_16(&sm.ab[0][rr & 31][ccol], pa + o, nb);
             cp_async_16(&sm.ab[1][rr & 31][ccol], pb + o, nb);
         };
-        for (int r0 = 4 * cw; r0 < DA; r0 += B) issue_ab4(r0);
+        if (loader)
+            for (int r0 = 4 * grp; r0 < DA; r0 += B) issue_ab4(r0);
         cp_async_commit();
         cp_async_wait<0>();   // the in-loop wait only covers groups committed inside the loop
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
-            const int n0 = b * B + 4 * cw;             // this warp's four rows of the batch
-            issue_ab4(n0 + DA);
+            if (loader) issue_ab4(b * B + 4 * grp + DA);
             cp_async_commit();
-            cp_async_wait<DA / B>();                   // this warp's rows up to n0 + 3 have landed
-            __syncwarp();
-            __syncthreads();                           // batch b is in ex[b & 1]
+            cp_async_wait<DA / B>();                   // the rows of batch b staged by this warp have landed
+            __syncthreads();                           // batch b is in ex[b & 1]; the pair's samples are visible
+            const int j0 = 2 * cw, n0 = b * B + j0;    // this warp's two rows
             float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            const float *ex = &sm.ex[b & 1][0][4 * cw][lane];
+            const float *ex = &sm.ex[b & 1][0][j0][lane];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 const int n = n0 + j;
                 if (col_ok && n < h)
                     error_maps(sm.ab[0][n & 31][lane], sm.ab[1][n & 31][lane], ex[(0 * B + j) * kIirVCols],
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
         }
         __syncthreads();
-        // fixed shuffle tree over the 32 columns, then the two consumers in fixed order
+        // fixed shuffle tree over the 32 columns, then the four consumers in fixed order
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             double x = dacc[j];
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();
         if (cw == 0 && lane < 6)
             a.partials[(long long)cand * a.partials_stride + (long long)blockIdx.x * 6 + lane] =
-                sm.red[0][lane] + sm.red[1][lane];
+                ((sm.red[0][lane] + sm.red[1][lane]) + sm.red[2][lane]) + sm.red[3][lane];
     }
 }
 
