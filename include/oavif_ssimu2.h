@@ -54,7 +54,9 @@ enum {
  *              (no intermediate planes); differs from RECURSIVE only by that round-off.      */
 enum { OAVIF_SSIMU2_BLUR_RECURSIVE = 0, OAVIF_SSIMU2_BLUR_FIR = 1 };
 
-enum { OAVIF_SSIMU2_OPT_BLUR = 1 };
+/* OPT_OVERLAP (RECURSIVE blur, default 1): issue the rows / columns passes channel by channel on
+ * separate streams so that they run next to each other; 0 serialises them (per-kernel timing). */
+enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_OVERLAP = 2 };
 
 typedef struct oavif_ssimu2_ctx oavif_ssimu2_ctx;
 
@@ -73,8 +75,8 @@ typedef struct {
     float h2d_ms;       /* host -> device copies of this call's pixels           */
     float pyramid_ms;   /* YUV->RGB8, sRGB->linear, 2x pyramid, XYB              */
     float blur_ms;      /* blur + error maps + pooling kernels (a + b)           */
-    float blur_a_ms;    /* RECURSIVE: rows pass.  FIR: the fused kernel          */
-    float blur_b_ms;    /* RECURSIVE: columns pass + maps + pooling.  FIR: 0     */
+    float blur_a_ms;    /* RECURSIVE: rows pass (with OPT_OVERLAP: until its last launch ends). FIR: the fused kernel */
+    float blur_b_ms;    /* RECURSIVE: columns pass + maps + pooling (with OPT_OVERLAP: the tail after the rows). FIR: 0 */
     float finalize_ms;  /* fixed-order reduction, weights, score, D2H of scores  */
     float total_ms;     /* first event to last event                             */
     uint32_t launches;  /* kernels of this library launched by the call          */

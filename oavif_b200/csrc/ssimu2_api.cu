@@ -44,6 +44,7 @@ struct oavif_ssimu2_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     IirStreams iir_streams{};
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
+    bool overlap = true;   // OAVIF_SSIMU2_OPT_OVERLAP
 
     // capacities (computed from max_w x max_h)
     long long cap_pyr_floats = 0, cap_in_bytes = 0, cap_ctas = 0, cap_hplane_floats = 0;
@@ -360,7 +361,7 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
         const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats,
                                               ctx->d_hplanes, ctx->cap_hplane_floats, ctx->d_partials,
                                               ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, (int)n,
-                                              ctx->stream, ctx->iir_streams, ctx->ev[3], &launches);
+                                              ctx->stream, ctx->iir_streams, ctx->ev[3], &launches, ctx->overlap);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "recursive blur launch: %s", cudaGetErrorString(e));
         ctx->timing.launches += launches;
     }
@@ -515,7 +516,12 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
         if (e) cudaEventDestroy(e);
     if (ctx->iir_streams.fork) cudaEventDestroy(ctx->iir_streams.fork);
     if (ctx->iir_streams.join) cudaEventDestroy(ctx->iir_streams.join);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->iir_streams.rows_a[i]) cudaEventDestroy(ctx->iir_streams.rows_a[i]);
+        if (ctx->iir_streams.rows_b[i]) cudaEventDestroy(ctx->iir_streams.rows_b[i]);
+    }
     if (ctx->iir_streams.side) cudaStreamDestroy(ctx->iir_streams.side);
+    if (ctx->iir_streams.cols) cudaStreamDestroy(ctx->iir_streams.cols);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -550,6 +556,11 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.side, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->iir_streams.fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->iir_streams.join, cudaEventDisableTiming));
+    CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.cols, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+        CKC(cudaEventCreateWithFlags(&ctx->iir_streams.rows_a[i], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&ctx->iir_streams.rows_b[i], cudaEventDisableTiming));
+    }
 
     const int mw = (int)max_w, mh = (int)max_h;
     ctx->cap_pyr_floats = std::max(pyr_capacity(mw, mh), pyr_capacity(mh, mw));
@@ -593,6 +604,10 @@ int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value)
     if (option == OAVIF_SSIMU2_OPT_BLUR &&
         (value == OAVIF_SSIMU2_BLUR_RECURSIVE || value == OAVIF_SSIMU2_BLUR_FIR)) {
         ctx->blur_mode = value;
+        return 0;
+    }
+    if (option == OAVIF_SSIMU2_OPT_OVERLAP && (value == 0 || value == 1)) {
+        ctx->overlap = value != 0;
         return 0;
     }
     return fail(ctx, OAVIF_SSIMU2_E_ARG, "unknown option %d / value %d", option, value);
@@ -845,7 +860,7 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
         const cudaError_t e = launch_iir_blur(ctx->g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats,
                                               ctx->d_hplanes, ctx->cap_hplane_floats, ctx->d_partials,
                                               ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, 1, ctx->stream,
-                                              ctx->iir_streams, nullptr, &launches, variant, true);
+                                              ctx->iir_streams, nullptr, &launches, false, variant, true);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));

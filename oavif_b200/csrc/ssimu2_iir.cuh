@@ -73,8 +73,10 @@ struct IirArgs {
     long long q_stride;         // floats between quantities
     double *partials;
     long long partials_stride;
-    int first_cta[kMaxScales + 1];
+    int first_cta[kMaxScales + 1];  // CTA ranges per scale of THIS launch (n_ch channels each)
     int blocks[kMaxScales];     // tasks per channel and scale
+    int ch0, n_ch;              // channels ch0 .. ch0+n_ch-1 are covered by this launch
+    int part_first[kMaxScales]; // columns pass: first partial-sum slot of a scale (3 channels x blocks each)
 };
 
 __device__ __forceinline__ void decode_cta(const IirArgs &a, int cta, int &s, int &c, int &blk)
@@ -84,8 +86,9 @@ __device__ __forceinline__ void decode_cta(const IirArgs &a, int cta, int &s, in
     for (int i = 1; i < kMaxScales; ++i)
         if (i < a.g.n_scales && cta >= a.first_cta[i]) s = i;
     const int local = cta - a.first_cta[s];
-    c = local / a.blocks[s];
-    blk = local - c * a.blocks[s];
+    const int cl = local / a.blocks[s];
+    c = a.ch0 + cl;
+    blk = local - cl * a.blocks[s];
 }
 
 __device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gmem_src, int src_bytes)
@@ -448,7 +451,8 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         }
         __syncthreads();
         if (cw == 0 && lane < 6)
-            a.partials[(long long)cand * a.partials_stride + (long long)blockIdx.x * 6 + lane] =
+            a.partials[(long long)cand * a.partials_stride +
+                       (long long)(a.part_first[s] + c * a.blocks[s] + cb) * 6 + lane] =
                 ((sm.red[0][lane] + sm.red[1][lane]) + sm.red[2][lane]) + sm.red[3][lane];
     }
 }
@@ -522,7 +526,9 @@ inline cudaError_t iir_configure()
 
 struct IirStreams {
     cudaStream_t side;       // runs the a*b rows tasks next to the single-plane ones
+    cudaStream_t cols;       // columns pass of channel c, overlapping the rows pass of channel c+1
     cudaEvent_t fork, join;
+    cudaEvent_t rows_a[3], rows_b[3];
 };
 
 template <int VARIANT>
@@ -533,11 +539,15 @@ inline void launch_rows_variant(const IirArgs &a1, int n1, const IirArgs &a2, in
     k_iir_rows<2, VARIANT><<<dim3(n2, ncand), 32, sizeof(IirRowsSmem<2>), side>>>(a2);
 }
 
+// Rows and columns passes of one scoring call.  overlap = true issues them channel by channel so that
+// the columns pass of channel c (stream `cols`) runs next to the rows pass of channel c+1 (streams
+// `st` / `side`): both passes leave issue slots and HBM bandwidth unused on their own.
 inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float *src, const float *dist,
                                    long long pyr_stride, float *hplanes, long long hplanes_stride,
                                    double *partials, long long partials_stride, const int *first_cta_cols,
                                    const int *col_blocks, int n, cudaStream_t st, const IirStreams &ss,
-                                   cudaEvent_t between, int *launches, int variant = 0, bool rows_only = false)
+                                   cudaEvent_t between, int *launches, bool overlap = true, int variant = 0,
+                                   bool rows_only = false)
 {
     IirArgs a{};
     a.g = g;
@@ -550,46 +560,73 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     a.q_stride = pyr_stride;
     a.partials = partials;
     a.partials_stride = partials_stride;
-    IirArgs a1 = a, a2 = a;   // single-plane quantities | a*b
-    int n1 = 0, n2 = 0;
-    for (int s = 0; s < g.n_scales; ++s) {
-        const int nrb = (g.h[s] + kIirRows - 1) / kIirRows;
-        a1.blocks[s] = 4 * nrb;
-        a1.first_cta[s] = n1;
-        n1 += 3 * 4 * nrb;
-        a2.blocks[s] = nrb;
-        a2.first_cta[s] = n2;
-        n2 += 3 * nrb;
-    }
-    for (int s = g.n_scales; s <= kMaxScales; ++s) {
-        a1.first_cta[s] = n1;
-        a2.first_cta[s] = n2;
-    }
+    for (int s = 0; s < kMaxScales; ++s) a.part_first[s] = first_cta_cols[s];
+    const int nch = (overlap && !rows_only) ? 1 : 3;   // channels per launch
+    *launches = 0;
     cudaEventRecord(ss.fork, st);
     cudaStreamWaitEvent(ss.side, ss.fork, 0);
-    switch (variant) {
-    case 0: launch_rows_variant<0>(a1, n1, a2, n2, n, st, ss.side); break;
-    case 1: launch_rows_variant<1>(a1, n1, a2, n2, n, st, ss.side); break;
-    case 2: launch_rows_variant<2>(a1, n1, a2, n2, n, st, ss.side); break;
-    default: launch_rows_variant<3>(a1, n1, a2, n2, n, st, ss.side); break;
+    if (nch == 1) cudaStreamWaitEvent(ss.cols, ss.fork, 0);
+    for (int ch0 = 0; ch0 < 3; ch0 += nch) {
+        IirArgs a1 = a, a2 = a, ac = a;   // single-plane quantities | a*b | columns
+        int n1 = 0, n2 = 0, nc = 0;
+        for (int s = 0; s < g.n_scales; ++s) {
+            const int nrb = (g.h[s] + kIirRows - 1) / kIirRows;
+            a1.blocks[s] = 4 * nrb;
+            a1.first_cta[s] = n1;
+            n1 += nch * 4 * nrb;
+            a2.blocks[s] = nrb;
+            a2.first_cta[s] = n2;
+            n2 += nch * nrb;
+            ac.blocks[s] = col_blocks[s];
+            ac.first_cta[s] = nc;
+            nc += nch * col_blocks[s];
+        }
+        for (int s = g.n_scales; s <= kMaxScales; ++s) {
+            a1.first_cta[s] = n1;
+            a2.first_cta[s] = n2;
+            ac.first_cta[s] = nc;
+        }
+        a1.ch0 = a2.ch0 = ac.ch0 = ch0;
+        a1.n_ch = a2.n_ch = ac.n_ch = nch;
+        switch (variant) {
+        case 0: launch_rows_variant<0>(a1, n1, a2, n2, n, st, ss.side); break;
+        case 1: launch_rows_variant<1>(a1, n1, a2, n2, n, st, ss.side); break;
+        case 2: launch_rows_variant<2>(a1, n1, a2, n2, n, st, ss.side); break;
+        default: launch_rows_variant<3>(a1, n1, a2, n2, n, st, ss.side); break;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        *launches += 2;
+        const int ci = ch0 < 3 ? ch0 : 2;
+        cudaEventRecord(ss.rows_b[ci], ss.side);
+        if (rows_only) {
+            cudaStreamWaitEvent(st, ss.rows_b[ci], 0);
+            continue;
+        }
+        cudaStream_t cst = nch == 1 ? ss.cols : st;
+        if (nch == 1) {
+            cudaEventRecord(ss.rows_a[ci], st);
+            cudaStreamWaitEvent(cst, ss.rows_a[ci], 0);
+        }
+        cudaStreamWaitEvent(cst, ss.rows_b[ci], 0);
+        if (nch == 3 && between) cudaEventRecord(between, st);
+        // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
+        const int scale0_tasks = 3 * col_blocks[0] * n;
+        if (scale0_tasks <= 148 * 3)
+            k_iir_cols<64><<<dim3(nc, n), kIirVThreads, sizeof(IirColsSmem<64>), cst>>>(ac);
+        else
+            k_iir_cols<32><<<dim3(nc, n), kIirVThreads, sizeof(IirColsSmem<32>), cst>>>(ac);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        *launches += 1;
     }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    cudaEventRecord(ss.join, ss.side);
-    cudaStreamWaitEvent(st, ss.join, 0);
-    if (between) cudaEventRecord(between, st);
-    *launches = 2;
     if (rows_only) return cudaSuccess;
-    for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
-    for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
-    // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
-    const int scale0_tasks = 3 * col_blocks[0] * n;
-    if (scale0_tasks <= 148 * 3)
-        k_iir_cols<64><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<64>), st>>>(a);
-    else
-        k_iir_cols<32><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<32>), st>>>(a);
-    *launches = 3;
-    return cudaGetLastError();
+    if (nch == 1) {
+        if (between) cudaEventRecord(between, st);  // end of the last rows launch on the main stream
+        cudaEventRecord(ss.join, ss.cols);
+        cudaStreamWaitEvent(st, ss.join, 0);
+    }
+    return cudaSuccess;
 }
 
 inline cudaError_t launch_debug_blur(bool fir, const float *taps, const IirCoef &k, const float *d_in, float *d_tmp,

@@ -228,6 +228,20 @@ def test_batch_equals_single_and_is_deterministic(scorer, mode, omode, name):
     assert all(a > b for a, b in zip(batch, batch[1:]))
 
 
+def test_overlapped_and_serialised_passes_give_identical_bits(scorer):
+    src = synth.synth(777, 555, "mixture", 6)
+    cands = [synth.distort(src, s, seed=i) for i, s in enumerate((0.2, 0.7))]
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    scorer.set_source(src)
+    scorer.set_overlap(True)
+    a = scorer.score_batch_rgb8(cands)
+    sa = scorer.sums(1).copy()
+    scorer.set_overlap(False)
+    b = scorer.score_batch_rgb8(cands)
+    assert a == b and (scorer.sums(1) == sa).all()
+    scorer.set_overlap(True)
+
+
 def test_modes_differ_only_by_recursion_roundoff(scorer):
     src = synth.synth(640, 360, "mixture", 4)
     dist = synth.distort(src, 0.6)
