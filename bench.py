@@ -327,7 +327,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        reps = 8  # ~10-20 s of CPU work in total
+        reps = 40  # ~15-25 s of CPU work in total
         rates = [cpu_oracle_rate(threads, 8.0) for _ in range(reps)]
         rate, rows, dt = float(np.mean([r[0] for r in rates])), rates[0][1], float(np.sum([r[2] for r in rates]))
         rate1, rows1, dt1 = cpu_oracle_rate(1, 4.0)
