@@ -249,7 +249,7 @@ def run_ours(args):
         ktimes["a"].append(t.blur_a_ms)
         ktimes["b"].append(t.blur_b_ms)
         ktimes["fin"].append(t.finalize_ms)
-        ktimes["launches"] += t.launches + 1  # + the source-pyramid launch of set_source
+        ktimes["launches"] += t.launches + 2  # + set_source: source pyramid and source-side rows pass
 
     sampler = ClockSampler(local)
     if rank == 0:

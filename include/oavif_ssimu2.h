@@ -54,11 +54,7 @@ enum {
  *              (no intermediate planes); differs from RECURSIVE only by that round-off.      */
 enum { OAVIF_SSIMU2_BLUR_RECURSIVE = 0, OAVIF_SSIMU2_BLUR_FIR = 1 };
 
-/* OPT_OVERLAP (RECURSIVE blur, default 0): issue the rows / columns passes channel by channel on
- * separate streams so that they run next to each other.  Kept as an experiment: on a single 4K pair
- * it is slower (0.77 ms vs 0.55 ms) because each pass is bound by the length of one row/column chain,
- * not by throughput, and three launches put three such chains in series. */
-enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_OVERLAP = 2 };
+enum { OAVIF_SSIMU2_OPT_BLUR = 1 };
 
 typedef struct oavif_ssimu2_ctx oavif_ssimu2_ctx;
 
@@ -77,8 +73,8 @@ typedef struct {
     float h2d_ms;       /* host -> device copies of this call's pixels           */
     float pyramid_ms;   /* YUV->RGB8, sRGB->linear, 2x pyramid, XYB              */
     float blur_ms;      /* blur + error maps + pooling kernels (a + b)           */
-    float blur_a_ms;    /* RECURSIVE: rows pass (with OPT_OVERLAP: until its last launch ends). FIR: the fused kernel */
-    float blur_b_ms;    /* RECURSIVE: columns pass + maps + pooling (with OPT_OVERLAP: the tail after the rows). FIR: 0 */
+    float blur_a_ms;    /* RECURSIVE: candidate rows pass (b, b*b, a*b). FIR: the fused kernel */
+    float blur_b_ms;    /* RECURSIVE: columns pass + maps + pooling.  FIR: 0             */
     float finalize_ms;  /* fixed-order reduction, weights, score, D2H of scores  */
     float total_ms;     /* first event to last event                             */
     uint32_t launches;  /* kernels of this library launched by the call          */
@@ -109,7 +105,8 @@ void oavif_ssimu2_pinned_free(void *p);
 /* ---- source side: once per image (main.zig:86) ------------------------------------------ */
 
 /* rgb: interleaved 8-bit RGB, `stride` bytes per row (>= 3*w).  Uploads, builds and caches
- * the source's six-scale XYB pyramid on the device. */
+ * the source's six-scale XYB pyramid on the device (and, for the RECURSIVE blur, the rows pass of
+ * the two source-only quantities, which then runs behind the call and is shared by all candidates). */
 int oavif_ssimu2_set_source_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w,
                                  uint32_t h, size_t stride);
 
@@ -175,7 +172,8 @@ int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, 
 
 /* Profiling aid: re-run only the RECURSIVE rows pass on the pyramids of the last score call,
  * `iters` times, and report its mean device time.  variant 0 is the product kernel; bit 0 drops
- * its stores, bit 1 its tile loads (to attribute time; the row-filtered planes are then garbage). */
+ * its stores, bit 1 its tile loads (to attribute time; the row-filtered planes are then garbage), bit 2
+ * leaves out the source half (a, a*a) that set_source normally runs once per image. */
 int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms);
 
 #ifdef __cplusplus

@@ -7,7 +7,8 @@
 //   in_src / in_dist[k]   staged input pixels (RGB8, or 3 YUV planes of u8/u16), tight rows
 //   src_pyr               source XYB pyramid: scales 0..5, 3 f32 planes each (Geom)
 //   dist_pyr[k]           one XYB pyramid per candidate
-//   hplanes[k]            RECURSIVE blur only: 5 row-filtered planes per channel and scale
+//   src_hplanes           RECURSIVE blur only: row-filtered a and a*a of the source (cached with the pyramid)
+//   hplanes[k]            RECURSIVE blur only: row-filtered b, b*b, a*b of candidate k
 //   partials[k][cta][6]   per-CTA pooled sums (double), reduced in fixed order by k_finalize
 //   sums[k][6][18], scores[k]
 #include "../../include/oavif_ssimu2.h"
@@ -44,7 +45,6 @@ struct oavif_ssimu2_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     IirStreams iir_streams{};
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
-    bool overlap = false;  // OAVIF_SSIMU2_OPT_OVERLAP (measured slower on a single 4K pair: off by default)
 
     // capacities (computed from max_w x max_h)
     long long cap_pyr_floats = 0, cap_in_bytes = 0, cap_ctas = 0, cap_hplane_floats = 0;
@@ -55,7 +55,9 @@ struct oavif_ssimu2_ctx {
     uint32_t last_n = 0;
 
     uint8_t *d_in_src = nullptr, *d_in_dist = nullptr;
-    float *d_src_pyr = nullptr, *d_dist_pyr = nullptr, *d_hplanes = nullptr, *d_lut = nullptr;
+    float *d_src_pyr = nullptr, *d_dist_pyr = nullptr, *d_hplanes = nullptr, *d_src_hplanes = nullptr, *d_lut = nullptr;
+    bool src_rows_valid = false;   // the cached rows pass of the source (RECURSIVE blur) matches the current source
+    bool src_rows_pending = false; // ... and may still be running on the side stream
     const void **d_tbl = nullptr, **h_tbl = nullptr;
     double *d_partials = nullptr, *d_sums = nullptr, *d_scores = nullptr;
     double *h_sums = nullptr, *h_scores = nullptr;
@@ -361,12 +363,19 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
     } else {
         plan_iir_v(g, &plan);
         int launches = 0;
-        const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats,
-                                              ctx->d_hplanes, ctx->cap_hplane_floats, ctx->d_partials,
-                                              ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, (int)n,
-                                              ctx->stream, ctx->iir_streams, ctx->ev[3], &launches, ctx->overlap);
+        const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
+        if (!ctx->src_rows_valid) {  // source set while another blur was selected
+            const cudaError_t e0 = launch_iir_source_rows(g, ctx->iir, ctx->d_src_pyr, B, ctx->stream, ctx->iir_streams, &launches);
+            if (e0 != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "source rows launch: %s", cudaGetErrorString(e0));
+            ctx->timing.launches += launches;
+            ctx->src_rows_valid = true;
+        }
+        const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
+                                              ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, (int)n,
+                                              ctx->stream, ctx->iir_streams, ctx->ev[3], &launches);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "recursive blur launch: %s", cudaGetErrorString(e));
         ctx->timing.launches += launches;
+        ctx->src_rows_pending = false;  // the join inside launch_iir_blur ordered the main stream behind them
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
 
@@ -455,9 +464,24 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w, uin
     d.on_device = on_device;
     HostPlanes hp{{rgb, nullptr, nullptr}};
     ctx->timing = oavif_ssimu2_timing{};
+    // a previous source's rows pass may still be reading the pyramid on the side stream
+    if (ctx->src_rows_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->iir_streams.src_done, 0));
+    ctx->src_rows_pending = false;
+    ctx->src_rows_valid = false;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = build_pyramids(ctx, d, 1, &hp, true, ctx->d_src_pyr, 0);
     if (rc) return rc;
+    if (ctx->blur_mode == OAVIF_SSIMU2_BLUR_RECURSIVE) {
+        // source half of the rows pass (a, a*a): once per source, on the side stream, so that it
+        // overlaps the candidate's upload and pyramid and is shared by every later candidate
+        int launches = 0;
+        const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
+        const cudaError_t e = launch_iir_source_rows(ctx->g, ctx->iir, ctx->d_src_pyr, B, ctx->stream, ctx->iir_streams, &launches);
+        if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "source rows launch: %s", cudaGetErrorString(e));
+        ctx->timing.launches += launches;
+        ctx->src_rows_valid = true;
+        ctx->src_rows_pending = true;
+    }
     // Return as soon as the caller's pixels (and the pointer table) have been consumed: the pyramid
     // kernel itself keeps running behind the next call on the same stream.
     CK(cudaEventSynchronize(ctx->ev[1]));
@@ -506,6 +530,7 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     cudaFree(ctx->d_src_pyr);
     cudaFree(ctx->d_dist_pyr);
     cudaFree(ctx->d_hplanes);
+    cudaFree(ctx->d_src_hplanes);
     cudaFree(ctx->d_lut);
     cudaFree((void *)ctx->d_tbl);
     cudaFree(ctx->d_partials);
@@ -519,12 +544,11 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
         if (e) cudaEventDestroy(e);
     if (ctx->iir_streams.fork) cudaEventDestroy(ctx->iir_streams.fork);
     if (ctx->iir_streams.join) cudaEventDestroy(ctx->iir_streams.join);
-    for (int i = 0; i < 3; ++i) {
-        if (ctx->iir_streams.rows_a[i]) cudaEventDestroy(ctx->iir_streams.rows_a[i]);
-        if (ctx->iir_streams.rows_b[i]) cudaEventDestroy(ctx->iir_streams.rows_b[i]);
+    if (ctx->iir_streams.src_done) cudaEventDestroy(ctx->iir_streams.src_done);
+    if (ctx->iir_streams.side) {
+        cudaStreamSynchronize(ctx->iir_streams.side);
+        cudaStreamDestroy(ctx->iir_streams.side);
     }
-    if (ctx->iir_streams.side) cudaStreamDestroy(ctx->iir_streams.side);
-    if (ctx->iir_streams.cols) cudaStreamDestroy(ctx->iir_streams.cols);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -559,11 +583,7 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.side, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->iir_streams.fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->iir_streams.join, cudaEventDisableTiming));
-    CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.cols, cudaStreamNonBlocking));
-    for (int i = 0; i < 3; ++i) {
-        CKC(cudaEventCreateWithFlags(&ctx->iir_streams.rows_a[i], cudaEventDisableTiming));
-        CKC(cudaEventCreateWithFlags(&ctx->iir_streams.rows_b[i], cudaEventDisableTiming));
-    }
+    CKC(cudaEventCreateWithFlags(&ctx->iir_streams.src_done, cudaEventDisableTiming));
 
     const int mw = (int)max_w, mh = (int)max_h;
     ctx->cap_pyr_floats = std::max(pyr_capacity(mw, mh), pyr_capacity(mh, mw));
@@ -576,6 +596,7 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     CKC(cudaMalloc(&ctx->d_src_pyr, sizeof(float) * ctx->cap_pyr_floats));
     CKC(cudaMalloc(&ctx->d_dist_pyr, sizeof(float) * ctx->cap_pyr_floats * max_batch));
     CKC(cudaMalloc(&ctx->d_hplanes, sizeof(float) * ctx->cap_hplane_floats * max_batch));
+    CKC(cudaMalloc(&ctx->d_src_hplanes, sizeof(float) * 2 * ctx->cap_pyr_floats));
     CKC(cudaMalloc(&ctx->d_lut, sizeof(float) * 256));
     CKC(cudaMalloc((void **)&ctx->d_tbl, sizeof(void *) * 3 * (max_batch + 1)));
     CKC(cudaHostAlloc((void **)&ctx->h_tbl, sizeof(void *) * 3 * (max_batch + 1), cudaHostAllocDefault));
@@ -607,10 +628,6 @@ int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value)
     if (option == OAVIF_SSIMU2_OPT_BLUR &&
         (value == OAVIF_SSIMU2_BLUR_RECURSIVE || value == OAVIF_SSIMU2_BLUR_FIR)) {
         ctx->blur_mode = value;
-        return 0;
-    }
-    if (option == OAVIF_SSIMU2_OPT_OVERLAP && (value == 0 || value == 1)) {
-        ctx->overlap = value != 0;
         return 0;
     }
     return fail(ctx, OAVIF_SSIMU2_E_ARG, "unknown option %d / value %d", option, value);
@@ -860,10 +877,14 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     for (int i = 0; i < iters; ++i) {
         int launches = 0;
-        const cudaError_t e = launch_iir_blur(ctx->g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats,
-                                              ctx->d_hplanes, ctx->cap_hplane_floats, ctx->d_partials,
-                                              ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, 1, ctx->stream,
-                                              ctx->iir_streams, nullptr, &launches, false, variant, true);
+        const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
+        if (!(variant & 4)) {  // bit 2: leave the source half out (candidate-only cost)
+            int l0 = 0;
+            launch_iir_source_rows(ctx->g, ctx->iir, ctx->d_src_pyr, B, ctx->stream, ctx->iir_streams, &l0);
+        }
+        const cudaError_t e = launch_iir_blur(ctx->g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
+                                              ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, 1,
+                                              ctx->stream, ctx->iir_streams, nullptr, &launches, variant & 3, true);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));

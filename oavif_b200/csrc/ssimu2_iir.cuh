@@ -68,15 +68,15 @@ struct IirArgs {
     const float *src;
     const float *dist;
     long long dist_stride;      // floats between candidates' pyramids
-    float *hplanes;             // [candidate][quantity][pyramid layout]
-    long long hplanes_stride;   // floats between candidates (= 5 * q_stride)
-    long long q_stride;         // floats between quantities
+    // row-filtered planes, pyramid layout each.  a and a*a only depend on the source: they live in a
+    // per-source cache (candidate stride 0) written once by set_source; b, b*b, a*b are per candidate.
+    float *hq[5];
+    long long hq_cand_stride[5];
+    int nq, qlist[4];           // rows pass, single-plane class: the quantities this launch computes
     double *partials;
     long long partials_stride;
-    int first_cta[kMaxScales + 1];  // CTA ranges per scale of THIS launch (n_ch channels each)
+    int first_cta[kMaxScales + 1];  // CTA ranges per scale
     int blocks[kMaxScales];     // tasks per channel and scale
-    int ch0, n_ch;              // channels ch0 .. ch0+n_ch-1 are covered by this launch
-    int part_first[kMaxScales]; // columns pass: first partial-sum slot of a scale (3 channels x blocks each)
 };
 
 __device__ __forceinline__ void decode_cta(const IirArgs &a, int cta, int &s, int &c, int &blk)
@@ -86,9 +86,8 @@ __device__ __forceinline__ void decode_cta(const IirArgs &a, int cta, int &s, in
     for (int i = 1; i < kMaxScales; ++i)
         if (i < a.g.n_scales && cta >= a.first_cta[i]) s = i;
     const int local = cta - a.first_cta[s];
-    const int cl = local / a.blocks[s];
-    c = a.ch0 + cl;
-    blk = local - cl * a.blocks[s];
+    c = local / a.blocks[s];
+    blk = local - c * a.blocks[s];
 }
 
 __device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gmem_src, int src_bytes)
@@ -182,8 +181,8 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
 
     int s, c, blk;
     decode_cta(a, blockIdx.x, s, c, blk);
-    const int q = NPLANES == 2 ? 4 : (blk & 3);
-    const int rb = NPLANES == 2 ? blk : (blk >> 2);
+    const int q = NPLANES == 2 ? 4 : a.qlist[blk % a.nq];
+    const int rb = NPLANES == 2 ? blk : blk / a.nq;
     const int cand = blockIdx.y;
     const int w = a.g.w[s], h = a.g.h[s], pitch = a.g.pitch[s];
     const int y0 = rb * kIirRows;
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
     const float *pa = a.src + poff;
     const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
     const int lane = threadIdx.x;
-    float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff;
+    float *ph = a.hq[q] + (long long)cand * a.hq_cand_stride[q] + poff;
     const int nch = (w + kIirChunk - 1) / kIirChunk;
     const IirCoef k = a.k;
     // plane 0 of the ring holds a for {a, a*a, a*b} and b for {b, b*b}; plane 1 (a*b only) holds b
@@ -351,7 +350,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     if (warp < 5) {
         // ---------------- producer: the column recursion of quantity `warp` ----------------
         const int q = warp;
-        const float *ph = a.hplanes + (long long)cand * a.hplanes_stride + (long long)q * a.q_stride + poff + ccol;
+        const float *ph = a.hq[q] + (long long)cand * a.hq_cand_stride[q] + poff + ccol;
         const IirCoef k = a.k;
         float *ring = &sm.ring[q][0][0];
         auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h): one 16-byte copy per lane
@@ -451,8 +450,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         }
         __syncthreads();
         if (cw == 0 && lane < 6)
-            a.partials[(long long)cand * a.partials_stride +
-                       (long long)(a.part_first[s] + c * a.blocks[s] + cb) * 6 + lane] =
+            a.partials[(long long)cand * a.partials_stride + (long long)blockIdx.x * 6 + lane] =
                 ((sm.red[0][lane] + sm.red[1][lane]) + sm.red[2][lane]) + sm.red[3][lane];
     }
 }
@@ -515,7 +513,7 @@ __global__ void k_plain_cols(const float *in, float *out, int w, int h, int pitc
 }
 
 // ---- host-side launch helpers ------------------------------------------------------------------
-inline long long iir_hplane_floats(long long pyr_floats) { return 5 * pyr_floats; }
+inline long long iir_hplane_floats(long long pyr_floats) { return 3 * pyr_floats; }  // per candidate: b, b*b, a*b
 
 inline cudaError_t iir_configure()
 {
@@ -525,108 +523,117 @@ inline cudaError_t iir_configure()
 }
 
 struct IirStreams {
-    cudaStream_t side;       // runs the a*b rows tasks next to the single-plane ones
-    cudaStream_t cols;       // columns pass of channel c, overlapping the rows pass of channel c+1
-    cudaEvent_t fork, join;
-    cudaEvent_t rows_a[3], rows_b[3];
+    cudaStream_t side;       // a second stream: source-side rows tasks / the a*b rows tasks
+    cudaEvent_t fork, join;  // main -> side, side -> main
+    cudaEvent_t src_done;    // the source's cached row-filtered planes are complete
 };
 
-template <int VARIANT>
-inline void launch_rows_variant(const IirArgs &a1, int n1, const IirArgs &a2, int n2, int ncand, cudaStream_t st,
-                                cudaStream_t side)
-{
-    k_iir_rows<1, VARIANT><<<dim3(n1, ncand), 32, sizeof(IirRowsSmem<1>), st>>>(a1);
-    k_iir_rows<2, VARIANT><<<dim3(n2, ncand), 32, sizeof(IirRowsSmem<2>), side>>>(a2);
-}
+struct IirBuffers {
+    float *src_hplanes;      // [2][pyramid]: rows pass of a and a*a, cached per source
+    float *cand_hplanes;     // [candidate][3][pyramid]: rows pass of b, b*b, a*b
+    long long pyr_stride;    // floats per pyramid (capacity)
+};
 
-// Rows and columns passes of one scoring call.  overlap = true issues them channel by channel so that
-// the columns pass of channel c (stream `cols`) runs next to the rows pass of channel c+1 (streams
-// `st` / `side`): both passes leave issue slots and HBM bandwidth unused on their own.
-inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float *src, const float *dist,
-                                   long long pyr_stride, float *hplanes, long long hplanes_stride,
-                                   double *partials, long long partials_stride, const int *first_cta_cols,
-                                   const int *col_blocks, int n, cudaStream_t st, const IirStreams &ss,
-                                   cudaEvent_t between, int *launches, bool overlap = true, int variant = 0,
-                                   bool rows_only = false)
+inline void iir_fill_common(IirArgs &a, const Geom &g, const IirCoef &k, const float *src, const float *dist,
+                            long long dist_stride, const IirBuffers &B)
 {
-    IirArgs a{};
     a.g = g;
     a.k = k;
     a.src = src;
     a.dist = dist;
-    a.dist_stride = pyr_stride;
-    a.hplanes = hplanes;
-    a.hplanes_stride = hplanes_stride;
-    a.q_stride = pyr_stride;
+    a.dist_stride = dist_stride;
+    const long long P = B.pyr_stride;
+    a.hq[0] = B.src_hplanes;               a.hq_cand_stride[0] = 0;          // a
+    a.hq[2] = B.src_hplanes + P;           a.hq_cand_stride[2] = 0;          // a*a
+    a.hq[1] = B.cand_hplanes;              a.hq_cand_stride[1] = 3 * P;      // b
+    a.hq[3] = B.cand_hplanes + P;          a.hq_cand_stride[3] = 3 * P;      // b*b
+    a.hq[4] = B.cand_hplanes + 2 * P;      a.hq_cand_stride[4] = 3 * P;      // a*b
+}
+
+inline int iir_rows_grid(IirArgs &a, const Geom &g, int per_rowblock)
+{
+    int n = 0;
+    for (int s = 0; s < g.n_scales; ++s) {
+        const int nrb = (g.h[s] + kIirRows - 1) / kIirRows;
+        a.blocks[s] = per_rowblock * nrb;
+        a.first_cta[s] = n;
+        n += 3 * per_rowblock * nrb;
+    }
+    for (int s = g.n_scales; s <= kMaxScales; ++s) a.first_cta[s] = n;
+    return n;
+}
+
+template <int NPLANES>
+inline void launch_rows_kernel(const IirArgs &a, int n_cta, int ncand, cudaStream_t st, int variant)
+{
+    const dim3 grid(n_cta, ncand);
+    const size_t sm = sizeof(IirRowsSmem<NPLANES>);
+    switch (variant) {
+    case 0: k_iir_rows<NPLANES, 0><<<grid, 32, sm, st>>>(a); break;
+    case 1: k_iir_rows<NPLANES, 1><<<grid, 32, sm, st>>>(a); break;
+    case 2: k_iir_rows<NPLANES, 2><<<grid, 32, sm, st>>>(a); break;
+    default: k_iir_rows<NPLANES, 3><<<grid, 32, sm, st>>>(a); break;
+    }
+}
+
+// Source side, once per set_source: rows pass of a and a*a into the per-source cache.  Runs on the side
+// stream behind the source pyramid, so it overlaps the candidate's upload and pyramid.
+inline cudaError_t launch_iir_source_rows(const Geom &g, const IirCoef &k, const float *src_pyr, const IirBuffers &B,
+                                          cudaStream_t st, const IirStreams &ss, int *launches)
+{
+    IirArgs a{};
+    iir_fill_common(a, g, k, src_pyr, src_pyr, 0, B);
+    a.nq = 2;
+    a.qlist[0] = 0;
+    a.qlist[1] = 2;
+    const int n = iir_rows_grid(a, g, 2);
+    cudaEventRecord(ss.fork, st);                 // after the source pyramid
+    cudaStreamWaitEvent(ss.side, ss.fork, 0);
+    launch_rows_kernel<1>(a, n, 1, ss.side, 0);
+    const cudaError_t e = cudaGetLastError();
+    cudaEventRecord(ss.src_done, ss.side);
+    *launches = 1;
+    return e;
+}
+
+// Candidate side: rows pass of b, b*b (main stream) and a*b (side stream), then the columns pass with
+// the maps and the pooling.  `between` is recorded between the two passes.
+inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float *src, const float *dist,
+                                   long long pyr_stride, const IirBuffers &B, double *partials,
+                                   long long partials_stride, const int *first_cta_cols, const int *col_blocks, int n,
+                                   cudaStream_t st, const IirStreams &ss, cudaEvent_t between, int *launches,
+                                   int variant = 0, bool rows_only = false)
+{
+    IirArgs a{};
+    iir_fill_common(a, g, k, src, dist, pyr_stride, B);
     a.partials = partials;
     a.partials_stride = partials_stride;
-    for (int s = 0; s < kMaxScales; ++s) a.part_first[s] = first_cta_cols[s];
-    const int nch = (overlap && !rows_only) ? 1 : 3;   // channels per launch
-    *launches = 0;
-    cudaEventRecord(ss.fork, st);
-    cudaStreamWaitEvent(ss.side, ss.fork, 0);
-    if (nch == 1) cudaStreamWaitEvent(ss.cols, ss.fork, 0);
-    for (int ch0 = 0; ch0 < 3; ch0 += nch) {
-        IirArgs a1 = a, a2 = a, ac = a;   // single-plane quantities | a*b | columns
-        int n1 = 0, n2 = 0, nc = 0;
-        for (int s = 0; s < g.n_scales; ++s) {
-            const int nrb = (g.h[s] + kIirRows - 1) / kIirRows;
-            a1.blocks[s] = 4 * nrb;
-            a1.first_cta[s] = n1;
-            n1 += nch * 4 * nrb;
-            a2.blocks[s] = nrb;
-            a2.first_cta[s] = n2;
-            n2 += nch * nrb;
-            ac.blocks[s] = col_blocks[s];
-            ac.first_cta[s] = nc;
-            nc += nch * col_blocks[s];
-        }
-        for (int s = g.n_scales; s <= kMaxScales; ++s) {
-            a1.first_cta[s] = n1;
-            a2.first_cta[s] = n2;
-            ac.first_cta[s] = nc;
-        }
-        a1.ch0 = a2.ch0 = ac.ch0 = ch0;
-        a1.n_ch = a2.n_ch = ac.n_ch = nch;
-        switch (variant) {
-        case 0: launch_rows_variant<0>(a1, n1, a2, n2, n, st, ss.side); break;
-        case 1: launch_rows_variant<1>(a1, n1, a2, n2, n, st, ss.side); break;
-        case 2: launch_rows_variant<2>(a1, n1, a2, n2, n, st, ss.side); break;
-        default: launch_rows_variant<3>(a1, n1, a2, n2, n, st, ss.side); break;
-        }
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        *launches += 2;
-        const int ci = ch0 < 3 ? ch0 : 2;
-        cudaEventRecord(ss.rows_b[ci], ss.side);
-        if (rows_only) {
-            cudaStreamWaitEvent(st, ss.rows_b[ci], 0);
-            continue;
-        }
-        cudaStream_t cst = nch == 1 ? ss.cols : st;
-        if (nch == 1) {
-            cudaEventRecord(ss.rows_a[ci], st);
-            cudaStreamWaitEvent(cst, ss.rows_a[ci], 0);
-        }
-        cudaStreamWaitEvent(cst, ss.rows_b[ci], 0);
-        if (nch == 3 && between) cudaEventRecord(between, st);
-        // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
-        const int scale0_tasks = 3 * col_blocks[0] * n;
-        if (scale0_tasks <= 148 * 3)
-            k_iir_cols<64><<<dim3(nc, n), kIirVThreads, sizeof(IirColsSmem<64>), cst>>>(ac);
-        else
-            k_iir_cols<32><<<dim3(nc, n), kIirVThreads, sizeof(IirColsSmem<32>), cst>>>(ac);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        *launches += 1;
-    }
+    IirArgs a1 = a, a2 = a;   // {b, b*b} | a*b
+    a1.nq = 2;
+    a1.qlist[0] = 1;
+    a1.qlist[1] = 3;
+    const int n1 = iir_rows_grid(a1, g, 2), n2 = iir_rows_grid(a2, g, 1);
+    cudaEventRecord(ss.fork, st);                 // after the candidate pyramid
+    cudaStreamWaitEvent(ss.side, ss.fork, 0);     // (the side stream already holds the source rows)
+    launch_rows_kernel<1>(a1, n1, n, st, variant);
+    launch_rows_kernel<2>(a2, n2, n, ss.side, variant);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    cudaEventRecord(ss.join, ss.side);
+    cudaStreamWaitEvent(st, ss.join, 0);          // a*b done, and with it the source rows queued before it
+    if (between) cudaEventRecord(between, st);
+    *launches = 2;
     if (rows_only) return cudaSuccess;
-    if (nch == 1) {
-        if (between) cudaEventRecord(between, st);  // end of the last rows launch on the main stream
-        cudaEventRecord(ss.join, ss.cols);
-        cudaStreamWaitEvent(st, ss.join, 0);
-    }
-    return cudaSuccess;
+    for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
+    for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
+    // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
+    const int scale0_tasks = 3 * col_blocks[0] * n;
+    if (scale0_tasks <= 148 * 3)
+        k_iir_cols<64><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<64>), st>>>(a);
+    else
+        k_iir_cols<32><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<32>), st>>>(a);
+    *launches = 3;
+    return cudaGetLastError();
 }
 
 inline cudaError_t launch_debug_blur(bool fir, const float *taps, const IirCoef &k, const float *d_in, float *d_tmp,

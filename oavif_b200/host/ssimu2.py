@@ -23,7 +23,7 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "liboavif_ssimu2.so
 
 MAX_SCALES = 6
 BLUR_RECURSIVE, BLUR_FIR = 0, 1
-OPT_BLUR, OPT_OVERLAP = 1, 2
+OPT_BLUR = 1
 
 E_ARG, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 _ENAMES = {E_ARG: "InvalidArgument", E_CUDA: "CudaError", E_NOMEM: "OutOfMemory",
@@ -168,9 +168,6 @@ class Scorer:
 
     def set_blur(self, mode: int):
         _check(self._L.oavif_ssimu2_set_option(self._ctx, OPT_BLUR, mode), self._ctx)
-
-    def set_overlap(self, on: bool):
-        _check(self._L.oavif_ssimu2_set_option(self._ctx, OPT_OVERLAP, int(on)), self._ctx)
 
     def set_stream(self, cuda_stream: int | None):
         _check(self._L.oavif_ssimu2_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)), self._ctx)

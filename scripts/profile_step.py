@@ -19,15 +19,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blur", default="recursive")
     ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--serial", action="store_true", help="serialise the rows / columns passes")
     a = ap.parse_args()
     import torch
     pairs = bench.make_pairs(0, 2)
     dev = [(torch.from_numpy(s).cuda(), tuple(torch.from_numpy(p.view(np.int16)).cuda() for p in yuv)) for s, yuv in pairs]
     torch.cuda.synchronize()
     with ssimu2.Scorer(bench.W, bench.H, 1, blur=ssimu2.BLUR_FIR if a.blur == "fir" else ssimu2.BLUR_RECURSIVE) as sc:
-        if a.serial:
-            sc.set_overlap(False)
         for i in range(a.steps):
             s, (y, u, v) = dev[i % 2]
             sc.set_source_dev(s.data_ptr(), bench.W, bench.H, 3 * bench.W)

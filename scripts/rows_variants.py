@@ -10,7 +10,7 @@ import torch
 with ssimu2.Scorer(bench.W, bench.H, 1) as sc:
     sc.set_source(src)
     sc.score_yuv444(*yuv, 10)
-    names = {0: "product", 1: "no stores", 2: "no loads", 3: "no stores, no loads"}
+    names = {0: "product", 1: "no stores", 2: "no loads", 3: "no stores, no loads", 4: "candidate half only"}
     for v, nm in names.items():
         sc.time_rows(v, 3)
         print(f"variant {v} ({nm}): {sc.time_rows(v, 20):.4f} ms")

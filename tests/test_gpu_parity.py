@@ -228,18 +228,26 @@ def test_batch_equals_single_and_is_deterministic(scorer, mode, omode, name):
     assert all(a > b for a, b in zip(batch, batch[1:]))
 
 
-def test_overlapped_and_serialised_passes_give_identical_bits(scorer):
-    src = synth.synth(777, 555, "mixture", 6)
-    cands = [synth.distort(src, s, seed=i) for i, s in enumerate((0.2, 0.7))]
+def test_source_rows_cache_follows_the_source_and_the_blur_mode(scorer, oracle):
+    """The rows pass of the source-only quantities is cached per source: it must be rebuilt for a new
+    source, built late when the source was set under the other blur, and shared by a batch."""
+    a = synth.synth(300, 200, "mixture", 1)
+    b = synth.synth(300, 200, "noise", 2)
+    da, db = synth.distort(a, 0.3), synth.distort(b, 0.3)
     scorer.set_blur(ssimu2.BLUR_RECURSIVE)
-    scorer.set_source(src)
-    scorer.set_overlap(True)
-    a = scorer.score_batch_rgb8(cands)
-    sa = scorer.sums(1).copy()
-    scorer.set_overlap(False)
-    b = scorer.score_batch_rgb8(cands)
-    assert a == b and (scorer.sums(1) == sa).all()
-    scorer.set_overlap(True)
+    scorer.set_source(a)
+    s_a = scorer.score_rgb8(da)
+    scorer.set_source(b)                       # new source right away: cache must not go stale
+    s_b = scorer.score_rgb8(db)
+    scorer.set_source(a)
+    scorer.set_source(b)                       # two set_source calls back to back, no score between
+    assert scorer.score_rgb8(db) == s_b
+    scorer.set_blur(ssimu2.BLUR_FIR)
+    scorer.set_source(a)                       # set under FIR ...
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    assert scorer.score_rgb8(da) == s_a        # ... scored under RECURSIVE: cache built on demand
+    assert scorer.score_batch_rgb8([da, a, da]) == [s_a, 100.0, s_a]
+    assert abs(s_a - oracle.ssimu2_rgb8(a, da)) <= SCORE_TOL and abs(s_b - oracle.ssimu2_rgb8(b, db)) <= SCORE_TOL
 
 
 def test_modes_differ_only_by_recursion_roundoff(scorer):
