@@ -106,12 +106,15 @@ def cfg4():
 def cfg5():
     import torch
     n_gpu = torch.cuda.device_count()
-    count = 48 if not QUICK else 8
+    count = (96 * n_gpu) if not QUICK else 8
     res = {"n_gpus_visible": n_gpu, "images": count, "size": [1920, 1080]}
     o = H.default_opts(tenbit=0, speed=9, max_pass=6)
     cores = os.cpu_count() or 1
+    H.corpus_synth(2, 256, 192, n_gpus=n_gpu, workers_per_gpu=1, opts=o)      # CUDA / libavif warm-up, untimed
+    # every GPU brings the same share of host cores for its libaom encodes: cores / visible GPUs each
+    wpg = max(1, cores // max(n_gpu, 1))
+    res["host_cores_per_gpu"] = wpg
     for g in sorted({1, n_gpu}):
-        wpg = max(1, cores // g)
         csvp = os.path.join(ROOT, "gpurun_out", f"corpus_{g}gpu.csv")
         r = H.corpus_synth(count, 1920, 1080, n_gpus=g, workers_per_gpu=wpg, opts=o, csv_path=csvp)
         res[f"{g}gpu"] = {"workers_per_gpu": wpg, "ok": r["ok"], "wall_s": r["wall_s"], "images_per_s": r["ok"] / r["wall_s"],
