@@ -110,10 +110,21 @@ void oavif_ssimu2_pinned_free(void *p);
 int oavif_ssimu2_set_source_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w,
                                  uint32_t h, size_t stride);
 
+/* The loaders' native layouts straight in: 1..4 interleaved channels of 8- or 16-bit samples (native
+ * endian), reduced to RGB8 on the device exactly like Image.toRGB8 (src/io.zig:57-133: 16-bit >> 8,
+ * alpha dropped, gray replicated).  channels outside 1..4 -> E_UNSUPPORTED (UnsupportedChannelCount). */
+int oavif_ssimu2_set_source_pixels(oavif_ssimu2_ctx *ctx, const void *pixels, uint32_t w, uint32_t h,
+                                   size_t stride, int channels, int bits);
+
 /* ---- distorted side: once per search pass (tq.zig:150) ------------------------------------- */
 
 int oavif_ssimu2_score_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *dist, size_t stride,
                             double *score);
+
+/* A decoded frame in the layout avifImageYUVToRGB leaves behind (RGB or RGBA, io.zig:473): the
+ * per-pixel repack of decodeAvifToRgb (io.zig:654-663) happens on the device. */
+int oavif_ssimu2_score_pixels(oavif_ssimu2_ctx *ctx, const void *pixels, size_t stride, int channels,
+                              int bits, double *score);
 
 /* Decoded planes as libavif hands them over: depth 8 -> uint8_t samples, depth 10 -> uint16_t;
  * strides in BYTES; full range; matrix = AV1 matrix_coefficients (1, 2, 5, 6, 9).
@@ -169,6 +180,11 @@ int oavif_ssimu2_debug_get_xyb(oavif_ssimu2_ctx *ctx, int which, int scale, int 
 /* Blur one host plane with the selected blur on the device (tests of the filter alone). */
 int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, uint32_t h,
                             float *out);
+
+/* Every large device buffer of a context is followed by a 4 KB guard band; returns 0 if all bands are
+ * intact, E_STATE (with the band index in last_error) if a kernel wrote past a buffer.  Stands in for
+ * compute-sanitizer, which the target pool does not allow. */
+int oavif_ssimu2_debug_check_guards(oavif_ssimu2_ctx *ctx);
 
 /* Profiling aid: re-run only the RECURSIVE rows pass on the pyramids of the last score call,
  * `iters` times, and report its mean device time.  variant 0 is the product kernel; bit 0 drops

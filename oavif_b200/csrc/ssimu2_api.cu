@@ -20,6 +20,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "ssimu2_common.cuh"
 #include "ssimu2_finalize.cuh"
@@ -68,9 +69,28 @@ struct oavif_ssimu2_ctx {
     float taps[9] = {};
     IirCoef iir{};
     std::string err;
+    // every large device buffer is followed by a 4 KB guard band filled with kGuardByte
+    // (compute-sanitizer is not available on the target pool: oavif_ssimu2_debug_check_guards)
+    std::vector<std::pair<unsigned char *, size_t>> guards;  // (start of guard, bytes)
 };
 
 namespace {
+
+constexpr size_t kGuardBytes = 4096;
+constexpr int kGuardByte = 0xA5;
+
+template <class T>
+cudaError_t alloc_guarded(oavif_ssimu2_ctx *ctx, T **out, size_t bytes)
+{
+    const size_t body = (bytes + 255) & ~(size_t)255;
+    unsigned char *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, body + kGuardBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(p + body, kGuardByte, kGuardBytes);
+    ctx->guards.emplace_back(p + body, kGuardBytes);
+    *out = reinterpret_cast<T *>(p);
+    return e;
+}
 
 int fail(oavif_ssimu2_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -262,7 +282,8 @@ void launch_pyramid(int kind, const PyrArgs &a, int n, cudaStream_t st)
     case IN_RGB8: launch_pyr_kind<IN_RGB8>(a, grid, st); break;
     case IN_YUV8: launch_pyr_kind<IN_YUV8>(a, grid, st); break;
     case IN_YUV10_RGB: launch_pyr_kind<IN_YUV10_RGB>(a, grid, st); break;
-    default: launch_pyr_kind<IN_YUV10_RGBA>(a, grid, st); break;
+    case IN_YUV10_RGBA: launch_pyr_kind<IN_YUV10_RGBA>(a, grid, st); break;
+    default: launch_pyr_kind<IN_PIXELS>(a, grid, st); break;
     }
 }
 
@@ -271,11 +292,20 @@ struct InputDesc {
     size_t stride[3];    // caller strides, bytes
     int matrix;
     bool on_device;      // caller pointers are device pointers
+    int channels = 3, hbd = 0;  // IN_PIXELS
 };
 
 // Bytes per row actually holding pixels, per plane.
-size_t row_bytes(int kind, int w) { return kind == IN_RGB8 ? 3u * w : (kind == IN_YUV8 ? (size_t)w : 2u * w); }
-int nplanes(int kind) { return kind == IN_RGB8 ? 1 : 3; }
+size_t row_bytes(const InputDesc &d, int w)
+{
+    switch (d.kind) {
+    case IN_RGB8: return 3u * (size_t)w;
+    case IN_YUV8: return (size_t)w;
+    case IN_PIXELS: return (size_t)w * d.channels * (d.hbd ? 2 : 1);
+    default: return 2u * (size_t)w;
+    }
+}
+int nplanes(int kind) { return (kind == IN_RGB8 || kind == IN_PIXELS) ? 1 : 3; }
 
 // Stage (if host) `n` images and build their pyramids into `out`.  `slot0` selects the staging
 // buffer: the source uses in_src, candidates use in_dist.
@@ -289,10 +319,12 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const 
     a.out = out;
     a.out_stride = out_stride;
     a.lut = ctx->d_lut;
-    if (d.kind != IN_RGB8 && !yuv_consts(d.matrix, &a.k))
+    if (d.kind != IN_RGB8 && d.kind != IN_PIXELS && !yuv_consts(d.matrix, &a.k))
         return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "matrix_coefficients %d not on the scored path", d.matrix);
-    const size_t rb = row_bytes(d.kind, w);
+    const size_t rb = row_bytes(d, w);
     const int np = nplanes(d.kind);
+    a.channels = d.channels;
+    a.hbd = d.hbd;
     const int tbl0 = is_source ? 0 : 3;  // table rows: [0..2] source, [3..] candidates
     if (d.on_device) {
         for (uint32_t i = 0; i < n; ++i)
@@ -331,7 +363,7 @@ int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
     // kernels address a plane with 32-bit element offsets
     if ((long long)rup(cdiv((int)w, kPyrTile) * kPyrTile, 32) * (cdiv((int)h, kPyrTile) * kPyrTile) >= (1LL << 31))
         return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "image %ux%u: a plane exceeds 2^31 samples", w, h);
-    if (pyr_capacity((int)w, (int)h) > ctx->cap_pyr_floats || (long long)w * h * 6 + 3 * 256 > ctx->cap_in_bytes)
+    if (pyr_capacity((int)w, (int)h) > ctx->cap_pyr_floats || (long long)w * h * 8 + 3 * 256 > ctx->cap_in_bytes)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "image %ux%u exceeds context capacity %ux%u", w, h, ctx->max_w,
                     ctx->max_h);
     return 0;
@@ -423,7 +455,7 @@ int score_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const Ho
         for (int p = 0; p < np; ++p)
             if (!imgs[i].p[p]) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null plane pointer (candidate %u)", i);
     for (int p = 0; p < np; ++p)
-        if (d.stride[p] < row_bytes(d.kind, w)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "stride smaller than a row");
+        if (d.stride[p] < row_bytes(d, w)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "stride smaller than a row");
     (void)h;
     CK(cudaSetDevice(ctx->device));
     ctx->timing = oavif_ssimu2_timing{};
@@ -441,14 +473,16 @@ int score_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const Ho
     return run_blur_and_finalize(ctx, n, scores);
 }
 
-int set_source_common(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, size_t stride,
-                      bool on_device)
+int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32_t h, size_t stride,
+                      bool on_device, int channels = 3, int bits = 8)
 {
     if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
     if (!rgb) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null source pointer");
+    if (channels < 1 || channels > 4 || (bits != 8 && bits != 16))
+        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "UnsupportedChannelCount: %d channels, %d bits", channels, bits);
     int rc = check_size(ctx, w, h);
     if (rc) return rc;
-    if (stride < (size_t)3 * w) return fail(ctx, OAVIF_SSIMU2_E_ARG, "source stride smaller than a row");
+    if (stride < (size_t)w * channels * (bits / 8)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "source stride smaller than a row");
     CK(cudaSetDevice(ctx->device));
     ctx->have_source = false;
     make_geom((int)w, (int)h, &ctx->g);
@@ -459,7 +493,9 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w, uin
         return 0;
     }
     InputDesc d{};
-    d.kind = IN_RGB8;
+    d.kind = (channels == 3 && bits == 8) ? IN_RGB8 : IN_PIXELS;
+    d.channels = channels;
+    d.hbd = bits == 16;
     d.stride[0] = stride;
     d.on_device = on_device;
     HostPlanes hp{{rgb, nullptr, nullptr}};
@@ -587,20 +623,20 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
 
     const int mw = (int)max_w, mh = (int)max_h;
     ctx->cap_pyr_floats = std::max(pyr_capacity(mw, mh), pyr_capacity(mh, mw));
-    ctx->cap_in_bytes = (long long)mw * mh * 6 + 3 * 256;
+    ctx->cap_in_bytes = (long long)mw * mh * 8 + 3 * 256;   // up to RGBA16 (8 B/px)
     ctx->cap_ctas = cta_capacity(mw, mh);
     ctx->cap_hplane_floats = iir_hplane_floats(ctx->cap_pyr_floats);
 
-    CKC(cudaMalloc(&ctx->d_in_src, (size_t)ctx->cap_in_bytes));
-    CKC(cudaMalloc(&ctx->d_in_dist, (size_t)ctx->cap_in_bytes * max_batch));
-    CKC(cudaMalloc(&ctx->d_src_pyr, sizeof(float) * ctx->cap_pyr_floats));
-    CKC(cudaMalloc(&ctx->d_dist_pyr, sizeof(float) * ctx->cap_pyr_floats * max_batch));
-    CKC(cudaMalloc(&ctx->d_hplanes, sizeof(float) * ctx->cap_hplane_floats * max_batch));
-    CKC(cudaMalloc(&ctx->d_src_hplanes, sizeof(float) * 2 * ctx->cap_pyr_floats));
+    CKC(alloc_guarded(ctx, &ctx->d_in_src, (size_t)ctx->cap_in_bytes));
+    CKC(alloc_guarded(ctx, &ctx->d_in_dist, (size_t)ctx->cap_in_bytes * max_batch));
+    CKC(alloc_guarded(ctx, &ctx->d_src_pyr, sizeof(float) * ctx->cap_pyr_floats));
+    CKC(alloc_guarded(ctx, &ctx->d_dist_pyr, sizeof(float) * ctx->cap_pyr_floats * max_batch));
+    CKC(alloc_guarded(ctx, &ctx->d_hplanes, sizeof(float) * ctx->cap_hplane_floats * max_batch));
+    CKC(alloc_guarded(ctx, &ctx->d_src_hplanes, sizeof(float) * 2 * ctx->cap_pyr_floats));
     CKC(cudaMalloc(&ctx->d_lut, sizeof(float) * 256));
     CKC(cudaMalloc((void **)&ctx->d_tbl, sizeof(void *) * 3 * (max_batch + 1)));
     CKC(cudaHostAlloc((void **)&ctx->h_tbl, sizeof(void *) * 3 * (max_batch + 1), cudaHostAllocDefault));
-    CKC(cudaMalloc(&ctx->d_partials, sizeof(double) * 6 * ctx->cap_ctas * max_batch));
+    CKC(alloc_guarded(ctx, &ctx->d_partials, sizeof(double) * 6 * ctx->cap_ctas * max_batch));
     CKC(cudaMalloc(&ctx->d_sums, sizeof(double) * kMaxScales * 18 * max_batch));
     CKC(cudaMalloc(&ctx->d_scores, sizeof(double) * max_batch));
     CKC(cudaHostAlloc((void **)&ctx->h_sums, sizeof(double) * kMaxScales * 18 * max_batch, cudaHostAllocDefault));
@@ -649,6 +685,26 @@ int oavif_ssimu2_set_source_rgb8_dev(oavif_ssimu2_ctx *ctx, const uint8_t *d_rgb
                                      size_t stride)
 {
     return set_source_common(ctx, d_rgb, w, h, stride, true);
+}
+
+int oavif_ssimu2_set_source_pixels(oavif_ssimu2_ctx *ctx, const void *pixels, uint32_t w, uint32_t h, size_t stride,
+                                   int channels, int bits)
+{
+    return set_source_common(ctx, pixels, w, h, stride, false, channels, bits);
+}
+
+int oavif_ssimu2_score_pixels(oavif_ssimu2_ctx *ctx, const void *pixels, size_t stride, int channels, int bits,
+                              double *score)
+{
+    if (channels < 1 || channels > 4 || (bits != 8 && bits != 16))
+        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "UnsupportedChannelCount: %d channels, %d bits", channels, bits);
+    InputDesc d{};
+    d.kind = (channels == 3 && bits == 8) ? IN_RGB8 : IN_PIXELS;
+    d.channels = channels;
+    d.hbd = bits == 16;
+    d.stride[0] = stride;
+    HostPlanes hp{{pixels, nullptr, nullptr}};
+    return score_common(ctx, d, 1, &hp, score);
 }
 
 int oavif_ssimu2_score_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *dist, size_t stride, double *score)
@@ -746,7 +802,7 @@ int oavif_ssimu2_compute_rgb8(const uint8_t *ref, const uint8_t *dist, uint32_t 
     if (w == 0 || h == 0) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "zero image dimension");
     std::lock_guard<std::mutex> lock(mu);
     if (cached && (pyr_capacity((int)w, (int)h) > cached->cap_pyr_floats ||
-                   (long long)w * h * 6 + 768 > cached->cap_in_bytes)) {
+                   (long long)w * h * 8 + 768 > cached->cap_in_bytes)) {
         oavif_ssimu2_ctx_destroy(cached);
         cached = nullptr;
     }
@@ -771,9 +827,11 @@ int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void
     Yuv2RgbArgs a{};
     if (!yuv_consts(matrix, &a.k))
         return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "matrix_coefficients %d not on the scored path", matrix);
-    if (w == 0 || h == 0 || (long long)w * h * 6 + 768 > ctx->cap_in_bytes)
+    if (w == 0 || h == 0 || (long long)w * h * 8 + 768 > ctx->cap_in_bytes)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "image %ux%u exceeds context capacity", w, h);
-    const size_t rb = row_bytes(kind, (int)w);
+    InputDesc dd{};
+    dd.kind = kind;
+    const size_t rb = row_bytes(dd, (int)w);
     if (ys < rb || us < rb || vs < rb) return fail(ctx, OAVIF_SSIMU2_E_ARG, "stride smaller than a row");
     CK(cudaSetDevice(ctx->device));
     const size_t plane_bytes = (rb * h + 255) & ~(size_t)255;
@@ -863,6 +921,23 @@ int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, 
     CK(cudaMemcpy2DAsync(out, sizeof(float) * w, d_out, sizeof(float) * pitch, sizeof(float) * w, h,
                          cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int oavif_ssimu2_debug_check_guards(oavif_ssimu2_ctx *ctx)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned char> host(kGuardBytes);
+    int idx = 0;
+    for (const auto &g : ctx->guards) {
+        CK(cudaMemcpy(host.data(), g.first, g.second, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < g.second; ++i)
+            if (host[i] != kGuardByte)
+                return fail(ctx, OAVIF_SSIMU2_E_STATE, "guard band %d overwritten at byte %zu", idx, i);
+        ++idx;
+    }
     return 0;
 }
 

@@ -21,6 +21,7 @@ struct PyrArgs {
     long long out_stride;       // floats between consecutive images' pyramids
     const float *lut;           // 256-entry sRGB->linear table
     YuvK k;
+    int channels, hbd;          // IN_PIXELS only: 1..4 interleaved channels, 16-bit samples if hbd
 };
 
 // Load pixels x0..x0+3 of row y (coordinates clamped to the image) as 8-bit RGB.
@@ -47,6 +48,24 @@ __device__ __forceinline__ void load4_rgb8(const PyrArgs &a, const void *p0, con
                 rgb[i][0] = __ldg(row + 3 * x);
                 rgb[i][1] = __ldg(row + 3 * x + 1);
                 rgb[i][2] = __ldg(row + 3 * x + 2);
+            }
+        }
+    } else if (KIND == IN_PIXELS) {
+        const uint8_t *row = (const uint8_t *)p0 + (long long)y * a.stride[0];
+        const int ch = a.channels, gstep = ch >= 3 ? 1 : 0, bstep = ch >= 3 ? 2 : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = min(x0 + i, w - 1);
+            if (a.hbd) {
+                const uint16_t *px = (const uint16_t *)row + (long long)x * ch;
+                rgb[i][0] = __ldg(px) >> 8;
+                rgb[i][1] = __ldg(px + gstep) >> 8;
+                rgb[i][2] = __ldg(px + bstep) >> 8;
+            } else {
+                const uint8_t *px = row + (long long)x * ch;
+                rgb[i][0] = __ldg(px);
+                rgb[i][1] = __ldg(px + gstep);
+                rgb[i][2] = __ldg(px + bstep);
             }
         }
     } else if (KIND == IN_YUV8) {

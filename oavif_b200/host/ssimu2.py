@@ -34,12 +34,13 @@ SYMBOLS = (
     "oavif_ssimu2_abi_version", "oavif_ssimu2_ctx_create", "oavif_ssimu2_ctx_destroy",
     "oavif_ssimu2_set_option", "oavif_ssimu2_set_stream", "oavif_ssimu2_last_error",
     "oavif_ssimu2_pinned_alloc", "oavif_ssimu2_pinned_free", "oavif_ssimu2_set_source_rgb8",
+    "oavif_ssimu2_set_source_pixels", "oavif_ssimu2_score_pixels",
     "oavif_ssimu2_score_rgb8", "oavif_ssimu2_score_yuv444", "oavif_ssimu2_score_batch_rgb8",
     "oavif_ssimu2_score_batch_yuv444", "oavif_ssimu2_set_source_rgb8_dev",
     "oavif_ssimu2_score_batch_rgb8_dev", "oavif_ssimu2_score_batch_yuv444_dev",
     "oavif_ssimu2_compute_rgb8", "oavif_ssimu2_yuv444_to_rgb8", "oavif_ssimu2_get_detail",
     "oavif_ssimu2_get_timing", "oavif_ssimu2_debug_get_xyb", "oavif_ssimu2_debug_blur",
-    "oavif_ssimu2_debug_time_rows",
+    "oavif_ssimu2_debug_time_rows", "oavif_ssimu2_debug_check_guards",
 )
 
 
@@ -87,6 +88,8 @@ def load() -> C.CDLL:
     L.oavif_ssimu2_set_source_rgb8.argtypes = [vp, u8p, u32, u32, szt]
     L.oavif_ssimu2_set_source_rgb8_dev.argtypes = [vp, u8p, u32, u32, szt]
     L.oavif_ssimu2_score_rgb8.argtypes = [vp, u8p, szt, dp]
+    L.oavif_ssimu2_set_source_pixels.argtypes = [vp, vp, u32, u32, szt, C.c_int, C.c_int]
+    L.oavif_ssimu2_score_pixels.argtypes = [vp, vp, szt, C.c_int, C.c_int, dp]
     L.oavif_ssimu2_score_yuv444.argtypes = [vp, vp, vp, vp, szt, szt, szt, C.c_int, C.c_int, C.c_int, dp]
     L.oavif_ssimu2_score_batch_rgb8.argtypes = [vp, u32, C.POINTER(vp), szt, dp]
     L.oavif_ssimu2_score_batch_rgb8_dev.argtypes = [vp, u32, C.POINTER(vp), szt, dp]
@@ -100,6 +103,7 @@ def load() -> C.CDLL:
     L.oavif_ssimu2_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.oavif_ssimu2_debug_get_xyb.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32), C.POINTER(u32)]
     L.oavif_ssimu2_debug_blur.argtypes = [vp, vp, u32, u32, vp]
+    L.oavif_ssimu2_debug_check_guards.argtypes = [vp]
     L.oavif_ssimu2_debug_time_rows.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _lib = L
     return L
@@ -179,6 +183,30 @@ class Scorer:
         self.h, self.w = a.shape[:2]
         _check(self._L.oavif_ssimu2_set_source_rgb8(self._ctx, a.ctypes.data, self.w, self.h, a.strides[0]),
                self._ctx)
+
+    @staticmethod
+    def _pixels(a):
+        a = np.ascontiguousarray(a)
+        if a.ndim == 2:
+            a = a[..., None]
+        if a.dtype not in (np.uint8, np.uint16) or a.ndim != 3:
+            raise Ssimu2Error(E_ARG, "expected HxW[xC] uint8/uint16 pixels")
+        return a
+
+    def set_source_pixels(self, pixels):
+        """Loader-native layouts (io.zig's Image): HxWxC, C in 1..4, uint8 or uint16 -> Image.toRGB8 on the GPU."""
+        a = self._pixels(pixels)
+        self._src_keep = a
+        self.h, self.w = a.shape[:2]
+        _check(self._L.oavif_ssimu2_set_source_pixels(self._ctx, a.ctypes.data, self.w, self.h, a.strides[0],
+                                                      a.shape[2], 8 * a.itemsize), self._ctx)
+
+    def score_pixels(self, pixels) -> float:
+        a = self._pixels(pixels)
+        out = C.c_double()
+        _check(self._L.oavif_ssimu2_score_pixels(self._ctx, a.ctypes.data, a.strides[0], a.shape[2], 8 * a.itemsize,
+                                                 C.byref(out)), self._ctx)
+        return out.value
 
     def set_source_dev(self, dptr: int, w: int, h: int, stride: int):
         self.w, self.h = w, h
@@ -296,6 +324,10 @@ class Scorer:
         _check(self._L.oavif_ssimu2_debug_get_xyb(self._ctx, which, scale, channel, buf.ctypes.data, C.byref(w),
                                                   C.byref(h)), self._ctx)
         return buf[: w.value * h.value].reshape(h.value, w.value).copy()
+
+    def check_guards(self):
+        """Raises if any kernel wrote past one of the context's device buffers."""
+        _check(self._L.oavif_ssimu2_debug_check_guards(self._ctx), self._ctx)
 
     def time_rows(self, variant: int = 0, iters: int = 10) -> float:
         ms = C.c_float()

@@ -103,6 +103,38 @@ def test_all_input_forms_build_the_same_pyramid(scorer, oracle):
                 np.testing.assert_array_equal(bits(planes[c]), bits(scorer.xyb(1, 0, c)))
 
 
+def test_loader_native_layouts_follow_toRGB8(scorer, oracle):
+    """Image.toRGB8 (io.zig:57-133) and the RGBA repack (io.zig:654-663) on the device: every channel
+    count and bit depth must score exactly like the CPU-reduced RGB8."""
+    rng = np.random.default_rng(12)
+    w, h = 150, 100
+    base = synth.synth(w, h, "mixture", 4)
+    dist = synth.distort(base, 0.3)
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    for ch in (1, 2, 3, 4):
+        for dt in (np.uint8, np.uint16):
+            px = np.empty((h, w, ch), dt)
+            hi = base.astype(np.uint16) * 257 + rng.integers(0, 200, base.shape).astype(np.uint16) if dt == np.uint16 else base
+            if ch >= 3:
+                px[..., :3] = hi
+            else:
+                px[..., 0] = hi[..., 1]
+            if ch in (2, 4):
+                px[..., -1] = rng.integers(0, np.iinfo(dt).max, (h, w))
+            want_rgb = oracle.to_rgb8(px, ch, dt == np.uint16)
+            scorer.set_source_pixels(px)
+            got = scorer.score_rgb8(dist)
+            scorer.set_source(want_rgb)
+            assert got == scorer.score_rgb8(dist), (ch, dt)
+            np.testing.assert_array_equal(bits(scorer.xyb(0, 0, 1)), bits(oracle.xyb_at_scale(want_rgb, 0)[1]))
+    scorer.set_source(base)
+    rgba = np.dstack([dist, rng.integers(0, 255, (h, w)).astype(np.uint8)])
+    assert scorer.score_pixels(rgba) == scorer.score_rgb8(dist)
+    with pytest.raises(ssimu2.Ssimu2Error) as e:
+        scorer.set_source_pixels(np.zeros((8, 8, 5), np.uint8))
+    assert e.value.code == ssimu2.E_UNSUPPORTED
+
+
 # ---- K4: the filter alone ----------------------------------------------------------------------------
 @pytest.mark.parametrize("mode,omode,name", MODES)
 @pytest.mark.parametrize("size", [(9, 9), (40, 33), (131, 97), (640, 360)])
@@ -324,6 +356,29 @@ def test_device_resident_inputs_and_external_stream(oracle):
         b = sc.score_batch_dev("rgb8", [[drgb.data_ptr()]], [3 * w])
         assert abs(b[0] - oracle.ssimu2_rgb8(src, dist)) <= SCORE_TOL
         sc.set_stream(None)
+
+
+@pytest.mark.parametrize("size", [(8, 8), (9, 65), (63, 64), (64, 65), (65, 127), (129, 31), (250, 250), (333, 511)])
+def test_no_kernel_writes_past_its_buffers(size):
+    """compute-sanitizer is closed on the target pool: contexts sized EXACTLY for the image, every
+    buffer followed by a guard band, all entry points exercised, bands verified."""
+    w, h = size
+    src = synth.synth(w, h, "noise", w + h)
+    d1, d2 = synth.distort(src, 0.2), synth.distort(src, 0.7)
+    with ssimu2.Scorer(w, h, 2) as sc:
+        for mode in (ssimu2.BLUR_RECURSIVE, ssimu2.BLUR_FIR):
+            sc.set_blur(mode)
+            sc.set_source(src)
+            sc.score_batch_rgb8([d1, d2])
+            for depth in (8, 10):
+                y, u, v = synth.rgb8_to_yuv444(d1, depth)
+                sc.score_yuv444(y, u, v, depth, 2, depth == 10)
+            sc.set_source_pixels(np.dstack([src, src[..., :1]]).astype(np.uint16) * 257)
+            sc.score_pixels(np.dstack([d2, d2[..., :1]]))
+            sc.check_guards()
+        y, u, v = synth.rgb8_to_yuv444(d1, 10)
+        sc.yuv444_to_rgb8(y, u, v, 10)
+        sc.check_guards()
 
 
 # ---- BASELINE.json full sizes: properties that do not need the oracle's minutes ----------------------------
