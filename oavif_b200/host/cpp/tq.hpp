@@ -222,11 +222,12 @@ inline std::vector<uint32_t> speculate(const TQSearch &s, const TQOptions &o, ui
     auto want = s.next();
     if (!want) return qs;
     qs.push_back(*want);
-    // hypothetical outcomes of the wanted probe: land a little/a lot above/below the target
-    const double deltas[] = {+1.5 * o.tolerance, -1.5 * o.tolerance, +4.0 * o.tolerance, -4.0 * o.tolerance,
-                             +8.0 * o.tolerance, -8.0 * o.tolerance};
-    for (double dlt : deltas) {
-        if (qs.size() >= width) break;
+    // Hypothetical outcomes of the wanted probe, nearest misses first, alternating sign: on the first
+    // pass the next q only depends on ceil(|err|) and the sign (tq.zig:155-164), so half-unit steps hit
+    // every bucket; on later passes they sample the interpolation densely enough around the target.
+    for (int i = 0; i < 80 && qs.size() < width; ++i) {
+        const double mag = o.tolerance + 0.25 + 0.5 * (i / 2);
+        const double dlt = (i & 1) ? -mag : mag;
         TQSearch h = s;
         h.record(*want, o.score_tgt + dlt);
         if (auto nq = h.next())
