@@ -314,26 +314,27 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
 // for two rows of the batch each (a producer step costs ~17 instructions, a map pixel ~70, so 5 + 4
 // warps are balanced).  Nine warps per task give a sub-partition enough independent work to hide
 // latencies when a single 4K pair is all the GPU has.  One block barrier per 8 rows.
-constexpr int kIirVBatch = 8;    // rows per exchange batch in the columns pass
 constexpr int kIirVThreads = 288;   // 5 producer warps + 4 consumer warps
 
-template <int RCAP>
+template <int RCAP, int B>
 struct IirColsSmem {
     float ring[5][RCAP][kIirVCols];            // producer input rows, row r at [r & (RCAP-1)]
     float ab[2][32][kIirVCols];                // consumer rows of the two XYB planes
-    float ex[2][5][kIirVBatch][kIirVCols];     // filtered values, double-buffered
+    float ex[2][5][B][kIirVCols];              // filtered values, double-buffered
     double red[4][6];
 };
 
-template <int RCAP>
+// B rows per exchange batch (16 with the deep ring, 8 with the shallow one): the per-batch overhead
+// (barrier, copy issue, address set-up) is paid once per B rows by each of the nine warps.
+template <int RCAP, int B>
 __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    IirColsSmem<RCAP> &sm = *reinterpret_cast<IirColsSmem<RCAP> *>(smem_raw);
-    constexpr int B = kIirVBatch;
+    IirColsSmem<RCAP, B> &sm = *reinterpret_cast<IirColsSmem<RCAP, B> *>(smem_raw);
     constexpr int D = ((RCAP - B - 10) / B) * B;   // rows of look-ahead: D + B + 10 <= RCAP, D % B == 0
     constexpr int DA = 16;                         // consumer look-ahead (ring of 32 rows)
-    static_assert(D >= B && DA % B == 0 && DA + B <= 32 && B % 4 == 0, "ring geometry");
+    constexpr int CR = B / 4;                      // rows per consumer warp and batch
+    static_assert(D >= B && DA % B == 0 && DA + B <= 32 && B % 8 == 0 && RCAP % B == 0, "ring geometry");
 
     int s, c, cb;
     decode_cta(a, blockIdx.x, s, c, cb);
@@ -381,15 +382,15 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             cp_async_commit();
             cp_async_wait<D / B>();                    // rows up to n0 + B + 3 have landed (this lane's copies)
             __syncwarp();                              // ... and every other lane's
-            // n0 is a multiple of 8 and so is RCAP: the left taps (rows n0-6+j) can only wrap at j = 6,
-            // the right taps (rows n0+4+j) only at j = 4 -> two bases each, static offsets otherwise
+            // n0 is a multiple of B (8 or 16) and so is RCAP: the left taps (rows n0-6+j) can only wrap at
+            // j = 6, the right taps (rows n0+4+j) only at j = B-4 -> two bases each, static offsets otherwise
             float sum[B];
             const float *l0 = col + ((n0 - 6) & (RCAP - 1)) * kIirVCols, *l1 = col + (n0 & (RCAP - 1)) * kIirVCols;
-            const float *r0 = col + ((n0 + 4) & (RCAP - 1)) * kIirVCols, *r1 = col + ((n0 + 8) & (RCAP - 1)) * kIirVCols;
+            const float *r0 = col + ((n0 + 4) & (RCAP - 1)) * kIirVCols, *r1 = col + ((n0 + B) & (RCAP - 1)) * kIirVCols;
 #pragma unroll
             for (int j = 0; j < B; ++j)
                 sum[j] = (j < 6 ? l0[j * kIirVCols] : l1[(j - 6) * kIirVCols]) +
-                         (j < 4 ? r0[j * kIirVCols] : r1[(j - 4) * kIirVCols]);
+                         (j < B - 4 ? r0[j * kIirVCols] : r1[(j - (B - 4)) * kIirVCols]);
             float *ex = &sm.ex[b & 1][q][0][lane];
             IirPipe P;
             pipe_begin(k, P, st, sum[0]);
@@ -401,10 +402,12 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();      // consumers' last batch
         __syncthreads();      // final reduction
     } else {
-        // ---------------- consumers: maps + pooling for rows 2*cw, 2*cw+1 of each batch ----------------
+        // ---------------- consumers: maps + pooling for CR rows of each batch ----------------
         const int cw = warp - 5;                       // 0..3
-        const int grp = cw >> 1;                       // rows 4*grp .. 4*grp+3 are staged by the even warp of a pair
-        const bool loader = (cw & 1) == 0;
+        // the XYB samples arrive in 4-row groups: with B = 16 each consumer stages its own four rows,
+        // with B = 8 the even warp of a pair stages the four rows the pair shares
+        const int grp = (CR == 4) ? cw : (cw >> 1);
+        const bool loader = (CR == 4) || ((cw & 1) == 0);
         const float *pa = a.src + poff + ccol;
         const float *pb = a.dist + (long long)cand * a.dist_stride + poff + ccol;
         double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -419,26 +422,33 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             for (int r0 = 4 * grp; r0 < DA; r0 += B) issue_ab4(r0);
         cp_async_commit();
         cp_async_wait<0>();   // the in-loop wait only covers groups committed inside the loop
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             if (loader) issue_ab4(b * B + 4 * grp + DA);
             cp_async_commit();
             cp_async_wait<DA / B>();                   // the rows of batch b staged by this warp have landed
-            __syncthreads();                           // batch b is in ex[b & 1]; the pair's samples are visible
-            const int j0 = 2 * cw, n0 = b * B + j0;    // this warp's two rows
-            float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            __syncthreads();                           // batch b is in ex[b & 1]; staged samples are visible
+            const int j0 = CR * cw, n0 = b * B + j0;   // this warp's rows
             const float *ex = &sm.ex[b & 1][0][j0][lane];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < CR; ++j) {
                 const int n = n0 + j;
                 if (col_ok && n < h)
                     error_maps(sm.ab[0][n & 31][lane], sm.ab[1][n & 31][lane], ex[(0 * B + j) * kIirVCols],
                                ex[(1 * B + j) * kIirVCols], ex[(2 * B + j) * kIirVCols],
                                ex[(3 * B + j) * kIirVCols], ex[(4 * B + j) * kIirVCols], acc);
             }
+            if ((b & 3) == 3) {   // binary32 over at most 16 pixels, binary64 from there on
 #pragma unroll
-            for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
+                for (int j = 0; j < 6; ++j) {
+                    dacc[j] += (double)acc[j];
+                    acc[j] = 0.f;
+                }
+            }
         }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
         __syncthreads();
         // fixed shuffle tree over the 32 columns, then the four consumers in fixed order
 #pragma unroll
@@ -517,8 +527,8 @@ inline long long iir_hplane_floats(long long pyr_floats) { return 3 * pyr_floats
 
 inline cudaError_t iir_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(IirColsSmem<64>));
+    cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(IirColsSmem<64, 16>));
     return e;
 }
 
@@ -629,9 +639,9 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
     const int scale0_tasks = 3 * col_blocks[0] * n;
     if (scale0_tasks <= 148 * 3)
-        k_iir_cols<64><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<64>), st>>>(a);
+        k_iir_cols<64, 16><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<64, 16>), st>>>(a);
     else
-        k_iir_cols<32><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<32>), st>>>(a);
+        k_iir_cols<32, 8><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<32, 8>), st>>>(a);
     *launches = 3;
     return cudaGetLastError();
 }
