@@ -164,8 +164,8 @@ __device__ __forceinline__ float pipe_end(const IirCoef &k, IirPipe &P, IirState
 // t+1, left taps (n-6) from tiles t-1 and t.  Tiles arrive by cp.async (16 bytes per lane) two chunks
 // ahead of use; results leave as whole 128-byte lines (streaming stores) through a staging tile that
 // reuses the slot of tile t-1, dead once the chunk's samples are in registers.
-// A quantity is x * (y*m + o) with (m, o) = (0, 1) for the plain planes and (1, 0) for the products:
-// y*0+1 and x*1 are exact, so every quantity is bit-identical to the direct expression, one code path.
+// The quantity kind (plane, square, product) is uniform per task, so the sample loads branch on it
+// without divergence.
 // VARIANT is a profiling aid (oavif_ssimu2_debug_time_rows): bit 0 drops the stores, bit 1 the tile
 // loads after the first ones.  0 is the product kernel.
 template <int NPLANES>
@@ -197,8 +197,6 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
     // plane 0 of the ring holds a for {a, a*a, a*b} and b for {b, b*b}; plane 1 (a*b only) holds b
     const float *p0 = (NPLANES == 1 && (q & 1)) ? pb : pa;
     const float *p1 = pb;
-    constexpr int yp = NPLANES - 1;  // y operand: the same plane for squares, plane 1 for a*b
-    const float ym = q < 2 ? 0.0f : 1.0f, yo = q < 2 ? 1.0f : 0.0f;
 
     // Stage tile t: lane l copies 16 bytes = columns 4*(l&7)..+3 of rows (l>>3) + 4i, i = 0..7.
     // All addresses are base + 32-bit element offsets (one IMAD.WIDE each); rows beyond the image are
@@ -228,13 +226,19 @@ __global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs
         }
         cp_async_commit();
     };
+    // four samples of the quantity at columns 4*j4..4*j4+3 of a ring slot.  KIND is warp-uniform
+    // (one warp per CTA): 0 = the plane itself, 1 = its square, 2 = the product of both planes.
+    const int kind = NPLANES == 2 ? 2 : (q < 2 ? 0 : 1);
     auto sample4 = [&](int slot, int j4, float *out) {
         const float4 xv = *reinterpret_cast<const float4 *>(&sm.tile[0][slot][lane][4 * j4]);
-        const float4 yv = *reinterpret_cast<const float4 *>(&sm.tile[yp][slot][lane][4 * j4]);
-        out[0] = xv.x * fmaf(yv.x, ym, yo);
-        out[1] = xv.y * fmaf(yv.y, ym, yo);
-        out[2] = xv.z * fmaf(yv.z, ym, yo);
-        out[3] = xv.w * fmaf(yv.w, ym, yo);
+        if (NPLANES == 2) {
+            const float4 yv = *reinterpret_cast<const float4 *>(&sm.tile[NPLANES - 1][slot][lane][4 * j4]);
+            out[0] = xv.x * yv.x; out[1] = xv.y * yv.y; out[2] = xv.z * yv.z; out[3] = xv.w * yv.w;
+        } else if (kind == 1) {
+            out[0] = xv.x * xv.x; out[1] = xv.y * xv.y; out[2] = xv.z * xv.z; out[3] = xv.w * xv.w;
+        } else {
+            out[0] = xv.x; out[1] = xv.y; out[2] = xv.z; out[3] = xv.w;
+        }
     };
 
 #pragma unroll 1
