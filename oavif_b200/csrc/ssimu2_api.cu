@@ -60,8 +60,9 @@ struct oavif_ssimu2_ctx {
     bool src_rows_valid = false;   // the cached rows pass of the source (RECURSIVE blur) matches the current source
     bool src_rows_pending = false; // ... and may still be running on the side stream
     const void **d_tbl = nullptr, **h_tbl = nullptr;
-    double *d_partials = nullptr, *d_sums = nullptr, *d_scores = nullptr;
-    double *h_sums = nullptr, *h_scores = nullptr;
+    double *d_partials = nullptr;
+    double *h_sums = nullptr, *h_scores = nullptr;      // pinned, mapped: k_finalize writes them directly
+    double *dm_sums = nullptr, *dm_scores = nullptr;    // device views of the two
     float *d_dbg = nullptr;
     long long dbg_floats = 0;
     cudaEvent_t ev[6] = {};  // start, h2d, pyramid, blur a, blur b, finalize
@@ -346,9 +347,14 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const 
                 ctx->h_tbl[tbl0 + 3 * i + 1] = ctx->h_tbl[tbl0 + 3 * i + 2] = ctx->h_tbl[tbl0 + 3 * i];
         for (int p = 0; p < 3; ++p) a.stride[p] = (long long)rb;
     }
-    CK(cudaMemcpyAsync(ctx->d_tbl + tbl0, ctx->h_tbl + tbl0, sizeof(void *) * 3 * n, cudaMemcpyHostToDevice,
-                       ctx->stream));
-    a.planes = ctx->d_tbl + tbl0;
+    if (n <= (uint32_t)kPyrInline) {  // pointers ride in the launch arguments: no table copy
+        for (uint32_t i = 0; i < 3 * n; ++i) a.inl[i] = ctx->h_tbl[tbl0 + i];
+        a.planes = nullptr;
+    } else {
+        CK(cudaMemcpyAsync(ctx->d_tbl + tbl0, ctx->h_tbl + tbl0, sizeof(void *) * 3 * n, cudaMemcpyHostToDevice,
+                           ctx->stream));
+        a.planes = ctx->d_tbl + tbl0;
+    }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     launch_pyramid(d.kind, a, (int)n, ctx->stream);
     CK(cudaGetLastError());
@@ -421,14 +427,11 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
     for (int s = 0; s <= kMaxScales; ++s) f.first_cta[s] = plan.first_cta[s];
     f.partials = ctx->d_partials;
     f.partials_stride = ctx->cap_ctas * 6;
-    f.sums = ctx->d_sums;
-    f.scores = ctx->d_scores;
+    f.sums = ctx->dm_sums;
+    f.scores = ctx->dm_scores;
     k_finalize<<<n, 1024, 0, ctx->stream>>>(f);
     CK(cudaGetLastError());
     ctx->timing.launches += 1;
-    CK(cudaMemcpyAsync(ctx->h_scores, ctx->d_scores, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, sizeof(double) * n * kMaxScales * 18, cudaMemcpyDeviceToHost,
-                       ctx->stream));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (uint32_t i = 0; i < n; ++i) scores[i] = ctx->h_scores[i];
@@ -518,12 +521,14 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
         ctx->src_rows_valid = true;
         ctx->src_rows_pending = true;
     }
-    // Return as soon as the caller's pixels (and the pointer table) have been consumed: the pyramid
-    // kernel itself keeps running behind the next call on the same stream.
-    CK(cudaEventSynchronize(ctx->ev[1]));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
-    ctx->timing.total_ms = ms;
+    // Return as soon as the caller's pixels have been consumed (host input: after the upload; device
+    // input: at once): the pyramid kernel itself keeps running behind the next call on the same stream.
+    if (!on_device) {
+        CK(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
+        ctx->timing.total_ms = ms;
+    }
     ctx->have_source = true;
     return 0;
 }
@@ -570,8 +575,6 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     cudaFree(ctx->d_lut);
     cudaFree((void *)ctx->d_tbl);
     cudaFree(ctx->d_partials);
-    cudaFree(ctx->d_sums);
-    cudaFree(ctx->d_scores);
     cudaFree(ctx->d_dbg);
     cudaFreeHost((void *)ctx->h_tbl);
     cudaFreeHost(ctx->h_sums);
@@ -637,10 +640,10 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     CKC(cudaMalloc((void **)&ctx->d_tbl, sizeof(void *) * 3 * (max_batch + 1)));
     CKC(cudaHostAlloc((void **)&ctx->h_tbl, sizeof(void *) * 3 * (max_batch + 1), cudaHostAllocDefault));
     CKC(alloc_guarded(ctx, &ctx->d_partials, sizeof(double) * 6 * ctx->cap_ctas * max_batch));
-    CKC(cudaMalloc(&ctx->d_sums, sizeof(double) * kMaxScales * 18 * max_batch));
-    CKC(cudaMalloc(&ctx->d_scores, sizeof(double) * max_batch));
-    CKC(cudaHostAlloc((void **)&ctx->h_sums, sizeof(double) * kMaxScales * 18 * max_batch, cudaHostAllocDefault));
-    CKC(cudaHostAlloc((void **)&ctx->h_scores, sizeof(double) * max_batch, cudaHostAllocDefault));
+    CKC(cudaHostAlloc((void **)&ctx->h_sums, sizeof(double) * kMaxScales * 18 * max_batch, cudaHostAllocMapped));
+    CKC(cudaHostAlloc((void **)&ctx->h_scores, sizeof(double) * max_batch, cudaHostAllocMapped));
+    CKC(cudaHostGetDevicePointer((void **)&ctx->dm_sums, ctx->h_sums, 0));
+    CKC(cudaHostGetDevicePointer((void **)&ctx->dm_scores, ctx->h_scores, 0));
 
     // sRGB -> linear table (v2.1 §1): double evaluation, one rounding to binary32
     float lut[256];

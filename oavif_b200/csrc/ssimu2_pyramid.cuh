@@ -13,9 +13,12 @@
 
 namespace oavif {
 
+constexpr int kPyrInline = 16;
+
 struct PyrArgs {
     Geom g;
-    const void *const *planes;  // device table, 3 pointers per image (RGB8 uses the first)
+    const void *const *planes;  // device table, 3 pointers per image (RGB8 uses the first) — or null:
+    const void *inl[3 * kPyrInline];  // up to kPyrInline images carry their pointers in the launch arguments
     long long stride[3];        // bytes per input row
     float *out;                 // pyramid of image 0
     long long out_stride;       // floats between consecutive images' pyramids
@@ -132,9 +135,9 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ PyrArgs
     const Geom &g = a.g;
     const int tx = tid & 15, ty = tid >> 4;
     const int bx = blockIdx.x, by = blockIdx.y, img = blockIdx.z;
-    const void *p0 = a.planes[3 * img + 0];
-    const void *p1 = a.planes[3 * img + 1];
-    const void *p2 = a.planes[3 * img + 2];
+    const void *p0 = a.planes ? a.planes[3 * img + 0] : a.inl[3 * img + 0];
+    const void *p1 = a.planes ? a.planes[3 * img + 1] : a.inl[3 * img + 1];
+    const void *p2 = a.planes ? a.planes[3 * img + 2] : a.inl[3 * img + 2];
     float *pyr = a.out + (long long)img * a.out_stride;
     const XybConst kx = xyb_consts();
 
