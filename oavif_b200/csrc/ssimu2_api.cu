@@ -588,6 +588,10 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
         cudaStreamSynchronize(ctx->iir_streams.side);
         cudaStreamDestroy(ctx->iir_streams.side);
     }
+    if (ctx->iir_streams.side2) {
+        cudaStreamSynchronize(ctx->iir_streams.side2);
+        cudaStreamDestroy(ctx->iir_streams.side2);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -620,6 +624,7 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     ctx->stream = ctx->own_stream;
     for (auto &e : ctx->ev) CKC(cudaEventCreate(&e));
     CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.side, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.side2, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->iir_streams.fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->iir_streams.join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->iir_streams.src_done, cudaEventDisableTiming));

@@ -537,9 +537,10 @@ inline cudaError_t iir_configure()
 }
 
 struct IirStreams {
-    cudaStream_t side;       // a second stream: source-side rows tasks / the a*b rows tasks
-    cudaEvent_t fork, join;  // main -> side, side -> main
-    cudaEvent_t src_done;    // the source's cached row-filtered planes are complete
+    cudaStream_t side;       // source-side rows tasks (a, a*a), behind set_source
+    cudaStream_t side2;      // the a*b rows tasks of a scoring call, next to {b, b*b} on the main stream
+    cudaEvent_t fork, join;  // main -> side / side2, side2 -> main
+    cudaEvent_t src_done;    // the source's cached row-filtered planes are complete (recorded on `side`)
 };
 
 struct IirBuffers {
@@ -628,13 +629,14 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     a1.qlist[1] = 3;
     const int n1 = iir_rows_grid(a1, g, 2), n2 = iir_rows_grid(a2, g, 1);
     cudaEventRecord(ss.fork, st);                 // after the candidate pyramid
-    cudaStreamWaitEvent(ss.side, ss.fork, 0);     // (the side stream already holds the source rows)
+    cudaStreamWaitEvent(ss.side2, ss.fork, 0);    // a*b must not queue behind the source rows: own stream
     launch_rows_kernel<1>(a1, n1, n, st, variant);
-    launch_rows_kernel<2>(a2, n2, n, ss.side, variant);
+    launch_rows_kernel<2>(a2, n2, n, ss.side2, variant);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    cudaEventRecord(ss.join, ss.side);
-    cudaStreamWaitEvent(st, ss.join, 0);          // a*b done, and with it the source rows queued before it
+    cudaEventRecord(ss.join, ss.side2);
+    cudaStreamWaitEvent(st, ss.join, 0);          // a*b done
+    cudaStreamWaitEvent(st, ss.src_done, 0);      // the source's cached rows done
     if (between) cudaEventRecord(between, st);
     *launches = 2;
     if (rows_only) return cudaSuccess;

@@ -31,9 +31,13 @@ class Detail(C.Structure):
 
 def build(force: bool = False) -> None:
     """Compile the oracle with its Makefile (gcc only; seconds)."""
-    if force or not (os.path.exists(os.path.join(_HERE, "liboracle.so"))
-                     and os.path.exists(os.path.join(_HERE, "liboracle_fast.so"))):
+    have = (os.path.exists(os.path.join(_HERE, "liboracle.so"))
+            and os.path.exists(os.path.join(_HERE, "liboracle_fast.so")))
+    try:    # make is incremental: a no-op when both libraries are newer than the sources
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    except (OSError, subprocess.CalledProcessError):
+        if force or not have:
+            raise
 
 
 _libs: dict[str, C.CDLL] = {}
