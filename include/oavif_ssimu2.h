@@ -187,9 +187,8 @@ int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, 
 int oavif_ssimu2_debug_check_guards(oavif_ssimu2_ctx *ctx);
 
 /* Profiling aid: re-run only the RECURSIVE rows pass on the pyramids of the last score call,
- * `iters` times, and report its mean device time.  variant 0 is the product kernel; bit 0 drops
- * its stores, bit 1 its tile loads (to attribute time; the row-filtered planes are then garbage), bit 2
- * leaves out the source half (a, a*a) that set_source normally runs once per image. */
+ * `iters` times, and report its mean device time.  variant 0 runs both halves; bit 2 (value 4) leaves
+ * out the source half (a, a*a) that set_source normally runs once per image; other bits are ignored. */
 int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms);
 
 #ifdef __cplusplus

@@ -413,7 +413,7 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
                                               ctx->stream, ctx->iir_streams, ctx->ev[3], &launches);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "recursive blur launch: %s", cudaGetErrorString(e));
         ctx->timing.launches += launches;
-        ctx->src_rows_pending = false;  // the join inside launch_iir_blur ordered the main stream behind them
+        ctx->src_rows_pending = false;  // launch_iir_blur ordered the main stream behind them
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
 
@@ -582,15 +582,10 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->iir_streams.fork) cudaEventDestroy(ctx->iir_streams.fork);
-    if (ctx->iir_streams.join) cudaEventDestroy(ctx->iir_streams.join);
     if (ctx->iir_streams.src_done) cudaEventDestroy(ctx->iir_streams.src_done);
     if (ctx->iir_streams.side) {
         cudaStreamSynchronize(ctx->iir_streams.side);
         cudaStreamDestroy(ctx->iir_streams.side);
-    }
-    if (ctx->iir_streams.side2) {
-        cudaStreamSynchronize(ctx->iir_streams.side2);
-        cudaStreamDestroy(ctx->iir_streams.side2);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -624,9 +619,7 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     ctx->stream = ctx->own_stream;
     for (auto &e : ctx->ev) CKC(cudaEventCreate(&e));
     CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.side, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.side2, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->iir_streams.fork, cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&ctx->iir_streams.join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->iir_streams.src_done, cudaEventDisableTiming));
 
     const int mw = (int)max_w, mh = (int)max_h;
@@ -961,13 +954,13 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
     for (int i = 0; i < iters; ++i) {
         int launches = 0;
         const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
-        if (!(variant & 4)) {  // bit 2: leave the source half out (candidate-only cost)
+        if (!(variant & 4)) {  // bit 2: leave the source half out (candidate-only cost); other bits are ignored
             int l0 = 0;
             launch_iir_source_rows(ctx->g, ctx->iir, ctx->d_src_pyr, B, ctx->stream, ctx->iir_streams, &l0);
         }
         const cudaError_t e = launch_iir_blur(ctx->g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
                                               ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, 1,
-                                              ctx->stream, ctx->iir_streams, nullptr, &launches, variant & 3, true);
+                                              ctx->stream, ctx->iir_streams, nullptr, &launches, true);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -4,14 +4,19 @@
 // from n = -N+1, because the recursion's round-off is not negligible at the metric's C2 = 9e-4
 // scale and is therefore part of the published result.
 //
-//   k_iir_rows  : rows.  One CTA = 32 rows of one channel; warp q owns quantity q of
-//                 {a, b, a^2, b^2, ab}; lane = row.  Pixels arrive as 32x32 tiles via cp.async into
-//                 a padded shared-memory ring (coalesced 128-byte row reads, conflict-free
-//                 transposed reads), results leave through a per-warp transposed staging tile.
-//   k_iir_cols  : columns + error maps + pooling.  One CTA = 32 columns; warp q owns quantity q;
-//                 lane = column, so every global access is a 128-byte row segment.  The five
-//                 filtered values of a pixel meet in shared memory every 20 rows and go straight
-//                 into the SSIM / edge-diff maps — blurred planes are never written to HBM.
+// Both passes are instruction-issue problems before they are bandwidth problems (a recursion step
+// is 12 floating-point operations on a 4-byte sample), so both run the recursion on PACKED pairs
+// (FFMA2 / FADD2 / FMUL2: two IEEE binary32 operations per issued instruction, same bits as scalar):
+//
+//   k_iir_rows  : rows.  One CTA = 32 rows of one channel; lane = row.  The pair is two QUANTITIES of
+//                 the same pixel: (a, a*a) on the source side, (b, b*b) on the candidate side, with
+//                 a*b in a second recursion warp.  A helper warp does all global memory traffic
+//                 (16-byte cp.async tile ring in, whole 128-byte lines out), so a recursion warp's
+//                 critical path is shared-memory loads, arithmetic, shared-memory stores.
+//   k_iir_cols  : columns + error maps + pooling.  One CTA = 64 columns of one channel; the pair is
+//                 two adjacent COLUMNS.  Five producer warps (one row-filtered plane each) feed four
+//                 consumer warps through shared memory; the five filtered values of a pixel go
+//                 straight into the SSIM / edge-diff maps — blurred planes are never written to HBM.
 //
 // HBM traffic per scale pixel and channel: rows pass reads 8 B, writes 20 B; columns pass reads
 // 20 B + 8 B.  No tensor cores (nothing here is a contraction).
@@ -47,19 +52,52 @@ __device__ __forceinline__ float iir_step(const IirCoef &k, IirState &s, float l
     return (o[0] + o[1]) + o[2];
 }
 
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// The same step on a packed pair of independent chains.
+struct IirCoef2 {
+    f32x2 n2[3], nd1[3];   // (n2, n2) and (-d1, -d1)
+    Unit2 u;               // +1 / -1 the compiler cannot see (see ssimu2_common.cuh)
+};
 
-// Work decomposition (v5): small independent tasks so that the hardware scheduler balances the
-// 4 x 148 sub-partitions by itself, and explicit software pipelining inside each task because a
-// sub-partition only ever hosts one or two of these warps (latency must be hidden by ILP, not TLP).
-//   rows pass   : task = (32 rows, 1 channel, 1 quantity); CTA = 1 warp; lane = row
-//   columns pass: task = (32 columns, 1 channel); CTA = 2 warps: warp 0 runs the five recursions,
-//                 warp 1 evaluates the maps one 5-row batch behind it; lane = column
+struct IirState2 {
+    f32x2 p[3], p2[3];
+};
+
+__device__ __forceinline__ IirCoef2 iir_coef2(const IirCoef &k, float one, float neg_one)
+{
+    IirCoef2 r;
+    r.u = unit2(one, neg_one);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        r.n2[i] = splat2(k.n2[i]);
+        r.nd1[i] = splat2(-k.d1[i]);
+    }
+    return r;
+}
+
+__device__ __forceinline__ f32x2 iir_step2(const IirCoef2 &k, IirState2 &s, f32x2 l, f32x2 r)
+{
+    const f32x2 sum = add2(l, r);
+    f32x2 o[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        f32x2 ok = mul2(sum, k.n2[i]);
+        ok = msub2(k.u, ok, s.p2[i]);
+        ok = fma2(k.nd1[i], s.p[i], ok);
+        s.p2[i] = s.p[i];
+        s.p[i] = ok;
+        o[i] = ok;
+    }
+    return add2(add2(o[0], o[1]), o[2]);
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+
 constexpr int kIirRows = 32;     // rows per rows-pass task
 constexpr int kIirChunk = 32;    // columns per staged tile
 constexpr int kIirPitch = 36;    // smem tile pitch in floats: 16-byte rows, conflict-free 128-bit access
-constexpr int kIirSlots = 4;     // tile ring: t-1, t, t+1 in use while t+2 lands
+constexpr int kIirSlots = 6;     // tile ring: t-1, t, t+1 in use, t+2 landed or landing, t+3, t+4 in flight
+constexpr int kIirAhead = 4;     // the helper requests tile t+4 while chunk t is computed
+constexpr int kIirPairPitch = 68;  // staging pitch of an interleaved (x, x*x) row: 64 floats + 16 bytes
 constexpr int kIirVCols = 32;    // columns per columns-pass task
 
 struct IirArgs {
@@ -72,9 +110,9 @@ struct IirArgs {
     // per-source cache (candidate stride 0) written once by set_source; b, b*b, a*b are per candidate.
     float *hq[5];
     long long hq_cand_stride[5];
-    int nq, qlist[4];           // rows pass, single-plane class: the quantities this launch computes
     double *partials;
     long long partials_stride;
+    float one, neg_one;         // 1.0f and -1.0f as run-time values (Unit2)
     int first_cta[kMaxScales + 1];  // CTA ranges per scale
     int blocks[kMaxScales];     // tasks per channel and scale
 };
@@ -95,13 +133,6 @@ __device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gmem_s
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     // bytes beyond src_bytes (0, 4, 8, 12 or 16) are zero-filled: the filter's zero padding
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
-}
-
-__device__ __forceinline__ void cp_async_4(float *smem_dst, const float *gmem_src, bool valid)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int bytes = valid ? 4 : 0;  // src-size 0 => the destination is zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes));
 }
 
 template <int N>
@@ -155,153 +186,264 @@ __device__ __forceinline__ float pipe_end(const IirCoef &k, IirPipe &P, IirState
     return (nw[0] + nw[1]) + nw[2];
 }
 
-// ------------------------------------------------------------------------------------------------
-// rows pass.  Two task classes, launched side by side on two streams because they need different
-// amounts of shared memory: NPLANES = 1 for the quantities made from one plane {a, b, a*a, b*b}
-// (grid = sum over scales of 3 * 4 * ceil(h/32)), NPLANES = 2 for a*b (3 * ceil(h/32)).  block = 32.
-//
-// Chunk t emits the 128-byte-aligned outputs n = 32t .. 32t+31: right taps (n+4) come from tiles t and
-// t+1, left taps (n-6) from tiles t-1 and t.  Tiles arrive by cp.async (16 bytes per lane) two chunks
-// ahead of use; results leave as whole 128-byte lines (streaming stores) through a staging tile that
-// reuses the slot of tile t-1, dead once the chunk's samples are in registers.
-// The quantity kind (plane, square, product) is uniform per task, so the sample loads branch on it
-// without divergence.
-// VARIANT is a profiling aid (oavif_ssimu2_debug_time_rows): bit 0 drops the stores, bit 1 the tile
-// loads after the first ones.  0 is the product kernel.
-template <int NPLANES>
-struct IirRowsSmem {
-    float tile[NPLANES][kIirSlots][kIirRows][kIirPitch];  // [plane][ring slot][row][column]
+// ... and on packed pairs
+struct IirPipe2 {
+    f32x2 p1[3], u[3];
 };
 
-template <int NPLANES, int VARIANT>
-__global__ void __launch_bounds__(32) k_iir_rows(const __grid_constant__ IirArgs a)
+__device__ __forceinline__ void pipe2_begin(const IirCoef2 &k, IirPipe2 &P, const IirState2 &st, f32x2 sum0)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        P.p1[i] = st.p[i];
+        P.u[i] = msub2(k.u, mul2(sum0, k.n2[i]), st.p2[i]);
+    }
+}
+
+__device__ __forceinline__ f32x2 pipe2_step(const IirCoef2 &k, IirPipe2 &P, f32x2 sum_next)
+{
+    f32x2 nw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) nw[i] = fma2(k.nd1[i], P.p1[i], P.u[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        P.u[i] = msub2(k.u, mul2(sum_next, k.n2[i]), P.p1[i]);
+        P.p1[i] = nw[i];
+    }
+    return add2(add2(nw[0], nw[1]), nw[2]);
+}
+
+__device__ __forceinline__ f32x2 pipe2_end(const IirCoef2 &k, IirPipe2 &P, IirState2 &st)
+{
+    f32x2 nw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        nw[i] = fma2(k.nd1[i], P.p1[i], P.u[i]);
+        st.p2[i] = P.p1[i];
+        st.p[i] = nw[i];
+    }
+    return add2(add2(nw[0], nw[1]), nw[2]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// rows pass.  MODE 0 (source side, once per set_source): the pair (a, a*a); block = 96.
+//             MODE 1 (candidate side): the pair (b, b*b) and a*b; block = 128.
+// grid = (sum over scales of 3 * ceil(h/32), n_candidates).
+//
+// Warp roles: warp 0 runs the packed recursion of the pair, warp 1 (MODE 1) the recursion of a*b, the
+// last two warps are the loader and the storer.  Chunk t emits the 128-byte-aligned outputs
+// n = 32t .. 32t+31: right taps (n+4) come from tiles t and t+1, left taps (n-6) from tiles t-1 and t.
+// While the recursion warps work on chunk t, the storer writes chunk t-1 out of the staging tiles (whole
+// 128-byte lines, streaming stores) and the loader requests tile t+4 (16-byte cp.async, zero-filled
+// beyond the image) and waits for tile t+2; one block barrier per chunk.
+template <int MODE>
+struct IirRowsSmem {
+    static constexpr int NPL = MODE == 0 ? 1 : 2;
+    float tile[NPL][kIirSlots][kIirRows][kIirPitch];   // [plane][ring slot][row][column]; plane 0 = a | b, plane 1 = a
+    float pair[2][kIirRows][kIirPairPitch];            // filtered (x, x*x), interleaved per pixel, double-buffered
+    float single[2][MODE == 0 ? 1 : kIirRows][kIirPitch];  // filtered a*b, double-buffered
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 0 ? 96 : 128) k_iir_rows(const __grid_constant__ IirArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    IirRowsSmem<NPLANES> &sm = *reinterpret_cast<IirRowsSmem<NPLANES> *>(smem_raw);
+    IirRowsSmem<MODE> &sm = *reinterpret_cast<IirRowsSmem<MODE> *>(smem_raw);
+    constexpr int NPL = IirRowsSmem<MODE>::NPL;
+    constexpr int NREC = MODE == 0 ? 1 : 2;   // recursion warps
 
-    int s, c, blk;
-    decode_cta(a, blockIdx.x, s, c, blk);
-    const int q = NPLANES == 2 ? 4 : a.qlist[blk % a.nq];
-    const int rb = NPLANES == 2 ? blk : blk / a.nq;
+    int s, c, rb;
+    decode_cta(a, blockIdx.x, s, c, rb);
     const int cand = blockIdx.y;
     const int w = a.g.w[s], h = a.g.h[s], pitch = a.g.pitch[s];
     const int y0 = rb * kIirRows;
     const int rows_here = min(kIirRows, h - y0);
     const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + (long long)y0 * pitch;
-    const float *pa = a.src + poff;
-    const float *pb = a.dist + (long long)cand * a.dist_stride + poff;
-    const int lane = threadIdx.x;
-    float *ph = a.hq[q] + (long long)cand * a.hq_cand_stride[q] + poff;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nch = (w + kIirChunk - 1) / kIirChunk;
     const IirCoef k = a.k;
-    // plane 0 of the ring holds a for {a, a*a, a*b} and b for {b, b*b}; plane 1 (a*b only) holds b
-    const float *p0 = (NPLANES == 1 && (q & 1)) ? pb : pa;
-    const float *p1 = pb;
 
-    // Stage tile t: lane l copies 16 bytes = columns 4*(l&7)..+3 of rows (l>>3) + 4i, i = 0..7.
-    // All addresses are base + 32-bit element offsets (one IMAD.WIDE each); rows beyond the image are
-    // clamped to a valid address and zero-filled through the copy's source size.
-    const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
-    const float *g0 = p0 + sub_col, *g1 = p1 + sub_col;
-    unsigned row_off[kIirRows / 4];
-    bool row_ok[kIirRows / 4];
-#pragma unroll
-    for (int i = 0; i < kIirRows / 4; ++i) {
-        const int row = sub_row + 4 * i;
-        row_ok[i] = row < rows_here;
-        row_off[i] = (unsigned)(min(row, rows_here - 1) * pitch);
-    }
-    auto issue_tile = [&](int t) {
-        const int slot = (t + kIirSlots) & (kIirSlots - 1);
-        const int gx = t * kIirChunk + sub_col;
-        int bytes = 0;
-        if (t >= 0 && gx < w) bytes = min(4, w - gx) * 4;
-        const unsigned col_off = bytes ? (unsigned)(t * kIirChunk) : 0u;
+    if (warp >= NREC) {
+        // ---------------- helpers: all global memory traffic ----------------
+        // lane l moves 16 bytes = columns 4*(l&7)..+3 of rows (l>>3) + 4i, i = 0..7.  Rows beyond the
+        // image are clamped to a valid address and zero-filled (loads) or skipped (stores).
+        const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
+        unsigned row_off[kIirRows / 4];
+        bool row_ok[kIirRows / 4];
 #pragma unroll
         for (int i = 0; i < kIirRows / 4; ++i) {
-            const int nb = row_ok[i] ? bytes : 0;
-            cp_async_16(&sm.tile[0][slot][sub_row + 4 * i][sub_col], g0 + (row_off[i] + col_off), nb);
-            if (NPLANES == 2)
-                cp_async_16(&sm.tile[NPLANES - 1][slot][sub_row + 4 * i][sub_col], g1 + (row_off[i] + col_off), nb);
+            const int row = sub_row + 4 * i;
+            row_ok[i] = row < rows_here;
+            row_off[i] = (unsigned)(min(row, rows_here - 1) * pitch) + sub_col;
         }
-        cp_async_commit();
-    };
-    // four samples of the quantity at columns 4*j4..4*j4+3 of a ring slot.  KIND is warp-uniform
-    // (one warp per CTA): 0 = the plane itself, 1 = its square, 2 = the product of both planes.
-    const int kind = NPLANES == 2 ? 2 : (q < 2 ? 0 : 1);
-    auto sample4 = [&](int slot, int j4, float *out) {
-        const float4 xv = *reinterpret_cast<const float4 *>(&sm.tile[0][slot][lane][4 * j4]);
-        if (NPLANES == 2) {
-            const float4 yv = *reinterpret_cast<const float4 *>(&sm.tile[NPLANES - 1][slot][lane][4 * j4]);
-            out[0] = xv.x * yv.x; out[1] = xv.y * yv.y; out[2] = xv.z * yv.z; out[3] = xv.w * yv.w;
-        } else if (kind == 1) {
-            out[0] = xv.x * xv.x; out[1] = xv.y * xv.y; out[2] = xv.z * xv.z; out[3] = xv.w * xv.w;
-        } else {
-            out[0] = xv.x; out[1] = xv.y; out[2] = xv.z; out[3] = xv.w;
-        }
-    };
-
+        if (warp == NREC) {
+            // loader: tile t lives in slot (t + 1) mod 6
+            const float *g0 = (MODE == 0 ? a.src : a.dist + (long long)cand * a.dist_stride) + poff;
+            const float *g1 = a.src + poff;
+            auto issue_tile = [&](int t, int slot) {
+                const int gx = t * kIirChunk + sub_col;
+                int bytes = 0;
+                if (t >= 0 && gx < w) bytes = min(4, w - gx) * 4;
+                const unsigned col_off = bytes ? (unsigned)(t * kIirChunk) : 0u;
+                const float *c0 = g0 + col_off, *c1 = g1 + col_off;
+#pragma unroll
+                for (int i = 0; i < kIirRows / 4; ++i) {
+                    const int nb = row_ok[i] ? bytes : 0;
+                    cp_async_16(&sm.tile[0][slot][sub_row + 4 * i][sub_col], c0 + row_off[i], nb);
+                    if (NPL == 2) cp_async_16(&sm.tile[NPL - 1][slot][sub_row + 4 * i][sub_col], c1 + row_off[i], nb);
+                }
+                cp_async_commit();
+            };
 #pragma unroll 1
-    for (int t = -1; t <= 1; ++t) issue_tile(t);
-    issue_tile(2);
-    cp_async_wait<1>();
-    __syncwarp();
-
-    IirState st;
+            for (int t = -1; t < kIirAhead; ++t) issue_tile(t, t + 1);
+            cp_async_wait<2>();           // tiles -1, 0, 1 have landed
+            __syncthreads();              // (P)
+            int slot = kIirAhead + 1;     // slot of tile t + 4
+#pragma unroll 1
+            for (int t = 0; t <= nch; ++t) {
+                issue_tile(t + kIirAhead, slot);   // into the slot of tile t-2: nobody reads it any more
+                slot = slot + 1 == kIirSlots ? 0 : slot + 1;
+                cp_async_wait<2>();                // tile t+2 (requested two chunks ago) has landed
+                __syncthreads();                   // (t)
+            }
+        } else {
+            // storer: chunk t-1 leaves staging buffer (t-1) & 1 while chunk t is computed
+            float *o0 = a.hq[MODE == 0 ? 0 : 1] + (long long)cand * a.hq_cand_stride[MODE == 0 ? 0 : 1] + poff;
+            float *o1 = a.hq[MODE == 0 ? 2 : 3] + (long long)cand * a.hq_cand_stride[MODE == 0 ? 2 : 3] + poff;
+            float *o2 = a.hq[4] + (long long)cand * a.hq_cand_stride[4] + poff;
+            __syncthreads();              // (P)
+#pragma unroll 1
+            for (int t = 0; t <= nch; ++t) {
+                if (t > 0) {
+                    const int buf = (t - 1) & 1;
+                    const unsigned col_off = (unsigned)((t - 1) * kIirChunk);
+                    float *c0 = o0 + col_off, *c1 = o1 + col_off, *c2 = o2 + col_off;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
-    {   // n = -4 .. -1: right taps are columns 0..3 of tile 0, left taps are padding, nothing emitted
-        float w4[4];
-        sample4(0, 0, w4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) (void)iir_step(k, st, 0.0f, w4[i]);
+                    for (int i = 0; i < kIirRows / 4; ++i) {
+                        const int row = sub_row + 4 * i;
+                        const float4 l0 = *reinterpret_cast<const float4 *>(&sm.pair[buf][row][2 * sub_col]);
+                        const float4 l1 = *reinterpret_cast<const float4 *>(&sm.pair[buf][row][2 * sub_col + 4]);
+                        if (row_ok[i]) {
+                            __stcs(reinterpret_cast<float4 *>(c0 + row_off[i]), make_float4(l0.x, l0.z, l1.x, l1.z));
+                            __stcs(reinterpret_cast<float4 *>(c1 + row_off[i]), make_float4(l0.y, l0.w, l1.y, l1.w));
+                        }
+                        if (MODE == 1) {
+                            const float4 l2 = *reinterpret_cast<const float4 *>(&sm.single[buf][row][sub_col]);
+                            if (row_ok[i]) __stcs(reinterpret_cast<float4 *>(c2 + row_off[i]), l2);
+                        }
+                    }
+                }
+                __syncthreads();                   // (t)
+            }
+        }
+        return;
     }
 
+    // ---------------- recursion warps: lane = row ----------------
+    __syncthreads();                           // (P)
+    int prev = 0, cur = 1, next = 2;           // slots of tiles t-1, t, t+1
+    if (warp == 0) {
+        // the pair (x, x*x) of plane 0
+        const IirCoef2 k2 = iir_coef2(k, a.one, a.neg_one);
+        IirState2 st;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = splat2(0.0f);
+        {   // n = -4 .. -1: right taps are columns 0..3 of tile 0, left taps are padding, nothing emitted
+            const float4 x = *reinterpret_cast<const float4 *>(&sm.tile[0][cur][lane][0]);
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) (void)iir_step2(k2, st, splat2(0.0f), pk2(xs[i], xs[i] * xs[i]));
+        }
 #pragma unroll 1
-    for (int t = 0; t < nch; ++t) {
-        const int cur = t & (kIirSlots - 1), prev = (t + kIirSlots - 1) & (kIirSlots - 1),
-                  next = (t + 1) & (kIirSlots - 1);
-        // samples v[i] = quantity at column 32t - 8 + i, i = 0..43 (columns 32t-8 .. 32t+35)
-        float v[44];
-        sample4(prev, 6, v);
-        sample4(prev, 7, v + 4);
+        for (int t = 0; t <= nch; ++t) {
+            if (t < nch) {
+                // samples v[i] = plane value at column 32t - 8 + i, i = 0..43; q[i] its square
+                float v[44], q[44];
+                auto load4 = [&](int slot_, int j4, int at) {
+                    const float4 x = *reinterpret_cast<const float4 *>(&sm.tile[0][slot_][lane][4 * j4]);
+                    v[at] = x.x; v[at + 1] = x.y; v[at + 2] = x.z; v[at + 3] = x.w;
+                    unpk2(mul2(pk2(x.x, x.y), pk2(x.x, x.y)), q[at], q[at + 1]);
+                    unpk2(mul2(pk2(x.z, x.w), pk2(x.z, x.w)), q[at + 2], q[at + 3]);
+                };
+                load4(prev, 6, 0);
+                load4(prev, 7, 4);
 #pragma unroll
-        for (int j4 = 0; j4 < kIirChunk / 4; ++j4) sample4(cur, j4, v + 8 + 4 * j4);
-        sample4(next, 0, v + 40);
-        // step j (output column 32t + j): left tap column 32t + j - 6 = v[j+2], right tap 32t + j + 4 = v[j+12]
-        float sum[kIirChunk];
+                for (int j4 = 0; j4 < kIirChunk / 4; ++j4) load4(cur, j4, 8 + 4 * j4);
+                load4(next, 0, 40);
+                // step j (output column 32t + j): left tap column 32t + j - 6 = [j+2], right tap 32t + j + 4 = [j+12]
+                float4 *o4 = reinterpret_cast<float4 *>(&sm.pair[t & 1][lane][0]);
+                IirPipe2 P;
+                pipe2_begin(k2, P, st, pk2(v[2] + v[12], q[2] + q[12]));
 #pragma unroll
-        for (int j = 0; j < kIirChunk; ++j) sum[j] = v[j + 2] + v[j + 12];
-        // tile t-1 is dead from here on (its samples are in registers): its slot is the staging tile
-        float4 *o4 = reinterpret_cast<float4 *>(&sm.tile[0][prev][lane][0]);
-        IirPipe P;
-        pipe_begin(k, P, st, sum[0]);
+                for (int j2 = 0; j2 < kIirChunk / 2; ++j2) {
+                    f32x2 o[2];
 #pragma unroll
-        for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
-            float o[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = 4 * j4 + jj;
-                o[jj] = (j + 1 < kIirChunk) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int j = 2 * j2 + jj;
+                        o[jj] = (j + 1 < kIirChunk)
+                                    ? pipe2_step(k2, P, pk2(v[j + 3] + v[j + 13], q[j + 3] + q[j + 13]))
+                                    : pipe2_end(k2, P, st);
+                    }
+                    float4 ov;
+                    unpk2(o[0], ov.x, ov.y);
+                    unpk2(o[1], ov.z, ov.w);
+                    o4[j2] = ov;
+                }
             }
-            o4[j4] = make_float4(o[0], o[1], o[2], o[3]);
+            prev = cur;
+            cur = next;
+            next = next + 1 == kIirSlots ? 0 : next + 1;
+            __syncthreads();                   // (t)
         }
-        __syncwarp();
-        // transposed write-out of output tile t: whole 128-byte lines, 4 rows per instruction
-        if (!(VARIANT & 1) || t == nch - 1) {
-            float *dst = ph + sub_col;
-            const unsigned col_off = (unsigned)(t * kIirChunk);
+    } else if (MODE == 1) {
+        // a*b: plane 0 = b, plane 1 = a
+        IirState st;
 #pragma unroll
-            for (int i = 0; i < kIirRows / 4; ++i)
-                if (row_ok[i])
-                    __stcs(reinterpret_cast<float4 *>(dst + (row_off[i] + col_off)),
-                           *reinterpret_cast<const float4 *>(&sm.tile[0][prev][sub_row + 4 * i][sub_col]));
+        for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
+        {
+            const float4 x = *reinterpret_cast<const float4 *>(&sm.tile[0][cur][lane][0]);
+            const float4 y = *reinterpret_cast<const float4 *>(&sm.tile[NPL - 1][cur][lane][0]);
+            const float xs[4] = {x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) (void)iir_step(k, st, 0.0f, xs[i]);
         }
-        __syncwarp();                 // staging consumed: the slot may be overwritten
-        if (!(VARIANT & 2)) issue_tile(t + 3);  // lands in the slot of tile t-1 / the staging tile
-        else cp_async_commit();
-        cp_async_wait<1>();           // tile t+2 (issued one chunk ago) has landed
-        __syncwarp();
+#pragma unroll 1
+        for (int t = 0; t <= nch; ++t) {
+            if (t < nch) {
+                float v[44];
+                auto load4 = [&](int slot_, int j4, int at) {
+                    const float4 x = *reinterpret_cast<const float4 *>(&sm.tile[0][slot_][lane][4 * j4]);
+                    const float4 y = *reinterpret_cast<const float4 *>(&sm.tile[NPL - 1][slot_][lane][4 * j4]);
+                    unpk2(mul2(pk2(x.x, x.y), pk2(y.x, y.y)), v[at], v[at + 1]);
+                    unpk2(mul2(pk2(x.z, x.w), pk2(y.z, y.w)), v[at + 2], v[at + 3]);
+                };
+                load4(prev, 6, 0);
+                load4(prev, 7, 4);
+#pragma unroll
+                for (int j4 = 0; j4 < kIirChunk / 4; ++j4) load4(cur, j4, 8 + 4 * j4);
+                load4(next, 0, 40);
+                float sum[kIirChunk];
+#pragma unroll
+                for (int j = 0; j < kIirChunk; ++j) sum[j] = v[j + 2] + v[j + 12];   // scalar: both are products
+                float4 *o4 = reinterpret_cast<float4 *>(&sm.single[t & 1][lane][0]);
+                IirPipe P;
+                pipe_begin(k, P, st, sum[0]);
+#pragma unroll
+                for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
+                    float o[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 4 * j4 + jj;
+                        o[jj] = (j + 1 < kIirChunk) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
+                    }
+                    o4[j4] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            prev = cur;
+            cur = next;
+            next = next + 1 == kIirSlots ? 0 : next + 1;
+            __syncthreads();                   // (t)
+        }
     }
 }
 
@@ -407,52 +549,79 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();      // final reduction
     } else {
         // ---------------- consumers: maps + pooling for CR rows of each batch ----------------
+        // Consumer cw owns rows 2*cw and 2*cw + 1 of every 8-row group (so the pooled sums do not depend on
+        // B) and evaluates the two rows as one packed pair per column.
         const int cw = warp - 5;                       // 0..3
         // the XYB samples arrive in 4-row groups: with B = 16 each consumer stages its own four rows,
         // with B = 8 the even warp of a pair stages the four rows the pair shares
-        const int grp = (CR == 4) ? cw : (cw >> 1);
         const bool loader = (CR == 4) || ((cw & 1) == 0);
+        const int srow = (CR == 4) ? 8 * (crow >> 1) + 2 * cw + (crow & 1) : 4 * (cw >> 1) + crow;
         const float *pa = a.src + poff + ccol;
         const float *pb = a.dist + (long long)cand * a.dist_stride + poff + ccol;
         double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        auto issue_ab4 = [&](int r0) {   // rows r0..r0+3 of both planes
-            const int rr = r0 + crow;
+        auto issue_ab4 = [&](int r0) {   // this lane's row of the batch starting at r0, both planes
+            const int rr = r0 + srow;
             const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
             const int nb = rr < h ? 16 : 0;
             cp_async_16(&sm.ab[0][rr & 31][ccol], pa + o, nb);
             cp_async_16(&sm.ab[1][rr & 31][ccol], pb + o, nb);
         };
         if (loader)
-            for (int r0 = 4 * grp; r0 < DA; r0 += B) issue_ab4(r0);
+            for (int r0 = 0; r0 < DA; r0 += B) issue_ab4(r0);
         cp_async_commit();
         cp_async_wait<0>();   // the in-loop wait only covers groups committed inside the loop
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const Unit2 u = unit2(a.one, a.neg_one);
+        const f32x2 zero = splat2(0.0f);
+        f32x2 acc[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[j] = zero;
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
-            if (loader) issue_ab4(b * B + 4 * grp + DA);
+            if (loader) issue_ab4(b * B + DA);
             cp_async_commit();
             cp_async_wait<DA / B>();                   // the rows of batch b staged by this warp have landed
             __syncthreads();                           // batch b is in ex[b & 1]; staged samples are visible
-            const int j0 = CR * cw, n0 = b * B + j0;   // this warp's rows
-            const float *ex = &sm.ex[b & 1][0][j0][lane];
+            const float *ex = &sm.ex[b & 1][0][0][lane];
 #pragma unroll
-            for (int j = 0; j < CR; ++j) {
-                const int n = n0 + j;
-                if (col_ok && n < h)
-                    error_maps(sm.ab[0][n & 31][lane], sm.ab[1][n & 31][lane], ex[(0 * B + j) * kIirVCols],
-                               ex[(1 * B + j) * kIirVCols], ex[(2 * B + j) * kIirVCols],
-                               ex[(3 * B + j) * kIirVCols], ex[(4 * B + j) * kIirVCols], acc);
+            for (int g = 0; g < CR / 2; ++g) {
+                const int j = 8 * g + 2 * cw;          // rows j, j + 1 of the batch
+                const int n = b * B + j;
+                if (col_ok && n < h) {
+                    f32x2 in[7];
+                    in[0] = pk2(sm.ab[0][n & 31][lane], sm.ab[0][(n + 1) & 31][lane]);
+                    in[1] = pk2(sm.ab[1][n & 31][lane], sm.ab[1][(n + 1) & 31][lane]);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                        in[2 + q] = pk2(ex[(q * B + j) * kIirVCols], ex[(q * B + j + 1) * kIirVCols]);
+                    if (n + 1 >= h) {   // odd height: the pair's second row is outside; all-zero inputs add exactly zero
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) {
+                            float lo, hi;
+                            unpk2(in[i], lo, hi);
+                            in[i] = pk2(lo, 0.0f);
+                        }
+                    }
+                    error_maps2(u, in[0], in[1], in[2], in[3], in[4], in[5], in[6], acc);
+                }
             }
-            if ((b & 3) == 3) {   // binary32 over at most 16 pixels, binary64 from there on
+            if ((((b + 1) * B) & 31) == 0) {   // binary32 over 4 pixels per accumulator (32 image rows), binary64 from there on
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
-                    dacc[j] += (double)acc[j];
-                    acc[j] = 0.f;
+                    float lo, hi;
+                    unpk2(acc[j], lo, hi);
+                    dacc[j] += (double)lo;
+                    dacc[j] += (double)hi;
+                    acc[j] = zero;
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < 6; ++j) dacc[j] += (double)acc[j];
+        for (int j = 0; j < 6; ++j) {
+            float lo, hi;
+            unpk2(acc[j], lo, hi);
+            dacc[j] += (double)lo;
+            dacc[j] += (double)hi;
+        }
         __syncthreads();
         // fixed shuffle tree over the 32 columns, then the four consumers in fixed order
 #pragma unroll
@@ -529,17 +698,22 @@ __global__ void k_plain_cols(const float *in, float *out, int w, int h, int pitc
 // ---- host-side launch helpers ------------------------------------------------------------------
 inline long long iir_hplane_floats(long long pyr_floats) { return 3 * pyr_floats; }  // per candidate: b, b*b, a*b
 
+typedef IirColsSmem<64, 16> IirColsDeep;
+typedef IirColsSmem<32, 8> IirColsShallow;
+
 inline cudaError_t iir_configure()
 {
     cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(IirColsSmem<64, 16>));
-    return e;
+                                         (int)sizeof(IirColsDeep));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_iir_rows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<0>));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_iir_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<1>));
 }
 
 struct IirStreams {
     cudaStream_t side;       // source-side rows tasks (a, a*a), behind set_source
-    cudaStream_t side2;      // the a*b rows tasks of a scoring call, next to {b, b*b} on the main stream
-    cudaEvent_t fork, join;  // main -> side / side2, side2 -> main
+    cudaEvent_t fork;        // main -> side
     cudaEvent_t src_done;    // the source's cached row-filtered planes are complete (recorded on `side`)
 };
 
@@ -554,6 +728,8 @@ inline void iir_fill_common(IirArgs &a, const Geom &g, const IirCoef &k, const f
 {
     a.g = g;
     a.k = k;
+    a.one = 1.0f;
+    a.neg_one = -1.0f;
     a.src = src;
     a.dist = dist;
     a.dist_stride = dist_stride;
@@ -565,30 +741,17 @@ inline void iir_fill_common(IirArgs &a, const Geom &g, const IirCoef &k, const f
     a.hq[4] = B.cand_hplanes + 2 * P;      a.hq_cand_stride[4] = 3 * P;      // a*b
 }
 
-inline int iir_rows_grid(IirArgs &a, const Geom &g, int per_rowblock)
+inline int iir_rows_grid(IirArgs &a, const Geom &g)
 {
     int n = 0;
     for (int s = 0; s < g.n_scales; ++s) {
         const int nrb = (g.h[s] + kIirRows - 1) / kIirRows;
-        a.blocks[s] = per_rowblock * nrb;
+        a.blocks[s] = nrb;
         a.first_cta[s] = n;
-        n += 3 * per_rowblock * nrb;
+        n += 3 * nrb;
     }
     for (int s = g.n_scales; s <= kMaxScales; ++s) a.first_cta[s] = n;
     return n;
-}
-
-template <int NPLANES>
-inline void launch_rows_kernel(const IirArgs &a, int n_cta, int ncand, cudaStream_t st, int variant)
-{
-    const dim3 grid(n_cta, ncand);
-    const size_t sm = sizeof(IirRowsSmem<NPLANES>);
-    switch (variant) {
-    case 0: k_iir_rows<NPLANES, 0><<<grid, 32, sm, st>>>(a); break;
-    case 1: k_iir_rows<NPLANES, 1><<<grid, 32, sm, st>>>(a); break;
-    case 2: k_iir_rows<NPLANES, 2><<<grid, 32, sm, st>>>(a); break;
-    default: k_iir_rows<NPLANES, 3><<<grid, 32, sm, st>>>(a); break;
-    }
 }
 
 // Source side, once per set_source: rows pass of a and a*a into the per-source cache.  Runs on the side
@@ -598,57 +761,46 @@ inline cudaError_t launch_iir_source_rows(const Geom &g, const IirCoef &k, const
 {
     IirArgs a{};
     iir_fill_common(a, g, k, src_pyr, src_pyr, 0, B);
-    a.nq = 2;
-    a.qlist[0] = 0;
-    a.qlist[1] = 2;
-    const int n = iir_rows_grid(a, g, 2);
+    const int n = iir_rows_grid(a, g);
     cudaEventRecord(ss.fork, st);                 // after the source pyramid
     cudaStreamWaitEvent(ss.side, ss.fork, 0);
-    launch_rows_kernel<1>(a, n, 1, ss.side, 0);
+    k_iir_rows<0><<<dim3(n, 1), 96, sizeof(IirRowsSmem<0>), ss.side>>>(a);
     const cudaError_t e = cudaGetLastError();
     cudaEventRecord(ss.src_done, ss.side);
     *launches = 1;
     return e;
 }
 
-// Candidate side: rows pass of b, b*b (main stream) and a*b (side stream), then the columns pass with
-// the maps and the pooling.  `between` is recorded between the two passes.
+// Candidate side: rows pass of b, b*b and a*b, then the columns pass with the maps and the pooling.
+// `between` is recorded between the two passes.
 inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float *src, const float *dist,
                                    long long pyr_stride, const IirBuffers &B, double *partials,
                                    long long partials_stride, const int *first_cta_cols, const int *col_blocks, int n,
                                    cudaStream_t st, const IirStreams &ss, cudaEvent_t between, int *launches,
-                                   int variant = 0, bool rows_only = false)
+                                   bool rows_only = false)
 {
     IirArgs a{};
     iir_fill_common(a, g, k, src, dist, pyr_stride, B);
     a.partials = partials;
     a.partials_stride = partials_stride;
-    IirArgs a1 = a, a2 = a;   // {b, b*b} | a*b
-    a1.nq = 2;
-    a1.qlist[0] = 1;
-    a1.qlist[1] = 3;
-    const int n1 = iir_rows_grid(a1, g, 2), n2 = iir_rows_grid(a2, g, 1);
-    cudaEventRecord(ss.fork, st);                 // after the candidate pyramid
-    cudaStreamWaitEvent(ss.side2, ss.fork, 0);    // a*b must not queue behind the source rows: own stream
-    launch_rows_kernel<1>(a1, n1, n, st, variant);
-    launch_rows_kernel<2>(a2, n2, n, ss.side2, variant);
+    IirArgs ar = a;
+    const int nr = iir_rows_grid(ar, g);
+    k_iir_rows<1><<<dim3(nr, n), 128, sizeof(IirRowsSmem<1>), st>>>(ar);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    cudaEventRecord(ss.join, ss.side2);
-    cudaStreamWaitEvent(st, ss.join, 0);          // a*b done
-    cudaStreamWaitEvent(st, ss.src_done, 0);      // the source's cached rows done
+    cudaStreamWaitEvent(st, ss.src_done, 0);      // the source's cached rows
     if (between) cudaEventRecord(between, st);
-    *launches = 2;
+    *launches = 1;
     if (rows_only) return cudaSuccess;
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
     // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
-    const int scale0_tasks = 3 * col_blocks[0] * n;
-    if (scale0_tasks <= 148 * 3)
-        k_iir_cols<64, 16><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<64, 16>), st>>>(a);
+    const int ctas = first_cta_cols[kMaxScales];
+    if (3 * col_blocks[0] * n <= 148 * 3)
+        k_iir_cols<64, 16><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
     else
-        k_iir_cols<32, 8><<<dim3(first_cta_cols[kMaxScales], n), kIirVThreads, sizeof(IirColsSmem<32, 8>), st>>>(a);
-    *launches = 3;
+        k_iir_cols<32, 8><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsShallow), st>>>(a);
+    *launches = 2;
     return cudaGetLastError();
 }
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Attribute the rows pass's time: product kernel vs. no stores / no loads / no prefetch (GPU only)."""
+"""Time the recursive rows pass alone: both halves vs. the candidate half only (GPU only)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,7 +10,7 @@ import torch
 with ssimu2.Scorer(bench.W, bench.H, 1) as sc:
     sc.set_source(src)
     sc.score_yuv444(*yuv, 10)
-    names = {0: "product", 1: "no stores", 2: "no loads", 3: "no stores, no loads", 4: "candidate half only"}
+    names = {0: "source + candidate halves", 4: "candidate half only"}
     for v, nm in names.items():
         sc.time_rows(v, 3)
         print(f"variant {v} ({nm}): {sc.time_rows(v, 20):.4f} ms")
