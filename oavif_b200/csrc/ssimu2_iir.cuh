@@ -460,14 +460,14 @@ __global__ void __launch_bounds__(MODE == 0 ? 96 : 128) k_iir_rows(const __grid_
 // for two rows of the batch each (a producer step costs ~17 instructions, a map pixel ~70, so 5 + 4
 // warps are balanced).  Nine warps per task give a sub-partition enough independent work to hide
 // latencies when a single 4K pair is all the GPU has.  One block barrier per 8 rows.
-constexpr int kIirVThreads = 288;   // 5 producer warps + 4 consumer warps
+constexpr int kIirVThreads = 256;   // 3 producer warps + 5 consumer warps
 
 template <int RCAP, int B>
 struct IirColsSmem {
     float ring[5][RCAP][kIirVCols];            // producer input rows, row r at [r & (RCAP-1)]
     float ab[2][32][kIirVCols];                // consumer rows of the two XYB planes
     float ex[2][5][B][kIirVCols];              // filtered values, double-buffered
-    double red[4][6];
+    double red[5][6];
 };
 
 // B rows per exchange batch (16 with the deep ring, 8 with the shallow one): the per-batch overhead
@@ -487,38 +487,43 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     const int cand = blockIdx.y;
     const int w = a.g.w[s], h = a.g.h[s], pitch = a.g.pitch[s];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gx = cb * kIirVCols + lane;
-    const bool col_ok = gx < w;
     // copy role of a lane: row (lane >> 3) of a 4-row group, columns 4*(lane & 7)..+3 of the 32
     const int crow = lane >> 3, ccol = (lane & 7) * 4;
     const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + cb * kIirVCols;
     const int nbatch = (h + B - 1) / B;
+    // bytes of this lane's 16-byte column group that lie inside the image: the rest is zero-filled
+    const int cbytes = max(0, min(16, (w - (cb * kIirVCols + ccol)) * 4));
 
-    if (warp < 5) {
-        // ---------------- producer: the column recursion of quantity `warp` ----------------
-        const int q = warp;
-        const float *ph = a.hq[q] + (long long)cand * a.hq_cand_stride[q] + poff + ccol;
-        const IirCoef k = a.k;
-        float *ring = &sm.ring[q][0][0];
-        auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h): one 16-byte copy per lane
+    if (warp < 2) {
+        // ---------------- pair producers: the column recursions of quantities 2*warp, 2*warp + 1 ----------------
+        // (a, b) and (a*a, b*b): two planes, one packed recursion per column
+        const int q0 = 2 * warp;
+        const float *ph0 = a.hq[q0] + (long long)cand * a.hq_cand_stride[q0] + poff + ccol;
+        const float *ph1 = a.hq[q0 + 1] + (long long)cand * a.hq_cand_stride[q0 + 1] + poff + ccol;
+        const IirCoef2 k = iir_coef2(a.k, a.one, a.neg_one);
+        float *ring0 = &sm.ring[q0][0][0], *ring1 = &sm.ring[q0 + 1][0][0];
+        auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h) of both planes: 16 bytes per lane each
             const int rr = r0 + crow;
-            cp_async_16(ring + (rr & (RCAP - 1)) * kIirVCols + ccol, ph + (unsigned)(min(rr, h - 1) * pitch),
-                        rr < h ? 16 : 0);
+            const unsigned go = (unsigned)(min(rr, h - 1) * pitch);
+            const int so = (rr & (RCAP - 1)) * kIirVCols + ccol, nb = rr < h ? cbytes : 0;
+            cp_async_16(ring0 + so, ph0 + go, nb);
+            cp_async_16(ring1 + so, ph1 + go, nb);
         };
         // rows -6..-1 are padding: their ring slots hold zeros until real rows wrap around to them
 #pragma unroll
-        for (int j = 1; j <= 6; ++j) ring[(RCAP - j) * kIirVCols + lane] = 0.0f;
+        for (int j = 1; j <= 6; ++j) ring0[(RCAP - j) * kIirVCols + lane] = ring1[(RCAP - j) * kIirVCols + lane] = 0.0f;
         for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0);   // everything before the first batch's request
         cp_async_commit();
-        IirState st;
+        IirState2 st;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
+        for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = splat2(0.0f);
         cp_async_wait<0>();
         __syncwarp();
-        const float *col = ring + lane;
+        const float *c0 = ring0 + lane, *c1 = ring1 + lane;
         // n = -4..-1: right taps are rows 0..3, left taps are padding, nothing emitted
 #pragma unroll
-        for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, col[(n + 4) * kIirVCols]);
+        for (int n = -4; n < 0; ++n)
+            (void)iir_step2(k, st, splat2(0.0f), pk2(c0[(n + 4) * kIirVCols], c1[(n + 4) * kIirVCols]));
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
@@ -530,6 +535,59 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             __syncwarp();                              // ... and every other lane's
             // n0 is a multiple of B (8 or 16) and so is RCAP: the left taps (rows n0-6+j) can only wrap at
             // j = 6, the right taps (rows n0+4+j) only at j = B-4 -> two bases each, static offsets otherwise
+            const int ol0 = ((n0 - 6) & (RCAP - 1)) * kIirVCols, ol1 = (n0 & (RCAP - 1)) * kIirVCols;
+            const int or0 = ((n0 + 4) & (RCAP - 1)) * kIirVCols, or1 = ((n0 + B) & (RCAP - 1)) * kIirVCols;
+            f32x2 sum[B];
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const int lo = j < 6 ? ol0 + j * kIirVCols : ol1 + (j - 6) * kIirVCols;
+                const int ro = j < B - 4 ? or0 + j * kIirVCols : or1 + (j - (B - 4)) * kIirVCols;
+                sum[j] = add2(pk2(c0[lo], c1[lo]), pk2(c0[ro], c1[ro]));
+            }
+            float *ex0 = &sm.ex[b & 1][q0][0][lane], *ex1 = &sm.ex[b & 1][q0 + 1][0][lane];
+            IirPipe2 P;
+            pipe2_begin(k, P, st, sum[0]);
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const f32x2 o = (j + 1 < B) ? pipe2_step(k, P, sum[j + 1]) : pipe2_end(k, P, st);
+                unpk2(o, ex0[j * kIirVCols], ex1[j * kIirVCols]);
+            }
+            __syncthreads();  // batch b published; the consumers are done with the other buffer
+        }
+        __syncthreads();      // consumers' last batch
+        __syncthreads();      // final reduction
+    } else if (warp == 2) {
+        // ---------------- single producer: the column recursion of a*b ----------------
+        const int q = 4;
+        const float *ph = a.hq[q] + (long long)cand * a.hq_cand_stride[q] + poff + ccol;
+        const IirCoef k = a.k;
+        float *ring = &sm.ring[q][0][0];
+        auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h): one 16-byte copy per lane
+            const int rr = r0 + crow;
+            cp_async_16(ring + (rr & (RCAP - 1)) * kIirVCols + ccol, ph + (unsigned)(min(rr, h - 1) * pitch),
+                        rr < h ? cbytes : 0);
+        };
+#pragma unroll
+        for (int j = 1; j <= 6; ++j) ring[(RCAP - j) * kIirVCols + lane] = 0.0f;
+        for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0);
+        cp_async_commit();
+        IirState st;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
+        cp_async_wait<0>();
+        __syncwarp();
+        const float *col = ring + lane;
+#pragma unroll
+        for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, col[(n + 4) * kIirVCols]);
+
+#pragma unroll 1
+        for (int b = 0; b < nbatch; ++b) {
+            const int n0 = b * B;
+#pragma unroll
+            for (int j = 0; j < B; j += 4) issue_rows4(n0 + 4 + D + j);
+            cp_async_commit();
+            cp_async_wait<D / B>();
+            __syncwarp();
             float sum[B];
             const float *l0 = col + ((n0 - 6) & (RCAP - 1)) * kIirVCols, *l1 = col + (n0 & (RCAP - 1)) * kIirVCols;
             const float *r0 = col + ((n0 + 4) & (RCAP - 1)) * kIirVCols, *r1 = col + ((n0 + B) & (RCAP - 1)) * kIirVCols;
@@ -543,31 +601,38 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
 #pragma unroll
             for (int j = 0; j < B; ++j)
                 ex[j * kIirVCols] = (j + 1 < B) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
-            __syncthreads();  // batch b published; the consumers are done with the other buffer
+            __syncthreads();
         }
-        __syncthreads();      // consumers' last batch
-        __syncthreads();      // final reduction
+        __syncthreads();
+        __syncthreads();
     } else {
-        // ---------------- consumers: maps + pooling for CR rows of each batch ----------------
-        // Consumer cw owns rows 2*cw and 2*cw + 1 of every 8-row group (so the pooled sums do not depend on
-        // B) and evaluates the two rows as one packed pair per column.
-        const int cw = warp - 5;                       // 0..3
-        // the XYB samples arrive in 4-row groups: with B = 16 each consumer stages its own four rows,
-        // with B = 8 the even warp of a pair stages the four rows the pair shares
-        const bool loader = (CR == 4) || ((cw & 1) == 0);
-        const int srow = (CR == 4) ? 8 * (crow >> 1) + 2 * cw + (crow & 1) : 4 * (cw >> 1) + crow;
+        // ---------------- consumers: maps + pooling ----------------
+        // Five consumer warps share the eight row pairs (2p, 2p+1), p = 0..7, of a 16-row batch so that the
+        // four sub-partitions of the SM carry equal work next to the three producers (warp w runs on
+        // sub-partition w % 4; a pair producer costs ~430 instructions per batch, the a*b producer ~340, a
+        // row pair of maps ~125):  warp 3: p0 p1, warp 7: p2 p3, warp 6: p4 p5, warp 4: p6, warp 5: p7.
+        // A consumer evaluates the two rows of a pair as one packed pair per column, and stages the XYB rows
+        // it needs itself.  Columns beyond the image need no test: every ring is zero-filled there by the
+        // copies, and all-zero inputs pool to exactly zero.
+        const int cw = warp - 3;                                   // 0..4
+        const int first_pair = cw == 0 ? 0 : cw == 4 ? 2 : cw == 3 ? 4 : cw == 1 ? 6 : 7;
+        const int npairs = (cw == 1 || cw == 2) ? 1 : 2;
+        const bool stager = crow < 2 * npairs;                     // lanes that copy: 8 per row
+        const int srow = 2 * first_pair + crow;
         const float *pa = a.src + poff + ccol;
         const float *pb = a.dist + (long long)cand * a.dist_stride + poff + ccol;
         double dacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        auto issue_ab4 = [&](int r0) {   // this lane's row of the batch starting at r0, both planes
+        auto issue_ab = [&](int r0) {   // this lane's row of the batch starting at r0, both planes
             const int rr = r0 + srow;
             const unsigned o = (unsigned)(min(rr, h - 1) * pitch);
-            const int nb = rr < h ? 16 : 0;
-            cp_async_16(&sm.ab[0][rr & 31][ccol], pa + o, nb);
-            cp_async_16(&sm.ab[1][rr & 31][ccol], pb + o, nb);
+            const int nb = rr < h ? cbytes : 0;
+            if (stager) {
+                cp_async_16(&sm.ab[0][rr & 31][ccol], pa + o, nb);
+                cp_async_16(&sm.ab[1][rr & 31][ccol], pb + o, nb);
+            }
         };
-        if (loader)
-            for (int r0 = 0; r0 < DA; r0 += B) issue_ab4(r0);
+        static_assert(B == 16 && DA == 16, "the pair assignment is written for 16-row batches");
+        issue_ab(0);
         cp_async_commit();
         cp_async_wait<0>();   // the in-loop wait only covers groups committed inside the loop
         const Unit2 u = unit2(a.one, a.neg_one);
@@ -575,25 +640,28 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         f32x2 acc[6];
 #pragma unroll
         for (int j = 0; j < 6; ++j) acc[j] = zero;
+        const float *abw = &sm.ab[0][2 * first_pair][lane];   // this warp's first row pair in ring rows 0..15
+        constexpr int kAbPlane = 32 * kIirVCols;               // floats between the two staged planes
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
-            if (loader) issue_ab4(b * B + DA);
+            issue_ab(b * B + DA);
             cp_async_commit();
             cp_async_wait<DA / B>();                   // the rows of batch b staged by this warp have landed
             __syncthreads();                           // batch b is in ex[b & 1]; staged samples are visible
-            const float *ex = &sm.ex[b & 1][0][0][lane];
+            const float *ex = &sm.ex[b & 1][0][2 * first_pair][lane];
+            const float *ab = abw + ((b * B) & 31) * kIirVCols;   // B divides 32: a batch never wraps inside the ring
+            const bool whole = (b + 1) * B <= h;       // every row of the batch is inside the image
 #pragma unroll
-            for (int g = 0; g < CR / 2; ++g) {
-                const int j = 8 * g + 2 * cw;          // rows j, j + 1 of the batch
-                const int n = b * B + j;
-                if (col_ok && n < h) {
+            for (int g = 0; g < 2; ++g) {
+                const int n = b * B + 2 * (first_pair + g);   // rows n, n + 1
+                if (g < npairs && (whole || n < h)) {
                     f32x2 in[7];
-                    in[0] = pk2(sm.ab[0][n & 31][lane], sm.ab[0][(n + 1) & 31][lane]);
-                    in[1] = pk2(sm.ab[1][n & 31][lane], sm.ab[1][(n + 1) & 31][lane]);
+                    in[0] = pk2(ab[(2 * g) * kIirVCols], ab[(2 * g + 1) * kIirVCols]);
+                    in[1] = pk2(ab[kAbPlane + (2 * g) * kIirVCols], ab[kAbPlane + (2 * g + 1) * kIirVCols]);
 #pragma unroll
                     for (int q = 0; q < 5; ++q)
-                        in[2 + q] = pk2(ex[(q * B + j) * kIirVCols], ex[(q * B + j + 1) * kIirVCols]);
-                    if (n + 1 >= h) {   // odd height: the pair's second row is outside; all-zero inputs add exactly zero
+                        in[2 + q] = pk2(ex[(q * B + 2 * g) * kIirVCols], ex[(q * B + 2 * g + 1) * kIirVCols]);
+                    if (!whole && n + 1 >= h) {   // odd height: the pair's second row is outside
 #pragma unroll
                         for (int i = 0; i < 7; ++i) {
                             float lo, hi;
@@ -604,7 +672,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
                     error_maps2(u, in[0], in[1], in[2], in[3], in[4], in[5], in[6], acc);
                 }
             }
-            if ((((b + 1) * B) & 31) == 0) {   // binary32 over 4 pixels per accumulator (32 image rows), binary64 from there on
+            if (b & 1) {   // binary32 over at most 4 pixels per accumulator (32 image rows), binary64 from there on
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     float lo, hi;
@@ -623,7 +691,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             dacc[j] += (double)hi;
         }
         __syncthreads();
-        // fixed shuffle tree over the 32 columns, then the four consumers in fixed order
+        // fixed shuffle tree over the 32 columns, then the five consumers in fixed order
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             double x = dacc[j];
@@ -634,7 +702,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();
         if (cw == 0 && lane < 6)
             a.partials[(long long)cand * a.partials_stride + (long long)blockIdx.x * 6 + lane] =
-                ((sm.red[0][lane] + sm.red[1][lane]) + sm.red[2][lane]) + sm.red[3][lane];
+                (((sm.red[0][lane] + sm.red[1][lane]) + sm.red[2][lane]) + sm.red[3][lane]) + sm.red[4][lane];
     }
 }
 
@@ -699,7 +767,6 @@ __global__ void k_plain_cols(const float *in, float *out, int w, int h, int pitc
 inline long long iir_hplane_floats(long long pyr_floats) { return 3 * pyr_floats; }  // per candidate: b, b*b, a*b
 
 typedef IirColsSmem<64, 16> IirColsDeep;
-typedef IirColsSmem<32, 8> IirColsShallow;
 
 inline cudaError_t iir_configure()
 {
@@ -794,12 +861,8 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     if (rows_only) return cudaSuccess;
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
-    // ring depth: the deep ring when every scale-0 task can still be resident, else the shallow one
     const int ctas = first_cta_cols[kMaxScales];
-    if (3 * col_blocks[0] * n <= 148 * 3)
-        k_iir_cols<64, 16><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
-    else
-        k_iir_cols<32, 8><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsShallow), st>>>(a);
+    k_iir_cols<64, 16><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
     *launches = 2;
     return cudaGetLastError();
 }
