@@ -320,6 +320,8 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const 
     a.out = out;
     a.out_stride = out_stride;
     a.lut = ctx->d_lut;
+    a.one = 1.0f;
+    a.neg_one = -1.0f;
     if (d.kind != IN_RGB8 && d.kind != IN_PIXELS && !yuv_consts(d.matrix, &a.k))
         return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "matrix_coefficients %d not on the scored path", d.matrix);
     const size_t rb = row_bytes(d, w);

@@ -25,6 +25,7 @@ struct PyrArgs {
     const float *lut;           // 256-entry sRGB->linear table
     YuvK k;
     int channels, hbd;          // IN_PIXELS only: 1..4 interleaved channels, 16-bit samples if hbd
+    float one, neg_one;         // 1.0f / -1.0f as run-time values (Unit2, ssimu2_common.cuh)
 };
 
 // Load pixels x0..x0+3 of row y (coordinates clamped to the image) as 8-bit RGB.
@@ -121,7 +122,7 @@ __device__ __forceinline__ void load4_rgb8(const PyrArgs &a, const void *p0, con
 
 // grid = (tiles_x, tiles_y, n_images), block = 256 (16x16 threads, 4x4 scale-0 pixels each).
 template <int KIND>
-__global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ PyrArgs a)
+__global__ void __launch_bounds__(256, 3) k_pyramid(const __grid_constant__ PyrArgs a)
 {
     __shared__ float s_lut[256];
     __shared__ float s_l2[3][16][17];  // scale-2 linear RGB of this tile
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ PyrArgs
     const void *p2 = a.planes ? a.planes[3 * img + 2] : a.inl[3 * img + 2];
     float *pyr = a.out + (long long)img * a.out_stride;
     const XybConst kx = xyb_consts();
+    const Unit2 un = unit2(a.one, a.neg_one);
 
     // ---- scale 0: 4x4 pixels per thread ------------------------------------------------
     const int x0 = bx * 64 + tx * 4, y0 = by * 64 + ty * 4;
@@ -161,10 +163,13 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ PyrArgs
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float4 vx, vy, vb;
-            linear_to_xyb(kx, lin[j][0][0], lin[j][0][1], lin[j][0][2], vx.x, vy.x, vb.x);
-            linear_to_xyb(kx, lin[j][1][0], lin[j][1][1], lin[j][1][2], vx.y, vy.y, vb.y);
-            linear_to_xyb(kx, lin[j][2][0], lin[j][2][1], lin[j][2][2], vx.z, vy.z, vb.z);
-            linear_to_xyb(kx, lin[j][3][0], lin[j][3][1], lin[j][3][2], vx.w, vy.w, vb.w);
+            f32x2 px, py, pb;   // pixels (0, 1) and (2, 3) of the row as packed pairs
+            linear_to_xyb2(kx, un, pk2(lin[j][0][0], lin[j][1][0]), pk2(lin[j][0][1], lin[j][1][1]),
+                           pk2(lin[j][0][2], lin[j][1][2]), px, py, pb);
+            unpk2(px, vx.x, vx.y); unpk2(py, vy.x, vy.y); unpk2(pb, vb.x, vb.y);
+            linear_to_xyb2(kx, un, pk2(lin[j][2][0], lin[j][3][0]), pk2(lin[j][2][1], lin[j][3][1]),
+                           pk2(lin[j][2][2], lin[j][3][2]), px, py, pb);
+            unpk2(px, vx.z, vx.w); unpk2(py, vy.z, vy.w); unpk2(pb, vb.z, vb.w);
             const long long o = (long long)(y0 + j) * g.pitch[0] + x0;
             *reinterpret_cast<float4 *>(X + o) = vx;
             *reinterpret_cast<float4 *>(Y + o) = vy;
@@ -189,8 +194,10 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ PyrArgs
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             float2 vx, vy, vb;
-            linear_to_xyb(kx, l1[j][0][0], l1[j][0][1], l1[j][0][2], vx.x, vy.x, vb.x);
-            linear_to_xyb(kx, l1[j][1][0], l1[j][1][1], l1[j][1][2], vx.y, vy.y, vb.y);
+            f32x2 px, py, pb;
+            linear_to_xyb2(kx, un, pk2(l1[j][0][0], l1[j][1][0]), pk2(l1[j][0][1], l1[j][1][1]),
+                           pk2(l1[j][0][2], l1[j][1][2]), px, py, pb);
+            unpk2(px, vx.x, vx.y); unpk2(py, vy.x, vy.y); unpk2(pb, vb.x, vb.y);
             const long long o = (long long)(y1 + j) * g.pitch[1] + x1;
             *reinterpret_cast<float2 *>(X + o) = vx;
             *reinterpret_cast<float2 *>(Y + o) = vy;
