@@ -44,7 +44,6 @@ struct oavif_ssimu2_ctx {
     int device = 0;
     uint32_t max_w = 0, max_h = 0, max_batch = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    IirStreams iir_streams{};
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
 
     // capacities (computed from max_w x max_h)
@@ -58,7 +57,6 @@ struct oavif_ssimu2_ctx {
     uint8_t *d_in_src = nullptr, *d_in_dist = nullptr;
     float *d_src_pyr = nullptr, *d_dist_pyr = nullptr, *d_hplanes = nullptr, *d_src_hplanes = nullptr, *d_lut = nullptr;
     bool src_rows_valid = false;   // the cached rows pass of the source (RECURSIVE blur) matches the current source
-    bool src_rows_pending = false; // ... and may still be running on the side stream
     const void **d_tbl = nullptr, **h_tbl = nullptr;
     double *d_partials = nullptr;
     double *h_sums = nullptr, *h_scores = nullptr;      // pinned, mapped: k_finalize writes them directly
@@ -404,18 +402,13 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
         plan_iir_v(g, &plan);
         int launches = 0;
         const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
-        if (!ctx->src_rows_valid) {  // source set while another blur was selected
-            const cudaError_t e0 = launch_iir_source_rows(g, ctx->iir, ctx->d_src_pyr, B, ctx->stream, ctx->iir_streams, &launches);
-            if (e0 != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "source rows launch: %s", cudaGetErrorString(e0));
-            ctx->timing.launches += launches;
-            ctx->src_rows_valid = true;
-        }
+        // the first call after set_source also runs the source's half of the rows pass and leaves it cached
         const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
                                               ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, (int)n,
-                                              ctx->stream, ctx->iir_streams, ctx->ev[3], &launches);
+                                              ctx->stream, !ctx->src_rows_valid, ctx->ev[3], &launches);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "recursive blur launch: %s", cudaGetErrorString(e));
         ctx->timing.launches += launches;
-        ctx->src_rows_pending = false;  // launch_iir_blur ordered the main stream behind them
+        ctx->src_rows_valid = true;
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
 
@@ -505,24 +498,10 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
     d.on_device = on_device;
     HostPlanes hp{{rgb, nullptr, nullptr}};
     ctx->timing = oavif_ssimu2_timing{};
-    // a previous source's rows pass may still be reading the pyramid on the side stream
-    if (ctx->src_rows_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->iir_streams.src_done, 0));
-    ctx->src_rows_pending = false;
-    ctx->src_rows_valid = false;
+    ctx->src_rows_valid = false;   // the next score call refills the cache of the source's row-filtered planes
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = build_pyramids(ctx, d, 1, &hp, true, ctx->d_src_pyr, 0);
     if (rc) return rc;
-    if (ctx->blur_mode == OAVIF_SSIMU2_BLUR_RECURSIVE) {
-        // source half of the rows pass (a, a*a): once per source, on the side stream, so that it
-        // overlaps the candidate's upload and pyramid and is shared by every later candidate
-        int launches = 0;
-        const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
-        const cudaError_t e = launch_iir_source_rows(ctx->g, ctx->iir, ctx->d_src_pyr, B, ctx->stream, ctx->iir_streams, &launches);
-        if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "source rows launch: %s", cudaGetErrorString(e));
-        ctx->timing.launches += launches;
-        ctx->src_rows_valid = true;
-        ctx->src_rows_pending = true;
-    }
     // Return as soon as the caller's pixels have been consumed (host input: after the upload; device
     // input: at once): the pyramid kernel itself keeps running behind the next call on the same stream.
     if (!on_device) {
@@ -583,12 +562,6 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     cudaFreeHost(ctx->h_scores);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
-    if (ctx->iir_streams.fork) cudaEventDestroy(ctx->iir_streams.fork);
-    if (ctx->iir_streams.src_done) cudaEventDestroy(ctx->iir_streams.src_done);
-    if (ctx->iir_streams.side) {
-        cudaStreamSynchronize(ctx->iir_streams.side);
-        cudaStreamDestroy(ctx->iir_streams.side);
-    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -620,9 +593,6 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     for (auto &e : ctx->ev) CKC(cudaEventCreate(&e));
-    CKC(cudaStreamCreateWithFlags(&ctx->iir_streams.side, cudaStreamNonBlocking));
-    CKC(cudaEventCreateWithFlags(&ctx->iir_streams.fork, cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&ctx->iir_streams.src_done, cudaEventDisableTiming));
 
     const int mw = (int)max_w, mh = (int)max_h;
     ctx->cap_pyr_floats = std::max(pyr_capacity(mw, mh), pyr_capacity(mh, mw));
@@ -956,13 +926,10 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
     for (int i = 0; i < iters; ++i) {
         int launches = 0;
         const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
-        if (!(variant & 4)) {  // bit 2: leave the source half out (candidate-only cost); other bits are ignored
-            int l0 = 0;
-            launch_iir_source_rows(ctx->g, ctx->iir, ctx->d_src_pyr, B, ctx->stream, ctx->iir_streams, &l0);
-        }
+        // bit 2: leave the source half out (what a call with a warm source cache runs); other bits are ignored
         const cudaError_t e = launch_iir_blur(ctx->g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
                                               ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, 1,
-                                              ctx->stream, ctx->iir_streams, nullptr, &launches, true);
+                                              ctx->stream, !(variant & 4), nullptr, &launches, true);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -95,10 +95,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 constexpr int kIirRows = 32;     // rows per rows-pass task
 constexpr int kIirChunk = 32;    // columns per staged tile
 constexpr int kIirPitch = 36;    // smem tile pitch in floats: 16-byte rows, conflict-free 128-bit access
-// tile ring of the rows pass: t-1, t, t+1 in use, t+2 landed or landing, then kAhead - 2 more in flight.
-// (Five slots on the candidate side would let three CTAs share an SM, but the shorter look-ahead costs
-// more than the extra residency gains: measured 0.158 ms against 0.137 ms on a 4K frame.)
-template <int MODE> struct IirRing { static constexpr int kSlots = 6, kAhead = kSlots - 2; };
 constexpr int kIirPairPitch = 68;  // staging pitch of an interleaved (x, x*x) row: 64 floats + 16 bytes
 constexpr int kIirVCols = 32;    // columns per columns-pass task
 
@@ -228,32 +224,241 @@ __device__ __forceinline__ f32x2 pipe2_end(const IirCoef2 &k, IirPipe2 &P, IirSt
 }
 
 // ------------------------------------------------------------------------------------------------
-// rows pass.  MODE 0 (source side, once per set_source): the pair (a, a*a); block = 96.
-//             MODE 1 (candidate side): the pair (b, b*b) and a*b; block = 128.
-// grid = (sum over scales of 3 * ceil(h/32), n_candidates).
+// rows pass.  grid = (sum over scales of 3 * ceil(h/32), n_candidates); one CTA = 32 rows of one channel.
+//   MODE 1 (source rows cached):  the pair (b, b*b) and a*b                       block = 128
+//   MODE 2 (first call after set_source): the same, and candidate 0's CTAs also run the pair (a, a*a)
+//           of the source, which every later candidate and call reads back from its cache   block = 192
 //
-// Warp roles: warp 0 runs the packed recursion of the pair, warp 1 (MODE 1) the recursion of a*b, the
-// last two warps are the loader and the storer.  Chunk t emits the 128-byte-aligned outputs
-// n = 32t .. 32t+31: right taps (n+4) come from tiles t and t+1, left taps (n-6) from tiles t-1 and t.
-// While the recursion warps work on chunk t, the storer writes chunk t-1 out of the staging tiles (whole
-// 128-byte lines, streaming stores) and the loader requests tile t+4 (16-byte cp.async, zero-filled
-// beyond the image) and waits for tile t+2; one block barrier per chunk.
-template <int MODE>
-struct IirRowsSmem {
-    static constexpr int NPL = MODE == 0 ? 1 : 2;
-    float tile[NPL][IirRing<MODE>::kSlots][kIirRows][kIirPitch];   // [plane][ring slot][row][column]; plane 0 = a | b, plane 1 = a
-    float pair[2][kIirRows][kIirPairPitch];            // filtered (x, x*x), interleaved per pixel, double-buffered
-    float single[2][MODE == 0 ? 1 : kIirRows][kIirPitch];  // filtered a*b, double-buffered
-};
+// Warp roles: one warp per packed pair recursion, one for a*b (lane = row), a loader and one or two
+// storers.  Chunk t emits the 128-byte-aligned outputs n = 32t .. 32t+31: right taps (n+4) come from
+// tiles t and t+1, left taps (n-6) from tiles t-1 and t.  While the recursion warps work on chunk t,
+// the storers write chunk t-1 out of the staging tiles (whole 128-byte lines, streaming stores) and
+// the loader requests tile t+4 (16-byte cp.async, zero-filled beyond the image) and waits for tile
+// t+2; one block barrier per chunk.  Tile ring: t-1, t, t+1 in use, t+2 landed or landing, t+3 and
+// t+4 in flight (five slots with a shorter look-ahead would let three CTAs share an SM, but measured
+// 0.158 ms against 0.137 ms on a 4K frame).
+constexpr int kRowSlots = 6, kRowAhead = kRowSlots - 2;
 
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 0 ? 96 : 128) k_iir_rows(const __grid_constant__ IirArgs a)
+struct IirRowsSmem {
+    static constexpr int NPAIR = MODE == 2 ? 2 : 1;
+    float tile[2][kRowSlots][kIirRows][kIirPitch];     // [plane][ring slot][row][column]; plane 0 = b, plane 1 = a
+    float pair[NPAIR][2][kIirRows][kIirPairPitch];     // filtered (x, x*x), interleaved per pixel, double-buffered
+    float single[2][kIirRows][kIirPitch];              // filtered a*b, double-buffered
+};
+
+typedef float RowTile[kIirRows][kIirPitch];
+typedef float RowPairStage[kIirRows][kIirPairPitch];
+
+// Every role below executes the same barriers: one before the first chunk, then one per t = 0 .. nch.
+
+// the packed recursion of (x, x*x) over the staged plane `tile`; inactive warps only keep the barriers
+__device__ __forceinline__ void rows_pair_warp(const RowTile *tile, RowPairStage *stage, const IirCoef &k, float one,
+                                               float neg_one, int lane, int nch, bool active)
+{
+    __syncthreads();
+    if (!active) {
+        for (int t = 0; t <= nch; ++t) __syncthreads();
+        return;
+    }
+    int prev = 0, cur = 1, next = 2;           // slots of tiles t-1, t, t+1 (tile t lives in slot (t + 1) mod 6)
+    const IirCoef2 k2 = iir_coef2(k, one, neg_one);
+    IirState2 st;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = splat2(0.0f);
+    {   // n = -4 .. -1: right taps are columns 0..3 of tile 0, left taps are padding, nothing emitted
+        const float4 x = *reinterpret_cast<const float4 *>(&tile[cur][lane][0]);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) (void)iir_step2(k2, st, splat2(0.0f), pk2(xs[i], xs[i] * xs[i]));
+    }
+#pragma unroll 1
+    for (int t = 0; t <= nch; ++t) {
+        if (t < nch) {
+            // samples v[i] = plane value at column 32t - 8 + i, i = 0..43; q[i] its square
+            float v[44], q[44];
+            auto load4 = [&](int slot_, int j4, int at) {
+                const float4 x = *reinterpret_cast<const float4 *>(&tile[slot_][lane][4 * j4]);
+                v[at] = x.x; v[at + 1] = x.y; v[at + 2] = x.z; v[at + 3] = x.w;
+                unpk2(mul2(pk2(x.x, x.y), pk2(x.x, x.y)), q[at], q[at + 1]);
+                unpk2(mul2(pk2(x.z, x.w), pk2(x.z, x.w)), q[at + 2], q[at + 3]);
+            };
+            load4(prev, 6, 0);
+            load4(prev, 7, 4);
+#pragma unroll
+            for (int j4 = 0; j4 < kIirChunk / 4; ++j4) load4(cur, j4, 8 + 4 * j4);
+            load4(next, 0, 40);
+            // step j (output column 32t + j): left tap column 32t + j - 6 = [j+2], right tap 32t + j + 4 = [j+12]
+            float4 *o4 = reinterpret_cast<float4 *>(&stage[t & 1][lane][0]);
+            IirPipe2 P;
+            pipe2_begin(k2, P, st, pk2(v[2] + v[12], q[2] + q[12]));
+#pragma unroll
+            for (int j2 = 0; j2 < kIirChunk / 2; ++j2) {
+                f32x2 o[2];
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = 2 * j2 + jj;
+                    o[jj] = (j + 1 < kIirChunk) ? pipe2_step(k2, P, pk2(v[j + 3] + v[j + 13], q[j + 3] + q[j + 13]))
+                                                : pipe2_end(k2, P, st);
+                }
+                float4 ov;
+                unpk2(o[0], ov.x, ov.y);
+                unpk2(o[1], ov.z, ov.w);
+                o4[j2] = ov;
+            }
+        }
+        prev = cur;
+        cur = next;
+        next = next + 1 == kRowSlots ? 0 : next + 1;
+        __syncthreads();
+    }
+}
+
+// the scalar recursion of a*b over the two staged planes
+__device__ __forceinline__ void rows_ab_warp(const RowTile *tb, const RowTile *ta, RowTile *stage, const IirCoef &k,
+                                             int lane, int nch)
+{
+    __syncthreads();
+    int prev = 0, cur = 1, next = 2;
+    IirState st;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
+    {
+        const float4 x = *reinterpret_cast<const float4 *>(&tb[cur][lane][0]);
+        const float4 y = *reinterpret_cast<const float4 *>(&ta[cur][lane][0]);
+        const float xs[4] = {x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) (void)iir_step(k, st, 0.0f, xs[i]);
+    }
+#pragma unroll 1
+    for (int t = 0; t <= nch; ++t) {
+        if (t < nch) {
+            float v[44];
+            auto load4 = [&](int slot_, int j4, int at) {
+                const float4 x = *reinterpret_cast<const float4 *>(&tb[slot_][lane][4 * j4]);
+                const float4 y = *reinterpret_cast<const float4 *>(&ta[slot_][lane][4 * j4]);
+                unpk2(mul2(pk2(x.x, x.y), pk2(y.x, y.y)), v[at], v[at + 1]);
+                unpk2(mul2(pk2(x.z, x.w), pk2(y.z, y.w)), v[at + 2], v[at + 3]);
+            };
+            load4(prev, 6, 0);
+            load4(prev, 7, 4);
+#pragma unroll
+            for (int j4 = 0; j4 < kIirChunk / 4; ++j4) load4(cur, j4, 8 + 4 * j4);
+            load4(next, 0, 40);
+            float sum[kIirChunk];
+#pragma unroll
+            for (int j = 0; j < kIirChunk; ++j) sum[j] = v[j + 2] + v[j + 12];   // scalar: both are products
+            float4 *o4 = reinterpret_cast<float4 *>(&stage[t & 1][lane][0]);
+            IirPipe P;
+            pipe_begin(k, P, st, sum[0]);
+#pragma unroll
+            for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
+                float o[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * j4 + jj;
+                    o[jj] = (j + 1 < kIirChunk) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
+                }
+                o4[j4] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        prev = cur;
+        cur = next;
+        next = next + 1 == kRowSlots ? 0 : next + 1;
+        __syncthreads();
+    }
+}
+
+// Helpers move 16 bytes per lane: columns 4*(l&7)..+3 of rows (l>>3) + 4i, i = 0..7.  Rows beyond the image
+// are clamped to a valid address and zero-filled (loads) or skipped (stores).
+struct RowsLanes {
+    int sub_row, sub_col;
+    unsigned row_off[kIirRows / 4];
+    bool row_ok[kIirRows / 4];
+};
+
+__device__ __forceinline__ RowsLanes rows_lanes(int lane, int rows_here, int pitch)
+{
+    RowsLanes L;
+    L.sub_row = lane >> 3;
+    L.sub_col = (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < kIirRows / 4; ++i) {
+        const int row = L.sub_row + 4 * i;
+        L.row_ok[i] = row < rows_here;
+        L.row_off[i] = (unsigned)(min(row, rows_here - 1) * pitch) + L.sub_col;
+    }
+    return L;
+}
+
+__device__ __forceinline__ void rows_loader_warp(RowTile *tb, RowTile *ta, const float *gb, const float *ga, int w,
+                                                 const RowsLanes &L, int nch)
+{
+    auto issue_tile = [&](int t, int slot) {
+        const int gx = t * kIirChunk + L.sub_col;
+        int bytes = 0;
+        if (t >= 0 && gx < w) bytes = min(4, w - gx) * 4;
+        const unsigned col_off = bytes ? (unsigned)(t * kIirChunk) : 0u;
+        const float *c0 = gb + col_off, *c1 = ga + col_off;
+#pragma unroll
+        for (int i = 0; i < kIirRows / 4; ++i) {
+            const int nb = L.row_ok[i] ? bytes : 0;
+            cp_async_16(&tb[slot][L.sub_row + 4 * i][L.sub_col], c0 + L.row_off[i], nb);
+            cp_async_16(&ta[slot][L.sub_row + 4 * i][L.sub_col], c1 + L.row_off[i], nb);
+        }
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (int t = -1; t < kRowAhead; ++t) issue_tile(t, t + 1);
+    cp_async_wait<kRowAhead - 2>();       // tiles -1, 0, 1 have landed
+    __syncthreads();
+    int slot = kRowAhead + 1;             // slot of tile t + kRowAhead
+#pragma unroll 1
+    for (int t = 0; t <= nch; ++t) {
+        issue_tile(t + kRowAhead, slot);  // into the slot of tile t-2: nobody reads it any more
+        slot = slot + 1 == kRowSlots ? 0 : slot + 1;
+        cp_async_wait<kRowAhead - 2>();   // tile t+2 has landed
+        __syncthreads();
+    }
+}
+
+// chunk t-1 leaves staging buffer (t-1) & 1 while chunk t is computed
+template <bool WITH_SINGLE>
+__device__ __forceinline__ void rows_storer_warp(const RowPairStage *pstage, const RowTile *sstage, float *o0, float *o1,
+                                                 float *o2, const RowsLanes &L, int nch, bool active)
+{
+    __syncthreads();
+#pragma unroll 1
+    for (int t = 0; t <= nch; ++t) {
+        if (t > 0 && active) {
+            const int buf = (t - 1) & 1;
+            const unsigned col_off = (unsigned)((t - 1) * kIirChunk);
+            float *c0 = o0 + col_off, *c1 = o1 + col_off, *c2 = o2 + col_off;
+#pragma unroll
+            for (int i = 0; i < kIirRows / 4; ++i) {
+                const int row = L.sub_row + 4 * i;
+                const float4 l0 = *reinterpret_cast<const float4 *>(&pstage[buf][row][2 * L.sub_col]);
+                const float4 l1 = *reinterpret_cast<const float4 *>(&pstage[buf][row][2 * L.sub_col + 4]);
+                if (L.row_ok[i]) {
+                    __stcs(reinterpret_cast<float4 *>(c0 + L.row_off[i]), make_float4(l0.x, l0.z, l1.x, l1.z));
+                    __stcs(reinterpret_cast<float4 *>(c1 + L.row_off[i]), make_float4(l0.y, l0.w, l1.y, l1.w));
+                }
+                if (WITH_SINGLE) {
+                    const float4 l2 = *reinterpret_cast<const float4 *>(&sstage[buf][row][L.sub_col]);
+                    if (L.row_ok[i]) __stcs(reinterpret_cast<float4 *>(c2 + L.row_off[i]), l2);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 2 ? 192 : 128) k_iir_rows(const __grid_constant__ IirArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IirRowsSmem<MODE> &sm = *reinterpret_cast<IirRowsSmem<MODE> *>(smem_raw);
-    constexpr int NPL = IirRowsSmem<MODE>::NPL;
-    constexpr int NREC = MODE == 0 ? 1 : 2;   // recursion warps
-    constexpr int kIirSlots = IirRing<MODE>::kSlots, kIirAhead = IirRing<MODE>::kAhead;
+    constexpr int NW = MODE == 2 ? 6 : 4;
 
     int s, c, rb;
     decode_cta(a, blockIdx.x, s, c, rb);
@@ -263,193 +468,36 @@ __global__ void __launch_bounds__(MODE == 0 ? 96 : 128) k_iir_rows(const __grid_
     const int rows_here = min(kIirRows, h - y0);
     const long long poff = a.g.off[s] + (long long)c * a.g.plane[s] + (long long)y0 * pitch;
     // Roles rotate with the CTA index: hardware warp w of a CTA runs on sub-partition w % 4, and the
-    // recursion warps are the long poles — co-resident CTAs must not stack them on one sub-partition.
+    // recursion warps are the long poles — co-resident CTAs should not stack them on one sub-partition.
     const int lane = threadIdx.x & 31;
-    const int warp = (int)(((threadIdx.x >> 5) + blockIdx.x) % (NREC + 2));
+    const int role = (int)(((threadIdx.x >> 5) + blockIdx.x) % NW);
     const int nch = (w + kIirChunk - 1) / kIirChunk;
-    const IirCoef k = a.k;
+    const bool with_src = MODE == 2 && cand == 0;
+    const float *gb = a.dist + (long long)cand * a.dist_stride + poff, *ga = a.src + poff;
 
-    if (warp >= NREC) {
-        // ---------------- helpers: all global memory traffic ----------------
-        // lane l moves 16 bytes = columns 4*(l&7)..+3 of rows (l>>3) + 4i, i = 0..7.  Rows beyond the
-        // image are clamped to a valid address and zero-filled (loads) or skipped (stores).
-        const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
-        unsigned row_off[kIirRows / 4];
-        bool row_ok[kIirRows / 4];
-#pragma unroll
-        for (int i = 0; i < kIirRows / 4; ++i) {
-            const int row = sub_row + 4 * i;
-            row_ok[i] = row < rows_here;
-            row_off[i] = (unsigned)(min(row, rows_here - 1) * pitch) + sub_col;
-        }
-        if (warp == NREC) {
-            // loader: tile t lives in slot (t + 1) mod 6
-            const float *g0 = (MODE == 0 ? a.src : a.dist + (long long)cand * a.dist_stride) + poff;
-            const float *g1 = a.src + poff;
-            auto issue_tile = [&](int t, int slot) {
-                const int gx = t * kIirChunk + sub_col;
-                int bytes = 0;
-                if (t >= 0 && gx < w) bytes = min(4, w - gx) * 4;
-                const unsigned col_off = bytes ? (unsigned)(t * kIirChunk) : 0u;
-                const float *c0 = g0 + col_off, *c1 = g1 + col_off;
-#pragma unroll
-                for (int i = 0; i < kIirRows / 4; ++i) {
-                    const int nb = row_ok[i] ? bytes : 0;
-                    cp_async_16(&sm.tile[0][slot][sub_row + 4 * i][sub_col], c0 + row_off[i], nb);
-                    if (NPL == 2) cp_async_16(&sm.tile[NPL - 1][slot][sub_row + 4 * i][sub_col], c1 + row_off[i], nb);
-                }
-                cp_async_commit();
-            };
-#pragma unroll 1
-            for (int t = -1; t < kIirAhead; ++t) issue_tile(t, t + 1);
-            cp_async_wait<kIirAhead - 2>();   // tiles -1, 0, 1 have landed
-            __syncthreads();              // (P)
-            int slot = kIirAhead + 1 == kIirSlots ? 0 : kIirAhead + 1;   // slot of tile t + kIirAhead
-#pragma unroll 1
-            for (int t = 0; t <= nch; ++t) {
-                issue_tile(t + kIirAhead, slot);   // into the slot of tile t-2: nobody reads it any more
-                slot = slot + 1 == kIirSlots ? 0 : slot + 1;
-                cp_async_wait<kIirAhead - 2>();    // tile t+2 has landed
-                __syncthreads();                   // (t)
-            }
-        } else {
-            // storer: chunk t-1 leaves staging buffer (t-1) & 1 while chunk t is computed
-            float *o0 = a.hq[MODE == 0 ? 0 : 1] + (long long)cand * a.hq_cand_stride[MODE == 0 ? 0 : 1] + poff;
-            float *o1 = a.hq[MODE == 0 ? 2 : 3] + (long long)cand * a.hq_cand_stride[MODE == 0 ? 2 : 3] + poff;
-            float *o2 = a.hq[4] + (long long)cand * a.hq_cand_stride[4] + poff;
-            __syncthreads();              // (P)
-#pragma unroll 1
-            for (int t = 0; t <= nch; ++t) {
-                if (t > 0) {
-                    const int buf = (t - 1) & 1;
-                    const unsigned col_off = (unsigned)((t - 1) * kIirChunk);
-                    float *c0 = o0 + col_off, *c1 = o1 + col_off, *c2 = o2 + col_off;
-#pragma unroll
-                    for (int i = 0; i < kIirRows / 4; ++i) {
-                        const int row = sub_row + 4 * i;
-                        const float4 l0 = *reinterpret_cast<const float4 *>(&sm.pair[buf][row][2 * sub_col]);
-                        const float4 l1 = *reinterpret_cast<const float4 *>(&sm.pair[buf][row][2 * sub_col + 4]);
-                        if (row_ok[i]) {
-                            __stcs(reinterpret_cast<float4 *>(c0 + row_off[i]), make_float4(l0.x, l0.z, l1.x, l1.z));
-                            __stcs(reinterpret_cast<float4 *>(c1 + row_off[i]), make_float4(l0.y, l0.w, l1.y, l1.w));
-                        }
-                        if (MODE == 1) {
-                            const float4 l2 = *reinterpret_cast<const float4 *>(&sm.single[buf][row][sub_col]);
-                            if (row_ok[i]) __stcs(reinterpret_cast<float4 *>(c2 + row_off[i]), l2);
-                        }
-                    }
-                }
-                __syncthreads();                   // (t)
-            }
-        }
-        return;
-    }
-
-    // ---------------- recursion warps: lane = row ----------------
-    __syncthreads();                           // (P)
-    int prev = 0, cur = 1, next = 2;           // slots of tiles t-1, t, t+1
-    if (warp == 0) {
-        // the pair (x, x*x) of plane 0
-        const IirCoef2 k2 = iir_coef2(k, a.one, a.neg_one);
-        IirState2 st;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = splat2(0.0f);
-        {   // n = -4 .. -1: right taps are columns 0..3 of tile 0, left taps are padding, nothing emitted
-            const float4 x = *reinterpret_cast<const float4 *>(&sm.tile[0][cur][lane][0]);
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) (void)iir_step2(k2, st, splat2(0.0f), pk2(xs[i], xs[i] * xs[i]));
-        }
-#pragma unroll 1
-        for (int t = 0; t <= nch; ++t) {
-            if (t < nch) {
-                // samples v[i] = plane value at column 32t - 8 + i, i = 0..43; q[i] its square
-                float v[44], q[44];
-                auto load4 = [&](int slot_, int j4, int at) {
-                    const float4 x = *reinterpret_cast<const float4 *>(&sm.tile[0][slot_][lane][4 * j4]);
-                    v[at] = x.x; v[at + 1] = x.y; v[at + 2] = x.z; v[at + 3] = x.w;
-                    unpk2(mul2(pk2(x.x, x.y), pk2(x.x, x.y)), q[at], q[at + 1]);
-                    unpk2(mul2(pk2(x.z, x.w), pk2(x.z, x.w)), q[at + 2], q[at + 3]);
-                };
-                load4(prev, 6, 0);
-                load4(prev, 7, 4);
-#pragma unroll
-                for (int j4 = 0; j4 < kIirChunk / 4; ++j4) load4(cur, j4, 8 + 4 * j4);
-                load4(next, 0, 40);
-                // step j (output column 32t + j): left tap column 32t + j - 6 = [j+2], right tap 32t + j + 4 = [j+12]
-                float4 *o4 = reinterpret_cast<float4 *>(&sm.pair[t & 1][lane][0]);
-                IirPipe2 P;
-                pipe2_begin(k2, P, st, pk2(v[2] + v[12], q[2] + q[12]));
-#pragma unroll
-                for (int j2 = 0; j2 < kIirChunk / 2; ++j2) {
-                    f32x2 o[2];
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        const int j = 2 * j2 + jj;
-                        o[jj] = (j + 1 < kIirChunk)
-                                    ? pipe2_step(k2, P, pk2(v[j + 3] + v[j + 13], q[j + 3] + q[j + 13]))
-                                    : pipe2_end(k2, P, st);
-                    }
-                    float4 ov;
-                    unpk2(o[0], ov.x, ov.y);
-                    unpk2(o[1], ov.z, ov.w);
-                    o4[j2] = ov;
-                }
-            }
-            prev = cur;
-            cur = next;
-            next = next + 1 == kIirSlots ? 0 : next + 1;
-            __syncthreads();                   // (t)
-        }
-    } else if (MODE == 1) {
-        // a*b: plane 0 = b, plane 1 = a
-        IirState st;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
-        {
-            const float4 x = *reinterpret_cast<const float4 *>(&sm.tile[0][cur][lane][0]);
-            const float4 y = *reinterpret_cast<const float4 *>(&sm.tile[NPL - 1][cur][lane][0]);
-            const float xs[4] = {x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) (void)iir_step(k, st, 0.0f, xs[i]);
-        }
-#pragma unroll 1
-        for (int t = 0; t <= nch; ++t) {
-            if (t < nch) {
-                float v[44];
-                auto load4 = [&](int slot_, int j4, int at) {
-                    const float4 x = *reinterpret_cast<const float4 *>(&sm.tile[0][slot_][lane][4 * j4]);
-                    const float4 y = *reinterpret_cast<const float4 *>(&sm.tile[NPL - 1][slot_][lane][4 * j4]);
-                    unpk2(mul2(pk2(x.x, x.y), pk2(y.x, y.y)), v[at], v[at + 1]);
-                    unpk2(mul2(pk2(x.z, x.w), pk2(y.z, y.w)), v[at + 2], v[at + 3]);
-                };
-                load4(prev, 6, 0);
-                load4(prev, 7, 4);
-#pragma unroll
-                for (int j4 = 0; j4 < kIirChunk / 4; ++j4) load4(cur, j4, 8 + 4 * j4);
-                load4(next, 0, 40);
-                float sum[kIirChunk];
-#pragma unroll
-                for (int j = 0; j < kIirChunk; ++j) sum[j] = v[j + 2] + v[j + 12];   // scalar: both are products
-                float4 *o4 = reinterpret_cast<float4 *>(&sm.single[t & 1][lane][0]);
-                IirPipe P;
-                pipe_begin(k, P, st, sum[0]);
-#pragma unroll
-                for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
-                    float o[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = 4 * j4 + jj;
-                        o[jj] = (j + 1 < kIirChunk) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
-                    }
-                    o4[j4] = make_float4(o[0], o[1], o[2], o[3]);
-                }
-            }
-            prev = cur;
-            cur = next;
-            next = next + 1 == kIirSlots ? 0 : next + 1;
-            __syncthreads();                   // (t)
-        }
+    switch (role) {
+    case 0:   // (b, b*b)
+        rows_pair_warp(sm.tile[0], sm.pair[0], a.k, a.one, a.neg_one, lane, nch, true);
+        break;
+    case 1:   // a*b
+        rows_ab_warp(sm.tile[0], sm.tile[1], sm.single, a.k, lane, nch);
+        break;
+    case 2:
+        rows_loader_warp(sm.tile[0], sm.tile[1], gb, ga, w, rows_lanes(lane, rows_here, pitch), nch);
+        break;
+    case 3:
+        rows_storer_warp<true>(sm.pair[0], sm.single, a.hq[1] + (long long)cand * a.hq_cand_stride[1] + poff,
+                               a.hq[3] + (long long)cand * a.hq_cand_stride[3] + poff,
+                               a.hq[4] + (long long)cand * a.hq_cand_stride[4] + poff,
+                               rows_lanes(lane, rows_here, pitch), nch, true);
+        break;
+    case 4:   // MODE 2: (a, a*a) of the source, by candidate 0's CTAs
+        rows_pair_warp(sm.tile[1], sm.pair[IirRowsSmem<MODE>::NPAIR - 1], a.k, a.one, a.neg_one, lane, nch, with_src);
+        break;
+    default:
+        rows_storer_warp<false>(sm.pair[IirRowsSmem<MODE>::NPAIR - 1], sm.single, a.hq[0] + poff, a.hq[2] + poff, nullptr,
+                                rows_lanes(lane, rows_here, pitch), nch, with_src);
+        break;
     }
 }
 
@@ -779,16 +827,10 @@ inline cudaError_t iir_configure()
     cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(IirColsDeep));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_iir_rows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<0>));
+    e = cudaFuncSetAttribute(k_iir_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<1>));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_iir_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<1>));
+    return cudaFuncSetAttribute(k_iir_rows<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<2>));
 }
-
-struct IirStreams {
-    cudaStream_t side;       // source-side rows tasks (a, a*a), behind set_source
-    cudaEvent_t fork;        // main -> side
-    cudaEvent_t src_done;    // the source's cached row-filtered planes are complete (recorded on `side`)
-};
 
 struct IirBuffers {
     float *src_hplanes;      // [2][pyramid]: rows pass of a and a*a, cached per source
@@ -827,29 +869,12 @@ inline int iir_rows_grid(IirArgs &a, const Geom &g)
     return n;
 }
 
-// Source side, once per set_source: rows pass of a and a*a into the per-source cache.  Runs on the side
-// stream behind the source pyramid, so it overlaps the candidate's upload and pyramid.
-inline cudaError_t launch_iir_source_rows(const Geom &g, const IirCoef &k, const float *src_pyr, const IirBuffers &B,
-                                          cudaStream_t st, const IirStreams &ss, int *launches)
-{
-    IirArgs a{};
-    iir_fill_common(a, g, k, src_pyr, src_pyr, 0, B);
-    const int n = iir_rows_grid(a, g);
-    cudaEventRecord(ss.fork, st);                 // after the source pyramid
-    cudaStreamWaitEvent(ss.side, ss.fork, 0);
-    k_iir_rows<0><<<dim3(n, 1), 96, sizeof(IirRowsSmem<0>), ss.side>>>(a);
-    const cudaError_t e = cudaGetLastError();
-    cudaEventRecord(ss.src_done, ss.side);
-    *launches = 1;
-    return e;
-}
-
-// Candidate side: rows pass of b, b*b and a*b, then the columns pass with the maps and the pooling.
-// `between` is recorded between the two passes.
+// Rows pass of b, b*b and a*b (and, when the source's cache is cold, of a and a*a), then the columns pass
+// with the maps and the pooling.  `between` is recorded between the two passes.
 inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float *src, const float *dist,
                                    long long pyr_stride, const IirBuffers &B, double *partials,
                                    long long partials_stride, const int *first_cta_cols, const int *col_blocks, int n,
-                                   cudaStream_t st, const IirStreams &ss, cudaEvent_t between, int *launches,
+                                   cudaStream_t st, bool with_source_rows, cudaEvent_t between, int *launches,
                                    bool rows_only = false)
 {
     IirArgs a{};
@@ -858,10 +883,12 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     a.partials_stride = partials_stride;
     IirArgs ar = a;
     const int nr = iir_rows_grid(ar, g);
-    k_iir_rows<1><<<dim3(nr, n), 128, sizeof(IirRowsSmem<1>), st>>>(ar);
+    if (with_source_rows)
+        k_iir_rows<2><<<dim3(nr, n), 192, sizeof(IirRowsSmem<2>), st>>>(ar);
+    else
+        k_iir_rows<1><<<dim3(nr, n), 128, sizeof(IirRowsSmem<1>), st>>>(ar);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    cudaStreamWaitEvent(st, ss.src_done, 0);      // the source's cached rows
     if (between) cudaEventRecord(between, st);
     *launches = 1;
     if (rows_only) return cudaSuccess;
