@@ -502,18 +502,17 @@ __global__ void __launch_bounds__(MODE == 2 ? 192 : 128) k_iir_rows(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 288.
+// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 256.
 //
 // One CTA owns 32 columns of one channel; lane = column in the arithmetic, so the recursions of a warp
-// are 32 independent columns.  Warps 0..4 (producers) each stream ONE row-filtered plane down the image
-// through a private shared-memory ring.  The ring is fed by 16-byte cp.async: one instruction moves
-// four whole 128-byte row segments (8 lanes per row), RCAP-18 rows ahead of use; both taps of the
-// recursion are read back from the ring (no register delay line).  Each producer drops its filtered
-// values into a double-buffered 8-row batch.  Warps 5..8 (consumers), one batch behind, stream the
-// pixel's own XYB samples the same way and evaluate the SSIM / edge-diff maps and the six pooled sums
-// for two rows of the batch each (a producer step costs ~17 instructions, a map pixel ~70, so 5 + 4
-// warps are balanced).  Nine warps per task give a sub-partition enough independent work to hide
-// latencies when a single 4K pair is all the GPU has.  One block barrier per 8 rows.
+// are 32 independent columns.  Warps 0..2 (producers) stream row-filtered planes down the image through
+// private shared-memory rings: warp 0 the pair (a, b), warp 1 the pair (a*a, b*b) — two planes, one
+// packed recursion —, warp 2 a*b alone.  The rings are fed by 16-byte cp.async: one instruction moves
+// four whole 128-byte row segments (8 lanes per row), 32 rows ahead of use; both taps of the recursion
+// are read back from the ring (no register delay line).  Each producer drops its filtered values into a
+// double-buffered 16-row batch.  Warps 3..7 (consumers), one batch behind, stream the pixel's own XYB
+// samples the same way and evaluate the SSIM / edge-diff maps and the six pooled sums, two rows of a
+// column as one packed pair.  One block barrier per 16 rows.
 constexpr int kIirVThreads = 256;   // 3 producer warps + 5 consumer warps
 
 template <int RCAP, int B>
@@ -524,8 +523,8 @@ struct IirColsSmem {
     double red[5][6];
 };
 
-// B rows per exchange batch (16 with the deep ring, 8 with the shallow one): the per-batch overhead
-// (barrier, copy issue, address set-up) is paid once per B rows by each of the nine warps.
+// B rows per exchange batch: the per-batch overhead (barrier, copy issue, address set-up) is paid once
+// per B rows by each of the eight warps.  RCAP = rows of a producer ring.
 template <int RCAP, int B>
 __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a)
 {

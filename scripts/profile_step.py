@@ -31,6 +31,11 @@ def main():
             sc.score_batch_dev("yuv444", [[y.data_ptr(), u.data_ptr(), v.data_ptr()]], [2 * bench.W] * 3, depth=10)
             t = sc.timing()
             print(f"step {i}: pyr {t.pyramid_ms:.3f} a {t.blur_a_ms:.3f} b {t.blur_b_ms:.3f} fin {t.finalize_ms:.3f} total {t.total_ms:.3f}")
+        # one more candidate against the same source: the cached-source path (k_iir_rows<1>)
+        s, (y, u, v) = dev[a.steps % 2]
+        sc.score_batch_dev("yuv444", [[y.data_ptr(), u.data_ptr(), v.data_ptr()]], [2 * bench.W] * 3, depth=10)
+        t = sc.timing()
+        print(f"cached: pyr {t.pyramid_ms:.3f} a {t.blur_a_ms:.3f} b {t.blur_b_ms:.3f} fin {t.finalize_ms:.3f} total {t.total_ms:.3f}")
 
 
 if __name__ == "__main__":
