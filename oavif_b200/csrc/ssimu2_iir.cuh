@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 192 : 128) k_iir_rows(const __grid
 // double-buffered 16-row batch.  Warps 3..7 (consumers), one batch behind, stream the pixel's own XYB
 // samples the same way and evaluate the SSIM / edge-diff maps and the six pooled sums, two rows of a
 // column as one packed pair.  One block barrier per 16 rows.
-constexpr int kIirVThreads = 256;   // 3 producer warps + 5 consumer warps
+constexpr int kIirVThreads = 288;   // 3 producer warps + 5 consumer warps + 1 loader warp
 
 template <int RCAP, int B>
 struct IirColsSmem {
@@ -547,32 +547,52 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     // bytes of this lane's 16-byte column group that lie inside the image: the rest is zero-filled
     const int cbytes = max(0, min(16, (w - (cb * kIirVCols + ccol)) * 4));
 
-    if (warp < 2) {
-        // ---------------- pair producers: the column recursions of quantities 2*warp, 2*warp + 1 ----------------
-        // (a, b) and (a*a, b*b): two planes, one packed recursion per column
-        const int q0 = 2 * warp;
-        const float *ph0 = a.hq[q0] + (long long)cand * a.hq_cand_stride[q0] + poff + ccol;
-        const float *ph1 = a.hq[q0 + 1] + (long long)cand * a.hq_cand_stride[q0 + 1] + poff + ccol;
-        const IirCoef2 k = iir_coef2(a.k, a.one, a.neg_one);
-        float *ring0 = &sm.ring[q0][0][0], *ring1 = &sm.ring[q0 + 1][0][0];
-        auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h) of both planes: 16 bytes per lane each
+    if (warp == 8) {
+        // ---------------- loader: feeds the five producer rings ----------------
+        // Batch b (rows n0 = 16b ..) reads ring rows n0-6 .. n0+B+3.  The loader requests rows n0+4+D .. n0+3+D+B
+        // while batch b runs (their slots held rows n0-28 .. n0-13, dead by then) and arrives at the barrier
+        // that ends batch b only when everything batch b+1 reads has landed.
+        const float *ph[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) ph[q] = a.hq[q] + (long long)cand * a.hq_cand_stride[q] + poff + ccol;
+        float *ring = &sm.ring[0][0][0] + ccol;
+        constexpr int kPlane = RCAP * kIirVCols;
+        auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h) of all five planes: 16 bytes per lane each
             const int rr = r0 + crow;
             const unsigned go = (unsigned)(min(rr, h - 1) * pitch);
-            const int so = (rr & (RCAP - 1)) * kIirVCols + ccol, nb = rr < h ? cbytes : 0;
-            cp_async_16(ring0 + so, ph0 + go, nb);
-            cp_async_16(ring1 + so, ph1 + go, nb);
+            const int so = (rr & (RCAP - 1)) * kIirVCols, nb = rr < h ? cbytes : 0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) cp_async_16(ring + q * kPlane + so, ph[q] + go, nb);
         };
         // rows -6..-1 are padding: their ring slots hold zeros until real rows wrap around to them
 #pragma unroll
-        for (int j = 1; j <= 6; ++j) ring0[(RCAP - j) * kIirVCols + lane] = ring1[(RCAP - j) * kIirVCols + lane] = 0.0f;
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int j = 1; j <= 6; ++j) sm.ring[q][RCAP - j][lane] = 0.0f;
         for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0);   // everything before the first batch's request
         cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();      // (S) rows 0 .. 3+D are in the rings
+#pragma unroll 1
+        for (int b = 0; b < nbatch; ++b) {
+#pragma unroll
+            for (int j = 0; j < B; j += 4) issue_rows4(b * B + 4 + D + j);
+            cp_async_commit();
+            cp_async_wait<D / B - 1>();   // rows up to (b+1)*B + B + 3 have landed
+            __syncthreads();              // (b)
+        }
+        __syncthreads();      // consumers' last batch
+        __syncthreads();      // final reduction
+    } else if (warp < 2) {
+        // ---------------- pair producers: the column recursions of quantities 2*warp, 2*warp + 1 ----------------
+        // (a, b) and (a*a, b*b): two planes, one packed recursion per column
+        const int q0 = 2 * warp;
+        const IirCoef2 k = iir_coef2(a.k, a.one, a.neg_one);
         IirState2 st;
 #pragma unroll
         for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = splat2(0.0f);
-        cp_async_wait<0>();
-        __syncwarp();
-        const float *c0 = ring0 + lane, *c1 = ring1 + lane;
+        const float *c0 = &sm.ring[q0][0][lane], *c1 = &sm.ring[q0 + 1][0][lane];
+        __syncthreads();      // (S)
         // n = -4..-1: right taps are rows 0..3, left taps are padding, nothing emitted
 #pragma unroll
         for (int n = -4; n < 0; ++n)
@@ -581,13 +601,8 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             const int n0 = b * B;
-#pragma unroll
-            for (int j = 0; j < B; j += 4) issue_rows4(n0 + 4 + D + j);
-            cp_async_commit();
-            cp_async_wait<D / B>();                    // rows up to n0 + B + 3 have landed (this lane's copies)
-            __syncwarp();                              // ... and every other lane's
-            // n0 is a multiple of B (8 or 16) and so is RCAP: the left taps (rows n0-6+j) can only wrap at
-            // j = 6, the right taps (rows n0+4+j) only at j = B-4 -> two bases each, static offsets otherwise
+            // n0 is a multiple of B and so is RCAP: the left taps (rows n0-6+j) can only wrap at j = 6, the
+            // right taps (rows n0+4+j) only at j = B-4 -> two bases each, static offsets otherwise
             const int ol0 = ((n0 - 6) & (RCAP - 1)) * kIirVCols, ol1 = (n0 & (RCAP - 1)) * kIirVCols;
             const int or0 = ((n0 + 4) & (RCAP - 1)) * kIirVCols, or1 = ((n0 + B) & (RCAP - 1)) * kIirVCols;
             f32x2 sum[B];
@@ -605,42 +620,25 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
                 const f32x2 o = (j + 1 < B) ? pipe2_step(k, P, sum[j + 1]) : pipe2_end(k, P, st);
                 unpk2(o, ex0[j * kIirVCols], ex1[j * kIirVCols]);
             }
-            __syncthreads();  // batch b published; the consumers are done with the other buffer
+            __syncthreads();  // (b) batch b published; the consumers are done with the other buffer
         }
         __syncthreads();      // consumers' last batch
         __syncthreads();      // final reduction
     } else if (warp == 2) {
         // ---------------- single producer: the column recursion of a*b ----------------
         const int q = 4;
-        const float *ph = a.hq[q] + (long long)cand * a.hq_cand_stride[q] + poff + ccol;
         const IirCoef k = a.k;
-        float *ring = &sm.ring[q][0][0];
-        auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h): one 16-byte copy per lane
-            const int rr = r0 + crow;
-            cp_async_16(ring + (rr & (RCAP - 1)) * kIirVCols + ccol, ph + (unsigned)(min(rr, h - 1) * pitch),
-                        rr < h ? cbytes : 0);
-        };
-#pragma unroll
-        for (int j = 1; j <= 6; ++j) ring[(RCAP - j) * kIirVCols + lane] = 0.0f;
-        for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0);
-        cp_async_commit();
         IirState st;
 #pragma unroll
         for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
-        cp_async_wait<0>();
-        __syncwarp();
-        const float *col = ring + lane;
+        const float *col = &sm.ring[q][0][lane];
+        __syncthreads();      // (S)
 #pragma unroll
         for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, col[(n + 4) * kIirVCols]);
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             const int n0 = b * B;
-#pragma unroll
-            for (int j = 0; j < B; j += 4) issue_rows4(n0 + 4 + D + j);
-            cp_async_commit();
-            cp_async_wait<D / B>();
-            __syncwarp();
             float sum[B];
             const float *l0 = col + ((n0 - 6) & (RCAP - 1)) * kIirVCols, *l1 = col + (n0 & (RCAP - 1)) * kIirVCols;
             const float *r0 = col + ((n0 + 4) & (RCAP - 1)) * kIirVCols, *r1 = col + ((n0 + B) & (RCAP - 1)) * kIirVCols;
@@ -654,22 +652,23 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
 #pragma unroll
             for (int j = 0; j < B; ++j)
                 ex[j * kIirVCols] = (j + 1 < B) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
-            __syncthreads();
+            __syncthreads();  // (b)
         }
         __syncthreads();
         __syncthreads();
     } else {
         // ---------------- consumers: maps + pooling ----------------
         // Five consumer warps share the eight row pairs (2p, 2p+1), p = 0..7, of a 16-row batch so that the
-        // four sub-partitions of the SM carry equal work next to the three producers (warp w runs on
-        // sub-partition w % 4; a pair producer costs ~430 instructions per batch, the a*b producer ~340, a
-        // row pair of maps ~125):  warp 3: p0 p1, warp 7: p2 p3, warp 6: p4 p5, warp 4: p6, warp 5: p7.
+        // four sub-partitions of the SM carry equal work next to the three producers and the loader (warp w
+        // runs on sub-partition w % 4; a pair producer costs ~310 instructions per batch, the a*b producer
+        // ~240, the loader ~150, a row pair of maps ~125):
+        //   warp 3: p0 p1, warp 5: p2 p3, warp 6: p4 p5, warp 4: p6, warp 7: p7.
         // A consumer evaluates the two rows of a pair as one packed pair per column, and stages the XYB rows
         // it needs itself.  Columns beyond the image need no test: every ring is zero-filled there by the
         // copies, and all-zero inputs pool to exactly zero.
         const int cw = warp - 3;                                   // 0..4
-        const int first_pair = cw == 0 ? 0 : cw == 4 ? 2 : cw == 3 ? 4 : cw == 1 ? 6 : 7;
-        const int npairs = (cw == 1 || cw == 2) ? 1 : 2;
+        const int first_pair = cw == 0 ? 0 : cw == 2 ? 2 : cw == 3 ? 4 : cw == 1 ? 6 : 7;
+        const int npairs = (cw == 1 || cw == 4) ? 1 : 2;
         const bool stager = crow < 2 * npairs;                     // lanes that copy: 8 per row
         const int srow = 2 * first_pair + crow;
         const float *pa = a.src + poff + ccol;
@@ -688,6 +687,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         issue_ab(0);
         cp_async_commit();
         cp_async_wait<0>();   // the in-loop wait only covers groups committed inside the loop
+        __syncthreads();      // (S)
         const Unit2 u = unit2(a.one, a.neg_one);
         const f32x2 zero = splat2(0.0f);
         f32x2 acc[6];
