@@ -104,10 +104,14 @@ struct IirArgs {
     const float *src;
     const float *dist;
     long long dist_stride;      // floats between candidates' pyramids
-    // row-filtered planes, pyramid layout each.  a and a*a only depend on the source: they live in a
-    // per-source cache (candidate stride 0) written once by set_source; b, b*b, a*b are per candidate.
-    float *hq[5];
-    long long hq_cand_stride[5];
+    // Row-filtered planes.  The pairs (a, a*a) and (b, b*b) are stored INTERLEAVED per pixel (one float2 per
+    // pixel: the rows pass produces them that way and the columns pass consumes them that way), pyramid
+    // layout with every offset and pitch doubled; a*b is a plain pyramid.  (a, a*a) only depends on the
+    // source and lives in a per-source cache; the other two are per candidate.
+    float *hpair_src;           // [2 * pyramid]
+    float *hpair_cand;          // [candidate][2 * pyramid], stride hcand_stride
+    float *hab;                 // [candidate][pyramid],     stride hcand_stride
+    long long hcand_stride;
     double *partials;
     long long partials_stride;
     float one, neg_one;         // 1.0f and -1.0f as run-time values (Unit2)
@@ -422,28 +426,31 @@ __device__ __forceinline__ void rows_loader_warp(RowTile *tb, RowTile *ta, const
     }
 }
 
-// chunk t-1 leaves staging buffer (t-1) & 1 while chunk t is computed
+// chunk t-1 leaves staging buffer (t-1) & 1 while chunk t is computed.  A pair row of a chunk is 256
+// contiguous bytes (32 pixels x float2): 16 lanes per row, two rows per instruction; an a*b row is 128.
 template <bool WITH_SINGLE>
-__device__ __forceinline__ void rows_storer_warp(const RowPairStage *pstage, const RowTile *sstage, float *o0, float *o1,
-                                                 float *o2, const RowsLanes &L, int nch, bool active)
+__device__ __forceinline__ void rows_storer_warp(const RowPairStage *pstage, const RowTile *sstage, float *opair,
+                                                 float *oab, const RowsLanes &L, int lane, int rows_here, int pitch,
+                                                 int nch, bool active)
 {
+    const int prow = lane >> 4, ppiece = (lane & 15) * 4;
     __syncthreads();
 #pragma unroll 1
     for (int t = 0; t <= nch; ++t) {
         if (t > 0 && active) {
             const int buf = (t - 1) & 1;
-            const unsigned col_off = (unsigned)((t - 1) * kIirChunk);
-            float *c0 = o0 + col_off, *c1 = o1 + col_off, *c2 = o2 + col_off;
+            float *cp = opair + 2 * (t - 1) * kIirChunk + ppiece;
 #pragma unroll
-            for (int i = 0; i < kIirRows / 4; ++i) {
-                const int row = L.sub_row + 4 * i;
-                const float4 l0 = *reinterpret_cast<const float4 *>(&pstage[buf][row][2 * L.sub_col]);
-                const float4 l1 = *reinterpret_cast<const float4 *>(&pstage[buf][row][2 * L.sub_col + 4]);
-                if (L.row_ok[i]) {
-                    __stcs(reinterpret_cast<float4 *>(c0 + L.row_off[i]), make_float4(l0.x, l0.z, l1.x, l1.z));
-                    __stcs(reinterpret_cast<float4 *>(c1 + L.row_off[i]), make_float4(l0.y, l0.w, l1.y, l1.w));
-                }
-                if (WITH_SINGLE) {
+            for (int i = 0; i < kIirRows / 2; ++i) {
+                const int row = prow + 2 * i;
+                const float4 v = *reinterpret_cast<const float4 *>(&pstage[buf][row][ppiece]);
+                if (row < rows_here) __stcs(reinterpret_cast<float4 *>(cp + (unsigned)(row * 2 * pitch)), v);
+            }
+            if (WITH_SINGLE) {
+                float *c2 = oab + (unsigned)((t - 1) * kIirChunk);
+#pragma unroll
+                for (int i = 0; i < kIirRows / 4; ++i) {
+                    const int row = L.sub_row + 4 * i;
                     const float4 l2 = *reinterpret_cast<const float4 *>(&sstage[buf][row][L.sub_col]);
                     if (L.row_ok[i]) __stcs(reinterpret_cast<float4 *>(c2 + L.row_off[i]), l2);
                 }
@@ -486,17 +493,16 @@ __global__ void __launch_bounds__(MODE == 2 ? 192 : 128) k_iir_rows(const __grid
         rows_loader_warp(sm.tile[0], sm.tile[1], gb, ga, w, rows_lanes(lane, rows_here, pitch), nch);
         break;
     case 3:
-        rows_storer_warp<true>(sm.pair[0], sm.single, a.hq[1] + (long long)cand * a.hq_cand_stride[1] + poff,
-                               a.hq[3] + (long long)cand * a.hq_cand_stride[3] + poff,
-                               a.hq[4] + (long long)cand * a.hq_cand_stride[4] + poff,
-                               rows_lanes(lane, rows_here, pitch), nch, true);
+        rows_storer_warp<true>(sm.pair[0], sm.single, a.hpair_cand + (long long)cand * a.hcand_stride + 2 * poff,
+                               a.hab + (long long)cand * a.hcand_stride + poff, rows_lanes(lane, rows_here, pitch), lane,
+                               rows_here, pitch, nch, true);
         break;
     case 4:   // MODE 2: (a, a*a) of the source, by candidate 0's CTAs
         rows_pair_warp(sm.tile[1], sm.pair[IirRowsSmem<MODE>::NPAIR - 1], a.k, a.one, a.neg_one, lane, nch, with_src);
         break;
     default:
-        rows_storer_warp<false>(sm.pair[IirRowsSmem<MODE>::NPAIR - 1], sm.single, a.hq[0] + poff, a.hq[2] + poff, nullptr,
-                                rows_lanes(lane, rows_here, pitch), nch, with_src);
+        rows_storer_warp<false>(sm.pair[IirRowsSmem<MODE>::NPAIR - 1], sm.single, a.hpair_src + 2 * poff, nullptr,
+                                rows_lanes(lane, rows_here, pitch), lane, rows_here, pitch, nch, with_src);
         break;
     }
 }
@@ -517,7 +523,8 @@ constexpr int kIirVThreads = 288;   // 3 producer warps + 5 consumer warps + 1 l
 
 template <int RCAP, int B>
 struct IirColsSmem {
-    float ring[5][RCAP][kIirVCols];            // producer input rows, row r at [r & (RCAP-1)]
+    float pring[2][RCAP][2 * kIirVCols];       // producer input rows of the pairs (a, a*a), (b, b*b), row r at [r & (RCAP-1)]
+    float sring[RCAP][kIirVCols];              // ... and of a*b
     float ab[2][32][kIirVCols];                // consumer rows of the two XYB planes
     float ex[2][5][B][kIirVCols];              // filtered values, double-buffered
     double red[5][6];
@@ -548,27 +555,35 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     const int cbytes = max(0, min(16, (w - (cb * kIirVCols + ccol)) * 4));
 
     if (warp == 8) {
-        // ---------------- loader: feeds the five producer rings ----------------
+        // ---------------- loader: feeds the three producer rings ----------------
         // Batch b (rows n0 = 16b ..) reads ring rows n0-6 .. n0+B+3.  The loader requests rows n0+4+D .. n0+3+D+B
         // while batch b runs (their slots held rows n0-28 .. n0-13, dead by then) and arrives at the barrier
         // that ends batch b only when everything batch b+1 reads has landed.
-        const float *ph[5];
+        // pair rows are 256 bytes: 16 lanes per row, two rows per instruction; a*b rows 128 bytes: four rows
+        const int prow = lane >> 4, pcol = (lane & 15) * 4;
+        const int pbytes = max(0, min(2, w - (cb * kIirVCols + (lane & 15) * 2))) * 8;
+        const float *gp0 = a.hpair_src + 2 * poff + pcol;
+        const float *gp1 = a.hpair_cand + (long long)cand * a.hcand_stride + 2 * poff + pcol;
+        const float *gs = a.hab + (long long)cand * a.hcand_stride + poff + ccol;
+        auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h) of all planes
 #pragma unroll
-        for (int q = 0; q < 5; ++q) ph[q] = a.hq[q] + (long long)cand * a.hq_cand_stride[q] + poff + ccol;
-        float *ring = &sm.ring[0][0][0] + ccol;
-        constexpr int kPlane = RCAP * kIirVCols;
-        auto issue_rows4 = [&](int r0) {   // rows r0..r0+3 (zeros beyond h) of all five planes: 16 bytes per lane each
+            for (int half = 0; half < 2; ++half) {
+                const int rr = r0 + 2 * half + prow;
+                const unsigned go = (unsigned)(min(rr, h - 1) * 2 * pitch);
+                const int nb = rr < h ? pbytes : 0;
+                cp_async_16(&sm.pring[0][rr & (RCAP - 1)][pcol], gp0 + go, nb);
+                cp_async_16(&sm.pring[1][rr & (RCAP - 1)][pcol], gp1 + go, nb);
+            }
             const int rr = r0 + crow;
-            const unsigned go = (unsigned)(min(rr, h - 1) * pitch);
-            const int so = (rr & (RCAP - 1)) * kIirVCols, nb = rr < h ? cbytes : 0;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) cp_async_16(ring + q * kPlane + so, ph[q] + go, nb);
+            cp_async_16(&sm.sring[rr & (RCAP - 1)][ccol], gs + (unsigned)(min(rr, h - 1) * pitch), rr < h ? cbytes : 0);
         };
         // rows -6..-1 are padding: their ring slots hold zeros until real rows wrap around to them
 #pragma unroll
-        for (int q = 0; q < 5; ++q)
-#pragma unroll
-            for (int j = 1; j <= 6; ++j) sm.ring[q][RCAP - j][lane] = 0.0f;
+        for (int j = 1; j <= 6; ++j) {
+            sm.pring[0][RCAP - j][lane] = sm.pring[0][RCAP - j][lane + 32] = 0.0f;
+            sm.pring[1][RCAP - j][lane] = sm.pring[1][RCAP - j][lane + 32] = 0.0f;
+            sm.sring[RCAP - j][lane] = 0.0f;
+        }
         for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0);   // everything before the first batch's request
         cp_async_commit();
         cp_async_wait<0>();
@@ -584,35 +599,32 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();      // consumers' last batch
         __syncthreads();      // final reduction
     } else if (warp < 2) {
-        // ---------------- pair producers: the column recursions of quantities 2*warp, 2*warp + 1 ----------------
-        // (a, b) and (a*a, b*b): two planes, one packed recursion per column
-        const int q0 = 2 * warp;
+        // ---------------- pair producers: the packed column recursions of (a, a*a) and (b, b*b) ----------------
+        // outputs: warp 0 -> mu1 (ex 0), s11 (ex 2); warp 1 -> mu2 (ex 1), s22 (ex 3)
         const IirCoef2 k = iir_coef2(a.k, a.one, a.neg_one);
         IirState2 st;
 #pragma unroll
         for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = splat2(0.0f);
-        const float *c0 = &sm.ring[q0][0][lane], *c1 = &sm.ring[q0 + 1][0][lane];
+        const float *col = &sm.pring[warp][0][2 * lane];
+        constexpr int kRow = 2 * kIirVCols;
         __syncthreads();      // (S)
         // n = -4..-1: right taps are rows 0..3, left taps are padding, nothing emitted
 #pragma unroll
-        for (int n = -4; n < 0; ++n)
-            (void)iir_step2(k, st, splat2(0.0f), pk2(c0[(n + 4) * kIirVCols], c1[(n + 4) * kIirVCols]));
+        for (int n = -4; n < 0; ++n) (void)iir_step2(k, st, splat2(0.0f), lds2(col + (n + 4) * kRow));
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             const int n0 = b * B;
             // n0 is a multiple of B and so is RCAP: the left taps (rows n0-6+j) can only wrap at j = 6, the
             // right taps (rows n0+4+j) only at j = B-4 -> two bases each, static offsets otherwise
-            const int ol0 = ((n0 - 6) & (RCAP - 1)) * kIirVCols, ol1 = (n0 & (RCAP - 1)) * kIirVCols;
-            const int or0 = ((n0 + 4) & (RCAP - 1)) * kIirVCols, or1 = ((n0 + B) & (RCAP - 1)) * kIirVCols;
+            const float *l0 = col + ((n0 - 6) & (RCAP - 1)) * kRow, *l1 = col + (n0 & (RCAP - 1)) * kRow;
+            const float *r0 = col + ((n0 + 4) & (RCAP - 1)) * kRow, *r1 = col + ((n0 + B) & (RCAP - 1)) * kRow;
             f32x2 sum[B];
 #pragma unroll
-            for (int j = 0; j < B; ++j) {
-                const int lo = j < 6 ? ol0 + j * kIirVCols : ol1 + (j - 6) * kIirVCols;
-                const int ro = j < B - 4 ? or0 + j * kIirVCols : or1 + (j - (B - 4)) * kIirVCols;
-                sum[j] = add2(pk2(c0[lo], c1[lo]), pk2(c0[ro], c1[ro]));
-            }
-            float *ex0 = &sm.ex[b & 1][q0][0][lane], *ex1 = &sm.ex[b & 1][q0 + 1][0][lane];
+            for (int j = 0; j < B; ++j)
+                sum[j] = add2(lds2(j < 6 ? l0 + j * kRow : l1 + (j - 6) * kRow),
+                              lds2(j < B - 4 ? r0 + j * kRow : r1 + (j - (B - 4)) * kRow));
+            float *ex0 = &sm.ex[b & 1][warp][0][lane], *ex1 = &sm.ex[b & 1][warp + 2][0][lane];
             IirPipe2 P;
             pipe2_begin(k, P, st, sum[0]);
 #pragma unroll
@@ -631,7 +643,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         IirState st;
 #pragma unroll
         for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
-        const float *col = &sm.ring[q][0][lane];
+        const float *col = &sm.sring[0][lane];
         __syncthreads();      // (S)
 #pragma unroll
         for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, col[(n + 4) * kIirVCols]);
@@ -662,7 +674,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         // four sub-partitions of the SM carry equal work next to the three producers and the loader (warp w
         // runs on sub-partition w % 4; a pair producer costs ~310 instructions per batch, the a*b producer
         // ~240, the loader ~150, a row pair of maps ~125):
-        //   warp 3: p0 p1, warp 5: p2 p3, warp 6: p4 p5, warp 4: p6, warp 7: p7.
+        //   warp 3: p0 p1, warp 5: p2 p3, warp 6: p4 p5, warp 4: p6, warp 7: p7  (the loader is warp 8).
         // A consumer evaluates the two rows of a pair as one packed pair per column, and stages the XYB rows
         // it needs itself.  Columns beyond the image need no test: every ring is zero-filled there by the
         // copies, and all-zero inputs pool to exactly zero.
@@ -832,8 +844,8 @@ inline cudaError_t iir_configure()
 }
 
 struct IirBuffers {
-    float *src_hplanes;      // [2][pyramid]: rows pass of a and a*a, cached per source
-    float *cand_hplanes;     // [candidate][3][pyramid]: rows pass of b, b*b, a*b
+    float *src_hplanes;      // [2 * pyramid]: rows pass of (a, a*a), interleaved, cached per source
+    float *cand_hplanes;     // [candidate][3 * pyramid]: rows pass of (b, b*b) interleaved, then a*b
     long long pyr_stride;    // floats per pyramid (capacity)
 };
 
@@ -848,11 +860,10 @@ inline void iir_fill_common(IirArgs &a, const Geom &g, const IirCoef &k, const f
     a.dist = dist;
     a.dist_stride = dist_stride;
     const long long P = B.pyr_stride;
-    a.hq[0] = B.src_hplanes;               a.hq_cand_stride[0] = 0;          // a
-    a.hq[2] = B.src_hplanes + P;           a.hq_cand_stride[2] = 0;          // a*a
-    a.hq[1] = B.cand_hplanes;              a.hq_cand_stride[1] = 3 * P;      // b
-    a.hq[3] = B.cand_hplanes + P;          a.hq_cand_stride[3] = 3 * P;      // b*b
-    a.hq[4] = B.cand_hplanes + 2 * P;      a.hq_cand_stride[4] = 3 * P;      // a*b
+    a.hpair_src = B.src_hplanes;           // (a, a*a)
+    a.hpair_cand = B.cand_hplanes;         // (b, b*b)
+    a.hab = B.cand_hplanes + 2 * P;        // a*b
+    a.hcand_stride = 3 * P;
 }
 
 inline int iir_rows_grid(IirArgs &a, const Geom &g)

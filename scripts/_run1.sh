@@ -1,2 +1,1 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 python scripts/profile_step.py --steps 6 | tail -3
