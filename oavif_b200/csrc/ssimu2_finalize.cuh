@@ -70,26 +70,26 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Final
     double *out = a.sums + (long long)cand * kMaxScales * 18;
     for (int i = threadIdx.x; i < kMaxScales * 18; i += blockDim.x) out[i] = s_sum[i];
 
+    // the 108 weighted terms in parallel (each is a couple of binary64 square roots), then ONE thread adds
+    // them in index order, so the sum is the same sequence of additions as a serial evaluation
+    __shared__ double s_term[108];
+    if (threadIdx.x < 108) {
+        const int i = threadIdx.x;           // i = ((c*6 + s)*2 + n)*3 + k
+        const int k = i % 3, n = (i / 3) & 1, s = (i / 6) % kMaxScales, c = i / (6 * kMaxScales);
+        double term = 0.0;
+        if (s < a.n_scales) {
+            const double opp = 1.0 / ((double)a.w[s] * (double)a.h[s]);
+            const double *v = s_sum + s * 18 + c * 6;
+            // n == 0: 1-norm averages; n == 1: 4-norm = (mean of 4th powers)^(1/4)
+            const double e = n ? sqrt(sqrt(opp * v[2 * k + 1])) : opp * v[2 * k];
+            term = c_weights[i] * fabs(e);
+        }
+        s_term[i] = term;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         double ssim = 0.0;
-        int i = 0;
-        for (int c = 0; c < 3; ++c)
-            for (int s = 0; s < kMaxScales; ++s)
-                for (int n = 0; n < 2; ++n) {
-                    if (s >= a.n_scales) {
-                        i += 3;
-                        continue;
-                    }
-                    const double opp = 1.0 / ((double)a.w[s] * (double)a.h[s]);
-                    const double *v = s_sum + s * 18 + c * 6;
-                    // n == 0: 1-norm averages; n == 1: 4-norm = (mean of 4th powers)^(1/4)
-                    const double e_ssim = n ? sqrt(sqrt(opp * v[1])) : opp * v[0];
-                    const double e_art = n ? sqrt(sqrt(opp * v[3])) : opp * v[2];
-                    const double e_det = n ? sqrt(sqrt(opp * v[5])) : opp * v[4];
-                    ssim += c_weights[i++] * fabs(e_ssim);
-                    ssim += c_weights[i++] * fabs(e_art);
-                    ssim += c_weights[i++] * fabs(e_det);
-                }
+        for (int i = 0; i < 108; ++i) ssim += s_term[i];
         ssim = ssim * 0.9562382616834844;
         ssim = 2.326765642916932 * ssim - 0.020884521182843837 * ssim * ssim +
                6.248496625763138e-05 * ssim * ssim * ssim;
