@@ -1,1 +1,2 @@
-python scripts/profile_step.py --steps 2 > gpurun_out/profile_step_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -o gpurun_out/r1_final_prof -f python scripts/profile_step.py --steps 1 > gpurun_out/ncu.log 2>&1; tail -2 gpurun_out/ncu.log; cat gpurun_out/profile_step_plain.log
+python scripts/run_configs.py > gpurun_out/r1_configs_1gpu.json 2> gpurun_out/configs.err; tail -5 gpurun_out/configs.err
+cp gpurun_out/corpus_1gpu.csv gpurun_out/r1_corpus_1gpu.csv 2>/dev/null
