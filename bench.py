@@ -179,7 +179,7 @@ def run_reference(args):
         "e2e": {"value": round(value, 3), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -394,11 +394,30 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": round(rate, 3), "unit": "Mpx/s", "cores": threads, "kind": "port",
                                 "sample": f"{reps} x ({threads} threads x one {W}x{rows} band of the 4K pair), {dt:.1f} s",
                                 "single_thread": {"value": round(rate1, 3), "sample": f"{W}x{rows1} band, {dt1:.1f} s"}}
-    print(json.dumps(line))
+    emit(line)
     dist.finalize()
 
 
+_result_fd = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _result_fd is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_result_fd, data)
+
+
 def main():
+    # Libraries write to fd 1 on their own (NCCL prints its version banner there): keep the original
+    # stdout for the result line and point fd 1 at stderr for everything else.
+    global _result_fd
+    sys.stdout.flush()
+    _result_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

@@ -22,8 +22,6 @@ def init(backend: str | None = None):
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         kw = {}
         if backend == "nccl":
-            # NCCL announces its version on stdout; stdout belongs to the caller's result line
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend, **kw)
