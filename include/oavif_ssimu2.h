@@ -73,7 +73,7 @@ typedef struct {
     float h2d_ms;       /* host -> device copies of this call's pixels           */
     float pyramid_ms;   /* YUV->RGB8, sRGB->linear, 2x pyramid, XYB              */
     float blur_ms;      /* blur + error maps + pooling kernels (a + b)           */
-    float blur_a_ms;    /* RECURSIVE: candidate rows pass (b, b*b, a*b). FIR: the fused kernel */
+    float blur_a_ms;    /* RECURSIVE: rows pass (b, b*b, a*b; + a, a*a on the first call after set_source). FIR: the fused kernel */
     float blur_b_ms;    /* RECURSIVE: columns pass + maps + pooling.  FIR: 0             */
     float finalize_ms;  /* fixed-order reduction, weights, score, D2H of scores  */
     float total_ms;     /* first event to last event                             */
@@ -105,8 +105,9 @@ void oavif_ssimu2_pinned_free(void *p);
 /* ---- source side: once per image (main.zig:86) ------------------------------------------ */
 
 /* rgb: interleaved 8-bit RGB, `stride` bytes per row (>= 3*w).  Uploads, builds and caches
- * the source's six-scale XYB pyramid on the device (and, for the RECURSIVE blur, the rows pass of
- * the two source-only quantities, which then runs behind the call and is shared by all candidates). */
+ * the source's six-scale XYB pyramid on the device.  For the RECURSIVE blur the rows pass of the two
+ * source-only quantities (a, a*a) is computed by the first scoring call that follows, cached with the
+ * pyramid, and shared by every later candidate of the search / batch. */
 int oavif_ssimu2_set_source_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w,
                                  uint32_t h, size_t stride);
 
@@ -188,7 +189,8 @@ int oavif_ssimu2_debug_check_guards(oavif_ssimu2_ctx *ctx);
 
 /* Profiling aid: re-run only the RECURSIVE rows pass on the pyramids of the last score call,
  * `iters` times, and report its mean device time.  variant 0 runs both halves; bit 2 (value 4) leaves
- * out the source half (a, a*a) that set_source normally runs once per image; other bits are ignored. */
+ * out the source half (a, a*a), i.e. times what a call with a warm source cache runs; other bits are
+ * ignored. */
 int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms);
 
 #ifdef __cplusplus
