@@ -156,7 +156,8 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     total = args.steps + args.warmup
-    per_step = max(0.05, min(6.0, 150.0 / max(total, 1)))   # seconds of CPU work per step: the whole run stays within ~3 minutes
+    # seconds of CPU work per step: the whole run stays within ~3 minutes
+    per_step = args.ref_seconds if args.ref_seconds > 0 else max(0.05, min(6.0, 150.0 / max(total, 1)))
     rate0, rows, _ = cpu_oracle_rate(threads, per_step)
     for _ in range(max(args.warmup - 1, 0)):
         cpu_oracle_rate(threads, per_step, rows)
@@ -425,6 +426,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blur", default="recursive", choices=["recursive", "fir"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-seconds", type=float, default=0.0,
+                    help="--impl reference: seconds of CPU work per step (default: scaled to --steps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
