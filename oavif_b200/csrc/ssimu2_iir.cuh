@@ -10,13 +10,15 @@
 //
 //   k_iir_rows  : rows.  One CTA = 32 rows of one channel; lane = row.  The pair is two QUANTITIES of
 //                 the same pixel: (a, a*a) on the source side, (b, b*b) on the candidate side, with
-//                 a*b in a second recursion warp.  A helper warp does all global memory traffic
+//                 a*b in a scalar recursion warp.  Loader and storer warps do all global memory traffic
 //                 (16-byte cp.async tile ring in, whole 128-byte lines out), so a recursion warp's
-//                 critical path is shared-memory loads, arithmetic, shared-memory stores.
-//   k_iir_cols  : columns + error maps + pooling.  One CTA = 64 columns of one channel; the pair is
-//                 two adjacent COLUMNS.  Five producer warps (one row-filtered plane each) feed four
-//                 consumer warps through shared memory; the five filtered values of a pixel go
-//                 straight into the SSIM / edge-diff maps — blurred planes are never written to HBM.
+//                 critical path is shared-memory loads, arithmetic, shared-memory stores.  The pairs
+//                 are written to HBM interleaved (one float2 per pixel), exactly as they are computed.
+//   k_iir_cols  : columns + error maps + pooling.  One CTA = 32 columns of one channel; lane = column.
+//                 Two producer warps run the packed recursions of (a, a*a) and (b, b*b) straight from the
+//                 interleaved planes, one the scalar recursion of a*b; a loader warp feeds their
+//                 shared-memory rings; five consumer warps evaluate the SSIM / edge-diff maps on packed
+//                 pairs of ROWS, one batch behind — blurred planes are never written to HBM.
 //
 // HBM traffic per scale pixel and channel: rows pass reads 8 B, writes 20 B; columns pass reads
 // 20 B + 8 B.  No tensor cores (nothing here is a contraction).
@@ -508,17 +510,17 @@ __global__ void __launch_bounds__(MODE == 2 ? 192 : 128) k_iir_rows(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 256.
+// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 288.
 //
 // One CTA owns 32 columns of one channel; lane = column in the arithmetic, so the recursions of a warp
-// are 32 independent columns.  Warps 0..2 (producers) stream row-filtered planes down the image through
-// private shared-memory rings: warp 0 the pair (a, b), warp 1 the pair (a*a, b*b) — two planes, one
-// packed recursion —, warp 2 a*b alone.  The rings are fed by 16-byte cp.async: one instruction moves
-// four whole 128-byte row segments (8 lanes per row), 32 rows ahead of use; both taps of the recursion
-// are read back from the ring (no register delay line).  Each producer drops its filtered values into a
-// double-buffered 16-row batch.  Warps 3..7 (consumers), one batch behind, stream the pixel's own XYB
-// samples the same way and evaluate the SSIM / edge-diff maps and the six pooled sums, two rows of a
-// column as one packed pair.  One block barrier per 16 rows.
+// are 32 independent columns.  Warps 0..2 (producers) run the column recursions out of shared-memory
+// rings: warp 0 the packed pair (a, a*a), warp 1 the packed pair (b, b*b) — each reads one float2 per
+// tap from its interleaved plane —, warp 2 a*b alone.  Warp 8 (loader) feeds the three rings with
+// 16-byte cp.async, 32 rows ahead of use, zero-filling rows and columns beyond the image; both taps of
+// the recursion are read back from the ring (no register delay line).  Each producer drops its filtered
+// values into a double-buffered 16-row batch.  Warps 3..7 (consumers), one batch behind, stage the pixel's
+// own XYB samples themselves and evaluate the SSIM / edge-diff maps and the six pooled sums, two rows
+// of a column as one packed pair.  One block barrier per 16 rows.
 constexpr int kIirVThreads = 288;   // 3 producer warps + 5 consumer warps + 1 loader warp
 
 template <int RCAP, int B>
@@ -531,7 +533,7 @@ struct IirColsSmem {
 };
 
 // B rows per exchange batch: the per-batch overhead (barrier, copy issue, address set-up) is paid once
-// per B rows by each of the eight warps.  RCAP = rows of a producer ring.
+// per B rows by each of the nine warps.  RCAP = rows of a producer ring.
 template <int RCAP, int B>
 __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a)
 {
