@@ -366,9 +366,9 @@ int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
 {
     if (w == 0 || h == 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "zero image dimension");
     if (w > (1u << 16) || h > (1u << 16)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "dimension above 65536");
-    // kernels address a plane with 32-bit element offsets
-    if ((long long)rup(cdiv((int)w, kPyrTile) * kPyrTile, 32) * (cdiv((int)h, kPyrTile) * kPyrTile) >= (1LL << 31))
-        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "image %ux%u: a plane exceeds 2^31 samples", w, h);
+    // kernels address a plane with 32-bit element offsets, and an interleaved pair plane is two planes wide
+    if ((long long)rup(cdiv((int)w, kPyrTile) * kPyrTile, 32) * (cdiv((int)h, kPyrTile) * kPyrTile) >= (1LL << 30))
+        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "image %ux%u: a plane exceeds 2^30 samples", w, h);
     if (pyr_capacity((int)w, (int)h) > ctx->cap_pyr_floats || (long long)w * h * 8 + 3 * 256 > ctx->cap_in_bytes)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "image %ux%u exceeds context capacity %ux%u", w, h, ctx->max_w,
                     ctx->max_h);
