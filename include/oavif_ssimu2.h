@@ -178,6 +178,12 @@ int oavif_ssimu2_get_timing(oavif_ssimu2_ctx *ctx, oavif_ssimu2_timing *out);
 int oavif_ssimu2_debug_get_xyb(oavif_ssimu2_ctx *ctx, int which, int scale, int channel,
                                float *out, uint32_t *w_out, uint32_t *h_out);
 
+/* The RECURSIVE rows pass as the scored path left it after the last score call: quantity 0..4 = a, b,
+ * a*a, b*b, a*b (row-filtered, before the columns pass), for one candidate, scale and channel; w*h floats.
+ * Lets a test compare the product kernel's recursion bit for bit with the CPU oracle's horizontal pass. */
+int oavif_ssimu2_debug_get_rows(oavif_ssimu2_ctx *ctx, int candidate, int quantity, int scale, int channel,
+                                float *out, uint32_t *w_out, uint32_t *h_out);
+
 /* Blur one host plane with the selected blur on the device (tests of the filter alone). */
 int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, uint32_t h,
                             float *out);

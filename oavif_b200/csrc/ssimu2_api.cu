@@ -872,6 +872,47 @@ int oavif_ssimu2_debug_get_xyb(oavif_ssimu2_ctx *ctx, int which, int scale, int 
     return 0;
 }
 
+int oavif_ssimu2_debug_get_rows(oavif_ssimu2_ctx *ctx, int candidate, int quantity, int scale, int channel, float *out,
+                                uint32_t *w_out, uint32_t *h_out)
+{
+    if (!ctx || !out || !w_out || !h_out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    if (!ctx->have_source || ctx->last_n == 0 || ctx->blur_mode != OAVIF_SSIMU2_BLUR_RECURSIVE || !ctx->src_rows_valid ||
+        scale < 0 || scale >= ctx->g.n_scales || channel < 0 || channel > 2 || quantity < 0 || quantity > 4 ||
+        candidate < 0 || candidate >= (int)ctx->last_n)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such row-filtered plane (needs a RECURSIVE score call first)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const Geom &g = ctx->g;
+    const long long P = ctx->cap_pyr_floats;
+    const long long poff = g.off[scale] + (long long)channel * g.plane[scale];
+    const int w = g.w[scale], h = g.h[scale], pitch = g.pitch[scale];
+    // quantities 0..4 = a, b, a*a, b*b, a*b.  (a, a*a) and (b, b*b) are interleaved pair planes, a*b is plain.
+    const float *p;
+    size_t spitch, elem;
+    if (quantity == 4) {
+        p = ctx->d_hplanes + (long long)candidate * 3 * P + 2 * P + poff;
+        spitch = sizeof(float) * pitch;
+        elem = sizeof(float);
+    } else {
+        const float *base = (quantity & 1) ? ctx->d_hplanes + (long long)candidate * 3 * P : ctx->d_src_hplanes;
+        p = base + 2 * poff + (quantity >> 1);
+        spitch = sizeof(float) * 2 * pitch;
+        elem = 2 * sizeof(float);
+    }
+    if (elem == sizeof(float)) {
+        CK(cudaMemcpy2D(out, sizeof(float) * w, p, spitch, sizeof(float) * w, h, cudaMemcpyDeviceToHost));
+    } else {
+        // one float out of every float2: copy the interleaved rows and pick on the host
+        std::vector<float> tmp((size_t)2 * w * h);
+        CK(cudaMemcpy2D(tmp.data(), sizeof(float) * 2 * w, p - (quantity >> 1), spitch, sizeof(float) * 2 * w, h,
+                        cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < (size_t)w * h; ++i) out[i] = tmp[2 * i + (quantity >> 1)];
+    }
+    *w_out = (uint32_t)w;
+    *h_out = (uint32_t)h;
+    return 0;
+}
+
 int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, uint32_t h, float *out)
 {
     if (!ctx || !in || !out || w == 0 || h == 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");

@@ -39,7 +39,7 @@ SYMBOLS = (
     "oavif_ssimu2_score_batch_yuv444", "oavif_ssimu2_set_source_rgb8_dev",
     "oavif_ssimu2_score_batch_rgb8_dev", "oavif_ssimu2_score_batch_yuv444_dev",
     "oavif_ssimu2_compute_rgb8", "oavif_ssimu2_yuv444_to_rgb8", "oavif_ssimu2_get_detail",
-    "oavif_ssimu2_get_timing", "oavif_ssimu2_debug_get_xyb", "oavif_ssimu2_debug_blur",
+    "oavif_ssimu2_get_timing", "oavif_ssimu2_debug_get_xyb", "oavif_ssimu2_debug_get_rows", "oavif_ssimu2_debug_blur",
     "oavif_ssimu2_debug_time_rows", "oavif_ssimu2_debug_check_guards",
 )
 
@@ -102,6 +102,7 @@ def load() -> C.CDLL:
     L.oavif_ssimu2_get_detail.argtypes = [vp, u32, C.POINTER(Detail)]
     L.oavif_ssimu2_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.oavif_ssimu2_debug_get_xyb.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32), C.POINTER(u32)]
+    L.oavif_ssimu2_debug_get_rows.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32), C.POINTER(u32)]
     L.oavif_ssimu2_debug_blur.argtypes = [vp, vp, u32, u32, vp]
     L.oavif_ssimu2_debug_check_guards.argtypes = [vp]
     L.oavif_ssimu2_debug_time_rows.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -323,6 +324,14 @@ class Scorer:
         w, h = C.c_uint32(), C.c_uint32()
         _check(self._L.oavif_ssimu2_debug_get_xyb(self._ctx, which, scale, channel, buf.ctypes.data, C.byref(w),
                                                   C.byref(h)), self._ctx)
+        return buf[: w.value * h.value].reshape(h.value, w.value).copy()
+
+    def rows(self, candidate: int, quantity: int, scale: int, channel: int) -> np.ndarray:
+        """Row-filtered plane of the last RECURSIVE score call; quantity 0..4 = a, b, a*a, b*b, a*b."""
+        buf = np.empty(self.w * self.h, np.float32)
+        w, h = C.c_uint32(), C.c_uint32()
+        _check(self._L.oavif_ssimu2_debug_get_rows(self._ctx, candidate, quantity, scale, channel, buf.ctypes.data,
+                                                   C.byref(w), C.byref(h)), self._ctx)
         return buf[: w.value * h.value].reshape(h.value, w.value).copy()
 
     def check_guards(self):

@@ -125,13 +125,14 @@ def xyb_at_scale(rgb: np.ndarray, scale: int) -> np.ndarray:
     return out.reshape(-1)[: 3 * ws.value * hs.value].reshape(3, hs.value, ws.value).copy()
 
 
-def blur(plane: np.ndarray, mode: int = BLUR_IIR) -> np.ndarray:
+def blur(plane: np.ndarray, mode: int = BLUR_IIR, rows_only: bool = False) -> np.ndarray:
+    """Both passes of the blur, or (rows_only) the horizontal pass alone as it stands before the vertical one."""
     plane = np.ascontiguousarray(plane, np.float32)
     h, w = plane.shape
     tmp = np.empty_like(plane)
     out = np.empty_like(plane)
     lib().oracle_blur(_f32(plane), w, h, mode, _f32(tmp), _f32(out))
-    return out
+    return tmp if rows_only else out
 
 
 def fir_taps(sigma: float = 1.5) -> np.ndarray:

@@ -85,6 +85,39 @@ def test_xyb_pyramid_bit_identical(scorer, oracle, size):
             np.testing.assert_array_equal(bits(scorer.xyb(1, s, c)), bits(wd[c]), err_msg=f"dist s{s} c{c}")
 
 
+# ---- K4, product kernel: the rows pass the scored path leaves behind ----------------------------------
+@pytest.mark.parametrize("size", [(64, 64), (65, 63), (100, 75), (333, 257), (1027, 771)])
+def test_rows_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size):
+    """k_iir_rows (packed-pair recursion, interleaved pair planes) against the oracle's horizontal pass, bit for
+    bit, for all five quantities, both call forms (first call after set_source / cached source) and a batch."""
+    w, h = size
+    src = synth.synth(w, h, "mixture", w + 1)
+    d0, d1 = synth.distort(src, 0.3, seed=h), synth.distort(src, 0.8, seed=h + 1)
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    scorer.set_source(src)
+    scorer.score_rgb8(d0)                      # first call: the source half rides along
+    n = scorer.detail().n_scales
+
+    def expect(s, c, cand_rgb):
+        a, b = oracle.xyb_at_scale(src, s)[c], oracle.xyb_at_scale(cand_rgb, s)[c]
+        return [oracle.blur(q, oracle.BLUR_IIR, rows_only=True) for q in (a, b, a * a, b * b, a * b)]
+
+    def check(cand_index, cand_rgb, what):
+        for s in range(n):
+            for c in range(3):
+                for q, want in enumerate(expect(s, c, cand_rgb)):
+                    np.testing.assert_array_equal(bits(scorer.rows(cand_index, q, s, c)), bits(want),
+                                                  err_msg=f"{what}: quantity {q} scale {s} channel {c}")
+
+    check(0, d0, "first call")
+    scorer.score_rgb8(d1)                      # cached source: candidate half only
+    check(0, d1, "cached source")
+    scorer.set_source(src)
+    scorer.score_batch_rgb8([d0, d1])          # batch: candidate 0's CTAs refill the source cache
+    check(0, d0, "batch[0]")
+    check(1, d1, "batch[1]")
+
+
 def test_all_input_forms_build_the_same_pyramid(scorer, oracle):
     w, h = 203, 117
     src = synth.synth(w, h, "noise", 8)
