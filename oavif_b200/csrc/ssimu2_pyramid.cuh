@@ -28,10 +28,18 @@ struct PyrArgs {
     float one, neg_one;         // 1.0f / -1.0f as run-time values (Unit2, ssimu2_common.cuh)
 };
 
-// Load pixels x0..x0+3 of row y (coordinates clamped to the image) as 8-bit RGB.
+// Four pixels of one row, as fetched: 3 words for the 8-bit layouts (RGB8: the 12 bytes r0 g0 b0 r1 ...;
+// YUV8: y[0..3], u[0..3], v[0..3]), 6 words for 10-bit YUV (two 16-bit samples per word: y01 y23 u01 u23
+// v01 v23).  fetch4 only loads (coordinates clamped to the image), decode4 only computes: the kernel
+// issues all of a tile's loads before it waits for anything else.
 template <int KIND>
-__device__ __forceinline__ void load4_rgb8(const PyrArgs &a, const void *p0, const void *p1,
-                                           const void *p2, int x0, int y, int rgb[4][3])
+struct PyrRaw {
+    static constexpr int N = (KIND == IN_YUV10_RGB || KIND == IN_YUV10_RGBA) ? 6 : 3;
+};
+
+template <int KIND>
+__device__ __forceinline__ void fetch4(const PyrArgs &a, const void *p0, const void *p1, const void *p2, int x0, int y,
+                                       uint32_t *raw)
 {
     const int w = a.g.w[0];
     const bool inside = (x0 + 3 < w);
@@ -39,84 +47,107 @@ __device__ __forceinline__ void load4_rgb8(const PyrArgs &a, const void *p0, con
         const uint8_t *row = (const uint8_t *)p0 + (long long)y * a.stride[0];
         const uint8_t *q = row + 3 * x0;
         if (inside && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
-            const uint32_t w0 = __ldg((const uint32_t *)q), w1 = __ldg((const uint32_t *)q + 1),
-                           w2 = __ldg((const uint32_t *)q + 2);
-            rgb[0][0] = w0 & 255; rgb[0][1] = (w0 >> 8) & 255; rgb[0][2] = (w0 >> 16) & 255;
-            rgb[1][0] = w0 >> 24; rgb[1][1] = w1 & 255; rgb[1][2] = (w1 >> 8) & 255;
-            rgb[2][0] = (w1 >> 16) & 255; rgb[2][1] = w1 >> 24; rgb[2][2] = w2 & 255;
-            rgb[3][0] = (w2 >> 8) & 255; rgb[3][1] = (w2 >> 16) & 255; rgb[3][2] = w2 >> 24;
+            raw[0] = __ldg((const uint32_t *)q);
+            raw[1] = __ldg((const uint32_t *)q + 1);
+            raw[2] = __ldg((const uint32_t *)q + 2);
         } else {
+            uint32_t b[12];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int x = min(x0 + i, w - 1);
-                rgb[i][0] = __ldg(row + 3 * x);
-                rgb[i][1] = __ldg(row + 3 * x + 1);
-                rgb[i][2] = __ldg(row + 3 * x + 2);
+                b[3 * i] = __ldg(row + 3 * x);
+                b[3 * i + 1] = __ldg(row + 3 * x + 1);
+                b[3 * i + 2] = __ldg(row + 3 * x + 2);
             }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) raw[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24);
         }
     } else if (KIND == IN_PIXELS) {
+        // the loaders' layouts (io.zig:57-133): 16-bit samples keep their high byte, gray is replicated, alpha dropped
         const uint8_t *row = (const uint8_t *)p0 + (long long)y * a.stride[0];
         const int ch = a.channels, gstep = ch >= 3 ? 1 : 0, bstep = ch >= 3 ? 2 : 0;
+        uint32_t b[12];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int x = min(x0 + i, w - 1);
             if (a.hbd) {
                 const uint16_t *px = (const uint16_t *)row + (long long)x * ch;
-                rgb[i][0] = __ldg(px) >> 8;
-                rgb[i][1] = __ldg(px + gstep) >> 8;
-                rgb[i][2] = __ldg(px + bstep) >> 8;
+                b[3 * i] = __ldg(px) >> 8;
+                b[3 * i + 1] = __ldg(px + gstep) >> 8;
+                b[3 * i + 2] = __ldg(px + bstep) >> 8;
             } else {
                 const uint8_t *px = row + (long long)x * ch;
-                rgb[i][0] = __ldg(px);
-                rgb[i][1] = __ldg(px + gstep);
-                rgb[i][2] = __ldg(px + bstep);
+                b[3 * i] = __ldg(px);
+                b[3 * i + 1] = __ldg(px + gstep);
+                b[3 * i + 2] = __ldg(px + bstep);
             }
         }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) raw[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24);
     } else if (KIND == IN_YUV8) {
-        const uint8_t *ry = (const uint8_t *)p0 + (long long)y * a.stride[0];
-        const uint8_t *ru = (const uint8_t *)p1 + (long long)y * a.stride[1];
-        const uint8_t *rv = (const uint8_t *)p2 + (long long)y * a.stride[2];
-        uint32_t Y[4], U[4], V[4];
-        const bool al = ((reinterpret_cast<uintptr_t>(ry + x0) | reinterpret_cast<uintptr_t>(ru + x0) |
-                          reinterpret_cast<uintptr_t>(rv + x0)) & 3) == 0;
+        const uint8_t *r[3] = {(const uint8_t *)p0 + (long long)y * a.stride[0], (const uint8_t *)p1 + (long long)y * a.stride[1],
+                               (const uint8_t *)p2 + (long long)y * a.stride[2]};
+        const bool al = ((reinterpret_cast<uintptr_t>(r[0] + x0) | reinterpret_cast<uintptr_t>(r[1] + x0) |
+                          reinterpret_cast<uintptr_t>(r[2] + x0)) & 3) == 0;
         if (inside && al) {
-            const uint32_t wy = __ldg((const uint32_t *)(ry + x0)), wu = __ldg((const uint32_t *)(ru + x0)),
-                           wv = __ldg((const uint32_t *)(rv + x0));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                Y[i] = (wy >> (8 * i)) & 255; U[i] = (wu >> (8 * i)) & 255; V[i] = (wv >> (8 * i)) & 255;
-            }
+            for (int k = 0; k < 3; ++k) raw[k] = __ldg((const uint32_t *)(r[k] + x0));
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int x = min(x0 + i, w - 1);
-                Y[i] = __ldg(ry + x); U[i] = __ldg(ru + x); V[i] = __ldg(rv + x);
+            for (int k = 0; k < 3; ++k) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v |= (uint32_t)__ldg(r[k] + min(x0 + i, w - 1)) << (8 * i);
+                raw[k] = v;
             }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) yuv_to_rgb8<KIND>(Y[i], U[i], V[i], a.k, rgb[i][0], rgb[i][1], rgb[i][2]);
     } else {
-        const uint16_t *ry = (const uint16_t *)((const uint8_t *)p0 + (long long)y * a.stride[0]);
-        const uint16_t *ru = (const uint16_t *)((const uint8_t *)p1 + (long long)y * a.stride[1]);
-        const uint16_t *rv = (const uint16_t *)((const uint8_t *)p2 + (long long)y * a.stride[2]);
-        uint32_t Y[4], U[4], V[4];
-        const bool al = ((reinterpret_cast<uintptr_t>(ry + x0) | reinterpret_cast<uintptr_t>(ru + x0) |
-                          reinterpret_cast<uintptr_t>(rv + x0)) & 7) == 0;
+        const uint16_t *r[3] = {(const uint16_t *)((const uint8_t *)p0 + (long long)y * a.stride[0]),
+                                (const uint16_t *)((const uint8_t *)p1 + (long long)y * a.stride[1]),
+                                (const uint16_t *)((const uint8_t *)p2 + (long long)y * a.stride[2])};
+        const bool al = ((reinterpret_cast<uintptr_t>(r[0] + x0) | reinterpret_cast<uintptr_t>(r[1] + x0) |
+                          reinterpret_cast<uintptr_t>(r[2] + x0)) & 7) == 0;
         if (inside && al) {
-            const uint2 wy = __ldg((const uint2 *)(ry + x0)), wu = __ldg((const uint2 *)(ru + x0)),
-                        wv = __ldg((const uint2 *)(rv + x0));
-            Y[0] = wy.x & 0xffff; Y[1] = wy.x >> 16; Y[2] = wy.y & 0xffff; Y[3] = wy.y >> 16;
-            U[0] = wu.x & 0xffff; U[1] = wu.x >> 16; U[2] = wu.y & 0xffff; U[3] = wu.y >> 16;
-            V[0] = wv.x & 0xffff; V[1] = wv.x >> 16; V[2] = wv.y & 0xffff; V[3] = wv.y >> 16;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint2 v = __ldg((const uint2 *)(r[k] + x0));
+                raw[2 * k] = v.x;
+                raw[2 * k + 1] = v.y;
+            }
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int x = min(x0 + i, w - 1);
-                Y[i] = __ldg(ry + x); U[i] = __ldg(ru + x); V[i] = __ldg(rv + x);
+            for (int k = 0; k < 3; ++k) {
+                uint32_t s4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = __ldg(r[k] + min(x0 + i, w - 1));
+                raw[2 * k] = s4[0] | (s4[1] << 16);
+                raw[2 * k + 1] = s4[2] | (s4[3] << 16);
             }
         }
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void decode4(const PyrArgs &a, const uint32_t *raw, int rgb[4][3])
+{
+    if (KIND == IN_RGB8 || KIND == IN_PIXELS) {
+        const uint32_t w0 = raw[0], w1 = raw[1], w2 = raw[2];
+        rgb[0][0] = w0 & 255; rgb[0][1] = (w0 >> 8) & 255; rgb[0][2] = (w0 >> 16) & 255;
+        rgb[1][0] = w0 >> 24; rgb[1][1] = w1 & 255; rgb[1][2] = (w1 >> 8) & 255;
+        rgb[2][0] = (w1 >> 16) & 255; rgb[2][1] = w1 >> 24; rgb[2][2] = w2 & 255;
+        rgb[3][0] = (w2 >> 8) & 255; rgb[3][1] = (w2 >> 16) & 255; rgb[3][2] = w2 >> 24;
+    } else if (KIND == IN_YUV8) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) yuv_to_rgb8<KIND>(Y[i], U[i], V[i], a.k, rgb[i][0], rgb[i][1], rgb[i][2]);
+        for (int i = 0; i < 4; ++i)
+            yuv_to_rgb8<KIND>((raw[0] >> (8 * i)) & 255, (raw[1] >> (8 * i)) & 255, (raw[2] >> (8 * i)) & 255, a.k,
+                              rgb[i][0], rgb[i][1], rgb[i][2]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int sh = 16 * (i & 1), wi = i >> 1;
+            yuv_to_rgb8<KIND>((raw[wi] >> sh) & 0xffff, (raw[2 + wi] >> sh) & 0xffff, (raw[4 + wi] >> sh) & 0xffff, a.k,
+                              rgb[i][0], rgb[i][1], rgb[i][2]);
+        }
     }
 }
 
@@ -130,9 +161,6 @@ __global__ void __launch_bounds__(256, 3) k_pyramid(const __grid_constant__ PyrA
     __shared__ float s_l4[3][4][5];
 
     const int tid = threadIdx.x;
-    s_lut[tid] = a.lut[tid];
-    __syncthreads();
-
     const Geom &g = a.g;
     const int tx = tid & 15, ty = tid >> 4;
     const int bx = blockIdx.x, by = blockIdx.y, img = blockIdx.z;
@@ -144,13 +172,18 @@ __global__ void __launch_bounds__(256, 3) k_pyramid(const __grid_constant__ PyrA
     const Unit2 un = unit2(a.one, a.neg_one);
 
     // ---- scale 0: 4x4 pixels per thread ------------------------------------------------
+    // all of the thread's pixel loads are issued first, then the table: the two latencies overlap
     const int x0 = bx * 64 + tx * 4, y0 = by * 64 + ty * 4;
+    uint32_t raw[4][PyrRaw<KIND>::N];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fetch4<KIND>(a, p0, p1, p2, x0, min(y0 + j, g.h[0] - 1), raw[j]);
+    s_lut[tid] = a.lut[tid];
+    __syncthreads();
     float lin[4][4][3];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int y = min(y0 + j, g.h[0] - 1);
         int rgb[4][3];
-        load4_rgb8<KIND>(a, p0, p1, p2, x0, y, rgb);
+        decode4<KIND>(a, raw[j], rgb);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             lin[j][i][0] = s_lut[rgb[i][0]];
