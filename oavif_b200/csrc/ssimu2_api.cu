@@ -394,6 +394,8 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
             b.tiles_y[s] = plan.tiles_y[s];
         }
         memcpy(b.taps, ctx->taps, sizeof b.taps);
+        b.one = 1.0f;
+        b.neg_one = -1.0f;
         k_fir_fused<<<dim3(plan.total, n), kFirThreads, kFirSmemBytes, ctx->stream>>>(b);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[3], ctx->stream));

@@ -16,6 +16,8 @@ constexpr int kFirTW = 64, kFirTH = 32, kFirR = 4;          // tile and filter r
 constexpr int kFirIW = kFirTW + 2 * kFirR;                  // 72 staged columns
 constexpr int kFirIH = kFirTH + 2 * kFirR;                  // 40 staged rows
 constexpr int kFirThreads = 256;
+// shared memory: staged (a, b) interleaved per pixel [40][72][2]; row-filtered pairs (a,b) and (a*a,b*b)
+// interleaved [2][40][64][2] and a*b [40][64]; the reduction scratch
 constexpr size_t kFirSmemBytes =
     (size_t)(2 * kFirIH * kFirIW + 5 * kFirIH * kFirTW) * sizeof(float) + 8 * 6 * sizeof(double);
 
@@ -29,6 +31,7 @@ struct BlurArgs {
     int first_cta[kMaxScales + 1];  // CTA index ranges per scale: 3 channels x tiles each
     int tiles_x[kMaxScales], tiles_y[kMaxScales];
     float taps[9];
+    float one, neg_one;      // 1.0f / -1.0f as run-time values (Unit2, ssimu2_common.cuh)
 };
 
 __device__ __forceinline__ float fir9(const float *v, const float *t)
@@ -39,14 +42,28 @@ __device__ __forceinline__ float fir9(const float *v, const float *t)
     return acc;
 }
 
+// the same accumulation on a packed pair (two quantities of one pixel)
+__device__ __forceinline__ f32x2 fir9x2(const f32x2 *v, const f32x2 *t)
+{
+    f32x2 acc = mul2(t[0], v[0]);
+#pragma unroll
+    for (int k = 1; k < 9; ++k) acc = fma2(t[k], v[k], acc);
+    return acc;
+}
+
 // grid = (total CTAs over scales/channels/tiles, n_candidates), block = 256, dynamic smem.
+//
+// The two planes are staged INTERLEAVED, (a, b) per pixel, so that every later load delivers aligned
+// register pairs: the horizontal pass filters the pairs (a, b) and (a*a, b*b) with packed FFMA2 — each
+// half is the scalar fmaf chain — and a*b alone; the vertical pass does the same on the row-filtered
+// pairs; the maps take the five values of a pixel as they come.
 __global__ void __launch_bounds__(kFirThreads, 3) k_fir_fused(const __grid_constant__ BlurArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *sa = reinterpret_cast<float *>(smem_raw);       // [40][72]
-    float *sb = sa + kFirIH * kFirIW;                      // [40][72]
-    float *sh = sb + kFirIH * kFirIW;                      // [5][40][64]
-    double *sred = reinterpret_cast<double *>(sh + 5 * kFirIH * kFirTW);
+    float *sab = reinterpret_cast<float *>(smem_raw);      // [40][72][2]  (a, b)
+    float *shp = sab + 2 * kFirIH * kFirIW;                // [2][40][64][2]  rows pass of (a, b), (a*a, b*b)
+    float *shs = shp + 4 * kFirIH * kFirTW;                // [40][64]        rows pass of a*b
+    double *sred = reinterpret_cast<double *>(shs + kFirIH * kFirTW);
 
     const int tid = threadIdx.x;
     const int cta = blockIdx.x, cand = blockIdx.y;
@@ -65,10 +82,14 @@ __global__ void __launch_bounds__(kFirThreads, 3) k_fir_fused(const __grid_const
     const float *pb = a.dist + (long long)cand * a.dist_stride + a.g.off[s] + (long long)c * a.g.plane[s];
 
     float taps[9];
+    f32x2 taps2[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) taps[k] = a.taps[k];
+    for (int k = 0; k < 9; ++k) {
+        taps[k] = a.taps[k];
+        taps2[k] = splat2(taps[k]);
+    }
 
-    // ---- stage a, b with a 4-pixel zero-padded halo (float4 granules) ----------------------
+    // ---- stage a, b with a 4-pixel zero-padded halo (float4 granules), interleaved per pixel -------
     for (int idx = tid; idx < kFirIH * (kFirIW / 4); idx += kFirThreads) {
         const int row = idx / (kFirIW / 4), c4 = idx - row * (kFirIW / 4);
         const int gx = x0 - kFirR + 4 * c4, gy = y0 - kFirR + row;
@@ -83,70 +104,99 @@ __global__ void __launch_bounds__(kFirThreads, 3) k_fir_fused(const __grid_const
                 va.w = 0.f; vb.w = 0.f;
             }
         }
-        *reinterpret_cast<float4 *>(sa + row * kFirIW + 4 * c4) = va;
-        *reinterpret_cast<float4 *>(sb + row * kFirIW + 4 * c4) = vb;
+        float4 *dst = reinterpret_cast<float4 *>(sab + 2 * (row * kFirIW + 4 * c4));
+        dst[0] = make_float4(va.x, vb.x, va.y, vb.y);
+        dst[1] = make_float4(va.z, vb.z, va.w, vb.w);
     }
     __syncthreads();
 
-    // ---- horizontal pass: 4 outputs per item, 12-sample register window ---------------------
+    // ---- horizontal pass: 4 outputs per item, 12-sample window of (a, b) pairs -----------------------
     for (int idx = tid; idx < kFirIH * (kFirTW / 4); idx += kFirThreads) {
         const int row = idx / (kFirTW / 4), g4 = idx - row * (kFirTW / 4);
-        float va[12], vb[12], q[12];
-        const float4 *ra = reinterpret_cast<const float4 *>(sa + row * kFirIW + 4 * g4);
-        const float4 *rb = reinterpret_cast<const float4 *>(sb + row * kFirIW + 4 * g4);
+        f32x2 v[12], q[12];
+        float p[12];
+        const float4 *r4 = reinterpret_cast<const float4 *>(sab + 2 * (row * kFirIW + 4 * g4));
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float4 x = ra[k], y = rb[k];
-            va[4 * k] = x.x; va[4 * k + 1] = x.y; va[4 * k + 2] = x.z; va[4 * k + 3] = x.w;
-            vb[4 * k] = y.x; vb[4 * k + 1] = y.y; vb[4 * k + 2] = y.z; vb[4 * k + 3] = y.w;
+        for (int k = 0; k < 6; ++k) {
+            const float4 x = r4[k];
+            v[2 * k] = pk2(x.x, x.y);
+            v[2 * k + 1] = pk2(x.z, x.w);
+            p[2 * k] = x.x * x.y;
+            p[2 * k + 1] = x.z * x.w;
         }
-        float4 o;
-        float *dst = sh + row * kFirTW + 4 * g4;
-        o.x = fir9(va, taps); o.y = fir9(va + 1, taps); o.z = fir9(va + 2, taps); o.w = fir9(va + 3, taps);
-        *reinterpret_cast<float4 *>(dst) = o;
-        o.x = fir9(vb, taps); o.y = fir9(vb + 1, taps); o.z = fir9(vb + 2, taps); o.w = fir9(vb + 3, taps);
-        *reinterpret_cast<float4 *>(dst + kFirIH * kFirTW) = o;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) q[k] = va[k] * va[k];
-        o.x = fir9(q, taps); o.y = fir9(q + 1, taps); o.z = fir9(q + 2, taps); o.w = fir9(q + 3, taps);
-        *reinterpret_cast<float4 *>(dst + 2 * kFirIH * kFirTW) = o;
+        for (int k = 0; k < 12; ++k) q[k] = mul2(v[k], v[k]);
+        float4 *d0 = reinterpret_cast<float4 *>(shp + 2 * (row * kFirTW + 4 * g4));
+        float4 *d1 = reinterpret_cast<float4 *>(shp + 2 * (kFirIH * kFirTW + row * kFirTW + 4 * g4));
+        f32x2 o[4];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) q[k] = vb[k] * vb[k];
-        o.x = fir9(q, taps); o.y = fir9(q + 1, taps); o.z = fir9(q + 2, taps); o.w = fir9(q + 3, taps);
-        *reinterpret_cast<float4 *>(dst + 3 * kFirIH * kFirTW) = o;
+        for (int i = 0; i < 4; ++i) o[i] = fir9x2(v + i, taps2);
+        float4 w4;
+        unpk2(o[0], w4.x, w4.y); unpk2(o[1], w4.z, w4.w); d0[0] = w4;
+        unpk2(o[2], w4.x, w4.y); unpk2(o[3], w4.z, w4.w); d0[1] = w4;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) q[k] = va[k] * vb[k];
-        o.x = fir9(q, taps); o.y = fir9(q + 1, taps); o.z = fir9(q + 2, taps); o.w = fir9(q + 3, taps);
-        *reinterpret_cast<float4 *>(dst + 4 * kFirIH * kFirTW) = o;
+        for (int i = 0; i < 4; ++i) o[i] = fir9x2(q + i, taps2);
+        unpk2(o[0], w4.x, w4.y); unpk2(o[1], w4.z, w4.w); d1[0] = w4;
+        unpk2(o[2], w4.x, w4.y); unpk2(o[3], w4.z, w4.w); d1[1] = w4;
+        w4.x = fir9(p, taps); w4.y = fir9(p + 1, taps); w4.z = fir9(p + 2, taps); w4.w = fir9(p + 3, taps);
+        *reinterpret_cast<float4 *>(shs + row * kFirTW + 4 * g4) = w4;
     }
     __syncthreads();
 
     // ---- vertical pass + maps: one column, 8 output rows per thread ---------------------------
     const int col = tid & (kFirTW - 1), rg = tid >> 6;  // 4 row groups of 8
-    float out[5][8];
+    f32x2 om[8], os[8];   // (mu1, mu2), (s11, s22)
+    float ox[8];          // s12
+    {
+        f32x2 v[16];
+        const float *p = shp + 2 * ((rg * 8) * kFirTW + col);
 #pragma unroll
-    for (int qn = 0; qn < 5; ++qn) {
-        float v[16];
-        const float *p = sh + qn * kFirIH * kFirTW + (rg * 8) * kFirTW + col;
+        for (int k = 0; k < 16; ++k) v[k] = lds2(p + 2 * k * kFirTW);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = p[k * kFirTW];
+        for (int r = 0; r < 8; ++r) om[r] = fir9x2(v + r, taps2);
+        p += 2 * kFirIH * kFirTW;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) out[qn][r] = fir9(v + r, taps);
+        for (int k = 0; k < 16; ++k) v[k] = lds2(p + 2 * k * kFirTW);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) os[r] = fir9x2(v + r, taps2);
+        float u[16];
+        const float *ps = shs + (rg * 8) * kFirTW + col;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) u[k] = ps[k * kFirTW];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ox[r] = fir9(u + r, taps);
     }
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // maps on packed pairs of rows (r, r+1) of this column; a row below the image enters as all-zero
+    // inputs, which pool to exactly zero
+    const Unit2 un = unit2(a.one, a.neg_one);
+    f32x2 acc[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[j] = splat2(0.0f);
     const int gx = x0 + col;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < 8; r += 2) {
         const int gy = y0 + rg * 8 + r;
         if (gx < w && gy < h) {
-            const float av = sa[(rg * 8 + r + kFirR) * kFirIW + col + kFirR];
-            const float bv = sb[(rg * 8 + r + kFirR) * kFirIW + col + kFirR];
-            error_maps(av, bv, out[0][r], out[1][r], out[2][r], out[3][r], out[4][r], acc);
+            const float2 ab0 = *reinterpret_cast<const float2 *>(sab + 2 * ((rg * 8 + r + kFirR) * kFirIW + col + kFirR));
+            const float2 ab1 = *reinterpret_cast<const float2 *>(sab + 2 * ((rg * 8 + r + 1 + kFirR) * kFirIW + col + kFirR));
+            float m1a, m2a, m1b, m2b, s1a, s2a, s1b, s2b;
+            unpk2(om[r], m1a, m2a);
+            unpk2(om[r + 1], m1b, m2b);
+            unpk2(os[r], s1a, s2a);
+            unpk2(os[r + 1], s1b, s2b);
+            const bool two = gy + 1 < h;
+            error_maps2(un, pk2(ab0.x, two ? ab1.x : 0.f), pk2(ab0.y, two ? ab1.y : 0.f), pk2(m1a, two ? m1b : 0.f),
+                        pk2(m2a, two ? m2b : 0.f), pk2(s1a, two ? s1b : 0.f), pk2(s2a, two ? s2b : 0.f),
+                        pk2(ox[r], two ? ox[r + 1] : 0.f), acc);
         }
     }
     double dacc[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) dacc[j] = (double)acc[j];
+    for (int j = 0; j < 6; ++j) {
+        float lo, hi;
+        unpk2(acc[j], lo, hi);
+        dacc[j] = (double)lo + (double)hi;
+    }
     block_reduce6<kFirThreads / 32>(dacc, sred,
                                     a.partials + (long long)cand * a.partials_stride + (long long)cta * 6);
 }
