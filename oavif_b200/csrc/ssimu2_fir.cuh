@@ -89,9 +89,20 @@ __global__ void __launch_bounds__(kFirThreads, 3) k_fir_fused(const __grid_const
         taps2[k] = splat2(taps[k]);
     }
 
+    // Shared-memory rows are stored in 16-byte chunks (two interleaved pixels); on ODD rows adjacent chunks
+    // are swapped (physical chunk = logical chunk ^ 1).  With eight-lane groups made of four consecutive
+    // chunk pairs on an even row and the same four on the next row, the eight 16-byte accesses of a phase
+    // then land on eight different bank groups (even chunks on the even row, odd ones on the odd row); without
+    // the swap every 128-bit access of the interleaved layout is a 2-way bank conflict.  The swap costs no
+    // instructions: even and odd logical chunks just use two base pointers, `+odd` and `-odd` chunks away.
+
     // ---- stage a, b with a 4-pixel zero-padded halo (float4 granules), interleaved per pixel -------
-    for (int idx = tid; idx < kFirIH * (kFirIW / 4); idx += kFirThreads) {
-        const int row = idx / (kFirIW / 4), c4 = idx - row * (kFirIW / 4);
+    // items: 20 row pairs x 5 groups x 8 lanes (4 granules x 2 rows); 18 granules per row, so the last group is half empty
+    for (int idx = tid; idx < (kFirIH / 2) * 5 * 8; idx += kFirThreads) {
+        const int l8 = idx & 7, j = idx >> 3;
+        const int grp = j % 5, rowpair = j / 5;
+        const int c4 = 4 * grp + (l8 & 3), odd = l8 >> 2, row = 2 * rowpair + odd;
+        if (c4 >= kFirIW / 4) continue;
         const int gx = x0 - kFirR + 4 * c4, gy = y0 - kFirR + row;
         float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
         if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
@@ -104,21 +115,24 @@ __global__ void __launch_bounds__(kFirThreads, 3) k_fir_fused(const __grid_const
                 va.w = 0.f; vb.w = 0.f;
             }
         }
-        float4 *dst = reinterpret_cast<float4 *>(sab + 2 * (row * kFirIW + 4 * c4));
-        dst[0] = make_float4(va.x, vb.x, va.y, vb.y);
-        dst[1] = make_float4(va.z, vb.z, va.w, vb.w);
+        float4 *dst = reinterpret_cast<float4 *>(sab + 2 * (row * kFirIW + 4 * c4));   // logical chunks 2*c4, 2*c4 + 1
+        dst[odd] = make_float4(va.x, vb.x, va.y, vb.y);
+        dst[1 - odd] = make_float4(va.z, vb.z, va.w, vb.w);
     }
     __syncthreads();
 
     // ---- horizontal pass: 4 outputs per item, 12-sample window of (a, b) pairs -----------------------
+    // items: 20 row pairs x 4 groups x 8 lanes (4 output granules x 2 rows)
     for (int idx = tid; idx < kFirIH * (kFirTW / 4); idx += kFirThreads) {
-        const int row = idx / (kFirTW / 4), g4 = idx - row * (kFirTW / 4);
+        const int l8 = idx & 7, j = idx >> 3;
+        const int g4 = 4 * (j & 3) + (l8 & 3), odd = l8 >> 2, row = 2 * (j >> 2) + odd;
         f32x2 v[12], q[12];
         float p[12];
         const float4 *r4 = reinterpret_cast<const float4 *>(sab + 2 * (row * kFirIW + 4 * g4));
+        const float4 *re = r4 + odd, *ro = r4 - odd;   // even / odd logical chunks of this row
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const float4 x = r4[k];
+            const float4 x = (k & 1) ? ro[k] : re[k];
             v[2 * k] = pk2(x.x, x.y);
             v[2 * k + 1] = pk2(x.z, x.w);
             p[2 * k] = x.x * x.y;
@@ -132,12 +146,12 @@ __global__ void __launch_bounds__(kFirThreads, 3) k_fir_fused(const __grid_const
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i] = fir9x2(v + i, taps2);
         float4 w4;
-        unpk2(o[0], w4.x, w4.y); unpk2(o[1], w4.z, w4.w); d0[0] = w4;
-        unpk2(o[2], w4.x, w4.y); unpk2(o[3], w4.z, w4.w); d0[1] = w4;
+        unpk2(o[0], w4.x, w4.y); unpk2(o[1], w4.z, w4.w); d0[odd] = w4;
+        unpk2(o[2], w4.x, w4.y); unpk2(o[3], w4.z, w4.w); d0[1 - odd] = w4;
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i] = fir9x2(q + i, taps2);
-        unpk2(o[0], w4.x, w4.y); unpk2(o[1], w4.z, w4.w); d1[0] = w4;
-        unpk2(o[2], w4.x, w4.y); unpk2(o[3], w4.z, w4.w); d1[1] = w4;
+        unpk2(o[0], w4.x, w4.y); unpk2(o[1], w4.z, w4.w); d1[odd] = w4;
+        unpk2(o[2], w4.x, w4.y); unpk2(o[3], w4.z, w4.w); d1[1 - odd] = w4;
         w4.x = fir9(p, taps); w4.y = fir9(p + 1, taps); w4.z = fir9(p + 2, taps); w4.w = fir9(p + 3, taps);
         *reinterpret_cast<float4 *>(shs + row * kFirTW + 4 * g4) = w4;
     }
@@ -149,14 +163,17 @@ __global__ void __launch_bounds__(kFirThreads, 3) k_fir_fused(const __grid_const
     float ox[8];          // s12
     {
         f32x2 v[16];
-        const float *p = shp + 2 * ((rg * 8) * kFirTW + col);
+        // window row k of this thread is tile row rg*8 + k: its parity is that of k.  Pixel `col` lives in
+        // logical chunk col >> 1; on odd rows the chunk is the neighbouring one.
+        const float *p = shp + 2 * ((rg * 8) * kFirTW) + 4 * (col >> 1) + 2 * (col & 1);
+        const int swap = (col & 2) ? -4 : 4;   // floats from a chunk to its partner
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = lds2(p + 2 * k * kFirTW);
+        for (int k = 0; k < 16; ++k) v[k] = lds2(p + 2 * k * kFirTW + ((k & 1) ? swap : 0));
 #pragma unroll
         for (int r = 0; r < 8; ++r) om[r] = fir9x2(v + r, taps2);
         p += 2 * kFirIH * kFirTW;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = lds2(p + 2 * k * kFirTW);
+        for (int k = 0; k < 16; ++k) v[k] = lds2(p + 2 * k * kFirTW + ((k & 1) ? swap : 0));
 #pragma unroll
         for (int r = 0; r < 8; ++r) os[r] = fir9x2(v + r, taps2);
         float u[16];
@@ -177,8 +194,12 @@ __global__ void __launch_bounds__(kFirThreads, 3) k_fir_fused(const __grid_const
     for (int r = 0; r < 8; r += 2) {
         const int gy = y0 + rg * 8 + r;
         if (gx < w && gy < h) {
-            const float2 ab0 = *reinterpret_cast<const float2 *>(sab + 2 * ((rg * 8 + r + kFirR) * kFirIW + col + kFirR));
-            const float2 ab1 = *reinterpret_cast<const float2 *>(sab + 2 * ((rg * 8 + r + 1 + kFirR) * kFirIW + col + kFirR));
+            // staged row rg*8 + r + 4: parity of r (r is even here, r + 1 odd); pixel col + 4
+            const int px = col + kFirR, sw = (px & 2) ? -4 : 4;
+            const float2 ab0 = *reinterpret_cast<const float2 *>(sab + 2 * ((rg * 8 + r + kFirR) * kFirIW) + 4 * (px >> 1) +
+                                                                 2 * (px & 1));
+            const float2 ab1 = *reinterpret_cast<const float2 *>(sab + 2 * ((rg * 8 + r + 1 + kFirR) * kFirIW) +
+                                                                 4 * (px >> 1) + 2 * (px & 1) + sw);
             float m1a, m2a, m1b, m2b, s1a, s2a, s1b, s2b;
             unpk2(om[r], m1a, m2a);
             unpk2(om[r + 1], m1b, m2b);
