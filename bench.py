@@ -217,10 +217,13 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     sc.set_stream(stream.cuda_stream)
 
+    dev_ptrs = [(s.data_ptr(), [[y.data_ptr(), u.data_ptr(), v.data_ptr()]]) for s, (y, u, v) in dev]
+    yuv_strides = [2 * W] * 3
+
     def step_dev(i):
-        s, (y, u, v) = dev[i % NSETS]
-        sc.set_source_dev(s.data_ptr(), W, H, 3 * W)
-        return sc.score_batch_dev("yuv444", [[y.data_ptr(), u.data_ptr(), v.data_ptr()]], [2 * W] * 3, depth=10)[0]
+        sp, cp = dev_ptrs[i % NSETS]
+        sc.set_source_dev(sp, W, H, 3 * W)
+        return sc.score_batch_dev("yuv444", cp, yuv_strides, depth=10)[0]
 
     def step_host(i):
         s, y, u, v = pin[i % len(pin)]
