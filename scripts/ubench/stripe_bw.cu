@@ -35,6 +35,53 @@ __global__ void k_linear(const float4 *base, size_t n16, float *sink)
     if (acc == 12345.678f) sink[0] = acc;
 }
 
+// rows-pass pattern: one warp per (plane, 32-row block) walks along the rows; per step it reads a
+// 32-row x 128-byte tile (4 rows per instruction, 8 lanes per row) and writes WOUT such tiles to WOUT
+// other planes as whole 128-byte lines (streaming stores), UNROLL steps in flight.
+template <int WOUT, int UNROLL>
+__global__ void k_rows(const float4 *src, float4 *dst, int pitch16, int h, int planes)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int blocks = h / 32, plane = warp / blocks, rb = warp % blocks;
+    if (plane >= planes) return;
+    const size_t pbytes16 = (size_t)pitch16 * h;
+    const float4 *p = src + plane * pbytes16 + (size_t)(rb * 32 + (lane >> 3)) * pitch16 + (lane & 7);
+    float4 *q = dst + (size_t)plane * WOUT * pbytes16 + (size_t)(rb * 32 + (lane >> 3)) * pitch16 + (lane & 7);
+    for (int c = 0; c + 8 * UNROLL <= pitch16; c += 8 * UNROLL) {
+        float4 v[UNROLL][8];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[u][i] = __ldcs(p + c + 8 * u + (size_t)(4 * i) * pitch16);
+#pragma unroll
+        for (int o = 0; o < WOUT; ++o)
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) __stcs(q + o * pbytes16 + c + 8 * u + (size_t)(4 * i) * pitch16, v[u][i]);
+    }
+}
+
+template <int WOUT, int UNROLL>
+void run_rows(const float4 *src, float4 *dst, int w, int h, int planes)
+{
+    const int pitch16 = w / 4, warps = planes * (h / 32), threads = 128;
+    const int blocks = (warps * 32 + threads - 1) / threads;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_rows<WOUT, UNROLL><<<blocks, threads>>>(src, dst, pitch16, h, planes);
+    cudaEventRecord(e0);
+    for (int i = 0; i < 5; ++i) k_rows<WOUT, UNROLL><<<blocks, threads>>>(src, dst, pitch16, h, planes);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double bytes = 5.0 * planes * (1 + WOUT) * (double)w * h * 4;
+    printf("rows pattern: read 1 plane, write %d, unroll %d, warps %5d : %7.1f GB/s (read + write)\n", WOUT, UNROLL, warps,
+           bytes / ms / 1e6);
+}
+
 template <int P, int UNROLL>
 void run(const float4 *d, int w, int h, int planes, float *sink, int threads)
 {
@@ -86,6 +133,20 @@ int main()
     run<512, 8>(d, w, h, planes, sink, 32);
     run<512, 8>(d, w, h, planes, sink, 128);
     run<512, 16>(d, w, h, planes, sink, 128);
+    {   // rows-pass pattern: 6 source planes -> 6 * WOUT destination planes
+        float4 *dst;
+        const int rp = 6;
+        cudaMalloc(&dst, (size_t)rp * 3 * w * h * 4);
+        run_rows<1, 1>(d, dst, w, 2144, rp);
+        run_rows<1, 2>(d, dst, w, 2144, rp);
+        run_rows<2, 1>(d, dst, w, 2144, rp);
+        run_rows<2, 2>(d, dst, w, 2144, rp);
+        run_rows<3, 1>(d, dst, w, 2144, rp);
+        run_rows<1, 4>(d, dst, w, 2144, rp);
+        run_rows<2, 4>(d, dst, w, 2144, rp);
+        run_rows<3, 3>(d, dst, w, 2144, rp);
+        cudaFree(dst);
+    }
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
