@@ -440,3 +440,34 @@ def test_full_size_4k_properties(oracle, mode, omode, name):
             sc.set_source(src)
             got = sc.score_rgb8(d2)
             assert abs(got - oracle.ssimu2_rgb8(src, d2, omode, fast=True)) <= SCORE_TOL
+
+
+# ---- several callers per GPU: one context per host thread (the corpus driver's workers-per-gpu) ------------
+def test_two_contexts_on_two_threads_score_like_one():
+    """Contexts are single-owner, but several may run on one GPU at once (each on its own stream): concurrent
+    callers must get bit-identical scores to a lone caller."""
+    import threading
+    w, h = 640, 360
+    srcs = [synth.synth(w, h, "mixture", 40 + k) for k in range(2)]
+    cands = [[synth.distort(s, 0.2 + 0.2 * i, seed=i) for i in range(3)] for s in srcs]
+    with ssimu2.Scorer(w, h, 1) as sc:
+        want = []
+        for s, cs in zip(srcs, cands):
+            sc.set_source(s)
+            want.append([sc.score_rgb8(c) for c in cs])
+    got = [None, None]
+
+    def work(k):
+        with ssimu2.Scorer(w, h, 1) as sck:
+            out = []
+            for _ in range(10):           # repeat: the two threads stay in flight together
+                sck.set_source(srcs[k])
+                out = [sck.score_rgb8(c) for c in cands[k]]
+            got[k] = out
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert got == want
