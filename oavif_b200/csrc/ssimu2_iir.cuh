@@ -510,18 +510,18 @@ __global__ void __launch_bounds__(MODE == 2 ? 192 : 128) k_iir_rows(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 288.
+// columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 256.
 //
 // One CTA owns 32 columns of one channel; lane = column in the arithmetic, so the recursions of a warp
 // are 32 independent columns.  Warps 0..2 (producers) run the column recursions out of shared-memory
 // rings: warp 0 the packed pair (a, a*a), warp 1 the packed pair (b, b*b) — each reads one float2 per
-// tap from its interleaved plane —, warp 2 a*b alone.  Warp 8 (loader) feeds the three rings with
+// tap from its interleaved plane —, warp 2 a*b alone.  Warp 7 (loader) feeds the three rings with
 // 16-byte cp.async, 32 rows ahead of use, zero-filling rows and columns beyond the image; both taps of
 // the recursion are read back from the ring (no register delay line).  Each producer drops its filtered
-// values into a double-buffered 16-row batch.  Warps 3..7 (consumers), one batch behind, stage the pixel's
+// values into a double-buffered 16-row batch.  Warps 3..6 (consumers), one batch behind, stage the pixel's
 // own XYB samples themselves and evaluate the SSIM / edge-diff maps and the six pooled sums, two rows
 // of a column as one packed pair.  One block barrier per 16 rows.
-constexpr int kIirVThreads = 288;   // 3 producer warps + 5 consumer warps + 1 loader warp
+constexpr int kIirVThreads = 256;   // 3 producer warps + 4 consumer warps + 1 loader warp
 
 template <int RCAP, int B>
 struct IirColsSmem {
@@ -529,11 +529,11 @@ struct IirColsSmem {
     float sring[RCAP][kIirVCols];              // ... and of a*b
     float ab[2][32][kIirVCols];                // consumer rows of the two XYB planes
     float ex[2][5][B][kIirVCols];              // filtered values, double-buffered
-    double red[5][6];
+    double red[4][6];
 };
 
 // B rows per exchange batch: the per-batch overhead (barrier, copy issue, address set-up) is paid once
-// per B rows by each of the nine warps.  RCAP = rows of a producer ring.
+// per B rows by each of the eight warps.  RCAP = rows of a producer ring.
 template <int RCAP, int B>
 __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a)
 {
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     // bytes of this lane's 16-byte column group that lie inside the image: the rest is zero-filled
     const int cbytes = max(0, min(16, (w - (cb * kIirVCols + ccol)) * 4));
 
-    if (warp == 8) {
+    if (warp == 7) {
         // ---------------- loader: feeds the three producer rings ----------------
         // Batch b (rows n0 = 16b ..) reads ring rows n0-6 .. n0+B+3.  The loader requests rows n0+4+D .. n0+3+D+B
         // while batch b runs (their slots held rows n0-28 .. n0-13, dead by then) and arrives at the barrier
@@ -672,17 +672,16 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();
     } else {
         // ---------------- consumers: maps + pooling ----------------
-        // Five consumer warps share the eight row pairs (2p, 2p+1), p = 0..7, of a 16-row batch so that the
-        // four sub-partitions of the SM carry equal work next to the three producers and the loader (warp w
-        // runs on sub-partition w % 4; a pair producer costs ~310 instructions per batch, the a*b producer
-        // ~240, the loader ~150, a row pair of maps ~125):
-        //   warp 3: p0 p1, warp 5: p2 p3, warp 6: p4 p5, warp 4: p6, warp 7: p7  (the loader is warp 8).
+        // Four consumer warps (3..6) take two of the eight row pairs (2p, 2p+1), p = 0..7, of a 16-row batch
+        // each: rows 4*cw .. 4*cw + 3.  With the loader as warp 7 the four sub-partitions of the SM (warp w
+        // runs on sub-partition w % 4) carry about equal work: a pair producer costs ~260 instructions per
+        // batch, the a*b producer ~260, the loader ~200, two row pairs of maps ~275.
         // A consumer evaluates the two rows of a pair as one packed pair per column, and stages the XYB rows
         // it needs itself.  Columns beyond the image need no test: every ring is zero-filled there by the
         // copies, and all-zero inputs pool to exactly zero.
-        const int cw = warp - 3;                                   // 0..4
-        const int first_pair = cw == 0 ? 0 : cw == 2 ? 2 : cw == 3 ? 4 : cw == 1 ? 6 : 7;
-        const int npairs = (cw == 1 || cw == 4) ? 1 : 2;
+        const int cw = warp - 3;                                   // 0..3
+        const int first_pair = 2 * cw;
+        constexpr int npairs = 2;
         const bool stager = crow < 2 * npairs;                     // lanes that copy: 8 per row
         const int srow = 2 * first_pair + crow;
         const float *pa = a.src + poff + ccol;
@@ -758,7 +757,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             dacc[j] += (double)hi;
         }
         __syncthreads();
-        // fixed shuffle tree over the 32 columns, then the five consumers in fixed order
+        // fixed shuffle tree over the 32 columns, then the four consumers in fixed order
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             double x = dacc[j];
@@ -769,7 +768,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();
         if (cw == 0 && lane < 6)
             a.partials[(long long)cand * a.partials_stride + (long long)blockIdx.x * 6 + lane] =
-                (((sm.red[0][lane] + sm.red[1][lane]) + sm.red[2][lane]) + sm.red[3][lane]) + sm.red[4][lane];
+                ((sm.red[0][lane] + sm.red[1][lane]) + sm.red[2][lane]) + sm.red[3][lane];
     }
 }
 
