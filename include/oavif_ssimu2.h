@@ -54,7 +54,16 @@ enum {
  *              (no intermediate planes); differs from RECURSIVE only by that round-off.      */
 enum { OAVIF_SSIMU2_BLUR_RECURSIVE = 0, OAVIF_SSIMU2_BLUR_FIR = 1 };
 
-enum { OAVIF_SSIMU2_OPT_BLUR = 1 };
+/* How the 108 weights of the final sum are laid over images with FEWER than six scales (min side < ~256; every
+ * BASELINE config has six, where both readings coincide).  Nothing in /root/reference settles which one
+ * fssimu2 0.1.1 uses (its source is un-vendored, build.zig.zon:7-10), so both are offered:
+ *   SIX_SLOTS:  weight index ((c*6 + scale)*2 + n)*3 + k, absent scales contribute zero (default; the
+ *               fixed six-scale table of the vszip lineage fssimu2 derives from)
+ *   CONTIGUOUS: libjxl tools/ssimulacra2.cc Msssim::Score(): `for scale < scales.size()` with a running
+ *               i++, i.e. index ((c*n_scales + scale)*2 + n)*3 + k                               */
+enum { OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS = 0, OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS = 1 };
+
+enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_WEIGHTS = 2 };
 
 typedef struct oavif_ssimu2_ctx oavif_ssimu2_ctx;
 
@@ -128,7 +137,11 @@ int oavif_ssimu2_score_pixels(oavif_ssimu2_ctx *ctx, const void *pixels, size_t 
                               int bits, double *score);
 
 /* Decoded planes as libavif hands them over: depth 8 -> uint8_t samples, depth 10 -> uint16_t;
- * strides in BYTES; full range; matrix = AV1 matrix_coefficients (1, 2, 5, 6, 9).
+ * strides in BYTES; matrix = AV1 matrix_coefficients (1, 2, 5, 6, 9).
+ * FULL RANGE ONLY, and there is no range argument: the caller must check avifImage.yuvRange ==
+ * AVIF_RANGE_FULL (what avifImageCreate defaults to, io.zig:546) and otherwise take the score_pixels path
+ * with libavif's own conversion.  The integer arithmetic is libavif's libyuv path (a libavif built without
+ * libyuv converts in float and can differ by 1 LSB; score_pixels is the bit-faithful route there too).
  * rgba_path != 0 reproduces the conversion libavif runs when the decoded image has an alpha
  * plane (io.zig:473); alpha itself is never scored (io.zig:654-663). */
 int oavif_ssimu2_score_yuv444(oavif_ssimu2_ctx *ctx, const void *y, const void *u, const void *v,
@@ -159,11 +172,17 @@ int oavif_ssimu2_score_batch_yuv444_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const
 /* ---- stateless forms ------------------------------------------------------------------------ */
 
 /* fssimu2.computeSsimu2(ref, dist, w, h, channels) — tq.zig:37.  channels must be 3 (the only
- * value oavif passes); tight rows.  Creates and destroys a context internally on device 0. */
+ * value oavif passes); tight rows.  Runs on ONE process-wide context that is created on first use on the
+ * default device (0 unless oavif_ssimu2_set_default_device was called), regrown when an image does not fit,
+ * serialised by a mutex, and kept alive (about 1 GB of HBM at 4K) until oavif_ssimu2_release_cached(). */
 int oavif_ssimu2_compute_rgb8(const uint8_t *ref, const uint8_t *dist, uint32_t w, uint32_t h,
                               uint32_t channels, double *score);
+int oavif_ssimu2_set_default_device(int device);
+void oavif_ssimu2_release_cached(void);
 
-/* decodeAvifToRgb's pixel work (io.zig:470-478, 654-663) alone: planes -> tight RGB8. */
+/* decodeAvifToRgb's pixel work (io.zig:470-478, 654-663) alone: planes -> tight RGB8.  Uses the candidate
+ * staging buffer and an output buffer of its own; the cached source is untouched, so it may be called in the
+ * middle of a search. */
 int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void *u, const void *v,
                                 size_t y_stride, size_t u_stride, size_t v_stride, uint32_t w,
                                 uint32_t h, int depth, int matrix, int rgba_path, uint8_t *rgb_out);
@@ -183,6 +202,14 @@ int oavif_ssimu2_debug_get_xyb(oavif_ssimu2_ctx *ctx, int which, int scale, int 
  * Lets a test compare the product kernel's recursion bit for bit with the CPU oracle's horizontal pass. */
 int oavif_ssimu2_debug_get_rows(oavif_ssimu2_ctx *ctx, int candidate, int quantity, int scale, int channel,
                                 float *out, uint32_t *w_out, uint32_t *h_out);
+
+/* The RECURSIVE columns pass of the scored path: re-runs the product kernel (k_iir_cols) over the row-filtered
+ * planes the last score call left and copies out the five fully blurred values it hands to the error maps —
+ * mu1, mu2, sigma11, sigma22, sigma12, in that order, each w*h floats — for one candidate, scale and channel.
+ * out: 5*w*h floats.  Blurred planes never exist in HBM on the scored path; this tap is how a test compares
+ * them bit for bit with the CPU oracle's full blur. */
+int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale, int channel, float *out,
+                                uint32_t *w_out, uint32_t *h_out);
 
 /* Blur one host plane with the selected blur on the device (tests of the filter alone). */
 int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, uint32_t h,

@@ -18,7 +18,7 @@ DEPS = [os.path.join(ROOT, "csrc", f) for f in os.listdir(os.path.join(ROOT, "cs
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-Xptxas", "-v",
 ]
 
 
@@ -51,14 +51,14 @@ def build_host(force: bool = False) -> str:
     cli_src = os.path.join(ROOT, "host", "cpp", "main.cpp")
     stale = force or not os.path.exists(HOST_OUT) or any(os.path.getmtime(HOST_OUT) < os.path.getmtime(d) for d in deps)
     if stale:
-        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", HOST_OUT,
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-ffp-contract=off", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", HOST_OUT,
                *HOST_SRC, "-L" + os.path.dirname(OUT), "-loavif_ssimu2", "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("g++ failed: " + " ".join(cmd))
     if os.path.exists(cli_src) and (stale or not os.path.exists(HOST_CLI)):
-        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", HOST_CLI, cli_src,
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-ffp-contract=off", "-std=c++17", "-Wall", "-Wextra", "-o", HOST_CLI, cli_src,
                "-L" + os.path.dirname(OUT), "-loavif_host", "-loavif_ssimu2", "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:

@@ -38,6 +38,11 @@ struct HostPlanes {  // one candidate's input, host or device pointers
     const void *p[3];
 };
 
+// the stateless entry point's process-wide context (oavif_ssimu2_compute_rgb8)
+std::mutex g_cached_mu;
+oavif_ssimu2_ctx *g_cached = nullptr;
+int g_default_device = 0;
+
 }  // namespace
 
 struct oavif_ssimu2_ctx {
@@ -45,6 +50,7 @@ struct oavif_ssimu2_ctx {
     uint32_t max_w = 0, max_h = 0, max_batch = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
+    int weight_layout = OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS;
 
     // capacities (computed from max_w x max_h)
     long long cap_pyr_floats = 0, cap_in_bytes = 0, cap_ctas = 0, cap_hplane_floats = 0;
@@ -63,6 +69,8 @@ struct oavif_ssimu2_ctx {
     double *dm_sums = nullptr, *dm_scores = nullptr;    // device views of the two
     float *d_dbg = nullptr;
     long long dbg_floats = 0;
+    uint8_t *d_conv = nullptr;     // oavif_ssimu2_yuv444_to_rgb8's output, grown on demand
+    size_t conv_bytes = 0;
     cudaEvent_t ev[6] = {};  // start, h2d, pyramid, blur a, blur b, finalize
     oavif_ssimu2_timing timing{};
     float taps[9] = {};
@@ -362,6 +370,25 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const 
     return 0;
 }
 
+// Everything a w x h image needs against what the context allocated: pyramid floats, staged input bytes and
+// — per-CTA partial sums are indexed by CTA — the CTA plans of both blur modes for THIS image (an image inside
+// the pyramid/input capacity can still need more CTAs than the max_w x max_h box or its transpose).
+long long ctas_needed(int w, int h)
+{
+    Geom g;
+    make_geom(w, h, &g);
+    BlurPlan a, b;
+    plan_fir(g, &a);
+    plan_iir_v(g, &b);
+    return a.total > b.total ? a.total : b.total;
+}
+
+bool fits_capacity(const oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
+{
+    return pyr_capacity((int)w, (int)h) <= ctx->cap_pyr_floats && (long long)w * h * 8 + 3 * 256 <= ctx->cap_in_bytes &&
+           ctas_needed((int)w, (int)h) <= ctx->cap_ctas;
+}
+
 int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
 {
     if (w == 0 || h == 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "zero image dimension");
@@ -369,7 +396,7 @@ int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
     // kernels address a plane with 32-bit element offsets, and an interleaved pair plane is two planes wide
     if ((long long)rup(cdiv((int)w, kPyrTile) * kPyrTile, 32) * (cdiv((int)h, kPyrTile) * kPyrTile) >= (1LL << 30))
         return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "image %ux%u: a plane exceeds 2^30 samples", w, h);
-    if (pyr_capacity((int)w, (int)h) > ctx->cap_pyr_floats || (long long)w * h * 8 + 3 * 256 > ctx->cap_in_bytes)
+    if (!fits_capacity(ctx, w, h))
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "image %ux%u exceeds context capacity %ux%u", w, h, ctx->max_w,
                     ctx->max_h);
     return 0;
@@ -426,6 +453,7 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
     f.partials_stride = ctx->cap_ctas * 6;
     f.sums = ctx->dm_sums;
     f.scores = ctx->dm_scores;
+    f.contiguous_weights = ctx->weight_layout == OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS;
     k_finalize<<<n, 1024, 0, ctx->stream>>>(f);
     CK(cudaGetLastError());
     ctx->timing.launches += 1;
@@ -559,6 +587,7 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     cudaFree((void *)ctx->d_tbl);
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_dbg);
+    cudaFree(ctx->d_conv);
     cudaFreeHost((void *)ctx->h_tbl);
     cudaFreeHost(ctx->h_sums);
     cudaFreeHost(ctx->h_scores);
@@ -639,6 +668,11 @@ int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value)
     if (option == OAVIF_SSIMU2_OPT_BLUR &&
         (value == OAVIF_SSIMU2_BLUR_RECURSIVE || value == OAVIF_SSIMU2_BLUR_FIR)) {
         ctx->blur_mode = value;
+        return 0;
+    }
+    if (option == OAVIF_SSIMU2_OPT_WEIGHTS &&
+        (value == OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS || value == OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS)) {
+        ctx->weight_layout = value;
         return 0;
     }
     return fail(ctx, OAVIF_SSIMU2_E_ARG, "unknown option %d / value %d", option, value);
@@ -769,26 +803,40 @@ int oavif_ssimu2_score_batch_yuv444_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const
 int oavif_ssimu2_compute_rgb8(const uint8_t *ref, const uint8_t *dist, uint32_t w, uint32_t h, uint32_t channels,
                               double *score)
 {
-    // The reference's stateless call (tq.zig:37).  One cached context per process, regrown on demand.
-    static std::mutex mu;
-    static oavif_ssimu2_ctx *cached = nullptr;
+    // The reference's stateless call (tq.zig:37).  One cached context per process on the default device,
+    // regrown on demand, released by oavif_ssimu2_release_cached().
     if (!ref || !dist || !score) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null argument");
     if (channels != 3) return fail(nullptr, OAVIF_SSIMU2_E_UNSUPPORTED, "channels = %u (oavif always passes 3)", channels);
     if (w == 0 || h == 0) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "zero image dimension");
-    std::lock_guard<std::mutex> lock(mu);
-    if (cached && (pyr_capacity((int)w, (int)h) > cached->cap_pyr_floats ||
-                   (long long)w * h * 8 + 768 > cached->cap_in_bytes)) {
+    std::lock_guard<std::mutex> lock(g_cached_mu);
+    oavif_ssimu2_ctx *&cached = g_cached;
+    if (cached && (cached->device != g_default_device || !fits_capacity(cached, w, h))) {
         oavif_ssimu2_ctx_destroy(cached);
         cached = nullptr;
     }
     if (!cached) {
-        const int rc = oavif_ssimu2_ctx_create(0, w, h, 1, &cached);
+        const int rc = oavif_ssimu2_ctx_create(g_default_device, w, h, 1, &cached);
         if (rc) return rc;
     }
     int rc = oavif_ssimu2_set_source_rgb8(cached, ref, w, h, (size_t)3 * w);
     if (rc == 0) rc = oavif_ssimu2_score_rgb8(cached, dist, (size_t)3 * w, score);
     if (rc) t_last_error = cached->err;
     return rc;
+}
+
+int oavif_ssimu2_set_default_device(int device)
+{
+    if (device < 0) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "bad device %d", device);
+    std::lock_guard<std::mutex> lock(g_cached_mu);
+    g_default_device = device;
+    return 0;
+}
+
+void oavif_ssimu2_release_cached(void)
+{
+    std::lock_guard<std::mutex> lock(g_cached_mu);
+    if (g_cached) oavif_ssimu2_ctx_destroy(g_cached);
+    g_cached = nullptr;
 }
 
 int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void *u, const void *v, size_t ys,
@@ -821,7 +869,16 @@ int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void
     a.stride[0] = a.stride[1] = a.stride[2] = (long long)rb;
     a.w = (int)w;
     a.h = (int)h;
-    a.out = ctx->d_in_src;  // 3 B/px fits the 6 B/px staging buffer
+    // RGB8 goes to a buffer of its own (grown on demand): the staged source and its cached pyramid stay valid
+    const size_t out_bytes = (size_t)w * h * 3;
+    if (out_bytes > ctx->conv_bytes) {
+        cudaFree(ctx->d_conv);
+        ctx->d_conv = nullptr;
+        ctx->conv_bytes = 0;
+        CK(cudaMalloc(&ctx->d_conv, out_bytes));
+        ctx->conv_bytes = out_bytes;
+    }
+    a.out = ctx->d_conv;
     const dim3 grid(cdiv((int)w, 256), h);
     if (kind == IN_YUV8) k_yuv_to_rgb8<IN_YUV8><<<grid, 256, 0, ctx->stream>>>(a);
     else if (kind == IN_YUV10_RGB) k_yuv_to_rgb8<IN_YUV10_RGB><<<grid, 256, 0, ctx->stream>>>(a);
@@ -829,7 +886,6 @@ int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rgb_out, a.out, (size_t)w * h * 3, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->have_source = false;  // the source staging buffer was reused
     return 0;
 }
 
@@ -915,6 +971,43 @@ int oavif_ssimu2_debug_get_rows(oavif_ssimu2_ctx *ctx, int candidate, int quanti
     return 0;
 }
 
+int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale, int channel, float *out,
+                                uint32_t *w_out, uint32_t *h_out)
+{
+    if (!ctx || !out || !w_out || !h_out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    if (!ctx->have_source || ctx->last_n == 0 || ctx->blur_mode != OAVIF_SSIMU2_BLUR_RECURSIVE || !ctx->src_rows_valid ||
+        scale < 0 || scale >= ctx->g.n_scales || channel < 0 || channel > 2 || candidate < 0 ||
+        candidate >= (int)ctx->last_n)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such blurred plane (needs a RECURSIVE score call first)");
+    CK(cudaSetDevice(ctx->device));
+    const Geom &g = ctx->g;
+    const int w = g.w[scale], h = g.h[scale];
+    const long long need = 5LL * w * h;
+    if (need > ctx->dbg_floats) {
+        cudaFree(ctx->d_dbg);
+        ctx->d_dbg = nullptr;
+        ctx->dbg_floats = 0;
+        CK(cudaMalloc(&ctx->d_dbg, sizeof(float) * need));
+        ctx->dbg_floats = need;
+    }
+    // the scored path's own columns kernel once more over the row-filtered planes the last call left, with the
+    // tap on; the pooled sums it rewrites are the ones already there (same inputs, fixed order)
+    BlurPlan plan;
+    plan_iir_v(g, &plan);
+    const IirDebugTap tap{ctx->d_dbg, scale, channel, candidate};
+    const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
+    int launches = 0;
+    const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
+                                          ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x,
+                                          (int)ctx->last_n, ctx->stream, false, nullptr, &launches, 2, &tap);
+    if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
+    CK(cudaMemcpyAsync(out, ctx->d_dbg, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *w_out = (uint32_t)w;
+    *h_out = (uint32_t)h;
+    return 0;
+}
+
 int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, uint32_t h, float *out)
 {
     if (!ctx || !in || !out || w == 0 || h == 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
@@ -972,7 +1065,7 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
         // bit 2: leave the source half out (what a call with a warm source cache runs); other bits are ignored
         const cudaError_t e = launch_iir_blur(ctx->g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
                                               ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, 1,
-                                              ctx->stream, !(variant & 4), nullptr, &launches, true);
+                                              ctx->stream, !(variant & 4), nullptr, &launches, 1);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));

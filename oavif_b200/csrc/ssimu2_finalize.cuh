@@ -19,6 +19,10 @@ struct FinalArgs {
     long long partials_stride;
     double *sums;                   // [candidate][6][18]
     double *scores;                 // [candidate]
+    // 0: weight i belongs to slot ((c*6 + scale)*2 + n)*3 + k whether or not the scale exists (missing scales
+    //    contribute zero); 1: the published loop's running index over the scales PRESENT
+    //    (`scale < scales.size()`, i++): slot ((c*n_scales + scale)*2 + n)*3 + k.  Identical for six scales.
+    int contiguous_weights;
 };
 
 __constant__ double c_weights[108] = {
@@ -82,7 +86,8 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Final
             const double *v = s_sum + s * 18 + c * 6;
             // n == 0: 1-norm averages; n == 1: 4-norm = (mean of 4th powers)^(1/4)
             const double e = n ? sqrt(sqrt(opp * v[2 * k + 1])) : opp * v[2 * k];
-            term = c_weights[i] * fabs(e);
+            const int wi = a.contiguous_weights ? ((c * a.n_scales + s) * 2 + n) * 3 + k : i;
+            term = c_weights[wi] * fabs(e);
         }
         s_term[i] = term;
     }

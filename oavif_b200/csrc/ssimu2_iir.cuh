@@ -117,6 +117,10 @@ struct IirArgs {
     double *partials;
     long long partials_stride;
     float one, neg_one;         // 1.0f and -1.0f as run-time values (Unit2)
+    // oavif_ssimu2_debug_get_cols: when set, the columns pass of (dbg_scale, dbg_channel, dbg_cand) also copies
+    // the five blurred values it hands to the maps — mu1, mu2, s11, s22, s12 — to dbg_cols[q][h][w] (tight)
+    float *dbg_cols;
+    int dbg_scale, dbg_channel, dbg_cand;
     int first_cta[kMaxScales + 1];  // CTA ranges per scale
     int blocks[kMaxScales];     // tasks per channel and scale
 };
@@ -541,7 +545,6 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     IirColsSmem<RCAP, B> &sm = *reinterpret_cast<IirColsSmem<RCAP, B> *>(smem_raw);
     constexpr int D = ((RCAP - B - 10) / B) * B;   // rows of look-ahead: D + B + 10 <= RCAP, D % B == 0
     constexpr int DA = 16;                         // consumer look-ahead (ring of 32 rows)
-    constexpr int CR = B / 4;                      // rows per consumer warp and batch
     static_assert(D >= B && DA % B == 0 && DA + B <= 32 && B % 8 == 0 && RCAP % B == 0, "ring geometry");
 
     int s, c, cb;
@@ -703,6 +706,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();      // (S)
         const Unit2 u = unit2(a.one, a.neg_one);
         const f32x2 zero = splat2(0.0f);
+        const bool dbg = a.dbg_cols != nullptr && s == a.dbg_scale && c == a.dbg_channel && cand == a.dbg_cand;
         f32x2 acc[6];
 #pragma unroll
         for (int j = 0; j < 6; ++j) acc[j] = zero;
@@ -727,6 +731,16 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 5; ++q)
                         in[2 + q] = pk2(ex[(q * B + 2 * g) * kIirVCols], ex[(q * B + 2 * g + 1) * kIirVCols]);
+                    if (dbg && cb * kIirVCols + lane < w) {   // test hook: what the maps are about to consume
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            float lo, hi;
+                            unpk2(in[2 + q], lo, hi);
+                            float *o = a.dbg_cols + ((long long)q * h + n) * w + cb * kIirVCols + lane;
+                            o[0] = lo;
+                            if (n + 1 < h) o[w] = hi;
+                        }
+                    }
                     if (!whole && n + 1 >= h) {   // odd height: the pair's second row is outside
 #pragma unroll
                         for (int i = 0; i < 7; ++i) {
@@ -880,34 +894,49 @@ inline int iir_rows_grid(IirArgs &a, const Geom &g)
     return n;
 }
 
+struct IirDebugTap {
+    float *out;      // device, 5 * w_s * h_s floats
+    int scale, channel, cand;
+};
+
 // Rows pass of b, b*b and a*b (and, when the source's cache is cold, of a and a*a), then the columns pass
-// with the maps and the pooling.  `between` is recorded between the two passes.
+// with the maps and the pooling.  `between` is recorded between the two passes.  phases: bit 0 = rows pass,
+// bit 1 = columns pass.
 inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float *src, const float *dist,
                                    long long pyr_stride, const IirBuffers &B, double *partials,
                                    long long partials_stride, const int *first_cta_cols, const int *col_blocks, int n,
                                    cudaStream_t st, bool with_source_rows, cudaEvent_t between, int *launches,
-                                   bool rows_only = false)
+                                   int phases = 3, const IirDebugTap *tap = nullptr)
 {
     IirArgs a{};
     iir_fill_common(a, g, k, src, dist, pyr_stride, B);
     a.partials = partials;
     a.partials_stride = partials_stride;
-    IirArgs ar = a;
-    const int nr = iir_rows_grid(ar, g);
-    if (with_source_rows)
-        k_iir_rows<2><<<dim3(nr, n), 192, sizeof(IirRowsSmem<2>), st>>>(ar);
-    else
-        k_iir_rows<1><<<dim3(nr, n), 128, sizeof(IirRowsSmem<1>), st>>>(ar);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    *launches = 0;
+    if (phases & 1) {
+        IirArgs ar = a;
+        const int nr = iir_rows_grid(ar, g);
+        if (with_source_rows)
+            k_iir_rows<2><<<dim3(nr, n), 192, sizeof(IirRowsSmem<2>), st>>>(ar);
+        else
+            k_iir_rows<1><<<dim3(nr, n), 128, sizeof(IirRowsSmem<1>), st>>>(ar);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        *launches += 1;
+    }
     if (between) cudaEventRecord(between, st);
-    *launches = 1;
-    if (rows_only) return cudaSuccess;
+    if (!(phases & 2)) return cudaSuccess;
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
+    if (tap) {
+        a.dbg_cols = tap->out;
+        a.dbg_scale = tap->scale;
+        a.dbg_channel = tap->channel;
+        a.dbg_cand = tap->cand;
+    }
     const int ctas = first_cta_cols[kMaxScales];
     k_iir_cols<64, 16><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
-    *launches = 2;
+    *launches += 1;
     return cudaGetLastError();
 }
 

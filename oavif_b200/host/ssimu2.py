@@ -23,7 +23,8 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "liboavif_ssimu2.so
 
 MAX_SCALES = 6
 BLUR_RECURSIVE, BLUR_FIR = 0, 1
-OPT_BLUR = 1
+WEIGHTS_SIX_SLOTS, WEIGHTS_CONTIGUOUS = 0, 1
+OPT_BLUR, OPT_WEIGHTS = 1, 2
 
 E_ARG, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 _ENAMES = {E_ARG: "InvalidArgument", E_CUDA: "CudaError", E_NOMEM: "OutOfMemory",
@@ -40,7 +41,8 @@ SYMBOLS = (
     "oavif_ssimu2_score_batch_rgb8_dev", "oavif_ssimu2_score_batch_yuv444_dev",
     "oavif_ssimu2_compute_rgb8", "oavif_ssimu2_yuv444_to_rgb8", "oavif_ssimu2_get_detail",
     "oavif_ssimu2_get_timing", "oavif_ssimu2_debug_get_xyb", "oavif_ssimu2_debug_get_rows", "oavif_ssimu2_debug_blur",
-    "oavif_ssimu2_debug_time_rows", "oavif_ssimu2_debug_check_guards",
+    "oavif_ssimu2_debug_time_rows", "oavif_ssimu2_debug_check_guards", "oavif_ssimu2_debug_get_cols",
+    "oavif_ssimu2_set_default_device", "oavif_ssimu2_release_cached",
 )
 
 
@@ -103,6 +105,9 @@ def load() -> C.CDLL:
     L.oavif_ssimu2_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.oavif_ssimu2_debug_get_xyb.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32), C.POINTER(u32)]
     L.oavif_ssimu2_debug_get_rows.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32), C.POINTER(u32)]
+    L.oavif_ssimu2_debug_get_cols.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32), C.POINTER(u32)]
+    L.oavif_ssimu2_set_default_device.argtypes = [C.c_int]
+    L.oavif_ssimu2_release_cached.restype = None
     L.oavif_ssimu2_debug_blur.argtypes = [vp, vp, u32, u32, vp]
     L.oavif_ssimu2_debug_check_guards.argtypes = [vp]
     L.oavif_ssimu2_debug_time_rows.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -173,6 +178,9 @@ class Scorer:
 
     def set_blur(self, mode: int):
         _check(self._L.oavif_ssimu2_set_option(self._ctx, OPT_BLUR, mode), self._ctx)
+
+    def set_weights(self, layout: int):
+        _check(self._L.oavif_ssimu2_set_option(self._ctx, OPT_WEIGHTS, layout), self._ctx)
 
     def set_stream(self, cuda_stream: int | None):
         _check(self._L.oavif_ssimu2_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)), self._ctx)
@@ -333,6 +341,14 @@ class Scorer:
         _check(self._L.oavif_ssimu2_debug_get_rows(self._ctx, candidate, quantity, scale, channel, buf.ctypes.data,
                                                    C.byref(w), C.byref(h)), self._ctx)
         return buf[: w.value * h.value].reshape(h.value, w.value).copy()
+
+    def cols(self, candidate: int, scale: int, channel: int) -> np.ndarray:
+        """(5, h, w): mu1, mu2, sigma11, sigma22, sigma12 as the product columns kernel hands them to the maps."""
+        buf = np.empty(5 * self.w * self.h, np.float32)
+        w, h = C.c_uint32(), C.c_uint32()
+        _check(self._L.oavif_ssimu2_debug_get_cols(self._ctx, candidate, scale, channel, buf.ctypes.data,
+                                                   C.byref(w), C.byref(h)), self._ctx)
+        return buf[: 5 * w.value * h.value].reshape(5, h.value, w.value).copy()
 
     def check_guards(self):
         """Raises if any kernel wrote past one of the context's device buffers."""

@@ -15,6 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 MAX_SCALES = 6
 BLUR_IIR, BLUR_FIR, BLUR_FIR64 = 0, 1, 2
+VARIANT_CONTIGUOUS_WEIGHTS, VARIANT_VERTICAL_ORDER = 1, 2
 
 
 class Detail(C.Structure):
@@ -64,6 +65,8 @@ def lib(fast: bool = False) -> C.CDLL:
     L.oracle_final_score.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
     L.oracle_final_score.restype = C.c_double
     L.oracle_weights.restype = f64p
+    L.oracle_set_variant.argtypes = [C.c_int]
+    L.oracle_set_libm_cbrt.argtypes = [C.c_int]
     L.oracle_ssimu2_rgb8.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      f64p, C.POINTER(Detail)]
     L.oracle_ssimu2_rgb8.restype = C.c_int
@@ -84,6 +87,12 @@ def _u8(a):
 
 def _f32(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def set_variant(flags: int, fast: bool = False, libm_cbrt: bool = False) -> None:
+    """Process-wide variant switches of one library (see ssimu2_oracle.h); 0 restores the default."""
+    lib(fast).oracle_set_variant(flags)
+    lib(fast).oracle_set_libm_cbrt(int(libm_cbrt))
 
 
 def srgb_lut() -> np.ndarray:

@@ -108,6 +108,13 @@ static const float kOpsinBias = 0.0037930732552754493f;
 static int g_use_libm_cbrt = 0;
 void oracle_set_libm_cbrt(int on) { g_use_libm_cbrt = on; }
 
+/* Plausible-variant switches (ORACLE_VARIANT_*): readings of the published code this restatement cannot
+ * settle without an authoritative copy.  Used by scripts/variant_envelope.py to bound how far "the"
+ * SSIMULACRA2 score moves between them — the honest error bar on "matches fssimu2".                    */
+static int g_variant = 0;
+void oracle_set_variant(int flags) { g_variant = flags; }
+int oracle_get_variant(void) { return g_variant; }
+
 float oracle_cbrtf(float x)
 {
     if (g_use_libm_cbrt) return cbrtf(x);
@@ -305,13 +312,21 @@ static void iir_cols(const blur_consts *bc, const float *in, int w, int h, float
         const float *lrow = l >= 0 ? in + (size_t)l * w : NULL;
         const float *rrow = r < h ? in + (size_t)r * w : NULL;
         float *orow = n >= 0 ? out + (size_t)n * w : NULL;
+        const int vorder = g_variant & ORACLE_VARIANT_VERTICAL_ORDER;
         for (int x = 0; x < w; ++x) {
             const float sum = (lrow ? lrow[x] : 0.0f) + (rrow ? rrow[x] : 0.0f);
             float acc = 0.0f;
             for (int k = 0; k < 3; ++k) {
-                float ok = sum * bc->n2[k];
-                ok = fmaf(-1.0f, p2[k][x], ok);
-                ok = fmaf(-bc->d1[k], p[k][x], ok);
+                float ok;
+                if (vorder) {
+                    /* lib/jxl/gauss_blur.cc VerticalBlock as recalled: MulAdd(n2, sum, NegMulSub(d1, y[n-1], y[n-2])),
+                     * i.e. the product n2*sum is NOT rounded on its own and -d1*y[n-1] - y[n-2] is formed first */
+                    ok = fmaf(bc->n2[k], sum, fmaf(-bc->d1[k], p[k][x], -p2[k][x]));
+                } else {
+                    ok = sum * bc->n2[k];
+                    ok = fmaf(-1.0f, p2[k][x], ok);
+                    ok = fmaf(-bc->d1[k], p[k][x], ok);
+                }
                 p2[k][x] = p[k][x];
                 p[k][x] = ok;
                 acc = (k == 0) ? ok : acc + ok;
@@ -411,8 +426,13 @@ double oracle_final_score(int n_scales, const double avg_ssim[][6], const double
 {
     double ssim = 0.0;
     int i = 0;
+    /* Two readings for images with fewer than six scales (identical at six):
+     *   default — a fixed six-scale weight table, absent scales contribute zero;
+     *   ORACLE_VARIANT_CONTIGUOUS_WEIGHTS — libjxl Msssim::Score() as recalled: `scale < scales.size()` with a
+     *   running i++, so the weights are consumed contiguously over the scales present.                      */
+    const int nloop = (g_variant & ORACLE_VARIANT_CONTIGUOUS_WEIGHTS) ? n_scales : 6;
     for (int c = 0; c < 3; ++c)
-        for (int scale = 0; scale < 6; ++scale)
+        for (int scale = 0; scale < nloop; ++scale)
             for (int n = 0; n < 2; ++n) {
                 if (scale >= n_scales) {
                     i += 3;

@@ -63,6 +63,15 @@ void oracle_downsample2x(const float *in, int w, int h, float *out);
 float oracle_cbrtf(float x);
 void oracle_set_libm_cbrt(int on);
 
+/* Variant switches for the envelope study (process-wide, not thread-safe; default 0 = the restatement the
+ * GPU path is held to bit for bit). */
+enum {
+    ORACLE_VARIANT_CONTIGUOUS_WEIGHTS = 1, /* final sum: running weight index over the scales present     */
+    ORACLE_VARIANT_VERTICAL_ORDER = 2      /* vertical recursion: fma(n2, sum, fma(-d1, y1, -y2)) per step */
+};
+void oracle_set_variant(int flags);
+int oracle_get_variant(void);
+
 /* planar linear RGB -> planar "positive" XYB (X,Y,B order), n pixels per plane. */
 void oracle_linear_to_xyb(const float *lin, int n, float *xyb);
 
@@ -75,7 +84,8 @@ int oracle_fir_taps(double sigma, double *taps, int max_taps);
 /* Separable blur of one plane, horizontal then vertical, zero padded. tmp: w*h floats. */
 void oracle_blur(const float *in, int w, int h, int mode, float *tmp, float *out);
 
-/* 108-weight sum + nonlinear map.  Missing scales contribute zero. */
+/* 108-weight sum + nonlinear map.  Missing scales contribute zero (or, under
+ * ORACLE_VARIANT_CONTIGUOUS_WEIGHTS, the weights run contiguously over the scales present). */
 double oracle_final_score(int n_scales, const double avg_ssim[][6], const double avg_edgediff[][12]);
 
 /* the 108 weights, in the order the final loop consumes them */

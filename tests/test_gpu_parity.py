@@ -118,6 +118,38 @@ def test_rows_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size):
     check(1, d1, "batch[1]")
 
 
+# ---- K4+K5, product kernel: what the columns pass hands to the error maps ----------------------------------
+@pytest.mark.parametrize("size", [(64, 64), (65, 63), (100, 75), (333, 257), (700, 300)])
+def test_cols_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size):
+    """k_iir_cols (the kernel on the scored path, not the plain debug filter): the five fully blurred values it
+    feeds the SSIM / edge-diff maps — mu1, mu2, sigma11, sigma22, sigma12 — against the oracle's two-pass blur,
+    bit for bit, every scale and channel, single call and second candidate of a batch."""
+    w, h = size
+    src = synth.synth(w, h, "mixture", w + 2)
+    d0, d1 = synth.distort(src, 0.3, seed=h), synth.distort(src, 0.8, seed=h + 1)
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    scorer.set_source(src)
+    s_single = scorer.score_rgb8(d0)
+    sums_single = scorer.sums(0).copy()
+    n = scorer.detail().n_scales
+
+    def check(cand_index, cand_rgb, what):
+        for s in range(n):
+            for c in range(3):
+                a, b = oracle.xyb_at_scale(src, s)[c], oracle.xyb_at_scale(cand_rgb, s)[c]
+                want = [oracle.blur(q, oracle.BLUR_IIR) for q in (a, b, a * a, b * b, a * b)]
+                got = scorer.cols(cand_index, s, c)
+                for q in range(5):
+                    np.testing.assert_array_equal(bits(got[q]), bits(want[q]),
+                                                  err_msg=f"{what}: quantity {q} scale {s} channel {c}")
+
+    check(0, d0, "single")
+    assert (scorer.sums(0) == sums_single).all()      # the tap's re-run rewrote the same pooled sums
+    batch = scorer.score_batch_rgb8([d0, d1])
+    assert batch[0] == s_single
+    check(1, d1, "batch[1]")
+
+
 def test_all_input_forms_build_the_same_pyramid(scorer, oracle):
     w, h = 203, 117
     src = synth.synth(w, h, "noise", 8)
@@ -440,6 +472,149 @@ def test_full_size_4k_properties(oracle, mode, omode, name):
             sc.set_source(src)
             got = sc.score_rgb8(d2)
             assert abs(got - oracle.ssimu2_rgb8(src, d2, omode, fast=True)) <= SCORE_TOL
+
+
+# ---- BASELINE.json configs 3, 4, 5 and config 2 in FIR mode: CUDA path vs the oracle at the full sizes --------
+def _tiled(img, ny, nx):
+    """A big image from a small procedural one (the generator is numpy and costs ~1 s/Mpx): tiles plus a smooth
+    image-wide ramp so that no two tiles carry the same pixels."""
+    big = np.tile(img, (ny, nx, 1)).astype(np.int16)
+    hh, ww = big.shape[:2]
+    ramp = (np.arange(ww, dtype=np.int32)[None, :] * 24 // ww + np.arange(hh, dtype=np.int32)[:, None] * 16 // hh)
+    big[..., :3] += ramp[..., None].astype(np.int16) - 20
+    return np.clip(big, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("kind", ["gradient", "edges", "noise", "mixture"])
+def test_cfg5_1080p_every_kind_vs_oracle(oracle, kind):
+    w, h = 1920, 1080
+    src = synth.synth(w, h, kind, 5)
+    dist = synth.distort(src, 0.3, seed=6)
+    y, u, v = synth.rgb8_to_yuv444(dist, 10)
+    rgb = oracle.yuv444_to_rgb8(y, u, v, 10)
+    with ssimu2.Scorer(w, h, 1) as sc:
+        for mode, omode, _ in MODES:
+            sc.set_blur(mode)
+            sc.set_source(src)
+            got = sc.score_yuv444(y, u, v, 10)
+            want, det = oracle.ssimu2_rgb8(src, rgb, omode, fast=True, detail=True)
+            assert abs(got - want) <= SCORE_TOL, (kind, mode, got, want)
+            np.testing.assert_allclose(sc.sums(), oracle.detail_sums(det), rtol=SUM_RTOL, atol=1e-12)
+
+
+@pytest.mark.slow
+def test_cfg2_4k_fir_vs_oracle(oracle):
+    w, h = 3840, 2160
+    src = _tiled(synth.synth(1920, 1080, "mixture", 0), 2, 2)
+    dist = _tiled(synth.distort(synth.synth(1920, 1080, "mixture", 0), 0.4, seed=3), 2, 2)
+    with ssimu2.Scorer(w, h, 1, blur=ssimu2.BLUR_FIR) as sc:
+        sc.set_source(src)
+        got = sc.score_rgb8(dist)
+        want, det = oracle.ssimu2_rgb8(src, dist, oracle.BLUR_FIR, fast=True, detail=True)
+        assert abs(got - want) <= SCORE_TOL, (got, want)
+        np.testing.assert_allclose(sc.sums(), oracle.detail_sums(det), rtol=SUM_RTOL, atol=1e-12)
+
+
+@pytest.mark.slow
+def test_cfg3_24mp_batch16_vs_oracle(oracle):
+    """Config 3: sixteen candidate decodes of one 6000x4000 image in one launch; candidates 0, 5 and 15 are
+    checked against the oracle, the rest against their duplicates (four distinct frames cycle through the batch)."""
+    w, h = 6000, 4000
+    small = synth.synth(2000, 1000, "mixture", 3)
+    src = _tiled(small, 4, 3)
+    frames = [_tiled(synth.distort(small, s, seed=10 + i), 4, 3) for i, s in enumerate((0.1, 0.25, 0.5, 0.9))]
+    cands = [frames[i % 4] for i in range(16)]
+    with ssimu2.Scorer(w, h, 16) as sc:
+        sc.set_source(src)
+        got = sc.score_batch_rgb8(cands)
+        assert all(got[i] == got[i % 4] for i in range(16))
+        assert got[0] > got[1] > got[2] > got[3]
+        for i in (0, 5, 15):
+            want, det = oracle.ssimu2_rgb8(src, cands[i], oracle.BLUR_IIR, fast=True, detail=True)
+            assert abs(got[i] - want) <= SCORE_TOL, (i, got[i], want)
+            np.testing.assert_allclose(sc.sums(i), oracle.detail_sums(det), rtol=SUM_RTOL, atol=1e-12)
+        sc.check_guards()
+
+
+@pytest.mark.slow
+def test_cfg4_8k_rgba_i410_path_vs_oracle(oracle):
+    """Config 4: 7680x4320 RGBA source (alpha never scored, io.zig:106-111), candidate = 10-bit planes of an image
+    that carries an alpha plane, i.e. libavif's I410 conversion (io.zig:473)."""
+    w, h = 7680, 4320
+    small = synth.synth_rgba(1920, 1080, "mixture", 7)
+    src_rgba = _tiled(small, 4, 4)
+    dist = _tiled(synth.distort(small[..., :3], 0.3, seed=8), 4, 4)
+    y, u, v = synth.rgb8_to_yuv444(dist, 10)
+    src_rgb = oracle.to_rgb8(src_rgba, 4, False)
+    dist_rgb = oracle.yuv444_to_rgb8(y, u, v, 10, 2, True)
+    with ssimu2.Scorer(w, h, 1) as sc:
+        sc.set_source_pixels(src_rgba)
+        got = sc.score_yuv444(y, u, v, 10, 2, True)
+        want, det = oracle.ssimu2_rgb8(src_rgb, dist_rgb, oracle.BLUR_IIR, fast=True, detail=True)
+        assert abs(got - want) <= SCORE_TOL, (got, want)
+        np.testing.assert_allclose(sc.sums(), oracle.detail_sums(det), rtol=SUM_RTOL, atol=1e-12)
+        assert sc.score_yuv444(y, u, v, 10, 2, False) != got      # the RGB and RGBA conversions are different functions
+        sc.check_guards()
+
+
+# ---- context capacity: an image that fits the pyramid and input buffers can still need more CTAs ---------------
+@pytest.mark.parametrize("ctx_size,img_size", [((100, 2426), (4509, 53)), ((3767, 3785), (3717, 3835)),
+                                               ((640, 360), (360, 640)), ((1000, 200), (500, 390))])
+def test_context_sized_for_another_shape(ctx_size, img_size):
+    """Per-CTA partial sums are indexed by CTA: an image of another shape must either be refused (E_STATE) or be
+    scored without touching a guard band, never silently overrun (the contexts above accept / refuse both ways)."""
+    w, h = img_size
+    rng = np.random.default_rng(w)
+    src = rng.integers(0, 255, (h, w, 3), dtype=np.uint8)
+    dist = np.clip(src.astype(np.int16) + rng.integers(-9, 9, src.shape), 0, 255).astype(np.uint8)
+    with ssimu2.Scorer(*ctx_size, 2) as sc:
+        for mode in (ssimu2.BLUR_RECURSIVE, ssimu2.BLUR_FIR):
+            sc.set_blur(mode)
+            try:
+                sc.set_source(src)
+            except ssimu2.Ssimu2Error as e:
+                assert e.code == ssimu2.E_STATE
+                continue
+            a = sc.score_batch_rgb8([dist, src])
+            sc.check_guards()
+            with ssimu2.Scorer(w, h, 2, blur=mode) as exact:
+                exact.set_source(src)
+                assert exact.score_batch_rgb8([dist, src]) == a
+
+
+def test_weight_layout_option_matches_the_oracle_variant(scorer, oracle):
+    """Images with fewer than six scales: the two readings of the final sum (include/oavif_ssimu2.h,
+    OAVIF_SSIMU2_OPT_WEIGHTS) against the oracle's two variants; with six scales they coincide."""
+    for (w, h) in [(100, 75), (31, 200), (640, 360)]:
+        src = synth.synth(w, h, "mixture", 9)
+        dist = synth.distort(src, 0.4)
+        scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+        scorer.set_source(src)
+        try:
+            six = scorer.score_rgb8(dist)
+            scorer.set_weights(ssimu2.WEIGHTS_CONTIGUOUS)
+            oracle.set_variant(oracle.VARIANT_CONTIGUOUS_WEIGHTS)
+            contiguous = scorer.score_rgb8(dist)
+            want_c = oracle.ssimu2_rgb8(src, dist)
+        finally:
+            scorer.set_weights(ssimu2.WEIGHTS_SIX_SLOTS)
+            oracle.set_variant(0)
+        assert abs(six - oracle.ssimu2_rgb8(src, dist)) <= SCORE_TOL
+        assert abs(contiguous - want_c) <= SCORE_TOL
+        assert (six == contiguous) == (scorer.detail().n_scales == 6)
+
+
+def test_conversion_call_leaves_the_cached_source_alone(scorer):
+    src = synth.synth(200, 120, "mixture", 3)
+    dist = synth.distort(src, 0.3)
+    y, u, v = synth.rgb8_to_yuv444(dist, 10)
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    scorer.set_source(src)
+    a = scorer.score_yuv444(y, u, v, 10)
+    rgb = scorer.yuv444_to_rgb8(y, u, v, 10)          # in the middle of a search
+    assert scorer.score_yuv444(y, u, v, 10) == a
+    assert scorer.score_rgb8(rgb) == a
 
 
 # ---- several callers per GPU: one context per host thread (the corpus driver's workers-per-gpu) ------------
