@@ -156,6 +156,23 @@ int oavif_ssimu2_score_batch_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const voi
                                     size_t u_stride, size_t v_stride, int depth, int matrix,
                                     int rgba_path, double *scores);
 
+/* ---- pipelined form ------------------------------------------------------------------------------
+ * submit_* enqueues the upload (on the context's copy stream) and the kernels (on its compute stream) of
+ * n candidates and returns at once; wait retires the OLDEST submission and stores its n scores.  Up to
+ * two submissions may be in flight, and set_source_* may be called while one is: the upload of image
+ * i+1 then runs under the kernels of image i, which is what one caller needs to keep the PCIe link busy
+ * (the synchronous score_* calls are submit + wait).  Caller memory passed to submit_* must stay valid
+ * and unmodified until the matching wait returns.  The staging buffer of the second slot is allocated
+ * by the first submit that finds another one in flight.  get_detail / get_timing describe the
+ * submission retired last. */
+int oavif_ssimu2_submit_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *dists,
+                             size_t stride);
+int oavif_ssimu2_submit_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y,
+                               const void *const *u, const void *const *v, size_t y_stride,
+                               size_t u_stride, size_t v_stride, int depth, int matrix, int rgba_path);
+int oavif_ssimu2_wait(oavif_ssimu2_ctx *ctx, double *scores);
+int oavif_ssimu2_in_flight(const oavif_ssimu2_ctx *ctx);
+
 /* ---- device-resident inputs (pointers are CUDA device pointers on the context's device) --
  * set_source_rgb8_dev only enqueues work: the buffer must stay unmodified until the next score call
  * on this context has returned. */

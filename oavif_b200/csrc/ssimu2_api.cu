@@ -45,10 +45,27 @@ int g_default_device = 0;
 
 }  // namespace
 
+constexpr int kSlots = 2;   // submissions that may be in flight at once (oavif_ssimu2_submit_* / _wait)
+
+// One submission: its staged candidates, its result buffers and its events.  Everything else (pyramids,
+// row-filtered planes, partial sums) is shared: the compute stream runs submissions in order.
+struct Slot {
+    uint8_t *d_in_dist = nullptr;                       // staged candidate pixels (slot 1: allocated on first use)
+    double *h_sums = nullptr, *h_scores = nullptr;      // pinned, mapped: k_finalize writes them directly
+    double *dm_sums = nullptr, *dm_scores = nullptr;    // device views of the two
+    cudaEvent_t up0 = nullptr, up1 = nullptr;           // copy stream: around the upload
+    cudaEvent_t k[5] = {};                              // compute stream: pyramid start / end, between the passes, blur end, finalize end
+    uint32_t n = 0;
+    bool degenerate = false, host_input = false;        // degenerate: below 8x8, nothing was launched
+    int n_scales = 0, w[kMaxScales] = {}, h[kMaxScales] = {};
+    uint32_t launches = 0;
+};
+
 struct oavif_ssimu2_ctx {
     int device = 0;
     uint32_t max_w = 0, max_h = 0, max_batch = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;   // compute stream (own or the caller's)
+    cudaStream_t copy_stream = nullptr;                    // host -> device uploads: run under the previous submission's kernels
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
     int weight_layout = OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS;
 
@@ -60,18 +77,21 @@ struct oavif_ssimu2_ctx {
     Geom g{};
     uint32_t last_n = 0;
 
-    uint8_t *d_in_src = nullptr, *d_in_dist = nullptr;
+    // source staging is double-buffered too: set_source of image i+1 uploads while image i is still being scored
+    uint8_t *d_in_src[2] = {nullptr, nullptr};
+    int src_buf = 0;
+    cudaEvent_t src_up0 = nullptr, src_up1 = nullptr, src_consumed[2] = {nullptr, nullptr};
+    Slot slot[kSlots];
+    int head = 0, tail = 0, inflight = 0, last_slot = 0;   // ring of submissions; last_slot: what get_detail / get_timing report
+
     float *d_src_pyr = nullptr, *d_dist_pyr = nullptr, *d_hplanes = nullptr, *d_src_hplanes = nullptr, *d_lut = nullptr;
     bool src_rows_valid = false;   // the cached rows pass of the source (RECURSIVE blur) matches the current source
-    const void **d_tbl = nullptr, **h_tbl = nullptr;
+    const void **d_tbl = nullptr, **h_tbl = nullptr;   // [slot][3 * (max_batch + 1)]
     double *d_partials = nullptr;
-    double *h_sums = nullptr, *h_scores = nullptr;      // pinned, mapped: k_finalize writes them directly
-    double *dm_sums = nullptr, *dm_scores = nullptr;    // device views of the two
     float *d_dbg = nullptr;
     long long dbg_floats = 0;
     uint8_t *d_conv = nullptr;     // oavif_ssimu2_yuv444_to_rgb8's output, grown on demand
     size_t conv_bytes = 0;
-    cudaEvent_t ev[6] = {};  // start, h2d, pyramid, blur a, blur b, finalize
     oavif_ssimu2_timing timing{};
     float taps[9] = {};
     IirCoef iir{};
@@ -314,10 +334,11 @@ size_t row_bytes(const InputDesc &d, int w)
 }
 int nplanes(int kind) { return (kind == IN_RGB8 || kind == IN_PIXELS) ? 1 : 3; }
 
-// Stage (if host) `n` images and build their pyramids into `out`.  `slot0` selects the staging
-// buffer: the source uses in_src, candidates use in_dist.
-int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const HostPlanes *imgs,
-                   bool is_source, float *out, long long out_stride)
+// Stage (if host) `n` images and build their pyramids into `out`.  Host pixels go up on the COPY stream into
+// `staging`; the compute stream waits for `up1` and runs the pyramid kernel.  `tbl0` selects the rows of the
+// pointer table this call owns.
+int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const HostPlanes *imgs, uint8_t *staging,
+                   int tbl0, cudaEvent_t up0, cudaEvent_t up1, cudaEvent_t k0, float *out, long long out_stride)
 {
     const Geom &g = ctx->g;
     const int w = g.w[0], h = g.h[0];
@@ -334,7 +355,6 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const 
     const int np = nplanes(d.kind);
     a.channels = d.channels;
     a.hbd = d.hbd;
-    const int tbl0 = is_source ? 0 : 3;  // table rows: [0..2] source, [3..] candidates
     if (d.on_device) {
         for (uint32_t i = 0; i < n; ++i)
             for (int p = 0; p < 3; ++p) ctx->h_tbl[tbl0 + 3 * i + p] = imgs[i].p[p < np ? p : 0];
@@ -342,14 +362,16 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const 
     } else {
         // tight rows on the device, each plane start 256-byte aligned
         const size_t plane_bytes = (rb * h + 255) & ~(size_t)255;
-        uint8_t *base = is_source ? ctx->d_in_src : ctx->d_in_dist;
+        CK(cudaEventRecord(up0, ctx->copy_stream));
         for (uint32_t i = 0; i < n; ++i)
             for (int p = 0; p < np; ++p) {
-                uint8_t *dst = base + ((size_t)i * np + p) * plane_bytes;
+                uint8_t *dst = staging + ((size_t)i * np + p) * plane_bytes;
                 CK(cudaMemcpy2DAsync(dst, rb, imgs[i].p[p], d.stride[p], rb, h, cudaMemcpyHostToDevice,
-                                     ctx->stream));
+                                     ctx->copy_stream));
                 ctx->h_tbl[tbl0 + 3 * i + p] = dst;
             }
+        CK(cudaEventRecord(up1, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, up1, 0));
         if (np == 1)
             for (uint32_t i = 0; i < n; ++i)
                 ctx->h_tbl[tbl0 + 3 * i + 1] = ctx->h_tbl[tbl0 + 3 * i + 2] = ctx->h_tbl[tbl0 + 3 * i];
@@ -363,10 +385,9 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const 
                            ctx->stream));
         a.planes = ctx->d_tbl + tbl0;
     }
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaEventRecord(k0, ctx->stream));
     launch_pyramid(d.kind, a, (int)n, ctx->stream);
     CK(cudaGetLastError());
-    ctx->timing.launches += 1;
     return 0;
 }
 
@@ -402,7 +423,8 @@ int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
     return 0;
 }
 
-int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
+// blur + maps + pooling + final score of the candidates whose pyramids were just enqueued, into slot S
+int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, uint32_t n)
 {
     const Geom &g = ctx->g;
     BlurPlan plan;
@@ -425,8 +447,8 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
         b.neg_one = -1.0f;
         k_fir_fused<<<dim3(plan.total, n), kFirThreads, kFirSmemBytes, ctx->stream>>>(b);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-        ctx->timing.launches += 1;
+        CK(cudaEventRecord(S.k[2], ctx->stream));
+        S.launches += 1;
     } else {
         plan_iir_v(g, &plan);
         int launches = 0;
@@ -434,12 +456,12 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
         // the first call after set_source also runs the source's half of the rows pass and leaves it cached
         const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
                                               ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, (int)n,
-                                              ctx->stream, !ctx->src_rows_valid, ctx->ev[3], &launches);
+                                              ctx->stream, !ctx->src_rows_valid, S.k[2], &launches);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "recursive blur launch: %s", cudaGetErrorString(e));
-        ctx->timing.launches += launches;
+        S.launches += launches;
         ctx->src_rows_valid = true;
     }
-    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(cudaEventRecord(S.k[3], ctx->stream));
 
     FinalArgs f{};
     f.n_scales = g.n_scales;
@@ -451,54 +473,102 @@ int run_blur_and_finalize(oavif_ssimu2_ctx *ctx, uint32_t n, double *scores)
     for (int s = 0; s <= kMaxScales; ++s) f.first_cta[s] = plan.first_cta[s];
     f.partials = ctx->d_partials;
     f.partials_stride = ctx->cap_ctas * 6;
-    f.sums = ctx->dm_sums;
-    f.scores = ctx->dm_scores;
+    f.sums = S.dm_sums;
+    f.scores = S.dm_scores;
     f.contiguous_weights = ctx->weight_layout == OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS;
     k_finalize<<<n, 1024, 0, ctx->stream>>>(f);
     CK(cudaGetLastError());
-    ctx->timing.launches += 1;
-    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t i = 0; i < n; ++i) scores[i] = ctx->h_scores[i];
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing.pyramid_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[4]); ctx->timing.blur_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.blur_a_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.blur_b_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.finalize_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]); ctx->timing.total_ms = ms;
+    S.launches += 1;
+    CK(cudaEventRecord(S.k[4], ctx->stream));
     return 0;
 }
 
-int score_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const HostPlanes *imgs, double *scores)
+// Enqueue one submission (upload on the copy stream, kernels on the compute stream) and return at once.
+int submit_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const HostPlanes *imgs)
 {
     if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
-    if (!scores || !imgs || n == 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument or empty batch");
+    if (!imgs || n == 0) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument or empty batch");
     if (!ctx->have_source) return fail(ctx, OAVIF_SSIMU2_E_STATE, "score called before set_source");
     if (n > ctx->max_batch) return fail(ctx, OAVIF_SSIMU2_E_STATE, "batch %u exceeds max_batch %u", n, ctx->max_batch);
-    const int w = ctx->g.w[0], h = ctx->g.h[0];
+    if (ctx->inflight == kSlots)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "%d submissions already in flight: call oavif_ssimu2_wait first", kSlots);
+    const int w = ctx->g.w[0];
     const int np = nplanes(d.kind);
     for (uint32_t i = 0; i < n; ++i)
         for (int p = 0; p < np; ++p)
             if (!imgs[i].p[p]) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null plane pointer (candidate %u)", i);
     for (int p = 0; p < np; ++p)
         if (d.stride[p] < row_bytes(d, w)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "stride smaller than a row");
-    (void)h;
     CK(cudaSetDevice(ctx->device));
-    ctx->timing = oavif_ssimu2_timing{};
+    Slot &S = ctx->slot[ctx->head];
+    if (!S.d_in_dist && !d.on_device && ctx->g.n_scales)   // the second staging slot exists only once submissions overlap
+        CK(alloc_guarded(ctx, &S.d_in_dist, (size_t)ctx->cap_in_bytes * ctx->max_batch));
+    S.n = n;
+    S.launches = 0;
+    S.host_input = !d.on_device;
+    S.n_scales = ctx->g.n_scales;
+    for (int s = 0; s < kMaxScales; ++s) {
+        S.w[s] = ctx->g.w[s];
+        S.h[s] = ctx->g.h[s];
+    }
+    S.degenerate = ctx->g.n_scales == 0;   // below 8x8 nothing is evaluated: the published result is 100
     ctx->last_n = n;
-    if (ctx->g.n_scales == 0) {  // below 8x8 nothing is evaluated: the published result is 100
-        for (uint32_t i = 0; i < n; ++i) scores[i] = 100.0;
-        memset(ctx->h_sums, 0, sizeof(double) * n * kMaxScales * 18);
-        for (uint32_t i = 0; i < n; ++i) ctx->h_scores[i] = 100.0;
+    if (!S.degenerate) {
+        const int tbl0 = ctx->head * 3 * (int)(ctx->max_batch + 1) + 3;   // row 0 of each table is the source's
+        int rc = build_pyramids(ctx, d, n, imgs, S.d_in_dist, tbl0, S.up0, S.up1, S.k[0], ctx->d_dist_pyr,
+                                ctx->cap_pyr_floats);
+        if (rc) return rc;
+        S.launches += 1;
+        CK(cudaEventRecord(S.k[1], ctx->stream));
+        rc = enqueue_blur_and_finalize(ctx, S, n);
+        if (rc) return rc;
+    }
+    ctx->head = (ctx->head + 1) % kSlots;
+    ctx->inflight += 1;
+    return 0;
+}
+
+// Retire the oldest submission: block until its score is there.
+int wait_common(oavif_ssimu2_ctx *ctx, double *scores)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (!scores) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    if (ctx->inflight == 0) return fail(ctx, OAVIF_SSIMU2_E_STATE, "wait without a submission in flight");
+    Slot &S = ctx->slot[ctx->tail];
+    ctx->last_slot = ctx->tail;
+    ctx->tail = (ctx->tail + 1) % kSlots;
+    ctx->inflight -= 1;
+    ctx->timing = oavif_ssimu2_timing{};
+    if (S.degenerate) {
+        memset(S.h_sums, 0, sizeof(double) * S.n * kMaxScales * 18);
+        for (uint32_t i = 0; i < S.n; ++i) scores[i] = S.h_scores[i] = 100.0;
         return 0;
     }
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    const int rc = build_pyramids(ctx, d, n, imgs, false, ctx->d_dist_pyr, ctx->cap_pyr_floats);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(S.k[4]));
+    for (uint32_t i = 0; i < S.n; ++i) scores[i] = S.h_scores[i];
+    float ms = 0.f;
+    oavif_ssimu2_timing &t = ctx->timing;
+    if (S.host_input) { cudaEventElapsedTime(&ms, S.up0, S.up1); t.h2d_ms = ms; }
+    cudaEventElapsedTime(&ms, S.k[0], S.k[1]); t.pyramid_ms = ms;
+    cudaEventElapsedTime(&ms, S.k[1], S.k[3]); t.blur_ms = ms;
+    cudaEventElapsedTime(&ms, S.k[1], S.k[2]); t.blur_a_ms = ms;
+    cudaEventElapsedTime(&ms, S.k[2], S.k[3]); t.blur_b_ms = ms;
+    cudaEventElapsedTime(&ms, S.k[3], S.k[4]); t.finalize_ms = ms;
+    cudaEventElapsedTime(&ms, S.host_input ? S.up0 : S.k[0], S.k[4]); t.total_ms = ms;
+    t.launches = S.launches;
+    return 0;
+}
+
+// the synchronous form: one submission, retired at once (nothing else may be in flight)
+int score_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const HostPlanes *imgs, double *scores)
+{
+    if (ctx && !scores) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument or empty batch");
+    if (ctx && ctx->inflight)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "a submission is in flight: retire it with oavif_ssimu2_wait first");
+    const int rc = submit_common(ctx, d, n, imgs);
     if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    return run_blur_and_finalize(ctx, n, scores);
+    return wait_common(ctx, scores);
 }
 
 int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32_t h, size_t stride,
@@ -529,15 +599,22 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
     HostPlanes hp{{rgb, nullptr, nullptr}};
     ctx->timing = oavif_ssimu2_timing{};
     ctx->src_rows_valid = false;   // the next score call refills the cache of the source's row-filtered planes
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = build_pyramids(ctx, d, 1, &hp, true, ctx->d_src_pyr, 0);
+    // A submission may still be in flight: its kernels read the OLD source pyramid, and this call's pyramid
+    // kernel queues behind them on the compute stream.  Only the staged pixels need a second buffer, and the
+    // copy stream must not overwrite one that an earlier source pyramid kernel has yet to read.
+    const int sb = ctx->src_buf ^= 1;
+    if (!on_device) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->src_consumed[sb], 0));
+    rc = build_pyramids(ctx, d, 1, &hp, ctx->d_in_src[sb], ctx->head * 3 * (int)(ctx->max_batch + 1), ctx->src_up0,
+                        ctx->src_up1, ctx->slot[ctx->head].k[0], ctx->d_src_pyr, 0);
     if (rc) return rc;
+    CK(cudaEventRecord(ctx->src_consumed[sb], ctx->stream));
+    ctx->timing.launches = 1;
     // Return as soon as the caller's pixels have been consumed (host input: after the upload; device
     // input: at once): the pyramid kernel itself keeps running behind the next call on the same stream.
     if (!on_device) {
-        CK(cudaEventSynchronize(ctx->ev[1]));
+        CK(cudaEventSynchronize(ctx->src_up1));
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->src_up0, ctx->src_up1); ctx->timing.h2d_ms = ms;
         ctx->timing.total_ms = ms;
     }
     ctx->have_source = true;
@@ -576,9 +653,18 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_in_src);
-    cudaFree(ctx->d_in_dist);
+    for (auto &p : ctx->d_in_src) cudaFree(p);
+    for (auto &S : ctx->slot) {
+        cudaFree(S.d_in_dist);
+        cudaFreeHost(S.h_sums);
+        cudaFreeHost(S.h_scores);
+        for (cudaEvent_t e : {S.up0, S.up1, S.k[0], S.k[1], S.k[2], S.k[3], S.k[4]})
+            if (e) cudaEventDestroy(e);
+    }
+    for (cudaEvent_t e : {ctx->src_up0, ctx->src_up1, ctx->src_consumed[0], ctx->src_consumed[1]})
+        if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_src_pyr);
     cudaFree(ctx->d_dist_pyr);
     cudaFree(ctx->d_hplanes);
@@ -589,11 +675,8 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     cudaFree(ctx->d_dbg);
     cudaFree(ctx->d_conv);
     cudaFreeHost((void *)ctx->h_tbl);
-    cudaFreeHost(ctx->h_sums);
-    cudaFreeHost(ctx->h_scores);
-    for (auto &e : ctx->ev)
-        if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
@@ -623,7 +706,15 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     CKC(cudaSetDevice(device));
     CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
-    for (auto &e : ctx->ev) CKC(cudaEventCreate(&e));
+    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto &S : ctx->slot) {
+        CKC(cudaEventCreate(&S.up0));
+        CKC(cudaEventCreate(&S.up1));
+        for (auto &e : S.k) CKC(cudaEventCreate(&e));
+    }
+    CKC(cudaEventCreate(&ctx->src_up0));
+    CKC(cudaEventCreate(&ctx->src_up1));
+    for (auto &e : ctx->src_consumed) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
     const int mw = (int)max_w, mh = (int)max_h;
     ctx->cap_pyr_floats = std::max(pyr_capacity(mw, mh), pyr_capacity(mh, mw));
@@ -631,20 +722,22 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     ctx->cap_ctas = cta_capacity(mw, mh);
     ctx->cap_hplane_floats = iir_hplane_floats(ctx->cap_pyr_floats);
 
-    CKC(alloc_guarded(ctx, &ctx->d_in_src, (size_t)ctx->cap_in_bytes));
-    CKC(alloc_guarded(ctx, &ctx->d_in_dist, (size_t)ctx->cap_in_bytes * max_batch));
+    for (auto &p : ctx->d_in_src) CKC(alloc_guarded(ctx, &p, (size_t)ctx->cap_in_bytes));
+    CKC(alloc_guarded(ctx, &ctx->slot[0].d_in_dist, (size_t)ctx->cap_in_bytes * max_batch));
     CKC(alloc_guarded(ctx, &ctx->d_src_pyr, sizeof(float) * ctx->cap_pyr_floats));
     CKC(alloc_guarded(ctx, &ctx->d_dist_pyr, sizeof(float) * ctx->cap_pyr_floats * max_batch));
     CKC(alloc_guarded(ctx, &ctx->d_hplanes, sizeof(float) * ctx->cap_hplane_floats * max_batch));
     CKC(alloc_guarded(ctx, &ctx->d_src_hplanes, sizeof(float) * 2 * ctx->cap_pyr_floats));
     CKC(cudaMalloc(&ctx->d_lut, sizeof(float) * 256));
-    CKC(cudaMalloc((void **)&ctx->d_tbl, sizeof(void *) * 3 * (max_batch + 1)));
-    CKC(cudaHostAlloc((void **)&ctx->h_tbl, sizeof(void *) * 3 * (max_batch + 1), cudaHostAllocDefault));
+    CKC(cudaMalloc((void **)&ctx->d_tbl, sizeof(void *) * 3 * (max_batch + 1) * kSlots));
+    CKC(cudaHostAlloc((void **)&ctx->h_tbl, sizeof(void *) * 3 * (max_batch + 1) * kSlots, cudaHostAllocDefault));
     CKC(alloc_guarded(ctx, &ctx->d_partials, sizeof(double) * 6 * ctx->cap_ctas * max_batch));
-    CKC(cudaHostAlloc((void **)&ctx->h_sums, sizeof(double) * kMaxScales * 18 * max_batch, cudaHostAllocMapped));
-    CKC(cudaHostAlloc((void **)&ctx->h_scores, sizeof(double) * max_batch, cudaHostAllocMapped));
-    CKC(cudaHostGetDevicePointer((void **)&ctx->dm_sums, ctx->h_sums, 0));
-    CKC(cudaHostGetDevicePointer((void **)&ctx->dm_scores, ctx->h_scores, 0));
+    for (auto &S : ctx->slot) {
+        CKC(cudaHostAlloc((void **)&S.h_sums, sizeof(double) * kMaxScales * 18 * max_batch, cudaHostAllocMapped));
+        CKC(cudaHostAlloc((void **)&S.h_scores, sizeof(double) * max_batch, cudaHostAllocMapped));
+        CKC(cudaHostGetDevicePointer((void **)&S.dm_sums, S.h_sums, 0));
+        CKC(cudaHostGetDevicePointer((void **)&S.dm_scores, S.h_scores, 0));
+    }
 
     // sRGB -> linear table (v2.1 §1): double evaluation, one rounding to binary32
     float lut[256];
@@ -800,6 +893,45 @@ int oavif_ssimu2_score_batch_yuv444_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const
     return batch_yuv(ctx, n, y, u, v, ys, us, vs, depth, matrix, rgba_path, scores, true);
 }
 
+// ---- pipelined form: submit (returns at once), wait (retires the oldest) ---------------------------------------
+int oavif_ssimu2_submit_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *dists, size_t stride)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (!dists || n == 0 || n > ctx->max_batch) return fail(ctx, OAVIF_SSIMU2_E_ARG, "bad batch (n=%u)", n);
+    InputDesc d{};
+    d.kind = IN_RGB8;
+    d.stride[0] = stride;
+    std::vector<HostPlanes> hp(n);
+    for (uint32_t i = 0; i < n; ++i) hp[i] = HostPlanes{{dists[i], nullptr, nullptr}};
+    return submit_common(ctx, d, n, hp.data());
+}
+
+int oavif_ssimu2_submit_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y, const void *const *u,
+                               const void *const *v, size_t ys, size_t us, size_t vs, int depth, int matrix,
+                               int rgba_path)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (!y || !u || !v || n == 0 || n > ctx->max_batch) return fail(ctx, OAVIF_SSIMU2_E_ARG, "bad batch (n=%u)", n);
+    const int kind = kind_of(depth, rgba_path);
+    if (kind < 0) return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "depth %d not on the scored path (8 or 10)", depth);
+    YuvK k;
+    if (!yuv_consts(matrix, &k))
+        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "matrix_coefficients %d not on the scored path", matrix);
+    InputDesc d{};
+    d.kind = kind;
+    d.stride[0] = ys;
+    d.stride[1] = us;
+    d.stride[2] = vs;
+    d.matrix = matrix;
+    std::vector<HostPlanes> hp(n);
+    for (uint32_t i = 0; i < n; ++i) hp[i] = HostPlanes{{y[i], u[i], v[i]}};
+    return submit_common(ctx, d, n, hp.data());
+}
+
+int oavif_ssimu2_wait(oavif_ssimu2_ctx *ctx, double *scores) { return wait_common(ctx, scores); }
+
+int oavif_ssimu2_in_flight(const oavif_ssimu2_ctx *ctx) { return ctx ? ctx->inflight : 0; }
+
 int oavif_ssimu2_compute_rgb8(const uint8_t *ref, const uint8_t *dist, uint32_t w, uint32_t h, uint32_t channels,
                               double *score)
 {
@@ -858,7 +990,8 @@ int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void
     if (ys < rb || us < rb || vs < rb) return fail(ctx, OAVIF_SSIMU2_E_ARG, "stride smaller than a row");
     CK(cudaSetDevice(ctx->device));
     const size_t plane_bytes = (rb * h + 255) & ~(size_t)255;
-    uint8_t *base = ctx->d_in_dist;
+    if (ctx->inflight) return fail(ctx, OAVIF_SSIMU2_E_STATE, "a submission is in flight: retire it first");
+    uint8_t *base = ctx->slot[0].d_in_dist;
     const void *src[3] = {y, u, v};
     const size_t st[3] = {ys, us, vs};
     for (int p = 0; p < 3; ++p)
@@ -892,15 +1025,16 @@ int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void
 int oavif_ssimu2_get_detail(oavif_ssimu2_ctx *ctx, uint32_t candidate, oavif_ssimu2_detail *out)
 {
     if (!ctx || !out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
-    if (candidate >= ctx->last_n) return fail(ctx, OAVIF_SSIMU2_E_STATE, "candidate %u not in the last call", candidate);
+    const Slot &S = ctx->slot[ctx->last_slot];   // the submission retired last
+    if (candidate >= S.n) return fail(ctx, OAVIF_SSIMU2_E_STATE, "candidate %u not in the last call", candidate);
     memset(out, 0, sizeof *out);
-    out->n_scales = ctx->g.n_scales;
-    for (int s = 0; s < ctx->g.n_scales; ++s) {
-        out->w[s] = ctx->g.w[s];
-        out->h[s] = ctx->g.h[s];
-        for (int i = 0; i < 18; ++i) out->sums[s][i] = ctx->h_sums[((size_t)candidate * kMaxScales + s) * 18 + i];
+    out->n_scales = S.n_scales;
+    for (int s = 0; s < S.n_scales; ++s) {
+        out->w[s] = S.w[s];
+        out->h[s] = S.h[s];
+        for (int i = 0; i < 18; ++i) out->sums[s][i] = S.h_sums[((size_t)candidate * kMaxScales + s) * 18 + i];
     }
-    out->score = ctx->h_scores[candidate];
+    out->score = S.h_scores[candidate];
     return 0;
 }
 
@@ -979,6 +1113,7 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
         scale < 0 || scale >= ctx->g.n_scales || channel < 0 || channel > 2 || candidate < 0 ||
         candidate >= (int)ctx->last_n)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such blurred plane (needs a RECURSIVE score call first)");
+    if (ctx->inflight) return fail(ctx, OAVIF_SSIMU2_E_STATE, "a submission is in flight: retire it first");
     CK(cudaSetDevice(ctx->device));
     const Geom &g = ctx->g;
     const int w = g.w[scale], h = g.h[scale];
@@ -1058,7 +1193,8 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
     CK(cudaSetDevice(ctx->device));
     BlurPlan plan;
     plan_iir_v(ctx->g, &plan);
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (ctx->inflight) return fail(ctx, OAVIF_SSIMU2_E_STATE, "a submission is in flight: retire it first");
+    CK(cudaEventRecord(ctx->src_up0, ctx->stream));
     for (int i = 0; i < iters; ++i) {
         int launches = 0;
         const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
@@ -1068,10 +1204,10 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
                                               ctx->stream, !(variant & 4), nullptr, &launches, 1);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
     }
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaEventRecord(ctx->src_up1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    CK(cudaEventElapsedTime(&ms, ctx->src_up0, ctx->src_up1));
     *mean_ms = ms / iters;
     return 0;
 }

@@ -538,7 +538,9 @@ struct IirColsSmem {
 
 // B rows per exchange batch: the per-batch overhead (barrier, copy issue, address set-up) is paid once
 // per B rows by each of the eight warps.  RCAP = rows of a producer ring.
-template <int RCAP, int B>
+// TAP: the test hook of oavif_ssimu2_debug_get_cols, compiled into a second instance so that the scored path's
+// kernel carries none of it (with the hook inline the kernel went from 70 to 128 registers).
+template <int RCAP, int B, bool TAP>
 __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -706,7 +708,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();      // (S)
         const Unit2 u = unit2(a.one, a.neg_one);
         const f32x2 zero = splat2(0.0f);
-        const bool dbg = a.dbg_cols != nullptr && s == a.dbg_scale && c == a.dbg_channel && cand == a.dbg_cand;
+        const bool dbg = TAP && a.dbg_cols != nullptr && s == a.dbg_scale && c == a.dbg_channel && cand == a.dbg_cand;
         f32x2 acc[6];
 #pragma unroll
         for (int j = 0; j < 6; ++j) acc[j] = zero;
@@ -731,7 +733,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 5; ++q)
                         in[2 + q] = pk2(ex[(q * B + 2 * g) * kIirVCols], ex[(q * B + 2 * g + 1) * kIirVCols]);
-                    if (dbg && cb * kIirVCols + lane < w) {   // test hook: what the maps are about to consume
+                    if (TAP && dbg && cb * kIirVCols + lane < w) {   // test hook: what the maps are about to consume
 #pragma unroll
                         for (int q = 0; q < 5; ++q) {
                             float lo, hi;
@@ -850,8 +852,11 @@ typedef IirColsSmem<64, 16> IirColsDeep;
 
 inline cudaError_t iir_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(IirColsDeep));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_iir_cols<64, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(IirColsDeep));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_iir_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<1>));
     if (e != cudaSuccess) return e;
@@ -928,14 +933,16 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     if (!(phases & 2)) return cudaSuccess;
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
+    const int ctas = first_cta_cols[kMaxScales];
     if (tap) {
         a.dbg_cols = tap->out;
         a.dbg_scale = tap->scale;
         a.dbg_channel = tap->channel;
         a.dbg_cand = tap->cand;
+        k_iir_cols<64, 16, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
+    } else {
+        k_iir_cols<64, 16, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
     }
-    const int ctas = first_cta_cols[kMaxScales];
-    k_iir_cols<64, 16><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
     *launches += 1;
     return cudaGetLastError();
 }

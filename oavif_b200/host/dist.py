@@ -28,6 +28,49 @@ def init(backend: str | None = None):
     return rank, world, local
 
 
+def _parse_cpulist(text: str) -> list[int]:
+    out: list[int] = []
+    for tok in text.strip().split(","):
+        if not tok:
+            continue
+        a, _, b = tok.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def gpu_local_cpus(pci_bus_id: str) -> list[int]:
+    """CPUs the kernel reports as local to a PCI function (sysfs local_cpulist); [] when unknown."""
+    try:
+        with open(f"/sys/bus/pci/devices/{pci_bus_id.lower()}/local_cpulist") as f:
+            return _parse_cpulist(f.read())
+    except OSError:
+        return []
+
+
+def bind_near_gpu(local_rank: int, local_world: int, pci_bus_id: str | None = None) -> dict:
+    """Pin this process (and the threads it starts later) BEFORE it allocates pinned host memory, so that the
+    staging buffers are first-touched on the memory node next to the GPU's PCIe root and the caller threads
+    stay there.  Uses the GPU's sysfs local_cpulist when it names a proper subset of the visible CPUs;
+    otherwise (one NUMA node visible, as on the single-socket VMs of this pool) the visible CPUs are split
+    evenly between the local ranks, which at least stops ranks from migrating across each other's caches.
+    Returns what was done, for the bench line."""
+    try:
+        visible = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return {"policy": "unavailable"}
+    local = [c for c in gpu_local_cpus(pci_bus_id) if c in visible] if pci_bus_id else []
+    if local and len(local) < len(visible):
+        share = [c for i, c in enumerate(local)]   # ranks that share a node share its CPUs
+        os.sched_setaffinity(0, share)
+        return {"policy": "gpu-local", "cpus": f"{share[0]}-{share[-1]}", "n": len(share)}
+    if local_world > 1 and len(visible) >= local_world:
+        per = len(visible) // local_world
+        mine = visible[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return {"policy": "even-split", "cpus": f"{mine[0]}-{mine[-1]}", "n": len(mine)}
+    return {"policy": "none", "n": len(visible)}
+
+
 def finalize():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():

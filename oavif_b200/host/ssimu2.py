@@ -43,6 +43,7 @@ SYMBOLS = (
     "oavif_ssimu2_get_timing", "oavif_ssimu2_debug_get_xyb", "oavif_ssimu2_debug_get_rows", "oavif_ssimu2_debug_blur",
     "oavif_ssimu2_debug_time_rows", "oavif_ssimu2_debug_check_guards", "oavif_ssimu2_debug_get_cols",
     "oavif_ssimu2_set_default_device", "oavif_ssimu2_release_cached",
+    "oavif_ssimu2_submit_rgb8", "oavif_ssimu2_submit_yuv444", "oavif_ssimu2_wait", "oavif_ssimu2_in_flight",
 )
 
 
@@ -98,6 +99,11 @@ def load() -> C.CDLL:
     for f in (L.oavif_ssimu2_score_batch_yuv444, L.oavif_ssimu2_score_batch_yuv444_dev):
         f.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), szt, szt, szt, C.c_int,
                       C.c_int, C.c_int, dp]
+    L.oavif_ssimu2_submit_rgb8.argtypes = [vp, u32, C.POINTER(vp), szt]
+    L.oavif_ssimu2_submit_yuv444.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), szt, szt, szt,
+                                             C.c_int, C.c_int, C.c_int]
+    L.oavif_ssimu2_wait.argtypes = [vp, dp]
+    L.oavif_ssimu2_in_flight.argtypes = [vp]
     L.oavif_ssimu2_compute_rgb8.argtypes = [u8p, u8p, u32, u32, u32, dp]
     L.oavif_ssimu2_yuv444_to_rgb8.argtypes = [vp, vp, vp, vp, szt, szt, szt, u32, u32, C.c_int, C.c_int,
                                               C.c_int, u8p]
@@ -282,6 +288,35 @@ class Scorer:
                                                        ps[0][1].strides[0], ps[0][2].strides[0], depth, matrix,
                                                        int(rgba_path), out), self._ctx)
         return list(out)
+
+    # ---- pipelined form: up to two submissions in flight, uploads run under the previous one's kernels ----------
+    def submit_rgb8(self, dists: Sequence[np.ndarray]):
+        arrs = [_rgb8(d) for d in dists]
+        n = len(arrs)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        _check(self._L.oavif_ssimu2_submit_rgb8(self._ctx, n, ptrs, arrs[0].strides[0]), self._ctx)
+        self._pending = getattr(self, "_pending", []) + [(n, arrs)]     # keeps the arrays alive until wait()
+
+    def submit_yuv444(self, cands: Sequence[tuple], depth: int, matrix: int = 2, rgba_path: bool = False):
+        n = len(cands)
+        ps = [self._planes(*c, depth) for c in cands]
+        ys = (C.c_void_p * n)(*[p[0].ctypes.data for p in ps])
+        us = (C.c_void_p * n)(*[p[1].ctypes.data for p in ps])
+        vs = (C.c_void_p * n)(*[p[2].ctypes.data for p in ps])
+        _check(self._L.oavif_ssimu2_submit_yuv444(self._ctx, n, ys, us, vs, ps[0][0].strides[0], ps[0][1].strides[0],
+                                                  ps[0][2].strides[0], depth, matrix, int(rgba_path)), self._ctx)
+        self._pending = getattr(self, "_pending", []) + [(n, ps)]
+
+    def wait(self) -> list[float]:
+        pend = getattr(self, "_pending", [])
+        n = pend[0][0] if pend else self.max_batch
+        out = (C.c_double * max(n, 1))()
+        _check(self._L.oavif_ssimu2_wait(self._ctx, out), self._ctx)
+        self._pending = pend[1:]
+        return list(out)[:n]
+
+    def in_flight(self) -> int:
+        return self._L.oavif_ssimu2_in_flight(self._ctx)
 
     def score_batch_dev(self, kind: str, ptrs: Sequence[Sequence[int]], strides: Sequence[int], depth: int = 8,
                         matrix: int = 2, rgba_path: bool = False) -> list[float]:

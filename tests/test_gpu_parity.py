@@ -617,6 +617,48 @@ def test_conversion_call_leaves_the_cached_source_alone(scorer):
     assert scorer.score_rgb8(rgb) == a
 
 
+# ---- pipelined form: submit / wait ---------------------------------------------------------------------------
+def test_submit_wait_equals_the_synchronous_calls():
+    """Two submissions in flight, set_source of the next image while the previous one is still being scored, results
+    retired in order and bit-identical to the synchronous calls."""
+    w, h = 640, 360
+    imgs = [synth.synth(w, h, "mixture", 60 + k) for k in range(4)]
+    cands = [[synth.distort(s, 0.15 + 0.2 * i, seed=i) for i in range(2)] for s in imgs]
+    yuv = [[synth.rgb8_to_yuv444(c, 10) for c in cs] for cs in cands]
+    with ssimu2.Scorer(w, h, 2) as sc:
+        want, want_sums = [], []
+        for s, ys in zip(imgs, yuv):
+            sc.set_source(s)
+            want.append(sc.score_batch_yuv444(ys, 10))
+            want_sums.append(sc.sums(1).copy())
+        for mode in (ssimu2.BLUR_RECURSIVE,):
+            got = []
+            for k, (s, ys) in enumerate(zip(imgs, yuv)):
+                sc.set_source(s)                      # image k+1 goes up while image k is in flight
+                sc.submit_yuv444(ys, 10)
+                assert sc.in_flight() == (1 if k == 0 else 2)
+                if k > 0:
+                    got.append(sc.wait())
+                    np.testing.assert_array_equal(sc.sums(1), want_sums[k - 1])
+            got.append(sc.wait())
+            assert got == want and sc.in_flight() == 0
+        # rgb8 form, two submissions against ONE source, then a third submit must be refused until a wait
+        sc.set_source(imgs[0])
+        sc.submit_rgb8([cands[0][0]])
+        sc.submit_rgb8([cands[0][1], cands[0][0]])
+        with pytest.raises(ssimu2.Ssimu2Error) as e:
+            sc.submit_rgb8([cands[0][0]])
+        assert e.value.code == ssimu2.E_STATE
+        with pytest.raises(ssimu2.Ssimu2Error):
+            sc.score_rgb8(cands[0][0])                # synchronous call while submissions are in flight
+        a, b = sc.wait(), sc.wait()
+        assert a == [b[1]] and abs(a[0] - want[0][0]) < 0.2      # (8-bit RGB vs its 10-bit YUV round trip)
+        with pytest.raises(ssimu2.Ssimu2Error):
+            sc.wait()
+        assert sc.score_rgb8(imgs[0]) == 100.0
+        sc.check_guards()
+
+
 # ---- several callers per GPU: one context per host thread (the corpus driver's workers-per-gpu) ------------
 def test_two_contexts_on_two_threads_score_like_one():
     """Contexts are single-owner, but several may run on one GPU at once (each on its own stream): concurrent
