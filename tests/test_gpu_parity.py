@@ -644,6 +644,7 @@ def test_submit_wait_equals_the_synchronous_calls():
             assert got == want and sc.in_flight() == 0
         # rgb8 form, two submissions against ONE source, then a third submit must be refused until a wait
         sc.set_source(imgs[0])
+        want_rgb = sc.score_rgb8(cands[0][0])
         sc.submit_rgb8([cands[0][0]])
         sc.submit_rgb8([cands[0][1], cands[0][0]])
         with pytest.raises(ssimu2.Ssimu2Error) as e:
@@ -652,7 +653,7 @@ def test_submit_wait_equals_the_synchronous_calls():
         with pytest.raises(ssimu2.Ssimu2Error):
             sc.score_rgb8(cands[0][0])                # synchronous call while submissions are in flight
         a, b = sc.wait(), sc.wait()
-        assert a == [b[1]] and abs(a[0] - want[0][0]) < 0.2      # (8-bit RGB vs its 10-bit YUV round trip)
+        assert a == [b[1]] == [want_rgb]
         with pytest.raises(ssimu2.Ssimu2Error):
             sc.wait()
         assert sc.score_rgb8(imgs[0]) == 100.0
