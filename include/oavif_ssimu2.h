@@ -63,7 +63,13 @@ enum { OAVIF_SSIMU2_BLUR_RECURSIVE = 0, OAVIF_SSIMU2_BLUR_FIR = 1 };
  *               i++, i.e. index ((c*n_scales + scale)*2 + n)*3 + k                               */
 enum { OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS = 0, OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS = 1 };
 
-enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_WEIGHTS = 2 };
+/* How the RECURSIVE kernels move their tiles.  TMA (default): cp.async.bulk.tensor loads and stores issued by one
+ * elected lane, completion on mbarriers, zero padding and edge clipping done by the hardware.  CP_ASYNC: the
+ * round-1 kernels (dedicated loader / storer warps, 16-byte cp.async, one block barrier per chunk), kept for A/B
+ * measurements and for drivers without a tensor-map encoder.  Same arithmetic, same bits. */
+enum { OAVIF_SSIMU2_TILES_TMA = 0, OAVIF_SSIMU2_TILES_CP_ASYNC = 1 };
+
+enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_WEIGHTS = 2, OAVIF_SSIMU2_OPT_TILE_PATH = 3 };
 
 typedef struct oavif_ssimu2_ctx oavif_ssimu2_ctx;
 
@@ -101,6 +107,7 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
 void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx);
 
 int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value);
+int oavif_ssimu2_get_option(const oavif_ssimu2_ctx *ctx, int option, int *value);
 
 /* Launch on a caller-owned cudaStream_t (passed as void*) instead of the context's own. */
 int oavif_ssimu2_set_stream(oavif_ssimu2_ctx *ctx, void *cuda_stream);
@@ -113,10 +120,12 @@ void oavif_ssimu2_pinned_free(void *p);
 
 /* ---- source side: once per image (main.zig:86) ------------------------------------------ */
 
-/* rgb: interleaved 8-bit RGB, `stride` bytes per row (>= 3*w).  Uploads, builds and caches
- * the source's six-scale XYB pyramid on the device.  For the RECURSIVE blur the rows pass of the two
- * source-only quantities (a, a*a) is computed by the first scoring call that follows, cached with the
- * pyramid, and shared by every later candidate of the search / batch. */
+/* rgb: interleaved 8-bit RGB, `stride` bytes per row (>= 3*w).  Uploads, builds and caches the source side
+ * on the device: the six-scale XYB pyramid and, for the RECURSIVE blur, the rows pass of the two source-only
+ * quantities (a, a*a).  Both kernels run on the context's SOURCE stream, next to whatever the compute stream is
+ * doing (the candidate's pyramid and rows pass of the same evaluation, or the previous image's submissions):
+ * the source side exists twice, so a new source never waits for submissions that still read the old one.
+ * Returns once the caller's pixels have been read. */
 int oavif_ssimu2_set_source_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w,
                                  uint32_t h, size_t stride);
 
@@ -170,12 +179,19 @@ int oavif_ssimu2_submit_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *c
 int oavif_ssimu2_submit_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y,
                                const void *const *u, const void *const *v, size_t y_stride,
                                size_t u_stride, size_t v_stride, int depth, int matrix, int rgba_path);
+int oavif_ssimu2_submit_rgb8_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *d_dists,
+                                 size_t stride);
+int oavif_ssimu2_submit_yuv444_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *d_y,
+                                   const void *const *d_u, const void *const *d_v, size_t y_stride,
+                                   size_t u_stride, size_t v_stride, int depth, int matrix, int rgba_path);
 int oavif_ssimu2_wait(oavif_ssimu2_ctx *ctx, double *scores);
 int oavif_ssimu2_in_flight(const oavif_ssimu2_ctx *ctx);
 
 /* ---- device-resident inputs (pointers are CUDA device pointers on the context's device) --
  * set_source_rgb8_dev only enqueues work: the buffer must stay unmodified until the next score call
- * on this context has returned. */
+ * on this context has returned.  Ordering: with a caller-owned stream (set_stream) the source is read
+ * after everything enqueued on that stream so far; with the context's own streams the pixels must already
+ * be complete when the call is made. */
 
 int oavif_ssimu2_set_source_rgb8_dev(oavif_ssimu2_ctx *ctx, const uint8_t *d_rgb, uint32_t w,
                                      uint32_t h, size_t stride);
@@ -239,8 +255,8 @@ int oavif_ssimu2_debug_check_guards(oavif_ssimu2_ctx *ctx);
 
 /* Profiling aid: re-run only the RECURSIVE rows pass on the pyramids of the last score call,
  * `iters` times, and report its mean device time.  variant 0 runs both halves; bit 2 (value 4) leaves
- * out the source half (a, a*a), i.e. times what a call with a warm source cache runs; other bits are
- * ignored. */
+ * out the source half (a, a*a), i.e. times what a call with a warm source cache runs; bit 3 (value 8) forces
+ * the cp.async kernels whatever OAVIF_SSIMU2_OPT_TILE_PATH says. */
 int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms);
 
 #ifdef __cplusplus

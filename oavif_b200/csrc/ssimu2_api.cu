@@ -61,6 +61,18 @@ struct Slot {
     uint32_t launches = 0;
 };
 
+// Everything that only depends on the source: its XYB pyramid, the rows pass of (a, a*a) (RECURSIVE blur) and the
+// TMA descriptors over both.
+struct SrcSet {
+    float *d_pyr = nullptr, *d_hplanes = nullptr;
+    bool rows_valid = false;               // d_hplanes holds the rows pass of the source in d_pyr
+    cudaEvent_t pyr_ready = nullptr;       // source stream: the pyramid is complete
+    cudaEvent_t ready = nullptr;           // source stream: ... and so is everything else enqueued by set_source
+    cudaEvent_t last_use = nullptr;        // compute stream: the last submission reading this set has finished
+    CUtensorMap in_src[kMaxScales], out_psrc[kMaxScales];
+    int maps_w = -1, maps_h = -1;
+};
+
 struct oavif_ssimu2_ctx {
     int device = 0;
     uint32_t max_w = 0, max_h = 0, max_batch = 0;
@@ -68,6 +80,9 @@ struct oavif_ssimu2_ctx {
     cudaStream_t copy_stream = nullptr;                    // host -> device uploads: run under the previous submission's kernels
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
     int weight_layout = OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS;
+    int tile_path = OAVIF_SSIMU2_TILES_TMA;
+    IirRowsTmaMaps cand_maps{};    // TMA descriptors of the candidates' planes (in_dist, out_pcand, out_ab) for maps_w x maps_h
+    int maps_w = -1, maps_h = -1;
 
     // capacities (computed from max_w x max_h)
     long long cap_pyr_floats = 0, cap_in_bytes = 0, cap_ctas = 0, cap_hplane_floats = 0;
@@ -84,8 +99,13 @@ struct oavif_ssimu2_ctx {
     Slot slot[kSlots];
     int head = 0, tail = 0, inflight = 0, last_slot = 0;   // ring of submissions; last_slot: what get_detail / get_timing report
 
-    float *d_src_pyr = nullptr, *d_dist_pyr = nullptr, *d_hplanes = nullptr, *d_src_hplanes = nullptr, *d_lut = nullptr;
-    bool src_rows_valid = false;   // the cached rows pass of the source (RECURSIVE blur) matches the current source
+    // The source side lives twice: set_source of image i+1 builds set (cur ^ 1) on the SOURCE stream while the
+    // submissions of image i still read set cur on the compute stream.
+    SrcSet src[2];
+    int cur = 0;
+    cudaStream_t src_stream = nullptr;
+    cudaEvent_t ev_user = nullptr;         // orders the source stream behind a caller-owned compute stream
+    float *d_dist_pyr = nullptr, *d_hplanes = nullptr, *d_lut = nullptr;
     const void **d_tbl = nullptr, **h_tbl = nullptr;   // [slot][3 * (max_batch + 1)]
     double *d_partials = nullptr;
     float *d_dbg = nullptr;
@@ -337,8 +357,9 @@ int nplanes(int kind) { return (kind == IN_RGB8 || kind == IN_PIXELS) ? 1 : 3; }
 // Stage (if host) `n` images and build their pyramids into `out`.  Host pixels go up on the COPY stream into
 // `staging`; the compute stream waits for `up1` and runs the pyramid kernel.  `tbl0` selects the rows of the
 // pointer table this call owns.
-int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const HostPlanes *imgs, uint8_t *staging,
-                   int tbl0, cudaEvent_t up0, cudaEvent_t up1, cudaEvent_t k0, float *out, long long out_stride)
+int build_pyramids(oavif_ssimu2_ctx *ctx, cudaStream_t st, const InputDesc &d, uint32_t n, const HostPlanes *imgs,
+                   uint8_t *staging, int tbl0, cudaEvent_t up0, cudaEvent_t up1, cudaEvent_t k0, float *out,
+                   long long out_stride)
 {
     const Geom &g = ctx->g;
     const int w = g.w[0], h = g.h[0];
@@ -371,7 +392,7 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const 
                 ctx->h_tbl[tbl0 + 3 * i + p] = dst;
             }
         CK(cudaEventRecord(up1, ctx->copy_stream));
-        CK(cudaStreamWaitEvent(ctx->stream, up1, 0));
+        CK(cudaStreamWaitEvent(st, up1, 0));
         if (np == 1)
             for (uint32_t i = 0; i < n; ++i)
                 ctx->h_tbl[tbl0 + 3 * i + 1] = ctx->h_tbl[tbl0 + 3 * i + 2] = ctx->h_tbl[tbl0 + 3 * i];
@@ -381,12 +402,11 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const 
         for (uint32_t i = 0; i < 3 * n; ++i) a.inl[i] = ctx->h_tbl[tbl0 + i];
         a.planes = nullptr;
     } else {
-        CK(cudaMemcpyAsync(ctx->d_tbl + tbl0, ctx->h_tbl + tbl0, sizeof(void *) * 3 * n, cudaMemcpyHostToDevice,
-                           ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_tbl + tbl0, ctx->h_tbl + tbl0, sizeof(void *) * 3 * n, cudaMemcpyHostToDevice, st));
         a.planes = ctx->d_tbl + tbl0;
     }
-    CK(cudaEventRecord(k0, ctx->stream));
-    launch_pyramid(d.kind, a, (int)n, ctx->stream);
+    if (k0) CK(cudaEventRecord(k0, st));
+    launch_pyramid(d.kind, a, (int)n, st);
     CK(cudaGetLastError());
     return 0;
 }
@@ -423,8 +443,52 @@ int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
     return 0;
 }
 
-// blur + maps + pooling + final score of the candidates whose pyramids were just enqueued, into slot S
-int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, uint32_t n)
+// TMA descriptors follow the geometry.  Fills `out` with the candidates' descriptors and those of source set `S`;
+// false selects the cp.async kernels (tile path switched off, or no descriptor encoder in this driver).
+bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
+{
+    if (ctx->tile_path != OAVIF_SSIMU2_TILES_TMA) return false;
+    const Geom &g = ctx->g;
+    const long long P = ctx->cap_pyr_floats;
+    bool ok = true;
+    if (ctx->maps_w != g.w[0] || ctx->maps_h != g.h[0]) {
+        ok = iir_rows_tma_maps_cand(&ctx->cand_maps, g, ctx->d_dist_pyr, P, ctx->d_hplanes, ctx->d_hplanes + 2 * P, 3 * P,
+                                    (int)ctx->max_batch);
+        if (ok) {
+            ctx->maps_w = g.w[0];
+            ctx->maps_h = g.h[0];
+        }
+    }
+    if (ok && (S.maps_w != g.w[0] || S.maps_h != g.h[0])) {
+        ok = iir_rows_tma_maps_src(S.in_src, S.out_psrc, g, S.d_pyr, S.d_hplanes);
+        if (ok) {
+            S.maps_w = g.w[0];
+            S.maps_h = g.h[0];
+        }
+    }
+    if (!ok) {
+        ctx->tile_path = OAVIF_SSIMU2_TILES_CP_ASYNC;
+        return false;
+    }
+    *out = ctx->cand_maps;
+    memcpy(out->in_src, S.in_src, sizeof S.in_src);
+    memcpy(out->out_psrc, S.out_psrc, sizeof S.out_psrc);
+    return true;
+}
+
+IirArgs iir_args_for(oavif_ssimu2_ctx *ctx, const SrcSet &S)
+{
+    IirArgs a{};
+    const IirBuffers B{S.d_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
+    iir_fill_common(a, ctx->g, ctx->iir, S.d_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B);
+    a.partials = ctx->d_partials;
+    a.partials_stride = ctx->cap_ctas * 6;
+    return a;
+}
+
+// blur + maps + pooling + final score of the candidates whose pyramids were just enqueued, into slot S.
+// The compute stream has waited for the source's pyramid; `Src.ready` covers the rest of the source side.
+int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, SrcSet &Src, uint32_t n)
 {
     const Geom &g = ctx->g;
     BlurPlan plan;
@@ -432,7 +496,7 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, uint32_t n)
         plan_fir(g, &plan);
         BlurArgs b{};
         b.g = g;
-        b.src = ctx->d_src_pyr;
+        b.src = Src.d_pyr;
         b.dist = ctx->d_dist_pyr;
         b.dist_stride = ctx->cap_pyr_floats;
         b.partials = ctx->d_partials;
@@ -451,15 +515,30 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, uint32_t n)
         S.launches += 1;
     } else {
         plan_iir_v(g, &plan);
-        int launches = 0;
-        const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
-        // the first call after set_source also runs the source's half of the rows pass and leaves it cached
-        const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
-                                              ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, (int)n,
-                                              ctx->stream, !ctx->src_rows_valid, S.k[2], &launches);
-        if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "recursive blur launch: %s", cudaGetErrorString(e));
-        S.launches += launches;
-        ctx->src_rows_valid = true;
+        const IirArgs a = iir_args_for(ctx, Src);
+        IirRowsTmaMaps maps;
+        const bool tma = rows_maps_for(ctx, Src, &maps);
+        cudaError_t e;
+        if (Src.rows_valid) {
+            // the usual case: the source's half was enqueued by set_source on the source stream and may still
+            // be running next to this launch; only the columns pass has to wait for it
+            e = launch_iir_rows(a, g, 1, (int)n, ctx->stream, tma ? &maps : nullptr);
+            S.launches += 1;
+        } else if (tma) {   // the source was set under FIR, or before the tile path changed: build its half now
+            e = launch_iir_rows(a, g, 3, 1, ctx->stream, &maps);
+            if (e == cudaSuccess) e = launch_iir_rows(a, g, 1, (int)n, ctx->stream, &maps);
+            S.launches += 2;
+        } else {            // cp.async kernels: candidate 0's CTAs carry the source's half along
+            e = launch_iir_rows(a, g, 2, (int)n, ctx->stream, nullptr);
+            S.launches += 1;
+        }
+        if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
+        Src.rows_valid = true;
+        CK(cudaEventRecord(S.k[2], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream, Src.ready, 0));
+        e = launch_iir_cols(a, plan.first_cta, plan.tiles_x, (int)n, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
+        S.launches += 1;
     }
     CK(cudaEventRecord(S.k[3], ctx->stream));
 
@@ -480,6 +559,7 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, uint32_t n)
     CK(cudaGetLastError());
     S.launches += 1;
     CK(cudaEventRecord(S.k[4], ctx->stream));
+    CK(cudaEventRecord(Src.last_use, ctx->stream));
     return 0;
 }
 
@@ -515,12 +595,14 @@ int submit_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const H
     ctx->last_n = n;
     if (!S.degenerate) {
         const int tbl0 = ctx->head * 3 * (int)(ctx->max_batch + 1) + 3;   // row 0 of each table is the source's
-        int rc = build_pyramids(ctx, d, n, imgs, S.d_in_dist, tbl0, S.up0, S.up1, S.k[0], ctx->d_dist_pyr,
+        SrcSet &Src = ctx->src[ctx->cur];
+        int rc = build_pyramids(ctx, ctx->stream, d, n, imgs, S.d_in_dist, tbl0, S.up0, S.up1, S.k[0], ctx->d_dist_pyr,
                                 ctx->cap_pyr_floats);
         if (rc) return rc;
         S.launches += 1;
         CK(cudaEventRecord(S.k[1], ctx->stream));
-        rc = enqueue_blur_and_finalize(ctx, S, n);
+        CK(cudaStreamWaitEvent(ctx->stream, Src.pyr_ready, 0));   // the candidate's pyramid did not need the source's
+        rc = enqueue_blur_and_finalize(ctx, S, Src, n);
         if (rc) return rc;
     }
     ctx->head = (ctx->head + 1) % kSlots;
@@ -598,19 +680,41 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
     d.on_device = on_device;
     HostPlanes hp{{rgb, nullptr, nullptr}};
     ctx->timing = oavif_ssimu2_timing{};
-    ctx->src_rows_valid = false;   // the next score call refills the cache of the source's row-filtered planes
-    // A submission may still be in flight: its kernels read the OLD source pyramid, and this call's pyramid
-    // kernel queues behind them on the compute stream.  Only the staged pixels need a second buffer, and the
-    // copy stream must not overwrite one that an earlier source pyramid kernel has yet to read.
+    // The source side is built on the SOURCE stream into the set no submission reads: submissions of the previous
+    // image may still be in flight on the compute stream (pipelined callers), and within one evaluation the
+    // source's pyramid and rows pass run next to the candidate's.
+    ctx->cur ^= 1;
+    SrcSet &Src = ctx->src[ctx->cur];
+    Src.rows_valid = false;
+    cudaStream_t ss = ctx->src_stream;
+    CK(cudaStreamWaitEvent(ss, Src.last_use, 0));     // submissions that read this set two images ago
     const int sb = ctx->src_buf ^= 1;
-    if (!on_device) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->src_consumed[sb], 0));
-    rc = build_pyramids(ctx, d, 1, &hp, ctx->d_in_src[sb], ctx->head * 3 * (int)(ctx->max_batch + 1), ctx->src_up0,
-                        ctx->src_up1, ctx->slot[ctx->head].k[0], ctx->d_src_pyr, 0);
+    if (on_device) {
+        if (ctx->stream != ctx->own_stream) {         // caller-owned compute stream: its earlier work produced the pixels
+            CK(cudaEventRecord(ctx->ev_user, ctx->stream));
+            CK(cudaStreamWaitEvent(ss, ctx->ev_user, 0));
+        }
+    } else {
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->src_consumed[sb], 0));   // the pyramid kernel that last read this staging buffer
+    }
+    rc = build_pyramids(ctx, ss, d, 1, &hp, ctx->d_in_src[sb], ctx->head * 3 * (int)(ctx->max_batch + 1), ctx->src_up0,
+                        ctx->src_up1, nullptr, Src.d_pyr, 0);
     if (rc) return rc;
-    CK(cudaEventRecord(ctx->src_consumed[sb], ctx->stream));
+    CK(cudaEventRecord(ctx->src_consumed[sb], ss));
+    CK(cudaEventRecord(Src.pyr_ready, ss));
     ctx->timing.launches = 1;
+    if (ctx->blur_mode == OAVIF_SSIMU2_BLUR_RECURSIVE) {
+        IirRowsTmaMaps maps;
+        if (rows_maps_for(ctx, Src, &maps)) {         // rows pass of (a, a*a), once per source
+            const cudaError_t e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, 3, 1, ss, &maps);
+            if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "source rows launch: %s", cudaGetErrorString(e));
+            Src.rows_valid = true;
+            ctx->timing.launches = 2;
+        }
+    }
+    CK(cudaEventRecord(Src.ready, ss));
     // Return as soon as the caller's pixels have been consumed (host input: after the upload; device
-    // input: at once): the pyramid kernel itself keeps running behind the next call on the same stream.
+    // input: at once): the kernels keep running behind the calls that follow.
     if (!on_device) {
         CK(cudaEventSynchronize(ctx->src_up1));
         float ms = 0.f;
@@ -654,6 +758,7 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->src_stream) cudaStreamSynchronize(ctx->src_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &p : ctx->d_in_src) cudaFree(p);
     for (auto &S : ctx->slot) {
@@ -665,10 +770,16 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     }
     for (cudaEvent_t e : {ctx->src_up0, ctx->src_up1, ctx->src_consumed[0], ctx->src_consumed[1]})
         if (e) cudaEventDestroy(e);
-    cudaFree(ctx->d_src_pyr);
+    for (auto &S : ctx->src) {
+        cudaFree(S.d_pyr);
+        cudaFree(S.d_hplanes);
+        for (cudaEvent_t e : {S.pyr_ready, S.ready, S.last_use})
+            if (e) cudaEventDestroy(e);
+    }
+    if (ctx->ev_user) cudaEventDestroy(ctx->ev_user);
+    if (ctx->src_stream) cudaStreamDestroy(ctx->src_stream);
     cudaFree(ctx->d_dist_pyr);
     cudaFree(ctx->d_hplanes);
-    cudaFree(ctx->d_src_hplanes);
     cudaFree(ctx->d_lut);
     cudaFree((void *)ctx->d_tbl);
     cudaFree(ctx->d_partials);
@@ -707,6 +818,10 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->src_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming));
+    for (auto &S : ctx->src)
+        for (cudaEvent_t *e : {&S.pyr_ready, &S.ready, &S.last_use}) CKC(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (auto &S : ctx->slot) {
         CKC(cudaEventCreate(&S.up0));
         CKC(cudaEventCreate(&S.up1));
@@ -724,10 +839,12 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
 
     for (auto &p : ctx->d_in_src) CKC(alloc_guarded(ctx, &p, (size_t)ctx->cap_in_bytes));
     CKC(alloc_guarded(ctx, &ctx->slot[0].d_in_dist, (size_t)ctx->cap_in_bytes * max_batch));
-    CKC(alloc_guarded(ctx, &ctx->d_src_pyr, sizeof(float) * ctx->cap_pyr_floats));
+    for (auto &S : ctx->src) {
+        CKC(alloc_guarded(ctx, &S.d_pyr, sizeof(float) * ctx->cap_pyr_floats));
+        CKC(alloc_guarded(ctx, &S.d_hplanes, sizeof(float) * 2 * ctx->cap_pyr_floats));
+    }
     CKC(alloc_guarded(ctx, &ctx->d_dist_pyr, sizeof(float) * ctx->cap_pyr_floats * max_batch));
     CKC(alloc_guarded(ctx, &ctx->d_hplanes, sizeof(float) * ctx->cap_hplane_floats * max_batch));
-    CKC(alloc_guarded(ctx, &ctx->d_src_hplanes, sizeof(float) * 2 * ctx->cap_pyr_floats));
     CKC(cudaMalloc(&ctx->d_lut, sizeof(float) * 256));
     CKC(cudaMalloc((void **)&ctx->d_tbl, sizeof(void *) * 3 * (max_batch + 1) * kSlots));
     CKC(cudaHostAlloc((void **)&ctx->h_tbl, sizeof(void *) * 3 * (max_batch + 1) * kSlots, cudaHostAllocDefault));
@@ -763,12 +880,28 @@ int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value)
         ctx->blur_mode = value;
         return 0;
     }
+    if (option == OAVIF_SSIMU2_OPT_TILE_PATH &&
+        (value == OAVIF_SSIMU2_TILES_TMA || value == OAVIF_SSIMU2_TILES_CP_ASYNC)) {
+        ctx->tile_path = value;
+        return 0;
+    }
     if (option == OAVIF_SSIMU2_OPT_WEIGHTS &&
         (value == OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS || value == OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS)) {
         ctx->weight_layout = value;
         return 0;
     }
     return fail(ctx, OAVIF_SSIMU2_E_ARG, "unknown option %d / value %d", option, value);
+}
+
+int oavif_ssimu2_get_option(const oavif_ssimu2_ctx *ctx, int option, int *value)
+{
+    if (!ctx || !value) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null argument");
+    switch (option) {
+    case OAVIF_SSIMU2_OPT_BLUR: *value = ctx->blur_mode; return 0;
+    case OAVIF_SSIMU2_OPT_WEIGHTS: *value = ctx->weight_layout; return 0;
+    case OAVIF_SSIMU2_OPT_TILE_PATH: *value = ctx->tile_path; return 0;
+    default: return OAVIF_SSIMU2_E_ARG;
+    }
 }
 
 int oavif_ssimu2_set_stream(oavif_ssimu2_ctx *ctx, void *cuda_stream)
@@ -894,21 +1027,21 @@ int oavif_ssimu2_score_batch_yuv444_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const
 }
 
 // ---- pipelined form: submit (returns at once), wait (retires the oldest) ---------------------------------------
-int oavif_ssimu2_submit_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *dists, size_t stride)
+static int submit_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *dists, size_t stride, bool dev)
 {
     if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
     if (!dists || n == 0 || n > ctx->max_batch) return fail(ctx, OAVIF_SSIMU2_E_ARG, "bad batch (n=%u)", n);
     InputDesc d{};
     d.kind = IN_RGB8;
     d.stride[0] = stride;
+    d.on_device = dev;
     std::vector<HostPlanes> hp(n);
     for (uint32_t i = 0; i < n; ++i) hp[i] = HostPlanes{{dists[i], nullptr, nullptr}};
     return submit_common(ctx, d, n, hp.data());
 }
 
-int oavif_ssimu2_submit_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y, const void *const *u,
-                               const void *const *v, size_t ys, size_t us, size_t vs, int depth, int matrix,
-                               int rgba_path)
+static int submit_yuv(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y, const void *const *u, const void *const *v,
+                      size_t ys, size_t us, size_t vs, int depth, int matrix, int rgba_path, bool dev)
 {
     if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
     if (!y || !u || !v || n == 0 || n > ctx->max_batch) return fail(ctx, OAVIF_SSIMU2_E_ARG, "bad batch (n=%u)", n);
@@ -923,9 +1056,34 @@ int oavif_ssimu2_submit_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const void *co
     d.stride[1] = us;
     d.stride[2] = vs;
     d.matrix = matrix;
+    d.on_device = dev;
     std::vector<HostPlanes> hp(n);
     for (uint32_t i = 0; i < n; ++i) hp[i] = HostPlanes{{y[i], u[i], v[i]}};
     return submit_common(ctx, d, n, hp.data());
+}
+
+int oavif_ssimu2_submit_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *dists, size_t stride)
+{
+    return submit_rgb8(ctx, n, dists, stride, false);
+}
+
+int oavif_ssimu2_submit_rgb8_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *d_dists, size_t stride)
+{
+    return submit_rgb8(ctx, n, d_dists, stride, true);
+}
+
+int oavif_ssimu2_submit_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y, const void *const *u,
+                               const void *const *v, size_t ys, size_t us, size_t vs, int depth, int matrix,
+                               int rgba_path)
+{
+    return submit_yuv(ctx, n, y, u, v, ys, us, vs, depth, matrix, rgba_path, false);
+}
+
+int oavif_ssimu2_submit_yuv444_dev(oavif_ssimu2_ctx *ctx, uint32_t n, const void *const *y, const void *const *u,
+                                   const void *const *v, size_t ys, size_t us, size_t vs, int depth, int matrix,
+                                   int rgba_path)
+{
+    return submit_yuv(ctx, n, y, u, v, ys, us, vs, depth, matrix, rgba_path, true);
 }
 
 int oavif_ssimu2_wait(oavif_ssimu2_ctx *ctx, double *scores) { return wait_common(ctx, scores); }
@@ -1053,9 +1211,10 @@ int oavif_ssimu2_debug_get_xyb(oavif_ssimu2_ctx *ctx, int which, int scale, int 
         which > (int)ctx->max_batch)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such plane");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));  // the source pyramid may still be in flight
+    CK(cudaStreamSynchronize(ctx->src_stream));  // the source pyramid may still be in flight
+    CK(cudaStreamSynchronize(ctx->stream));
     const Geom &g = ctx->g;
-    const float *base = which == 0 ? ctx->d_src_pyr : ctx->d_dist_pyr + (long long)(which - 1) * ctx->cap_pyr_floats;
+    const float *base = which == 0 ? ctx->src[ctx->cur].d_pyr : ctx->d_dist_pyr + (long long)(which - 1) * ctx->cap_pyr_floats;
     const float *p = base + g.off[scale] + (long long)channel * g.plane[scale];
     CK(cudaMemcpy2D(out, sizeof(float) * g.w[scale], p, sizeof(float) * g.pitch[scale], sizeof(float) * g.w[scale],
                     g.h[scale], cudaMemcpyDeviceToHost));
@@ -1068,7 +1227,7 @@ int oavif_ssimu2_debug_get_rows(oavif_ssimu2_ctx *ctx, int candidate, int quanti
                                 uint32_t *w_out, uint32_t *h_out)
 {
     if (!ctx || !out || !w_out || !h_out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
-    if (!ctx->have_source || ctx->last_n == 0 || ctx->blur_mode != OAVIF_SSIMU2_BLUR_RECURSIVE || !ctx->src_rows_valid ||
+    if (!ctx->have_source || ctx->last_n == 0 || ctx->blur_mode != OAVIF_SSIMU2_BLUR_RECURSIVE || !ctx->src[ctx->cur].rows_valid ||
         scale < 0 || scale >= ctx->g.n_scales || channel < 0 || channel > 2 || quantity < 0 || quantity > 4 ||
         candidate < 0 || candidate >= (int)ctx->last_n)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such row-filtered plane (needs a RECURSIVE score call first)");
@@ -1086,7 +1245,7 @@ int oavif_ssimu2_debug_get_rows(oavif_ssimu2_ctx *ctx, int candidate, int quanti
         spitch = sizeof(float) * pitch;
         elem = sizeof(float);
     } else {
-        const float *base = (quantity & 1) ? ctx->d_hplanes + (long long)candidate * 3 * P : ctx->d_src_hplanes;
+        const float *base = (quantity & 1) ? ctx->d_hplanes + (long long)candidate * 3 * P : ctx->src[ctx->cur].d_hplanes;
         p = base + 2 * poff + (quantity >> 1);
         spitch = sizeof(float) * 2 * pitch;
         elem = 2 * sizeof(float);
@@ -1109,7 +1268,7 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
                                 uint32_t *w_out, uint32_t *h_out)
 {
     if (!ctx || !out || !w_out || !h_out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
-    if (!ctx->have_source || ctx->last_n == 0 || ctx->blur_mode != OAVIF_SSIMU2_BLUR_RECURSIVE || !ctx->src_rows_valid ||
+    if (!ctx->have_source || ctx->last_n == 0 || ctx->blur_mode != OAVIF_SSIMU2_BLUR_RECURSIVE || !ctx->src[ctx->cur].rows_valid ||
         scale < 0 || scale >= ctx->g.n_scales || channel < 0 || channel > 2 || candidate < 0 ||
         candidate >= (int)ctx->last_n)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such blurred plane (needs a RECURSIVE score call first)");
@@ -1130,11 +1289,8 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
     BlurPlan plan;
     plan_iir_v(g, &plan);
     const IirDebugTap tap{ctx->d_dbg, scale, channel, candidate};
-    const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
-    int launches = 0;
-    const cudaError_t e = launch_iir_blur(g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
-                                          ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x,
-                                          (int)ctx->last_n, ctx->stream, false, nullptr, &launches, 2, &tap);
+    const cudaError_t e = launch_iir_cols(iir_args_for(ctx, ctx->src[ctx->cur]), plan.first_cta, plan.tiles_x, (int)ctx->last_n,
+                                          ctx->stream, &tap);
     if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
     CK(cudaMemcpyAsync(out, ctx->d_dbg, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1194,14 +1350,16 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
     BlurPlan plan;
     plan_iir_v(ctx->g, &plan);
     if (ctx->inflight) return fail(ctx, OAVIF_SSIMU2_E_STATE, "a submission is in flight: retire it first");
+    SrcSet &Src = ctx->src[ctx->cur];
+    IirRowsTmaMaps maps;
+    const bool tma = !(variant & 8) && rows_maps_for(ctx, Src, &maps);
+    const int which = (variant & 128) ? 3 : (variant & 4) ? 1 : 2;
+    if (which == 3 && !tma) return fail(ctx, OAVIF_SSIMU2_E_ARG, "the source-only rows kernel exists in the TMA form only");
+    CK(cudaStreamSynchronize(ctx->src_stream));
     CK(cudaEventRecord(ctx->src_up0, ctx->stream));
     for (int i = 0; i < iters; ++i) {
-        int launches = 0;
-        const IirBuffers B{ctx->d_src_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
-        // bit 2: leave the source half out (what a call with a warm source cache runs); other bits are ignored
-        const cudaError_t e = launch_iir_blur(ctx->g, ctx->iir, ctx->d_src_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B,
-                                              ctx->d_partials, ctx->cap_ctas * 6, plan.first_cta, plan.tiles_x, 1,
-                                              ctx->stream, !(variant & 4), nullptr, &launches, 1);
+        const cudaError_t e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, which, 1, ctx->stream, tma ? &maps : nullptr,
+                                              (variant >> 4) & 7);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
     }
     CK(cudaEventRecord(ctx->src_up1, ctx->stream));

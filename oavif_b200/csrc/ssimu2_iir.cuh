@@ -25,6 +25,7 @@
 #pragma once
 
 #include "ssimu2_common.cuh"
+#include "ssimu2_tma.cuh"
 
 namespace oavif {
 
@@ -514,6 +515,294 @@ __global__ void __launch_bounds__(MODE == 2 ? 192 : 128) k_iir_rows(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
+// rows pass, TMA form (the default).  Same decomposition and the same arithmetic as k_iir_rows above — one CTA =
+// 32 rows of one channel, lane = row, a packed-pair recursion warp for (b, b*b), a scalar one for a*b and, on
+// the first call after set_source, a pair warp for the source's (a, a*a) — but no loader warp, no storer warps and
+// no block barrier:
+//   * one elected lane of a producer warp issues, per 32-column chunk, two cp.async.bulk.tensor loads (planes b
+//     and a) of a 44-column x 32-row box starting 8 columns left of the chunk: the chunk's own samples, the
+//     left taps (n-6) and the right taps (n+4) in one tile.  Columns left of 0, right of w and rows below h
+//     arrive as zeros — the filter's zero padding.  Completion is counted on the ring slot's `full` mbarrier.
+//     A 44-float row pitch keeps the lane = row 128-bit reads conflict-free without padding tricks.
+//   * each recursion warp waits on `full[slot]`, pulls its 44 samples into registers, and releases the slot on
+//     `empty[slot]` at once; the warps never wait for each other.
+//   * a finished 32 x 32 chunk is staged in 128-byte-swizzled shared memory (lane = row 128-bit stores land on
+//     32 distinct banks) and leaves through cp.async.bulk.tensor stores issued by the warp's own lane 0; rows
+//     below h and columns right of w are clipped by the hardware.  Two staging buffers per warp: the buffer of
+//     chunk t is reused once the store of chunk t-2 has read it (cp.async.bulk.wait_group.read 1).
+constexpr int kRtTileW = 44;                              // staged columns per chunk: 8 of history + 32 + 4 ahead
+constexpr int kRtTileBytes = kIirRows * kRtTileW * 4;     // 5632 bytes per plane and chunk
+
+struct IirRowsTmaMaps {   // one descriptor per scale; see iir_rows_tma_maps() for the shapes
+    CUtensorMap in_src[kMaxScales], in_dist[kMaxScales];
+    CUtensorMap out_psrc[kMaxScales], out_pcand[kMaxScales], out_ab[kMaxScales];
+};
+
+// STAGES: tile ring depth (STAGES - 1 chunks of look-ahead).  NBUF: staging buffers per recursion warp (the
+// buffer of chunk t is reused once the store of chunk t - NBUF has read it).
+// MODE 1: the candidate's half — (b, b*b) and a*b.  MODE 3: the source's half alone — (a, a*a), run once per source
+// at set_source time on the context's source stream.  MODE 2: both halves in one launch (A/B timing only).
+template <int MODE, int STAGES, int NBUF>
+struct IirRowsTmaSmem {
+    static constexpr int NPAIR = MODE == 2 ? 2 : 1;
+    static constexpr int NPLANES = MODE == 3 ? 1 : 2;
+    static constexpr int NSINGLE = MODE == 3 ? 1 : NBUF;
+    float pstage[NPAIR][NBUF][2][kIirRows][32];      // [pair][buffer][half of a 64-float pair row][row][32]: 4 KB blocks, 128B-swizzled
+    float sstage[NSINGLE][kIirRows][32];             // a*b: [buffer][row][32], 128B-swizzled
+    float tile[NPLANES][STAGES][kIirRows][kRtTileW]; // [plane: 0 = b, 1 = a; MODE 3: 0 = a][ring slot][row][column]
+    uint64_t full[STAGES], empty[STAGES];
+};
+
+typedef float RtTile[kIirRows][kRtTileW];
+typedef float RtBlock[kIirRows][32];
+
+template <int STAGES, int NBUF, bool NOCOMP>
+__device__ __forceinline__ void rows_tma_pair_warp(const RtTile *tile, RtBlock (*stage)[2], uint64_t *full, uint64_t *empty,
+                                                   const CUtensorMap *omap, const IirCoef &k, float one, float neg_one,
+                                                   int lane, int nch, int y0, int c, int cand)
+{
+    const IirCoef2 k2 = iir_coef2(k, one, neg_one);
+    IirState2 st;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = splat2(0.0f);
+    const int sw = lane & 7;
+    int slot = 0, buf = 0;
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int t = 0; t < nch; ++t) {
+        mbar_wait(&full[slot], phase);
+        // samples v[i] = plane value at column 32t - 8 + i, i = 0..43; q[i] its square
+        float v[kRtTileW], q[kRtTileW];
+        const float *row = &tile[slot][lane][0];
+#pragma unroll
+        for (int j4 = 0; j4 < kRtTileW / 4; ++j4) {
+            const float4 x = *reinterpret_cast<const float4 *>(row + 4 * j4);
+            v[4 * j4] = x.x; v[4 * j4 + 1] = x.y; v[4 * j4 + 2] = x.z; v[4 * j4 + 3] = x.w;
+            unpk2(mul2(pk2(x.x, x.y), pk2(x.x, x.y)), q[4 * j4], q[4 * j4 + 1]);
+            unpk2(mul2(pk2(x.z, x.w), pk2(x.z, x.w)), q[4 * j4 + 2], q[4 * j4 + 3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);     // the tile is in registers: the producer may refill the slot
+        if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+        if (t == 0) {   // n = -4 .. -1: right taps are columns 0..3, left taps are padding, nothing emitted
+#pragma unroll
+            for (int i = 0; i < 4; ++i) (void)iir_step2(k2, st, splat2(0.0f), pk2(v[8 + i], q[8 + i]));
+        }
+        if (t >= NBUF) {   // this staging buffer went out with chunk t - NBUF
+            if (lane == 0) tma_store_wait_read<NBUF - 1>();
+            __syncwarp();
+        }
+        // step j (output column 32t + j): left tap column 32t + j - 6 = [j+2], right tap 32t + j + 4 = [j+12]
+        RtBlock *blk = stage[buf];
+        IirPipe2 P;
+        pipe2_begin(k2, P, st, pk2(v[2] + v[12], q[2] + q[12]));
+#pragma unroll
+        for (int j2 = 0; j2 < kIirChunk / 2; ++j2) {
+            f32x2 o[2];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = 2 * j2 + jj;
+                if (NOCOMP)   // timing experiment only: the data movement without the recursion
+                    o[jj] = pk2(v[j + 8], q[j + 8]);
+                else
+                    o[jj] = (j + 1 < kIirChunk) ? pipe2_step(k2, P, pk2(v[j + 3] + v[j + 13], q[j + 3] + q[j + 13]))
+                                                : pipe2_end(k2, P, st);
+            }
+            float4 ov;
+            unpk2(o[0], ov.x, ov.y);
+            unpk2(o[1], ov.z, ov.w);
+            // 16-byte piece j2 of the 256-byte pair row: block j2 / 8, piece j2 % 8, swizzled with the row
+            *reinterpret_cast<float4 *>(&blk[j2 >> 3][lane][((j2 & 7) ^ sw) << 2]) = ov;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_4d(omap, 64 * t, y0, c, cand, &blk[0][0][0]);
+            tma_store_4d(omap, 64 * t + 32, y0, c, cand, &blk[1][0][0]);
+            tma_store_commit();
+        }
+        if (++buf == NBUF) buf = 0;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+}
+
+template <int STAGES, int NBUF, bool NOCOMP>
+__device__ __forceinline__ void rows_tma_ab_warp(const RtTile *tb, const RtTile *ta, RtBlock *stage, uint64_t *full,
+                                                 uint64_t *empty, const CUtensorMap *omap, const IirCoef &k, int lane,
+                                                 int nch, int y0, int c, int cand)
+{
+    IirState st;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
+    const int sw = lane & 7;
+    int slot = 0, buf = 0;
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int t = 0; t < nch; ++t) {
+        mbar_wait(&full[slot], phase);
+        float v[kRtTileW];   // a*b at column 32t - 8 + i
+        const float *rb = &tb[slot][lane][0], *ra = &ta[slot][lane][0];
+#pragma unroll
+        for (int j4 = 0; j4 < kRtTileW / 4; ++j4) {
+            const float4 x = *reinterpret_cast<const float4 *>(rb + 4 * j4);
+            const float4 y = *reinterpret_cast<const float4 *>(ra + 4 * j4);
+            unpk2(mul2(pk2(x.x, x.y), pk2(y.x, y.y)), v[4 * j4], v[4 * j4 + 1]);
+            unpk2(mul2(pk2(x.z, x.w), pk2(y.z, y.w)), v[4 * j4 + 2], v[4 * j4 + 3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+        if (t == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) (void)iir_step(k, st, 0.0f, v[8 + i]);
+        }
+        if (t >= NBUF) {
+            if (lane == 0) tma_store_wait_read<NBUF - 1>();
+            __syncwarp();
+        }
+        float sum[kIirChunk];
+#pragma unroll
+        for (int j = 0; j < kIirChunk; ++j) sum[j] = v[j + 2] + v[j + 12];   // scalar: both are products
+        float(*blk)[32] = stage[buf];
+        IirPipe P;
+        pipe_begin(k, P, st, sum[0]);
+#pragma unroll
+        for (int j4 = 0; j4 < kIirChunk / 4; ++j4) {
+            float o[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * j4 + jj;
+                o[jj] = NOCOMP ? v[j + 8] : ((j + 1 < kIirChunk) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st));
+            }
+            *reinterpret_cast<float4 *>(&blk[lane][(j4 ^ sw) << 2]) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_4d(omap, 32 * t, y0, c, cand, &blk[0][0]);
+            tma_store_commit();
+        }
+        if (++buf == NBUF) buf = 0;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+}
+
+template <int MODE, int STAGES, int NBUF, bool NOCOMP = false>
+__global__ void __launch_bounds__(MODE == 2 ? 128 : MODE == 3 ? 64 : 96)
+    k_iir_rows_tma(const __grid_constant__ IirArgs a, const __grid_constant__ IirRowsTmaMaps tm)
+{
+    // 128-byte-swizzled staging blocks need 1024-byte alignment.  The array is declared with it (no pointer
+    // arithmetic on the base: that would turn every shared-memory access into a generic one) and checked once.
+    extern __shared__ __align__(1024) unsigned char smem_swz[];
+    typedef IirRowsTmaSmem<MODE, STAGES, NBUF> Smem;
+    Smem &sm = *reinterpret_cast<Smem *>(smem_swz);
+    constexpr int NW = MODE == 2 ? 4 : MODE == 3 ? 2 : 3;
+
+    int s, c, rb;
+    decode_cta(a, blockIdx.x, s, c, rb);
+    const int cand = blockIdx.y;
+    const int w = a.g.w[s];
+    const int y0 = rb * kIirRows;
+    const int lane = threadIdx.x & 31;
+    // roles rotate with the CTA index so that co-resident CTAs do not stack their recursion warps on one
+    // sub-partition (hardware warp w runs on sub-partition w % 4)
+    const int role = (int)(((threadIdx.x >> 5) + blockIdx.x) % NW);
+    const int nch = (w + kIirChunk - 1) / kIirChunk;
+    const bool with_src = MODE == 2 && cand == 0;
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem_swz) & 1023u) __trap();
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], MODE == 3 ? 1 : (with_src ? 3 : 2));   // one arrival per recursion warp that reads the slot
+        }
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    if (MODE == 3) {
+        if (role == 0) {          // (a, a*a)
+            rows_tma_pair_warp<STAGES, NBUF, NOCOMP>(sm.tile[0], sm.pstage[0], sm.full, sm.empty, &tm.out_psrc[s], a.k, a.one,
+                                                     a.neg_one, lane, nch, y0, c, 0);
+        } else if (lane == 0) {   // producer
+            tma_prefetch_desc(&tm.in_src[s]);
+            int slot = 0;
+            uint32_t phase = 1;
+#pragma unroll 1
+            for (int t = 0; t < nch; ++t) {
+                mbar_wait(&sm.empty[slot], phase);
+                mbar_arrive_expect_tx(&sm.full[slot], kRtTileBytes);
+                tma_load_4d(&sm.tile[0][slot][0][0], &tm.in_src[s], kIirChunk * t - 8, y0, c, 0, &sm.full[slot]);
+                if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+            }
+        }
+        return;
+    }
+    constexpr int PA = Smem::NPLANES - 1;   // plane a's tiles
+    switch (role) {
+    case 0:   // (b, b*b)
+        rows_tma_pair_warp<STAGES, NBUF, NOCOMP>(sm.tile[0], sm.pstage[0], sm.full, sm.empty, &tm.out_pcand[s], a.k, a.one, a.neg_one,
+                                         lane, nch, y0, c, cand);
+        break;
+    case 1:   // a*b
+        rows_tma_ab_warp<STAGES, NBUF, NOCOMP>(sm.tile[0], sm.tile[PA], sm.sstage, sm.full, sm.empty, &tm.out_ab[s], a.k, lane, nch, y0,
+                                       c, cand);
+        break;
+    case 2:   // producer: one lane feeds the ring
+        if (lane == 0) {
+            tma_prefetch_desc(&tm.in_dist[s]);
+            tma_prefetch_desc(&tm.in_src[s]);
+            int slot = 0;
+            uint32_t phase = 1;   // waiting on the phase BEFORE the first passes at once: the ring starts empty
+#pragma unroll 1
+            for (int t = 0; t < nch; ++t) {
+                mbar_wait(&sm.empty[slot], phase);
+                mbar_arrive_expect_tx(&sm.full[slot], 2 * kRtTileBytes);
+                tma_load_4d(&sm.tile[0][slot][0][0], &tm.in_dist[s], kIirChunk * t - 8, y0, c, cand, &sm.full[slot]);
+                tma_load_4d(&sm.tile[PA][slot][0][0], &tm.in_src[s], kIirChunk * t - 8, y0, c, 0, &sm.full[slot]);
+                if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+            }
+        }
+        break;
+    default:  // MODE 2: (a, a*a) of the source, by candidate 0's CTAs
+        if (with_src)
+            rows_tma_pair_warp<STAGES, NBUF, NOCOMP>(sm.tile[PA], sm.pstage[Smem::NPAIR - 1], sm.full, sm.empty, &tm.out_psrc[s], a.k,
+                                             a.one, a.neg_one, lane, nch, y0, c, 0);
+        break;
+    }
+}
+
+// the shipped instance, and what oavif_ssimu2_debug_time_rows can time against it (variant bits 4..6)
+constexpr int kRtStages = 4, kRtBufs = 3;
+
+template <int MODE, int STAGES, int NBUF, bool NOCOMP = false>
+inline cudaError_t iir_rows_tma_launch(const IirArgs &ar, const IirRowsTmaMaps &maps, int nr, int n, cudaStream_t st)
+{
+    typedef IirRowsTmaSmem<MODE, STAGES, NBUF> Smem;
+    static bool configured = false;   // per instance; every context of the process uses the same attribute
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(k_iir_rows_tma<MODE, STAGES, NBUF, NOCOMP>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_iir_rows_tma<MODE, STAGES, NBUF, NOCOMP><<<dim3(nr, n), MODE == 2 ? 128 : MODE == 3 ? 64 : 96, sizeof(Smem), st>>>(ar, maps);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+inline cudaError_t iir_rows_tma_dispatch(int shape, const IirArgs &ar, const IirRowsTmaMaps &maps, int nr, int n, cudaStream_t st)
+{
+    switch (shape) {
+    case 1: return iir_rows_tma_launch<MODE, 4, 2>(ar, maps, nr, n, st);
+    case 2: return iir_rows_tma_launch<MODE, 6, 3>(ar, maps, nr, n, st);
+    case 4: return iir_rows_tma_launch<MODE, 4, 3, true>(ar, maps, nr, n, st);   // data movement only (timing experiment)
+    default: return iir_rows_tma_launch<MODE, kRtStages, kRtBufs>(ar, maps, nr, n, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // columns pass + maps + pooling.  grid = (sum over scales of 3 * ceil(w/32), n_candidates), block = 256.
 //
 // One CTA owns 32 columns of one channel; lane = column in the arithmetic, so the recursions of a warp
@@ -850,8 +1139,42 @@ inline long long iir_hplane_floats(long long pyr_floats) { return 3 * pyr_floats
 
 typedef IirColsSmem<64, 16> IirColsDeep;
 
+// Descriptors of the rows pass for one geometry.  Loads: XYB planes as {w, h, 3 channels, images}, box 44 x 32
+// (out-of-bounds -> zeros).  Stores: the interleaved pair planes as {2w, h, 3, images} and the a*b planes as
+// {w, h, 3, images}, box 32 floats x 32 rows, 128-byte swizzle (out-of-bounds -> clipped).
+// The source's descriptors (one set per source buffer set) and the candidates' are built separately.
+inline bool iir_rows_tma_maps_src(CUtensorMap in_src[kMaxScales], CUtensorMap out_psrc[kMaxScales], const Geom &g,
+                                  const float *src, float *hpair_src)
+{
+    bool ok = true;
+    for (int s = 0; s < g.n_scales && ok; ++s) {
+        const uint64_t w = (uint64_t)g.w[s], h = (uint64_t)g.h[s], rowb = (uint64_t)g.pitch[s] * 4, planeb = (uint64_t)g.plane[s] * 4;
+        ok = ok && tma_make_4d(&in_src[s], src + g.off[s], w, h, 3, 1, rowb, planeb, 0, kRtTileW, kIirRows, false);
+        ok = ok && tma_make_4d(&out_psrc[s], hpair_src + 2 * g.off[s], 2 * w, h, 3, 1, 2 * rowb, 2 * planeb, 0, 32,
+                               kIirRows, true);
+    }
+    return ok;
+}
+
+inline bool iir_rows_tma_maps_cand(IirRowsTmaMaps *m, const Geom &g, const float *dist, long long pyr_stride,
+                                   float *hpair_cand, float *hab, long long hcand_stride, int n_images)
+{
+    bool ok = true;
+    for (int s = 0; s < g.n_scales && ok; ++s) {
+        const uint64_t w = (uint64_t)g.w[s], h = (uint64_t)g.h[s], rowb = (uint64_t)g.pitch[s] * 4, planeb = (uint64_t)g.plane[s] * 4;
+        ok = ok && tma_make_4d(&m->in_dist[s], dist + g.off[s], w, h, 3, (uint64_t)n_images, rowb, planeb,
+                               (uint64_t)pyr_stride * 4, kRtTileW, kIirRows, false);
+        ok = ok && tma_make_4d(&m->out_pcand[s], hpair_cand + 2 * g.off[s], 2 * w, h, 3, (uint64_t)n_images, 2 * rowb,
+                               2 * planeb, (uint64_t)hcand_stride * 4, 32, kIirRows, true);
+        ok = ok && tma_make_4d(&m->out_ab[s], hab + g.off[s], w, h, 3, (uint64_t)n_images, rowb, planeb,
+                               (uint64_t)hcand_stride * 4, 32, kIirRows, true);
+    }
+    return ok;
+}
+
 inline cudaError_t iir_configure()
 {
+
     cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(IirColsDeep));
     if (e != cudaSuccess) return e;
@@ -904,33 +1227,35 @@ struct IirDebugTap {
     int scale, channel, cand;
 };
 
-// Rows pass of b, b*b and a*b (and, when the source's cache is cold, of a and a*a), then the columns pass
-// with the maps and the pooling.  `between` is recorded between the two passes.  phases: bit 0 = rows pass,
-// bit 1 = columns pass.
-inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float *src, const float *dist,
-                                   long long pyr_stride, const IirBuffers &B, double *partials,
-                                   long long partials_stride, const int *first_cta_cols, const int *col_blocks, int n,
-                                   cudaStream_t st, bool with_source_rows, cudaEvent_t between, int *launches,
-                                   int phases = 3, const IirDebugTap *tap = nullptr)
+// Rows pass.  which: 1 = the candidates' half (b, b*b, a*b), 3 = the source's half (a, a*a) alone, 2 = both in
+// one launch.  maps != nullptr selects the TMA kernels (rows_shape: the instance, 0 = the shipped one), else the
+// cp.async ones (which have no source-only form: 3 is not accepted there).
+inline cudaError_t launch_iir_rows(const IirArgs &base, const Geom &g, int which, int n, cudaStream_t st,
+                                   const IirRowsTmaMaps *maps, int rows_shape = 0)
 {
-    IirArgs a{};
-    iir_fill_common(a, g, k, src, dist, pyr_stride, B);
-    a.partials = partials;
-    a.partials_stride = partials_stride;
-    *launches = 0;
-    if (phases & 1) {
-        IirArgs ar = a;
-        const int nr = iir_rows_grid(ar, g);
-        if (with_source_rows)
-            k_iir_rows<2><<<dim3(nr, n), 192, sizeof(IirRowsSmem<2>), st>>>(ar);
-        else
-            k_iir_rows<1><<<dim3(nr, n), 128, sizeof(IirRowsSmem<1>), st>>>(ar);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        *launches += 1;
+    IirArgs ar = base;
+    const int nr = iir_rows_grid(ar, g);
+    if (maps) {
+        switch (which) {
+        case 1: return iir_rows_tma_dispatch<1>(rows_shape, ar, *maps, nr, n, st);
+        case 2: return iir_rows_tma_dispatch<2>(rows_shape, ar, *maps, nr, n, st);
+        default: return iir_rows_tma_dispatch<3>(rows_shape, ar, *maps, nr, 1, st);
+        }
     }
-    if (between) cudaEventRecord(between, st);
-    if (!(phases & 2)) return cudaSuccess;
+    if (which == 2)
+        k_iir_rows<2><<<dim3(nr, n), 192, sizeof(IirRowsSmem<2>), st>>>(ar);
+    else if (which == 1)
+        k_iir_rows<1><<<dim3(nr, n), 128, sizeof(IirRowsSmem<1>), st>>>(ar);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+// Columns pass with the maps and the pooling.
+inline cudaError_t launch_iir_cols(const IirArgs &base, const int *first_cta_cols, const int *col_blocks, int n,
+                                   cudaStream_t st, const IirDebugTap *tap = nullptr)
+{
+    IirArgs a = base;
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
     const int ctas = first_cta_cols[kMaxScales];
@@ -943,7 +1268,6 @@ inline cudaError_t launch_iir_blur(const Geom &g, const IirCoef &k, const float 
     } else {
         k_iir_cols<64, 16, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
     }
-    *launches += 1;
     return cudaGetLastError();
 }
 

@@ -24,7 +24,8 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "liboavif_ssimu2.so
 MAX_SCALES = 6
 BLUR_RECURSIVE, BLUR_FIR = 0, 1
 WEIGHTS_SIX_SLOTS, WEIGHTS_CONTIGUOUS = 0, 1
-OPT_BLUR, OPT_WEIGHTS = 1, 2
+TILES_TMA, TILES_CP_ASYNC = 0, 1
+OPT_BLUR, OPT_WEIGHTS, OPT_TILE_PATH = 1, 2, 3
 
 E_ARG, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 _ENAMES = {E_ARG: "InvalidArgument", E_CUDA: "CudaError", E_NOMEM: "OutOfMemory",
@@ -43,7 +44,8 @@ SYMBOLS = (
     "oavif_ssimu2_get_timing", "oavif_ssimu2_debug_get_xyb", "oavif_ssimu2_debug_get_rows", "oavif_ssimu2_debug_blur",
     "oavif_ssimu2_debug_time_rows", "oavif_ssimu2_debug_check_guards", "oavif_ssimu2_debug_get_cols",
     "oavif_ssimu2_set_default_device", "oavif_ssimu2_release_cached",
-    "oavif_ssimu2_submit_rgb8", "oavif_ssimu2_submit_yuv444", "oavif_ssimu2_wait", "oavif_ssimu2_in_flight",
+    "oavif_ssimu2_get_option", "oavif_ssimu2_submit_rgb8", "oavif_ssimu2_submit_yuv444",
+    "oavif_ssimu2_submit_rgb8_dev", "oavif_ssimu2_submit_yuv444_dev", "oavif_ssimu2_wait", "oavif_ssimu2_in_flight",
 )
 
 
@@ -81,6 +83,7 @@ def load() -> C.CDLL:
     L.oavif_ssimu2_ctx_destroy.argtypes = [vp]
     L.oavif_ssimu2_ctx_destroy.restype = None
     L.oavif_ssimu2_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.oavif_ssimu2_get_option.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     L.oavif_ssimu2_set_stream.argtypes = [vp, vp]
     L.oavif_ssimu2_last_error.argtypes = [vp]
     L.oavif_ssimu2_last_error.restype = C.c_char_p
@@ -102,6 +105,8 @@ def load() -> C.CDLL:
     L.oavif_ssimu2_submit_rgb8.argtypes = [vp, u32, C.POINTER(vp), szt]
     L.oavif_ssimu2_submit_yuv444.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), szt, szt, szt,
                                              C.c_int, C.c_int, C.c_int]
+    L.oavif_ssimu2_submit_rgb8_dev.argtypes = L.oavif_ssimu2_submit_rgb8.argtypes
+    L.oavif_ssimu2_submit_yuv444_dev.argtypes = L.oavif_ssimu2_submit_yuv444.argtypes
     L.oavif_ssimu2_wait.argtypes = [vp, dp]
     L.oavif_ssimu2_in_flight.argtypes = [vp]
     L.oavif_ssimu2_compute_rgb8.argtypes = [u8p, u8p, u32, u32, u32, dp]
@@ -184,6 +189,14 @@ class Scorer:
 
     def set_blur(self, mode: int):
         _check(self._L.oavif_ssimu2_set_option(self._ctx, OPT_BLUR, mode), self._ctx)
+
+    def set_tile_path(self, path: int):
+        _check(self._L.oavif_ssimu2_set_option(self._ctx, OPT_TILE_PATH, path), self._ctx)
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int()
+        _check(self._L.oavif_ssimu2_get_option(self._ctx, option, C.byref(v)), self._ctx)
+        return v.value
 
     def set_weights(self, layout: int):
         _check(self._L.oavif_ssimu2_set_option(self._ctx, OPT_WEIGHTS, layout), self._ctx)
@@ -306,6 +319,21 @@ class Scorer:
         _check(self._L.oavif_ssimu2_submit_yuv444(self._ctx, n, ys, us, vs, ps[0][0].strides[0], ps[0][1].strides[0],
                                                   ps[0][2].strides[0], depth, matrix, int(rgba_path)), self._ctx)
         self._pending = getattr(self, "_pending", []) + [(n, ps)]
+
+    def submit_dev(self, kind: str, ptrs: Sequence[Sequence[int]], strides: Sequence[int], depth: int = 8,
+                   matrix: int = 2, rgba_path: bool = False):
+        """Device-resident candidates, pipelined form (see score_batch_dev for the pointer layout)."""
+        n = len(ptrs)
+        if kind == "rgb8":
+            arr = (C.c_void_p * n)(*[p[0] for p in ptrs])
+            _check(self._L.oavif_ssimu2_submit_rgb8_dev(self._ctx, n, arr, strides[0]), self._ctx)
+        else:
+            ys = (C.c_void_p * n)(*[p[0] for p in ptrs])
+            us = (C.c_void_p * n)(*[p[1] for p in ptrs])
+            vs = (C.c_void_p * n)(*[p[2] for p in ptrs])
+            _check(self._L.oavif_ssimu2_submit_yuv444_dev(self._ctx, n, ys, us, vs, strides[0], strides[1], strides[2],
+                                                          depth, matrix, int(rgba_path)), self._ctx)
+        self._pending = getattr(self, "_pending", []) + [(n, None)]
 
     def wait(self) -> list[float]:
         pend = getattr(self, "_pending", [])

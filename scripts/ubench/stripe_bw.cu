@@ -62,6 +62,55 @@ __global__ void k_rows(const float4 *src, float4 *dst, int pitch16, int h, int p
     }
 }
 
+// the same walk, but tiles live in HBM as contiguous 4 KB blocks ([row block][column block][32 rows][128 B]):
+// BIN: the source plane is blocked too; the destination always is.  One instruction moves 512 contiguous bytes.
+template <int WOUT, int UNROLL, bool BIN>
+__global__ void k_rows_blocked(const float4 *src, float4 *dst, int pitch16, int h, int planes)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int blocks = h / 32, plane = warp / blocks, rb = warp % blocks;
+    if (plane >= planes) return;
+    const size_t pbytes16 = (size_t)pitch16 * h;
+    const int tiles_x = pitch16 / 8;
+    const float4 *p = src + plane * pbytes16 + (size_t)(rb * 32 + (lane >> 3)) * pitch16 + (lane & 7);
+    const float4 *pb = src + plane * pbytes16 + (size_t)rb * tiles_x * 256 + lane;
+    float4 *q = dst + (size_t)plane * WOUT * pbytes16 + (size_t)rb * tiles_x * 256 + lane;
+    for (int c = 0; c + UNROLL <= tiles_x; c += UNROLL) {
+        float4 v[UNROLL][8];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                v[u][i] = BIN ? __ldcs(pb + (size_t)(c + u) * 256 + 32 * i) : __ldcs(p + 8 * (c + u) + (size_t)(4 * i) * pitch16);
+#pragma unroll
+        for (int o = 0; o < WOUT; ++o)
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) __stcs(q + o * pbytes16 + (size_t)(c + u) * 256 + 32 * i, v[u][i]);
+    }
+}
+
+template <int WOUT, int UNROLL, bool BIN>
+void run_rows_blocked(const float4 *src, float4 *dst, int w, int h, int planes)
+{
+    const int pitch16 = w / 4, warps = planes * (h / 32), threads = 128;
+    const int blocks = (warps * 32 + threads - 1) / threads;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_rows_blocked<WOUT, UNROLL, BIN><<<blocks, threads>>>(src, dst, pitch16, h, planes);
+    cudaEventRecord(e0);
+    for (int i = 0; i < 5; ++i) k_rows_blocked<WOUT, UNROLL, BIN><<<blocks, threads>>>(src, dst, pitch16, h, planes);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double bytes = 5.0 * planes * (1 + WOUT) * (double)w * h * 4;
+    printf("rows pattern, 4 KB-blocked %s: read 1 plane, write %d, unroll %d, warps %5d : %7.1f GB/s (read + write)\n",
+           BIN ? "in+out" : "out   ", WOUT, UNROLL, warps, bytes / ms / 1e6);
+}
+
 template <int WOUT, int UNROLL>
 void run_rows(const float4 *src, float4 *dst, int w, int h, int planes)
 {
@@ -145,6 +194,11 @@ int main()
         run_rows<1, 4>(d, dst, w, 2144, rp);
         run_rows<2, 4>(d, dst, w, 2144, rp);
         run_rows<3, 3>(d, dst, w, 2144, rp);
+        run_rows_blocked<2, 4, false>(d, dst, w, 2144, rp);
+        run_rows_blocked<2, 4, true>(d, dst, w, 2144, rp);
+        run_rows_blocked<3, 3, false>(d, dst, w, 2144, rp);
+        run_rows_blocked<3, 3, true>(d, dst, w, 2144, rp);
+        run_rows_blocked<1, 4, true>(d, dst, w, 2144, rp);
         cudaFree(dst);
     }
     cudaError_t e = cudaDeviceSynchronize();

@@ -86,10 +86,20 @@ def test_xyb_pyramid_bit_identical(scorer, oracle, size):
 
 
 # ---- K4, product kernel: the rows pass the scored path leaves behind ----------------------------------
+@pytest.fixture(params=[ssimu2.TILES_TMA, ssimu2.TILES_CP_ASYNC], ids=["tma", "cp_async"])
+def tile_path(request, scorer):
+    """Both tile-movement forms of the RECURSIVE kernels (include/oavif_ssimu2.h, OAVIF_SSIMU2_OPT_TILE_PATH)."""
+    scorer.set_tile_path(request.param)
+    yield request.param
+    assert scorer.get_option(ssimu2.OPT_TILE_PATH) == request.param   # no silent switch to the other form
+    scorer.set_tile_path(ssimu2.TILES_TMA)
+
+
 @pytest.mark.parametrize("size", [(64, 64), (65, 63), (100, 75), (333, 257), (1027, 771)])
-def test_rows_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size):
-    """k_iir_rows (packed-pair recursion, interleaved pair planes) against the oracle's horizontal pass, bit for
-    bit, for all five quantities, both call forms (first call after set_source / cached source) and a batch."""
+def test_rows_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size, tile_path):
+    """k_iir_rows_tma / k_iir_rows (packed-pair recursion, interleaved pair planes) against the oracle's horizontal
+    pass, bit for bit, for all five quantities, both call forms (first call after set_source / cached source) and
+    a batch."""
     w, h = size
     src = synth.synth(w, h, "mixture", w + 1)
     d0, d1 = synth.distort(src, 0.3, seed=h), synth.distort(src, 0.8, seed=h + 1)
@@ -120,7 +130,7 @@ def test_rows_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size):
 
 # ---- K4+K5, product kernel: what the columns pass hands to the error maps ----------------------------------
 @pytest.mark.parametrize("size", [(64, 64), (65, 63), (100, 75), (333, 257), (700, 300)])
-def test_cols_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size):
+def test_cols_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size, tile_path):
     """k_iir_cols (the kernel on the scored path, not the plain debug filter): the five fully blurred values it
     feeds the SSIM / edge-diff maps — mu1, mu2, sigma11, sigma22, sigma12 — against the oracle's two-pass blur,
     bit for bit, every scale and channel, single call and second candidate of a batch."""
@@ -347,6 +357,27 @@ def test_source_rows_cache_follows_the_source_and_the_blur_mode(scorer, oracle):
     assert abs(s_a - oracle.ssimu2_rgb8(a, da)) <= SCORE_TOL and abs(s_b - oracle.ssimu2_rgb8(b, db)) <= SCORE_TOL
 
 
+def test_tile_paths_give_the_same_bits(scorer):
+    """TMA and cp.async forms of the recursive kernels: identical pooled sums and scores, single and batch."""
+    src = synth.synth(1000, 700, "mixture", 14)
+    cands = [synth.distort(src, s, seed=i) for i, s in enumerate((0.2, 0.5, 0.9))]
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    res = {}
+    for path in (ssimu2.TILES_TMA, ssimu2.TILES_CP_ASYNC):
+        scorer.set_tile_path(path)
+        scorer.set_source(src)
+        single = [scorer.score_rgb8(c) for c in cands]
+        scorer.set_source(src)
+        batch = scorer.score_batch_rgb8(cands)
+        res[path] = (single, batch, [scorer.sums(i).copy() for i in range(3)])
+        assert scorer.get_option(ssimu2.OPT_TILE_PATH) == path
+    scorer.set_tile_path(ssimu2.TILES_TMA)
+    a, b = res[ssimu2.TILES_TMA], res[ssimu2.TILES_CP_ASYNC]
+    assert a[0] == b[0] == a[1] == b[1]
+    for x, y in zip(a[2], b[2]):
+        np.testing.assert_array_equal(x, y)
+
+
 def test_modes_differ_only_by_recursion_roundoff(scorer):
     src = synth.synth(640, 360, "mixture", 4)
     dist = synth.distort(src, 0.6)
@@ -431,8 +462,10 @@ def test_no_kernel_writes_past_its_buffers(size):
     src = synth.synth(w, h, "noise", w + h)
     d1, d2 = synth.distort(src, 0.2), synth.distort(src, 0.7)
     with ssimu2.Scorer(w, h, 2) as sc:
-        for mode in (ssimu2.BLUR_RECURSIVE, ssimu2.BLUR_FIR):
+        for mode, path in ((ssimu2.BLUR_RECURSIVE, ssimu2.TILES_TMA), (ssimu2.BLUR_RECURSIVE, ssimu2.TILES_CP_ASYNC),
+                           (ssimu2.BLUR_FIR, ssimu2.TILES_TMA)):
             sc.set_blur(mode)
+            sc.set_tile_path(path)
             sc.set_source(src)
             sc.score_batch_rgb8([d1, d2])
             for depth in (8, 10):
