@@ -49,6 +49,12 @@ typedef int (*oavif_host_score_fn)(void *user, const void *y, const void *u, con
                                    uint32_t u_stride, uint32_t v_stride, uint32_t w, uint32_t h, int depth,
                                    int matrix, int rgba_path, double *score);
 
+/* Stateless form for the corpus driver's CPU-scored arm (many workers call it concurrently): source RGB8 and one
+ * decoded candidate in, one score out. */
+typedef int (*oavif_host_score_pair_fn)(void *user, const uint8_t *src_rgb, const void *y, const void *u, const void *v,
+                                        uint32_t y_stride, uint32_t u_stride, uint32_t v_stride, uint32_t w, uint32_t h,
+                                        int depth, int matrix, int rgba_path, double *score);
+
 void oavif_host_default_opts(oavif_host_opts *o);
 const char *oavif_host_last_error(void);
 
@@ -69,12 +75,28 @@ int oavif_host_search_image(const char *libavif_path, const uint8_t *pixels, uin
                             int blur_mode, oavif_host_set_source_fn set_source, oavif_host_score_fn score,
                             void *user, oavif_host_result *out, uint8_t *avif_out, size_t avif_cap);
 
-/* scripts/measure.py over a procedural corpus (seed = index, kind = seed mod 4) sharded over GPUs
- * first_gpu .. first_gpu+n_gpus-1; writes the CSV and returns the summary text. */
+/* tq.hpp decisionMargins: for each pass of a finished search, the smallest increase / decrease of that pass's score
+ * that would have changed what the search did (next quantizer, stop, final choice); `limit` = none within it. */
+int oavif_host_tq_margins(double score_tgt, double tolerance, uint32_t max_pass, const uint32_t *qs, const double *scores,
+                          uint32_t n, double limit, double *flip_up, double *flip_down);
+
+typedef struct {
+    double wall_s, scorer_device_ms;
+    uint32_t n_ok, n_err, workers, host_cpus;
+    double mean_encode_ms, mean_decode_ms, mean_score_ms, mean_passes;
+    uint64_t final_bytes_total;
+    uint32_t margin_hist[7];        /* <=1e-4, <=1e-3, <=0.01, <=0.05, <=0.1, <=0.5, >0.5 */
+} oavif_host_corpus_stats;
+
+/* scripts/measure.py over a procedural corpus (seed = index, kind = seed mod 4).  n_gpus x workers_per_gpu host
+ * threads pull images from one shared counter; GPU arm: CUDA scorer on devices first_gpu.. (pinned_staging: decode
+ * hand-off through pinned memory); CPU arm: pass score_pair (then no GPU is touched).  Writes the measure.py CSV
+ * (csv_path) and the per-image trace (csv_path + ".trace.csv"), returns the summary text. */
 int oavif_host_corpus_synth(const char *libavif_path, uint32_t count, uint32_t w, uint32_t h, int first_gpu,
                             int n_gpus, uint32_t workers_per_gpu, uint32_t batch_width, int blur_mode,
+                            int pinned_staging, oavif_host_score_pair_fn score_pair, void *user,
                             const oavif_host_opts *opts, const char *csv_path, char *summary, size_t summary_cap,
-                            double *wall_s, uint32_t *n_ok);
+                            oavif_host_corpus_stats *stats);
 
 /* Encode / decode helpers for fixtures: io.zig:544-636 and io.zig:638-666. */
 int oavif_host_encode(const char *libavif_path, const uint8_t *pixels, uint32_t w, uint32_t h, uint32_t channels,

@@ -114,7 +114,12 @@ int oavif_ssimu2_set_stream(oavif_ssimu2_ctx *ctx, void *cuda_stream);
 
 const char *oavif_ssimu2_last_error(const oavif_ssimu2_ctx *ctx); /* ctx may be NULL */
 
-/* Pinned host staging for src/io.zig's decode buffers (cudaHostAlloc / cudaFreeHost). */
+/* "0000:c0:00.0" of a CUDA device, lower case as sysfs spells it: /sys/bus/pci/devices/<id>/local_cpulist and
+ * numa_node tell a caller where to run (and first-touch its staging) to be next to that GPU's PCIe root. */
+int oavif_ssimu2_device_pci_bus_id(int device, char *out, size_t cap);
+
+/* Pinned host staging for src/io.zig's decode buffers (cudaHostAlloc / cudaFreeHost).  The pages are pinned
+ * where the CALLING thread runs: bind the thread next to the GPU first (see above). */
 void *oavif_ssimu2_pinned_alloc(size_t bytes);
 void oavif_ssimu2_pinned_free(void *p);
 

@@ -738,6 +738,15 @@ const char *oavif_ssimu2_last_error(const oavif_ssimu2_ctx *ctx)
     return ctx ? ctx->err.c_str() : t_last_error.c_str();
 }
 
+int oavif_ssimu2_device_pci_bus_id(int device, char *out, size_t cap)
+{
+    if (!out || cap < 16) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "buffer too small");
+    if (cudaDeviceGetPCIBusId(out, (int)cap, device) != cudaSuccess) return fail(nullptr, OAVIF_SSIMU2_E_CUDA, "no such device %d", device);
+    for (char *p = out; *p; ++p)
+        if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');   // sysfs spells the address in lower case
+    return 0;
+}
+
 void *oavif_ssimu2_pinned_alloc(size_t bytes)
 {
     void *p = nullptr;

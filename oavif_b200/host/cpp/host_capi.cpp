@@ -75,6 +75,31 @@ struct CallbackScorer : ScorerIface {
         return out;
     }
 };
+// the corpus driver's CPU arm: keeps the source pointer (alive for the whole search) and calls a stateless scorer
+struct PairCallbackScorer : ScorerIface {
+    oavif_host_score_pair_fn fn;
+    void *user;
+    const uint8_t *src = nullptr;
+    uint32_t w = 0, h = 0;
+    PairCallbackScorer(oavif_host_score_pair_fn f, void *u) : fn(f), user(u) {}
+    void set_source(const uint8_t *rgb, uint32_t w_, uint32_t h_) override
+    {
+        src = rgb;
+        w = w_;
+        h = h_;
+    }
+    std::vector<double> score(const std::vector<const Decoded *> &c) override
+    {
+        std::vector<double> out(c.size());
+        for (size_t i = 0; i < c.size(); ++i) {
+            const AvifImageView &im = c[i]->img;
+            if (fn(user, src, im.plane(0), im.plane(1), im.plane(2), im.rowBytes(0), im.rowBytes(1), im.rowBytes(2), w, h,
+                   (int)im.depth(), (int)im.matrixCoefficients(), im.alphaPlane() != nullptr, &out[i]) != 0)
+                throw std::runtime_error("injected score failed");
+        }
+        return out;
+    }
+};
 }  // namespace
 
 extern "C" {
@@ -193,10 +218,28 @@ int oavif_host_search_image(const char *libavif_path, const uint8_t *pixels, uin
     }
 }
 
+int oavif_host_tq_margins(double tgt, double tol, uint32_t max_pass, const uint32_t *qs, const double *scores, uint32_t n,
+                          double limit, double *flip_up, double *flip_down)
+{
+    TQOptions o;
+    o.score_tgt = tgt;
+    o.tolerance = tol;
+    o.max_pass = max_pass;
+    std::vector<PassResult> h;
+    for (uint32_t i = 0; i < n; ++i) h.push_back({qs[i], scores[i]});
+    const auto ms = decisionMargins(o, h, limit);
+    for (uint32_t i = 0; i < n; ++i) {
+        flip_up[i] = ms[i].flip_up;
+        flip_down[i] = ms[i].flip_down;
+    }
+    return 0;
+}
+
 int oavif_host_corpus_synth(const char *libavif_path, uint32_t count, uint32_t w, uint32_t h, int first_gpu,
                             int n_gpus, uint32_t workers_per_gpu, uint32_t batch_width, int blur_mode,
+                            int pinned_staging, oavif_host_score_pair_fn score_pair, void *user,
                             const oavif_host_opts *opts, const char *csv_path, char *summary, size_t summary_cap,
-                            double *wall_s, uint32_t *n_ok)
+                            oavif_host_corpus_stats *stats)
 {
     try {
         CorpusSpec spec;
@@ -208,24 +251,58 @@ int oavif_host_corpus_synth(const char *libavif_path, uint32_t count, uint32_t w
         spec.workers_per_gpu = workers_per_gpu;
         spec.batch_width = batch_width;
         spec.blur_mode = blur_mode;
-        double wall = 0;
-        const auto rows = run_corpus(libavif_path, spec, to_cpp(opts), &wall);
+        spec.pinned_staging = pinned_staging != 0;
+        if (score_pair)
+            spec.scorer_factory = [score_pair, user](int) {
+                return std::unique_ptr<ScorerIface>(new PairCallbackScorer(score_pair, user));
+            };
+        CorpusStats st;
+        const auto rows = run_corpus(libavif_path, spec, to_cpp(opts), &st);
         if (csv_path) {
-            const std::string csv = corpus_csv(rows);
-            FILE *f = fopen(csv_path, "wb");
-            if (!f) throw std::runtime_error(std::string("cannot write ") + csv_path);
-            fwrite(csv.data(), 1, csv.size(), f);
-            fclose(f);
+            const std::string files[2][2] = {{csv_path, corpus_csv(rows)},
+                                             {std::string(csv_path) + ".trace.csv", corpus_trace_csv(rows)}};
+            for (const auto &fc : files) {
+                FILE *f = fopen(fc[0].c_str(), "wb");
+                if (!f) throw std::runtime_error("cannot write " + fc[0]);
+                fwrite(fc[1].data(), 1, fc[1].size(), f);
+                fclose(f);
+            }
         }
         if (summary && summary_cap) {
-            const std::string s = corpus_summary(rows, wall);
+            const std::string s = corpus_summary(rows, st);
             strncpy(summary, s.c_str(), summary_cap - 1);
             summary[summary_cap - 1] = 0;
         }
-        if (wall_s) *wall_s = wall;
-        if (n_ok) {
-            *n_ok = 0;
-            for (const auto &r : rows) *n_ok += r.status == "ok";
+        if (stats) {
+            memset(stats, 0, sizeof *stats);
+            stats->wall_s = st.wall_s;
+            stats->scorer_device_ms = st.scorer_device_ms;
+            stats->workers = st.workers;
+            stats->host_cpus = st.host_cpus;
+            const double edges[] = {1e-4, 1e-3, 1e-2, 0.05, 0.1, 0.5, 1e30};
+            for (const auto &r : rows) {
+                if (r.status != "ok") {
+                    ++stats->n_err;
+                    continue;
+                }
+                ++stats->n_ok;
+                stats->mean_encode_ms += r.encode_ms;
+                stats->mean_decode_ms += r.decode_ms;
+                stats->mean_score_ms += r.score_ms;
+                stats->mean_passes += r.passes;
+                stats->final_bytes_total += r.final_bytes;
+                for (int b = 0; b < 7; ++b)
+                    if (r.margin <= edges[b]) {
+                        ++stats->margin_hist[b];
+                        break;
+                    }
+            }
+            if (stats->n_ok) {
+                stats->mean_encode_ms /= stats->n_ok;
+                stats->mean_decode_ms /= stats->n_ok;
+                stats->mean_score_ms /= stats->n_ok;
+                stats->mean_passes /= stats->n_ok;
+            }
         }
         for (const auto &r : rows)
             if (r.status != "ok") t_err = r.error;

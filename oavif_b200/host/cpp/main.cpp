@@ -59,7 +59,7 @@ int main(int argc, char **argv)
     fprintf(stderr, "\x1b[31moavif\x1b[0m | b200 host harness\n");
     EncOptions o;
     std::string in, out, corpus;
-    long v = 0, batch = 1, gpus = 1, workers = 1, device = 0, blur = 0;
+    long v = 0, batch = 1, gpus = 1, workers = 1, device = 0, blur = 0, pinned = 1;
     double d = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -90,6 +90,7 @@ int main(int argc, char **argv)
         else if (a == "--workers-per-gpu") { if (!int_arg(i, argc, argv, 1, 64, "--workers-per-gpu", workers)) return 2; }
         else if (a == "--device") { if (!int_arg(i, argc, argv, 0, 7, "--device", device)) return 2; }
         else if (a == "--blur") { if (!int_arg(i, argc, argv, 0, 1, "--blur", blur)) return 2; }
+        else if (a == "--pinned-staging") { if (!int_arg(i, argc, argv, 0, 1, "--pinned-staging", pinned)) return 2; }
         else if (a == "--corpus") { if (!arg_val(i, argc, argv, corpus, "--corpus")) return 2; }
         else if (in.empty()) in = a;
         else if (out.empty()) out = a;
@@ -105,17 +106,18 @@ int main(int argc, char **argv)
             spec.synth_count = n; spec.synth_w = w; spec.synth_h = h;
             spec.first_gpu = (int)device; spec.n_gpus = (int)gpus; spec.workers_per_gpu = (uint32_t)workers;
             spec.batch_width = (uint32_t)batch; spec.blur_mode = (int)blur;
-            double wall = 0;
-            const auto rows = run_corpus(lib, spec, o, &wall);
+            spec.pinned_staging = pinned != 0;
+            CorpusStats st;
+            const auto rows = run_corpus(lib, spec, o, &st);
             const std::string csv_path = in.empty() ? "corpus.csv" : in;
-            {
-                const std::string csv = corpus_csv(rows);
-                FILE *f = fopen(csv_path.c_str(), "wb");
-                if (!f) throw std::runtime_error("cannot write " + csv_path);
-                fwrite(csv.data(), 1, csv.size(), f);
+            const std::string files[2][2] = {{csv_path, corpus_csv(rows)}, {csv_path + ".trace.csv", corpus_trace_csv(rows)}};
+            for (const auto &fc : files) {
+                FILE *f = fopen(fc[0].c_str(), "wb");
+                if (!f) throw std::runtime_error("cannot write " + fc[0]);
+                fwrite(fc[1].data(), 1, fc[1].size(), f);
                 fclose(f);
             }
-            fprintf(stderr, "%s\nResults written to %s\n", corpus_summary(rows, wall).c_str(), csv_path.c_str());
+            fprintf(stderr, "%s\nResults written to %s\n", corpus_summary(rows, st).c_str(), csv_path.c_str());
             return 0;
         }
         if (in.empty() || out.empty()) { fprintf(stderr, "error: MissingInputOrOutput\n"); return 2; }
@@ -135,6 +137,9 @@ int main(int argc, char **argv)
             r = search_image(codec, scorer, img, o, (uint32_t)batch, (uint32_t)batch);
         }
         fputs(r.log.c_str(), stderr);
+        if (getenv("OAVIF_MARGINS"))   // trace tooling: how far each pass's score was from changing the search
+            for (const auto &m : r.margins)
+                fprintf(stderr, "pass %u: q%u score %.6f  flips at +%.6f / -%.6f\n", m.pass, m.q, m.score, m.flip_up, m.flip_down);
         {
             FILE *f = fopen(out.c_str(), "wb");
             if (!f) throw std::runtime_error("cannot write " + out);

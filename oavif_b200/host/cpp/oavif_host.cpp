@@ -12,6 +12,9 @@
 #include <stdexcept>
 #include <thread>
 #include <cstdarg>
+#include <cstring>
+#include <sched.h>
+#include <unistd.h>
 
 #include "../../../include/oavif_ssimu2.h"
 
@@ -286,15 +289,25 @@ std::vector<uint8_t> Codec::decode_to_rgb8(const std::vector<uint8_t> &avif) con
 // ------------------------------------------------------------------------------------------------
 // scorer
 
-GpuScorer::GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode)
-    : max_batch_(max_batch)
+GpuScorer::GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode, bool pinned_staging)
+    : max_batch_(max_batch), pinned_(pinned_staging)
 {
     if (oavif_ssimu2_ctx_create(device, max_w, max_h, max_batch, &ctx_) != 0)
         throw std::runtime_error(std::string("oavif_ssimu2_ctx_create: ") + oavif_ssimu2_last_error(nullptr));
     oavif_ssimu2_set_option(ctx_, OAVIF_SSIMU2_OPT_BLUR, blur_mode);
+    if (pinned_) {
+        plane_cap_ = ((size_t)max_w * max_h * 2 + 255) & ~(size_t)255;   // up to 10-bit samples
+        stage_bytes_ = plane_cap_ * 3 * max_batch;
+        stage_ = static_cast<uint8_t *>(oavif_ssimu2_pinned_alloc(stage_bytes_));
+        if (!stage_) pinned_ = false;   // pinning refused (ulimit): fall back to the pageable hand-off
+    }
 }
 
-GpuScorer::~GpuScorer() { oavif_ssimu2_ctx_destroy(ctx_); }
+GpuScorer::~GpuScorer()
+{
+    oavif_ssimu2_ctx_destroy(ctx_);
+    oavif_ssimu2_pinned_free(stage_);
+}
 
 void GpuScorer::set_source(const uint8_t *rgb, uint32_t w, uint32_t h)
 {
@@ -309,17 +322,39 @@ std::vector<double> GpuScorer::score(const std::vector<const Decoded *> &cands)
         const size_t n = std::min<size_t>(max_batch_, cands.size() - base);
         std::vector<const void *> y(n), u(n), v(n);
         const AvifImageView &i0 = cands[base]->img;
+        size_t strides[3] = {i0.rowBytes(0), i0.rowBytes(1), i0.rowBytes(2)};
         for (size_t i = 0; i < n; ++i) {
             const AvifImageView &im = cands[base + i]->img;
             if (im.depth() != i0.depth() || im.rowBytes(0) != i0.rowBytes(0) || im.rowBytes(1) != i0.rowBytes(1) ||
                 im.rowBytes(2) != i0.rowBytes(2))
                 throw std::runtime_error("batched candidates differ in layout");
+            // The C ABI converts full-range planes only and has no range argument: refuse anything else here
+            // rather than score it silently wrong (avifImageCreate's default is full range, io.zig:546).
+            if (im.yuvRange() != 1) throw std::runtime_error("decoded image is limited-range YUV: not on the scored path");
             y[i] = im.plane(0);
             u[i] = im.plane(1);
             v[i] = im.plane(2);
         }
-        const int rc = oavif_ssimu2_score_batch_yuv444(ctx_, (uint32_t)n, y.data(), u.data(), v.data(), i0.rowBytes(0),
-                                                       i0.rowBytes(1), i0.rowBytes(2), (int)i0.depth(),
+        if (pinned_) {   // decode hand-off through pinned staging: tight rows, one memcpy per plane row
+            const size_t rb = (size_t)i0.width() * (i0.depth() > 8 ? 2 : 1);
+            const uint32_t h = i0.height();
+            if (rb * h <= plane_cap_) {
+                for (size_t i = 0; i < n; ++i) {
+                    const void **pl[3] = {&y[i], &u[i], &v[i]};
+                    for (int p = 0; p < 3; ++p) {
+                        uint8_t *dst = stage_ + (i * 3 + p) * plane_cap_;
+                        const uint8_t *src = static_cast<const uint8_t *>(*pl[p]);
+                        if (strides[p] == rb) memcpy(dst, src, rb * h);
+                        else
+                            for (uint32_t r = 0; r < h; ++r) memcpy(dst + r * rb, src + r * strides[p], rb);
+                        *pl[p] = dst;
+                    }
+                }
+                strides[0] = strides[1] = strides[2] = rb;
+            }
+        }
+        const int rc = oavif_ssimu2_score_batch_yuv444(ctx_, (uint32_t)n, y.data(), u.data(), v.data(), strides[0],
+                                                       strides[1], strides[2], (int)i0.depth(),
                                                        (int)i0.matrixCoefficients(), i0.alphaPlane() != nullptr,
                                                        out.data() + base);
         if (rc != 0) throw std::runtime_error(std::string("score: ") + oavif_ssimu2_last_error(ctx_));
@@ -426,6 +461,7 @@ SearchResult search_image(const Codec &codec, ScorerIface &scorer, const HostIma
         // the reference's cache holds the last pass of the sequential procedure
         if (!R.tq.history.empty()) take_bytes(R.tq.history.back().q);
     }
+    R.margins = decisionMargins(topt, R.tq.history);
     R.log += fmt("Found q%u (score %.2f, %u passes)\n", R.tq.q, R.tq.score, R.tq.num_pass);
     if (buf_q == R.tq.q && !buf.empty()) {  // main.zig:109-112
         R.avif = buf;
@@ -450,8 +486,46 @@ SearchResult search_image(const Codec &codec, ScorerIface &scorer, const HostIma
 // ------------------------------------------------------------------------------------------------
 // corpus driver: scripts/measure.py
 
+namespace {
+// CPUs the kernel reports as local to a GPU's PCI function; empty when sysfs has nothing useful
+std::vector<int> gpu_local_cpus(int device)
+{
+    std::vector<int> cpus;
+    char id[64] = {0};
+    if (oavif_ssimu2_device_pci_bus_id(device, id, sizeof id) != 0) return cpus;
+    const std::string path = std::string("/sys/bus/pci/devices/") + id + "/local_cpulist";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) return cpus;
+    char buf[512] = {0};
+    const bool ok = fgets(buf, sizeof buf, f) != nullptr;
+    fclose(f);
+    if (!ok) return cpus;
+    for (char *tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k >= 1)
+            for (int c = a; c <= b; ++c) cpus.push_back(c);
+    }
+    return cpus;
+}
+
+// Bind the calling worker next to its GPU before it allocates pinned staging: the GPU's local CPUs when sysfs
+// names a proper subset of the machine, otherwise leave the scheduler alone (one visible NUMA node).
+void bind_worker_near_gpu(int device)
+{
+    const std::vector<int> cpus = gpu_local_cpus(device);
+    const long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    if (cpus.empty() || (long)cpus.size() >= ncpu) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int c : cpus) CPU_SET(c, &set);
+    sched_setaffinity(0, sizeof set, &set);
+}
+}  // namespace
+
 std::vector<CorpusRow> run_corpus(const std::string &libavif_path, const CorpusSpec &spec, const EncOptions &o,
-                                  double *wall_s)
+                                  CorpusStats *stats)
 {
     const size_t n = spec.files.empty() ? spec.synth_count : spec.files.size();
     std::vector<CorpusRow> rows(n);
@@ -461,17 +535,20 @@ std::vector<CorpusRow> run_corpus(const std::string &libavif_path, const CorpusS
     const uint32_t W = std::max(1u, spec.workers_per_gpu);
     const double t0 = now_ms();
     std::vector<std::thread> workers;
-    std::vector<std::string> fatal((size_t)G * W);
+    std::vector<double> device_ms((size_t)G * W, 0.0);
+    std::atomic<size_t> next{0};   // the shared work counter: whoever is free takes the next image
     for (int g = 0; g < G; ++g)
         for (uint32_t wk = 0; wk < W; ++wk)
             workers.emplace_back([&, g, wk] {
-                std::unique_ptr<GpuScorer> scorer;  // one context per worker, sized on first use
+                const int widx = g * (int)W + (int)wk;
+                const bool gpu_arm = !spec.scorer_factory;
+                if (gpu_arm) bind_worker_near_gpu(spec.first_gpu + g);
+                std::unique_ptr<ScorerIface> scorer;  // one context per worker, sized on first use
                 uint32_t cap_w = 0, cap_h = 0;
-                // image i belongs to GPU (i mod G); within a GPU, to worker ((i div G) mod W)
-                for (size_t i = (size_t)g + (size_t)G * wk; i < n; i += (size_t)G * W) {
+                for (size_t i; (i = next.fetch_add(1)) < n;) {
                     CorpusRow &r = rows[i];
-                    r.gpu = spec.first_gpu + g;
-                    const double ti = now_ms();
+                    r.gpu = gpu_arm ? spec.first_gpu + g : -1;
+                    r.worker = widx;
                     try {
                         HostImage img = spec.files.empty()
                                             ? synth_image(spec.synth_w, spec.synth_h, (uint32_t)(i & 3), i)
@@ -481,9 +558,13 @@ std::vector<CorpusRow> run_corpus(const std::string &libavif_path, const CorpusS
                         if (!scorer || img.w > cap_w || img.h > cap_h) {
                             cap_w = std::max(cap_w, img.w);
                             cap_h = std::max(cap_h, img.h);
+                            if (auto *gs = dynamic_cast<GpuScorer *>(scorer.get())) device_ms[widx] += gs->device_ms;
                             scorer.reset();
-                            scorer.reset(new GpuScorer(spec.first_gpu + g, cap_w, cap_h, std::max(1u, spec.batch_width),
-                                                       spec.blur_mode));
+                            if (gpu_arm)
+                                scorer.reset(new GpuScorer(spec.first_gpu + g, cap_w, cap_h, std::max(1u, spec.batch_width),
+                                                           spec.blur_mode, spec.pinned_staging));
+                            else
+                                scorer = spec.scorer_factory(widx);
                         }
                         const double te = now_ms();  // measure.py times the oavif process: load excluded is closest
                         SearchResult sr = search_image(codec, *scorer, img, o, spec.batch_width, spec.batch_width);
@@ -492,17 +573,28 @@ std::vector<CorpusRow> run_corpus(const std::string &libavif_path, const CorpusS
                         r.passes = sr.tq.num_pass;
                         r.q = sr.tq.q;
                         r.score = sr.tq.score;
-                        r.status = "ok";
+                        r.encode_ms = sr.encode_ms;
+                        r.decode_ms = sr.decode_ms;
+                        r.score_ms = sr.score_ms;
+                        r.margin = minMargin(sr.margins);
+                        for (const auto &h : sr.tq.history) r.trace += fmt("%s%u:%.6f", r.trace.empty() ? "" : " ", h.q, h.score);
+                        r.status = sr.avif.empty() ? "no-output" : "ok";   // measure.py:90
                     } catch (const std::exception &e) {  // one bad image must not kill the sweep
                         r.status = "error";
                         r.error = e.what();
                         if (r.image.empty()) r.image = spec.files.empty() ? fmt("synth_%05zu", i) : spec.files[i];
-                        (void)ti;
                     }
                 }
+                if (auto *gs = dynamic_cast<GpuScorer *>(scorer.get())) device_ms[widx] += gs->device_ms;
             });
     for (auto &t : workers) t.join();
-    if (wall_s) *wall_s = (now_ms() - t0) / 1e3;
+    if (stats) {
+        stats->wall_s = (now_ms() - t0) / 1e3;
+        stats->workers = (uint32_t)(G * W);
+        stats->host_cpus = std::thread::hardware_concurrency();
+        stats->scorer_device_ms = 0;
+        for (double d : device_ms) stats->scorer_device_ms += d;
+    }
     return rows;
 }
 
@@ -515,6 +607,8 @@ std::string corpus_csv(const std::vector<CorpusRow> &rows)
             const double pct = r.orig_bytes ? 100.0 * (double)sav / (double)r.orig_bytes : 0.0;
             s += r.image + fmt(",%zu,%zu,%zu,%.2f,%.2f,%u,ok,\r\n", r.orig_bytes, r.final_bytes, sav, pct,
                                r.encoding_time_ms, r.passes);
+        } else if (r.status == "no-output") {   // measure.py:70-91: time and passes known, no file
+            s += r.image + fmt(",%zu,,,,%.2f,%u,no-output,\r\n", r.orig_bytes, r.encoding_time_ms, r.passes);
         } else {
             std::string e = r.error;
             std::replace(e.begin(), e.end(), ',', ';');
@@ -524,11 +618,34 @@ std::string corpus_csv(const std::vector<CorpusRow> &rows)
     return s;
 }
 
-std::string corpus_summary(const std::vector<CorpusRow> &rows, double wall_s)
-{  // measure.py:208-269
-    std::vector<double> t;
-    std::vector<double> p;
-    size_t ok = 0, err = 0, orig = 0, fin = 0;
+std::string corpus_trace_csv(const std::vector<CorpusRow> &rows)
+{
+    std::string s = "Image,Q,Score,Passes,Final Bytes,Encode ms,Decode ms,Score ms,GPU,Worker,Margin,Trace\r\n";
+    for (const auto &r : rows)
+        s += r.image + fmt(",%u,%.6f,%u,%zu,%.2f,%.2f,%.3f,%d,%d,%.6f,", r.q, r.score, r.passes, r.final_bytes, r.encode_ms,
+                           r.decode_ms, r.score_ms, r.gpu, r.worker, r.margin) + r.trace + "\r\n";
+    return s;
+}
+
+namespace {
+std::string human_bytes(double n)
+{  // measure.py:31-38
+    const char *units[] = {"B", "KiB", "MiB", "GiB", "TiB"};
+    double size = n;
+    for (int i = 0; i < 5; ++i) {
+        if (size < 1024.0 || i == 4) return fmt("%.2f %s", size, units[i]);
+        size /= 1024.0;
+    }
+    return "";
+}
+}  // namespace
+
+std::string corpus_summary(const std::vector<CorpusRow> &rows, const CorpusStats &st)
+{  // measure.py:208-269, line for line (rich markup dropped), then the figures this driver adds
+    const double wall_s = st.wall_s;
+    std::vector<double> t, p, ratios;
+    size_t ok = 0, err = 0, no_out = 0, orig = 0, fin = 0;
+    double enc = 0, dec = 0, sc = 0;
     for (const auto &r : rows) {
         if (r.status == "ok") {
             ++ok;
@@ -536,6 +653,12 @@ std::string corpus_summary(const std::vector<CorpusRow> &rows, double wall_s)
             p.push_back(r.passes);
             orig += r.orig_bytes;
             fin += r.final_bytes;
+            if (r.orig_bytes > 0) ratios.push_back((double)r.final_bytes / (double)r.orig_bytes);
+            enc += r.encode_ms;
+            dec += r.decode_ms;
+            sc += r.score_ms;
+        } else if (r.status == "no-output") {
+            ++no_out;
         } else {
             ++err;
         }
@@ -557,19 +680,57 @@ std::string corpus_summary(const std::vector<CorpusRow> &rows, double wall_s)
         std::sort(v.begin(), v.end());
         return v.size() % 2 ? v[v.size() / 2] : 0.5 * (v[v.size() / 2 - 1] + v[v.size() / 2]);
     };
-    std::string s = "Run Summary\n";
-    s += fmt("Images: %zu ok, 0 no-output, %zu errors\n", ok, err);
+    const size_t savings = ok && orig > fin ? orig - fin : 0;
+    std::string s = "\nRun Summary\n";
+    s += fmt("Images: %zu ok, %zu no-output, %zu errors\n", ok, no_out, err);
     s += fmt("Total wall time: %.2f s\n", wall_s);
     s += fmt("Throughput: %.2f images/s\n", wall_s > 0 ? ok / wall_s : 0.0);
-    s += fmt("Input bytes throughput: %.2f MiB/s\n", wall_s > 0 ? orig / wall_s / 1048576.0 : 0.0);
-    s += fmt("Output bytes throughput: %.2f MiB/s\n", wall_s > 0 ? fin / wall_s / 1048576.0 : 0.0);
-    s += fmt("Original total bytes: %zu\nFinal total bytes:    %zu\n", orig, fin);
-    s += fmt("%% saved (overall):    %.2f%%\n", orig ? 100.0 * (double)(orig > fin ? orig - fin : 0) / orig : 0.0);
-    s += fmt("Average encoding time: %.2f ms ± %.2f\n", mean(t), stdev(t));
-    s += fmt("Median encoding time:  %.2f ms\n", median(t));
-    const double mx = p.empty() ? 0 : *std::max_element(p.begin(), p.end());
-    const double mn = p.empty() ? 0 : *std::min_element(p.begin(), p.end());
-    s += fmt("Average passes:        %.2f ± %.2f (max: %.0f, min: %.0f)\n", mean(p), stdev(p), mx, mn);
+    s += "Input bytes throughput: " + human_bytes(std::floor(wall_s > 0 ? orig / wall_s : 0.0)) + "/s\n";
+    s += "Output bytes throughput: " + human_bytes(std::floor(wall_s > 0 ? fin / wall_s : 0.0)) + "/s\n";
+    s += "\nCompression Totals\n";
+    s += fmt("Original total bytes: %zu (", orig) + human_bytes((double)orig) + ")\n";
+    s += fmt("Final total bytes:    %zu (", fin) + human_bytes((double)fin) + ")\n";
+    s += fmt("Savings (bytes):      %zu (", savings) + human_bytes((double)savings) + ")\n";
+    s += fmt("%% saved (overall):    %.2f%%\n", orig ? 100.0 * (double)savings / orig : 0.0);
+    bool geo_ok = !ratios.empty();
+    double logsum = 0;
+    for (double r : ratios) {
+        if (r <= 0) geo_ok = false;   // statistics.geometric_mean raises on non-positive data: the line is skipped
+        else logsum += std::log(r);
+    }
+    if (geo_ok) s += fmt("%% saved (geometric mean across files): %.2f%%\n", (1.0 - std::exp(logsum / ratios.size())) * 100.0);
+    if (!t.empty()) {
+        s += "\nTiming & Passes\n";
+        s += fmt("Average encoding time: %.2f ms ± %.2f\n", mean(t), stdev(t));
+        s += fmt("Median encoding time:  %.2f ms\n", median(t));
+        const double mx = p.empty() ? 0 : *std::max_element(p.begin(), p.end());
+        const double mn = p.empty() ? 0 : *std::min_element(p.begin(), p.end());
+        s += fmt("Average passes:        %.2f ± %.2f (max: %.0f, min: %.0f)\n", mean(p), stdev(p), mx, mn);
+    }
+    // ---- not in measure.py: where the time went, and how close any decision came to flipping ----
+    s += "\nDriver (oavif-b200)\n";
+    s += fmt("Workers: %u host threads on %u CPUs\n", st.workers, st.host_cpus);
+    if (ok) {
+        s += fmt("Per image, mean: encode %.1f ms, decode %.1f ms, score %.2f ms (host wall, incl. upload)\n", enc / ok, dec / ok,
+                 sc / ok);
+        s += fmt("Scoring share of the search: %.2f%%\n", 100.0 * sc / std::max(1e-9, enc + dec + sc));
+    }
+    if (st.scorer_device_ms > 0 && wall_s > 0)
+        s += fmt("Scorer device time: %.1f ms in total = %.3f%% of wall x workers' GPUs\n", st.scorer_device_ms,
+                 100.0 * st.scorer_device_ms / (wall_s * 1e3));
+    const double edges[] = {1e-4, 1e-3, 1e-2, 0.05, 0.1, 0.5, 1e30};
+    const char *names[] = {"<= 1e-4", "<= 1e-3", "<= 0.01", "<= 0.05", "<= 0.1", "<= 0.5", "> 0.5"};
+    size_t hist[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (const auto &r : rows)
+        if (r.status == "ok")
+            for (int b = 0; b < 7; ++b)
+                if (r.margin <= edges[b]) {
+                    ++hist[b];
+                    break;
+                }
+    s += "Decision margin per image (smallest score change that alters the search):";
+    for (int b = 0; b < 7; ++b) s += fmt(" [%s] %zu", names[b], hist[b]);
+    s += "\n";
     return s;
 }
 

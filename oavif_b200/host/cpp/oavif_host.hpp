@@ -87,7 +87,10 @@ struct ScorerIface {
 
 class GpuScorer : public ScorerIface {  // include/oavif_ssimu2.h
   public:
-    GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode);
+    // pinned_staging: copy the decoder's planes into a per-scorer pinned ring (oavif_ssimu2_pinned_alloc — the
+    // "pinned host staging in src/io.zig" of the north star) and upload from there by DMA; off: hand libavif's
+    // pageable planes to the library, which then stages them itself inside cudaMemcpy2DAsync.
+    GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode, bool pinned_staging = true);
     ~GpuScorer() override;
     void set_source(const uint8_t *rgb, uint32_t w, uint32_t h) override;
     std::vector<double> score(const std::vector<const Decoded *> &cands) override;
@@ -95,11 +98,15 @@ class GpuScorer : public ScorerIface {  // include/oavif_ssimu2.h
   private:
     oavif_ssimu2_ctx *ctx_ = nullptr;
     uint32_t max_batch_;
+    bool pinned_;
+    uint8_t *stage_ = nullptr;   // pinned: max_batch x 3 planes
+    size_t stage_bytes_ = 0, plane_cap_ = 0;
 };
 
 struct SearchResult {
     TQResult tq;
     BatchedStats batched;
+    std::vector<DecisionMargin> margins;   // tq.hpp: how far each pass's score was from changing the search
     std::vector<uint8_t> avif;   // the bytes oavif would write
     size_t size = 0;             // e.buf.size as printed by main.zig:116
     bool reencoded = false;      // main.zig:113 path (extra encode, not counted in num_pass)
@@ -113,13 +120,16 @@ struct SearchResult {
 SearchResult search_image(const Codec &codec, ScorerIface &scorer, const HostImage &img, const EncOptions &o,
                           uint32_t batch_width, uint32_t host_threads);
 
-struct CorpusRow {  // measure.py:178-206
+struct CorpusRow {  // measure.py:178-206, plus what the trace file carries
     std::string image, status, error;
     size_t orig_bytes = 0, final_bytes = 0;
     double encoding_time_ms = 0;
     uint32_t passes = 0, q = 0;
     double score = 0;
-    int gpu = -1;
+    int gpu = -1, worker = -1;
+    double encode_ms = 0, decode_ms = 0, score_ms = 0;   // per-stage host wall time of this image's search
+    double margin = 0;                                    // min over passes of min(flip_up, flip_down) (tq.hpp)
+    std::string trace;                                    // "q:score q:score ..." in probe order
 };
 
 struct CorpusSpec {
@@ -128,13 +138,26 @@ struct CorpusSpec {
     int first_gpu = 0, n_gpus = 1;
     uint32_t workers_per_gpu = 1, batch_width = 1;
     int blur_mode = 0;
+    bool pinned_staging = true;
+    // The CPU-scored arm: when set, every worker scores through this factory instead of the CUDA library (tests and
+    // bench tooling inject the CPU oracle here; the product never does).  n_gpus * workers_per_gpu workers still.
+    std::function<std::unique_ptr<ScorerIface>(int worker)> scorer_factory;
 };
 
-// scripts/measure.py as a library call: images sharded over GPUs by index (i mod G), one scorer
-// context per worker, no collective; rows come back in image order.
+struct CorpusStats {
+    double wall_s = 0;
+    double scorer_device_ms = 0;     // sum over workers of the device time of their score calls (GPU arm)
+    uint32_t workers = 0, host_cpus = 0;
+};
+
+// scripts/measure.py as a library call.  Workers (n_gpus x workers_per_gpu host threads, one scorer context
+// each, each bound to its GPU) pull image indices from ONE shared atomic counter — per-image time varies
+// 250-830 ms x 2-6 passes, so a static i mod (G*W) shard leaves GPUs idle at the end — and there is no
+// collective: rows come back in image order whatever worker produced them.
 std::vector<CorpusRow> run_corpus(const std::string &libavif_path, const CorpusSpec &spec, const EncOptions &o,
-                                  double *wall_s);
-std::string corpus_csv(const std::vector<CorpusRow> &rows);
-std::string corpus_summary(const std::vector<CorpusRow> &rows, double wall_s);
+                                  CorpusStats *stats);
+std::string corpus_csv(const std::vector<CorpusRow> &rows);            // the nine columns of measure.py:180-192
+std::string corpus_trace_csv(const std::vector<CorpusRow> &rows);      // per image: q, score, passes, stage times, margin, trace
+std::string corpus_summary(const std::vector<CorpusRow> &rows, const CorpusStats &stats);   // measure.py:250-269 + extras
 
 }  // namespace oavif_host

@@ -187,6 +187,7 @@ class TQSearch {
 
     uint32_t lo() const { return lo_; }
     uint32_t hi() const { return hi_; }
+    bool early_exit() const { return early_exit_; }
     const std::vector<PassResult> &history() const { return history_; }
 
   private:
@@ -204,6 +205,83 @@ inline TQResult findTargetQuality(const TQOptions &o, const std::function<double
     TQSearch s(o);
     while (auto q = s.next()) s.record(*q, probe(*q));
     return s.finish();
+}
+
+// ---- margin report ------------------------------------------------------------------------------------------
+// How far each score of a finished search was from changing what the search did next.  Every decision of
+// tq.zig:135-209 that reads a score is covered at once by replaying the procedure with that one score moved:
+//   * the pass's own outcome — sign of score - target (tq.zig:157, 172), ceil(|err|) * 4 (tq.zig:156), the
+//     tolerance exit (tq.zig:167), the collapse test (tq.zig:179) and, through the next predicted quantizer,
+//     every @round / clamp of interpolateQuantizer (tq.zig:109-121) and the already-probed break (tq.zig:141-148);
+//   * the post-loop choice `score >= target` / highest score (tq.zig:189-196).
+// flip_up / flip_down are the smallest increase / decrease of the pass's score (searched up to `limit`, resolved
+// by bisection to 1e-9) after which the search would have asked for a different next quantizer, stopped or
+// continued differently, or returned a different final q; `limit` itself means "no flip within the limit".
+// A scorer that agrees with the reference's to better than min(flip_up, flip_down) of every pass provably
+// reproduces the whole search: same probes, same q, same bytes.
+struct DecisionMargin {
+    uint32_t pass, q;
+    double score, flip_up, flip_down;
+};
+
+inline std::vector<DecisionMargin> decisionMargins(const TQOptions &o, const std::vector<PassResult> &history,
+                                                   double limit = 4.0)
+{
+    struct Key {
+        bool has_next, early;
+        uint32_t next_q, final_q;
+        bool operator==(const Key &k) const
+        {
+            return has_next == k.has_next && early == k.early && next_q == k.next_q && final_q == k.final_q;
+        }
+    };
+    // outcome of the search when pass i's score is moved by delta and nothing else changes
+    auto outcome = [&](size_t i, double delta) {
+        TQSearch s(o);
+        for (size_t j = 0; j <= i; ++j) s.record(history[j].q, history[j].score + (j == i ? delta : 0.0));
+        const auto nq = s.next();
+        Key k{nq.has_value(), s.early_exit(), nq ? *nq : 0u, 0u};
+        // the final choice with the REAL later passes appended (it only reads scores): stays comparable as long
+        // as the next quantizer is unchanged, and a changed one is a flip anyway
+        TQSearch f(o);
+        for (size_t j = 0; j < history.size(); ++j) {
+            f.record(history[j].q, history[j].score + (j == i ? delta : 0.0));
+            if (f.early_exit()) break;
+        }
+        k.final_q = f.finish().q;
+        return k;
+    };
+    std::vector<DecisionMargin> out;
+    for (size_t i = 0; i < history.size(); ++i) {
+        const Key ref = outcome(i, 0.0);
+        DecisionMargin m{(uint32_t)i, history[i].q, history[i].score, limit, limit};
+        for (int sign = -1; sign <= 1; sign += 2) {
+            double lo = 0.0, hi = -1.0;
+            for (double d = 1e-7; d <= limit * 1.0000001; d *= 1.25) {   // the outcome is piecewise constant, not monotone
+                if (!(outcome(i, sign * d) == ref)) {
+                    hi = d;
+                    break;
+                }
+                lo = d;
+            }
+            if (hi < 0.0) continue;
+            for (int it = 0; it < 60 && hi - lo > 1e-9; ++it) {
+                const double mid = 0.5 * (lo + hi);
+                if (outcome(i, sign * mid) == ref) lo = mid;
+                else hi = mid;
+            }
+            (sign > 0 ? m.flip_up : m.flip_down) = hi;
+        }
+        out.push_back(m);
+    }
+    return out;
+}
+
+inline double minMargin(const std::vector<DecisionMargin> &ms, double limit = 4.0)
+{
+    double m = limit;
+    for (const auto &d : ms) m = std::min(m, std::min(d.flip_up, d.flip_down));
+    return m;
 }
 
 // Batched mode (new, additive).  `probe_batch` scores several quantizers in one device pass.  The

@@ -43,6 +43,20 @@ SET_SOURCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_uint3
 SCORE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                        C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
 
+SCORE_PAIR_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                            C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                            C.POINTER(C.c_double))
+
+
+class CorpusStats(C.Structure):
+    _fields_ = [("wall_s", C.c_double), ("scorer_device_ms", C.c_double), ("n_ok", C.c_uint32), ("n_err", C.c_uint32),
+                ("workers", C.c_uint32), ("host_cpus", C.c_uint32), ("mean_encode_ms", C.c_double),
+                ("mean_decode_ms", C.c_double), ("mean_score_ms", C.c_double), ("mean_passes", C.c_double),
+                ("final_bytes_total", C.c_uint64), ("margin_hist", C.c_uint32 * 7)]
+
+
+MARGIN_BUCKETS = ("<=1e-4", "<=1e-3", "<=0.01", "<=0.05", "<=0.1", "<=0.5", ">0.5")
+
 _lib = None
 
 
@@ -65,8 +79,12 @@ def load() -> C.CDLL:
                                               C.POINTER(Opts), C.c_uint32, C.c_int, C.c_int, SET_SOURCE_FN, SCORE_FN,
                                               C.c_void_p, C.POINTER(Result), C.c_void_p, C.c_size_t]
         L.oavif_host_corpus_synth.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
-                                              C.c_uint32, C.c_uint32, C.c_int, C.POINTER(Opts), C.c_char_p, C.c_char_p,
-                                              C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
+                                              C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.POINTER(Opts), C.c_char_p, C.c_char_p, C.c_size_t,
+                                              C.POINTER(CorpusStats)]
+        L.oavif_host_tq_margins.argtypes = [C.c_double, C.c_double, C.c_uint32, C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_double), C.c_uint32, C.c_double, C.POINTER(C.c_double),
+                                            C.POINTER(C.c_double)]
         L.oavif_host_encode.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.POINTER(Opts), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.oavif_host_decode_rgb8.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
@@ -175,19 +193,57 @@ def search_image(pixels: np.ndarray, opts: Opts | None = None, batch_width: int 
     return r, (bytes(buf[: r.size]) if want_bytes else None)
 
 
+def tq_margins(history, tgt=80.0, tol=2.0, max_pass=6, limit=4.0):
+    """[(flip_up, flip_down)] per pass: the smallest change of that pass's score that alters the search (tq.hpp)."""
+    n = len(history)
+    qs = (C.c_uint32 * n)(*[h[0] for h in history])
+    sc = (C.c_double * n)(*[h[1] for h in history])
+    up, dn = (C.c_double * n)(), (C.c_double * n)()
+    assert load().oavif_host_tq_margins(tgt, tol, max_pass, qs, sc, n, limit, up, dn) == 0
+    return list(zip(up, dn))
+
+
 def corpus_synth(count: int, w: int, h: int, n_gpus: int = 1, first_gpu: int = 0, workers_per_gpu: int = 1,
                  batch_width: int = 1, blur_mode: int = 0, opts: Opts | None = None, csv_path: str | None = None,
-                 libavif: str | None = None):
+                 libavif: str | None = None, pinned_staging: bool = True, score_pair=None):
+    """The corpus sweep.  score_pair=None: the CUDA scorer.  Otherwise the CPU-scored arm: a callable
+    (src_rgb HxWx3, y, u, v, depth, matrix, rgba) -> score that worker threads call concurrently (test / bench
+    tooling passes the CPU oracle; ctypes releases the GIL inside its C calls)."""
     libavif = libavif or find_libavif()
     opts = opts or default_opts()
-    summary = C.create_string_buffer(4096)
-    wall, n_ok = C.c_double(), C.c_uint32()
+    summary = C.create_string_buffer(8192)
+    st = CorpusStats()
+    keep = {}
+    cb = None
+    if score_pair is not None:
+        def pair(_u, src, y, u, v, ys, us, vs, ww, hh, depth, matrix, rgba, out):
+            try:
+                dt, bps = (np.uint8, 1) if depth == 8 else (np.uint16, 2)
+
+                def plane(ptr, stride):
+                    raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(hh, stride))
+                    return raw[:, : ww * bps].view(dt).reshape(hh, ww) if stride == ww * bps else \
+                        raw[:, : ww * bps].copy().view(dt).reshape(hh, ww)
+
+                rgb = np.ctypeslib.as_array(src, shape=(hh, ww, 3))
+                out[0] = float(score_pair(rgb, plane(y, ys), plane(u, us), plane(v, vs), depth, matrix, bool(rgba)))
+                return 0
+            except Exception as e:  # pragma: no cover
+                keep["err"] = e
+                return -1
+
+        cb = SCORE_PAIR_FN(pair)
     rc = load().oavif_host_corpus_synth(libavif.encode(), count, w, h, first_gpu, n_gpus, workers_per_gpu, batch_width,
-                                        blur_mode, C.byref(opts), csv_path.encode() if csv_path else None, summary,
-                                        4096, C.byref(wall), C.byref(n_ok))
+                                        blur_mode, int(pinned_staging), C.cast(cb, C.c_void_p) if cb else None, None,
+                                        C.byref(opts), csv_path.encode() if csv_path else None, summary, 8192,
+                                        C.byref(st))
     if rc != 0:
-        raise RuntimeError(f"corpus failed: {_err()}")
-    return dict(wall_s=wall.value, ok=n_ok.value, summary=summary.value.decode(), last_error=_err())
+        raise RuntimeError(f"corpus failed: {_err()} {keep.get('err', '')}")
+    return dict(wall_s=st.wall_s, ok=st.n_ok, errors=st.n_err, summary=summary.value.decode(), last_error=_err(),
+                workers=st.workers, host_cpus=st.host_cpus, scorer_device_ms=st.scorer_device_ms,
+                mean_encode_ms=st.mean_encode_ms, mean_decode_ms=st.mean_decode_ms, mean_score_ms=st.mean_score_ms,
+                mean_passes=st.mean_passes, final_bytes_total=int(st.final_bytes_total),
+                margin_hist=dict(zip(MARGIN_BUCKETS, [int(x) for x in st.margin_hist])))
 
 
 def encode(pixels: np.ndarray, q: int, opts: Opts | None = None, libavif: str | None = None) -> bytes:

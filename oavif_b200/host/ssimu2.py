@@ -44,7 +44,7 @@ SYMBOLS = (
     "oavif_ssimu2_get_timing", "oavif_ssimu2_debug_get_xyb", "oavif_ssimu2_debug_get_rows", "oavif_ssimu2_debug_blur",
     "oavif_ssimu2_debug_time_rows", "oavif_ssimu2_debug_check_guards", "oavif_ssimu2_debug_get_cols",
     "oavif_ssimu2_set_default_device", "oavif_ssimu2_release_cached",
-    "oavif_ssimu2_get_option", "oavif_ssimu2_submit_rgb8", "oavif_ssimu2_submit_yuv444",
+    "oavif_ssimu2_get_option", "oavif_ssimu2_device_pci_bus_id", "oavif_ssimu2_submit_rgb8", "oavif_ssimu2_submit_yuv444",
     "oavif_ssimu2_submit_rgb8_dev", "oavif_ssimu2_submit_yuv444_dev", "oavif_ssimu2_wait", "oavif_ssimu2_in_flight",
 )
 

@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""Config 5 of BASELINE.json — the corpus sweep north_star names: N procedural 1920x1080 images through the full
+target-quality search (libaom encode, dav1d decode, CUDA scoring), images pulled from one shared counter by
+`--gpus` x workers host threads (one scorer context per worker, no NCCL), measure.py's CSV and summary, and the
+CPU-scored arm on the same host cores beside it.
+
+    python scripts/corpus_bench.py --gpus G [--count 2000] [--cpu-count 192] [--out profiles/r2_cfg5_Ggpu.json]
+
+One process drives all G GPUs (that is the driver's design: images are independent, the only shared state is the
+work counter).  Emits one JSON object: encodes/s, passes, per-stage ms, host cores, scorer busy fraction, the
+decision-margin histogram, a digest of the (Image, Final Bytes, Passes) columns that must be identical for every
+G, and the CPU arm's encodes/s on a bounded subset (same images, same cores, oracle scorer).
+
+All encodes are 8-bit (--tenbit 0): the libaom inside the only libavif of this image cannot encode 10-bit.
+"""
+from __future__ import annotations
+
+import argparse
+import csv
+import hashlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oavif_b200.host import harness as H  # noqa: E402
+
+
+def digest(csv_path: str, limit: int | None = None):
+    rows = list(csv.reader(open(csv_path, newline="")))[1:]
+    if limit is not None:
+        rows = rows[:limit]
+    key = "\n".join(f"{r[0]},{r[2]},{r[6]}" for r in rows)
+    return hashlib.sha256(key.encode()).hexdigest()[:16], len(rows)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--count", type=int, default=2000)
+    ap.add_argument("--cpu-count", type=int, default=192, help="images of the CPU-scored arm (0: skip)")
+    ap.add_argument("--size", default="1920x1080")
+    ap.add_argument("--workers-per-gpu", type=int, default=0, help="0: host cores / gpus")
+    ap.add_argument("--pinned-ab", type=int, default=0, help="also time N images with the pageable hand-off")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    w, h = (int(x) for x in a.size.split("x"))
+    cores = os.cpu_count() or 1
+    wpg = a.workers_per_gpu or max(1, cores // a.gpus)
+    o = H.default_opts(tenbit=0, speed=9, max_pass=6)
+    outdir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(outdir, exist_ok=True)
+    res = {"config": f"cfg5: {a.count} procedural {w}x{h} images, oavif defaults (-t 80 -s 9 --max-pass 6, tolerance 2) "
+                     f"with --tenbit 0", "gpus": a.gpus, "host_cores": cores, "workers_per_gpu": wpg}
+
+    H.corpus_synth(2 * a.gpus, 256, 192, n_gpus=a.gpus, workers_per_gpu=1, opts=o)      # CUDA / libavif warm-up, untimed
+    csvp = os.path.join(outdir, f"r2_cfg5_{a.gpus}gpu.csv")
+    r = H.corpus_synth(a.count, w, h, n_gpus=a.gpus, workers_per_gpu=wpg, opts=o, csv_path=csvp)
+    dg, n = digest(csvp)
+    res["gpu_arm"] = {
+        "ok": r["ok"], "errors": r["errors"], "wall_s": round(r["wall_s"], 3),
+        "encodes_per_s": round(r["ok"] / r["wall_s"], 3), "mean_passes": round(r["mean_passes"], 3),
+        "per_image_ms": {"encode": round(r["mean_encode_ms"], 2), "decode": round(r["mean_decode_ms"], 2),
+                         "score": round(r["mean_score_ms"], 3)},
+        "scoring_share_of_search": round(r["mean_score_ms"] / max(1e-9, r["mean_encode_ms"] + r["mean_decode_ms"] + r["mean_score_ms"]), 5),
+        "scorer_device_ms_total": round(r["scorer_device_ms"], 1),
+        "scorer_busy_fraction_per_gpu": round(r["scorer_device_ms"] / 1e3 / (r["wall_s"] * a.gpus), 5),
+        "final_bytes_total": r["final_bytes_total"], "margin_hist": r["margin_hist"],
+        "csv_digest_image_bytes_passes": dg, "csv_rows": n, "csv": os.path.relpath(csvp, ROOT),
+        "summary": r["summary"],
+    }
+    # cores a GPU would need before it, not libaom, bounds the sweep: host CPU-seconds per image / device-seconds per image
+    cpu_s_per_image = r["wall_s"] * min(cores, wpg * a.gpus) / max(1, r["ok"])
+    dev_s_per_image = r["scorer_device_ms"] / 1e3 / max(1, r["ok"])
+    res["cores_per_gpu_to_saturate_scorer"] = round(cpu_s_per_image / max(dev_s_per_image, 1e-9))
+
+    if a.pinned_ab:
+        ab = {}
+        for pinned in (1, 0):
+            rr = H.corpus_synth(a.pinned_ab, w, h, n_gpus=a.gpus, workers_per_gpu=wpg, opts=o, pinned_staging=bool(pinned))
+            ab["pinned" if pinned else "pageable"] = {"mean_score_ms": round(rr["mean_score_ms"], 3),
+                                                      "encodes_per_s": round(rr["ok"] / rr["wall_s"], 3)}
+        res["decode_handoff"] = ab
+
+    if a.cpu_count:
+        from oracle import oracle as O
+        O.build()
+
+        def score_pair(src_rgb, y, u, v, depth, matrix, rgba):
+            return O.ssimu2_rgb8(src_rgb, O.yuv444_to_rgb8(y, u, v, depth, matrix, rgba), O.BLUR_IIR, fast=True)
+
+        csvc = os.path.join(outdir, f"r2_cfg5_cpu_arm_{a.gpus}gpu_box.csv")
+        t0 = time.time()
+        rc = H.corpus_synth(a.cpu_count, w, h, n_gpus=1, workers_per_gpu=min(cores, wpg * a.gpus), opts=o, csv_path=csvc,
+                            score_pair=score_pair)
+        dgc, nc = digest(csvc)
+        dgg, _ = digest(csvp, a.cpu_count)
+        res["cpu_arm"] = {
+            "kind": "port (oracle/: SSIMULACRA2 v2.1 restatement, -O3; fssimu2 itself cannot be built here)",
+            "images": a.cpu_count, "ok": rc["ok"], "workers": rc["workers"], "wall_s": round(rc["wall_s"], 3),
+            "encodes_per_s": round(rc["ok"] / rc["wall_s"], 3), "mean_passes": round(rc["mean_passes"], 3),
+            "per_image_ms": {"encode": round(rc["mean_encode_ms"], 2), "decode": round(rc["mean_decode_ms"], 2),
+                             "score": round(rc["mean_score_ms"], 2)},
+            "scoring_share_of_search": round(rc["mean_score_ms"] / max(1e-9, rc["mean_encode_ms"] + rc["mean_decode_ms"] + rc["mean_score_ms"]), 4),
+            "same_bytes_and_passes_as_gpu_arm": dgc == dgg, "elapsed_s": round(time.time() - t0, 1),
+        }
+        res["speedup_encodes_per_s"] = round(res["gpu_arm"]["encodes_per_s"] / max(1e-9, res["cpu_arm"]["encodes_per_s"]), 3)
+
+    text = json.dumps(res, indent=1)
+    print(text)
+    if a.out:
+        with open(os.path.join(ROOT, a.out) if not os.path.isabs(a.out) else a.out, "w") as f:
+            f.write(text + "\n")
+
+
+if __name__ == "__main__":
+    main()

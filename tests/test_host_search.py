@@ -109,6 +109,49 @@ def test_corpus_driver_without_a_gpu_records_errors_and_keeps_going(tmp_path):
     assert len(rows) == 4 and all(x[7] == "error" and "oavif_ssimu2_ctx_create" in x[8] for x in rows[1:])  # no CPU fallback
 
 
+def _oracle_pair(oracle):
+    def score_pair(src_rgb, y, u, v, depth, matrix, rgba):
+        return oracle.ssimu2_rgb8(src_rgb, oracle.yuv444_to_rgb8(y, u, v, depth, matrix, rgba), oracle.BLUR_IIR, fast=True)
+    return score_pair
+
+
+def test_corpus_cpu_scored_arm_summary_and_trace(tmp_path, oracle):
+    """The corpus driver with the injected CPU scorer (the arm bench tooling times beside the GPU): measure.py's CSV
+    and summary text line for line (measure.py:178-269), the per-image trace, dynamic work sharing."""
+    o = opts(max_pass=4, speed=10)
+    path = str(tmp_path / "cpu.csv")
+    r = H.corpus_synth(5, 160, 96, n_gpus=1, workers_per_gpu=3, opts=o, csv_path=path, score_pair=_oracle_pair(oracle))
+    assert r["ok"] == 5 and r["errors"] == 0 and r["workers"] == 3, r
+    rows = list(csv.reader(open(path, newline="")))
+    assert rows[0] == ["Image", "Original Bytes", "Final Bytes", "Savings Bytes", "Savings %", "Encoding Time (ms)",
+                       "Passes", "Status", "Error"]
+    assert [x[0] for x in rows[1:]] == [f"synth_{i:05d}_k{i % 4}_160x96" for i in range(5)]     # image order, whoever ran it
+    orig = sum(int(x[1]) for x in rows[1:])
+    fin = sum(int(x[2]) for x in rows[1:])
+    lines = r["summary"].splitlines()
+    for want in ("Run Summary", "Images: 5 ok, 0 no-output, 0 errors", "Compression Totals",
+                 f"Original total bytes: {orig} ({orig / 1024:.2f} KiB)", f"Final total bytes:    {fin} ({fin / 1024:.2f} KiB)",
+                 f"Savings (bytes):      {orig - fin} ({(orig - fin) / 1024:.2f} KiB)",
+                 f"% saved (overall):    {100.0 * (orig - fin) / orig:.2f}%", "Timing & Passes"):
+        assert want in lines, (want, r["summary"])
+    import statistics
+    geo = (1.0 - statistics.geometric_mean([int(x[2]) / int(x[1]) for x in rows[1:]])) * 100.0
+    assert f"% saved (geometric mean across files): {geo:.2f}%" in lines
+    assert any(l.startswith("Input bytes throughput: ") and l.endswith("/s") for l in lines)
+    passes = [int(x[6]) for x in rows[1:]]
+    assert any(l.startswith(f"Average passes:        {sum(passes) / 5:.2f} ± ") and
+               l.endswith(f"(max: {max(passes)}, min: {min(passes)})") for l in lines)
+    assert sum(r["margin_hist"].values()) == 5 and r["scorer_device_ms"] == 0.0
+    trace = list(csv.reader(open(path + ".trace.csv", newline="")))
+    assert trace[0][:4] == ["Image", "Q", "Score", "Passes"] and len(trace) == 6
+    for t, x in zip(trace[1:], rows[1:]):
+        assert t[0] == x[0] and t[3] == x[6] and len(t[11].split()) == int(t[3]) and float(t[10]) >= 0.0
+    # one worker, same per-image results: the shared counter changes who runs what, never what comes out
+    r1 = H.corpus_synth(5, 160, 96, n_gpus=1, workers_per_gpu=1, opts=o, csv_path=path + ".1", score_pair=_oracle_pair(oracle))
+    rows1 = list(csv.reader(open(path + ".1", newline="")))
+    assert r1["ok"] == 5 and [(x[0], x[2], x[6]) for x in rows1] == [(x[0], x[2], x[6]) for x in rows]
+
+
 def test_cli_reads_pam_and_ppm_and_reports_like_the_reference(tmp_path):
     import subprocess
     cli = os.path.join(os.path.dirname(H.LIB_PATH), "oavif-b200")

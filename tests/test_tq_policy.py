@@ -184,3 +184,45 @@ def test_randomised_curves_sequential_and_batched(seed):
         assert bat.probes == len(calls) and len(set(calls)) == len(calls)          # no q probed twice
         assert bat.wasted == bat.probes - bat.num_pass
         assert bat.device_passes <= bat.num_pass                                   # never more round trips
+
+
+# ---- margin report (tq.hpp decisionMargins) -----------------------------------------------------------------------
+def test_decision_margins_bracket_every_flip():
+    """Moving a pass's score by less than its margin never changes the search; moving it by just more does."""
+    rng = np.random.default_rng(5)
+    checked = 0
+    for trial in range(30):
+        a, b = rng.uniform(0.15, 0.5), rng.uniform(40, 75)
+        curve = lambda q: min(99.0, b + a * q + 0.002 * q * q)                     # monotone score(q)
+        tgt, tol = float(rng.choice([70, 80, 85, 90])), float(rng.choice([1.0, 2.0]))
+        r = H.tq_search(curve, tgt, tol, 6)
+        hist = r.history()
+        margins = H.tq_margins(hist, tgt, tol, 6)
+        assert len(margins) == len(hist)
+
+        def replay(i, delta):   # what the search asks for after pass i when that score moves, and its final pick
+            moved = [(q, s + (delta if j == i else 0.0)) for j, (q, s) in enumerate(hist)]
+            nxt = H.tq_search(lambda q: dict(moved)[q] if q in dict(moved) else curve(q), tgt, tol, 6)
+            return [q for q, _ in nxt.history()][: i + 2], nxt.early_exit if len(nxt.history()) == i + 1 else None
+
+        for i, (up, dn) in enumerate(margins):
+            assert up > 0 and dn > 0
+            for sign, m in ((1, up), (-1, dn)):
+                if m >= 4.0:
+                    continue
+                base = replay(i, 0.0)
+                assert replay(i, sign * m * 0.98) [0][: i + 1] == base[0][: i + 1]
+                inside, outside = replay(i, sign * m * 0.98), replay(i, sign * m * 1.02)
+                if inside == base and outside != base:
+                    checked += 1
+    assert checked > 20     # most finite margins are flips of the NEXT quantizer / the stop, which this replay sees
+
+
+def test_decision_margins_known_cases():
+    # one pass inside the tolerance: the exit flips when |score - tgt| reaches the tolerance
+    (up, dn), = H.tq_margins([(65, 80.5)], 80.0, 2.0, 6)
+    assert abs(up - 1.5) < 1e-6          # 80.5 + 1.5 = 82.0 -> no longer < tolerance
+    assert abs(dn - 2.5) < 1e-6          # 80.5 - 2.5 = 78.0
+    # first pass outside the tolerance: the sign and ceil(|err|) * 4 decide the bracket (tq.zig:155-164)
+    (up, dn), = H.tq_margins([(65, 84.3)], 80.0, 2.0, 1)
+    assert up >= 4.0 and abs(dn - 2.3) < 1e-6    # max_pass 1: nothing follows, only the tolerance exit can change
