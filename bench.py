@@ -114,50 +114,64 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def bench_config(blur: str) -> dict:
+    """The workload both arms run (`config` of the JSON line is this dict for `ours` and for `--impl reference`)."""
+    return {"workload": f"cfg2 scoring-only {W}x{H} RGB8 source vs decoded 10-bit YUV444, full SSIMULACRA2 eval per step",
+            "blur": blur, "pairs_per_rank": NSETS,
+            "l2": f"inputs rotate over {NSETS} pairs ({NSETS * (W * H * 9) / 1e6:.0f} MB) > 126 MB L2; "
+                  f"intermediates per step {(W * H * S_SCALES * 12 * 7) / 1e6:.0f} MB"}
+
+
 _cpu_data = None
 
 
 def cpu_oracle_rate(threads: int, seconds_budget: float, rows_hint: int | None = None):
-    """Mpx/s of the CPU oracle on `threads` host threads, each scoring its own horizontal band of
-    the 4K pair (bounded sample; input generation is outside the timed region).
-    Returns (mpx_per_s, rows_per_band, elapsed_s)."""
+    """Mpx/s of the CPU implementation of the path on `threads` host threads: every thread takes the SAME work the
+    GPU arm does per step — the decoded 10-bit YUV444 planes -> RGB8 (libavif's integer conversion) and one full
+    SSIMULACRA2 evaluation against the RGB8 source — on the full 3840x2160 pair when the budget allows, else on a
+    horizontal band of it (bounded sample; input generation is outside the timed region).
+    Returns (mpx_per_s, rows_per_thread, elapsed_s)."""
     global _cpu_data
     from concurrent.futures import ThreadPoolExecutor
-    from oavif_b200.host import synth
     from oracle import oracle as O
     if _cpu_data is None:
         O.build()
-        src = synth.synth(W, 540, "mixture", 0)
-        _cpu_data = (src, synth.distort(src, 0.25, seed=1000))
-    src, dist_rgb = _cpu_data
+        src, (y, u, v) = make_pairs(0, 1)[0]
+        _cpu_data = (src, y, u, v)
+    src, y, u, v = _cpu_data
+
+    def work_rows(rows):
+        rgb = O.yuv444_to_rgb8(y[:rows], u[:rows], v[:rows], 10, 2, False)
+        return O.ssimu2_rgb8(src[:rows], rgb, O.BLUR_IIR, fast=True)
+
     if rows_hint is None:  # calibrate on one 3840x135 strip
         t0 = time.perf_counter()
-        O.ssimu2_rgb8(src[:135], dist_rgb[:135], O.BLUR_IIR, fast=True)
+        work_rows(135)
         per_row = (time.perf_counter() - t0) / 135
-        rows = int(max(64, min(540, seconds_budget / max(per_row, 1e-6))))
+        rows = int(max(64, min(H, seconds_budget / max(per_row, 1e-6))))
+        if rows > 0.8 * H:
+            rows = H            # close enough: take the whole frame
     else:
         rows = rows_hint
-
-    def work(i):
-        return O.ssimu2_rgb8(src[:rows], dist_rgb[:rows], O.BLUR_IIR, fast=True)
-
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(work, range(threads)))
+        list(ex.map(lambda i: work_rows(rows), range(threads)))
     dt = time.perf_counter() - t0
     return threads * W * rows / 1e6 / dt, rows, dt
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on the host cores.  fssimu2 0.1.1 (Zig)
-    is neither in /root/reference nor buildable here, so this is the oracle port (kind "port")."""
+    """--impl reference: the CPU implementation of the path on the host cores.  fssimu2 0.1.1 (Zig) is neither in
+    /root/reference nor buildable here, so this is the oracle port (kind "port", built -O3 -march=native on the
+    box); the real fssimu2 is hand-vectorised and expected to be faster than this port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import oracle as O
     threads = os.cpu_count() or 1
     total = args.steps + args.warmup
-    # seconds of CPU work per step: the whole run stays within ~3 minutes
-    per_step = args.ref_seconds if args.ref_seconds > 0 else max(0.05, min(6.0, 150.0 / max(total, 1)))
+    # seconds of CPU work per step: the whole run stays within ~4 minutes; a full 4K frame per thread costs ~1.6 s
+    per_step = args.ref_seconds if args.ref_seconds > 0 else max(0.05, min(3.0, 240.0 / max(total, 1)))
     rate0, rows, _ = cpu_oracle_rate(threads, per_step)
     for _ in range(max(args.warmup - 1, 0)):
         cpu_oracle_rate(threads, per_step, rows)
@@ -168,14 +182,16 @@ def run_reference(args):
         px += threads * W * rows / 1e6
     dt = time.perf_counter() - t0
     value = px / dt
-    sample = f"{threads} threads x one {W}x{rows} band of the 4K pair per step (RGB8 pair; oracle -O3 x86-64-v3)"
+    what = "the full 3840x2160 pair" if rows == H else f"one {W}x{rows} band of the 4K pair"
+    sample = (f"{threads} threads x {what} per step: 10-bit YUV444 planes -> RGB8 (libavif integer conversion) + "
+              f"SSIMULACRA2 vs the RGB8 source; oracle port, -O3 {O.fast_flavour()}; fssimu2 itself (hand-vectorised Zig) "
+              f"is not buildable here and is expected to be faster")
     line = {
         "impl": "reference", "metric": "SSIMULACRA2 scorer throughput", "value": round(value, 3), "unit": "Mpx/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg2 scoring-only {W}x{H} RGB8 source vs decoded frame, full SSIMULACRA2 eval",
-                   "sample": sample},
+        "config": bench_config(args.blur),
         "cpu_baseline": {"value": round(value, 3), "unit": "Mpx/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -403,12 +419,9 @@ def run_ours(args):
         "metric": "SSIMULACRA2 scorer throughput", "value": round(value, 1), "unit": "Mpx/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg2 scoring-only {W}x{H} RGB8 source vs decoded 10-bit YUV444, full SSIMULACRA2 eval per step",
-                   "blur": args.blur, "pairs_per_rank": NSETS,
-                   "issue": "one caller, one context; step i is submitted (set_source + submit) before step i-1 is retired (wait)",
-                   "tile_path": "tma" if sc.get_option(ssimu2.OPT_TILE_PATH) == ssimu2.TILES_TMA else "cp.async",
-                   "l2": f"inputs rotate over {NSETS} pairs ({NSETS * (W * H * 9) / 1e6:.0f} MB) > 126 MB L2; "
-                         f"intermediates per step {(W * H * S_SCALES * 12 * 7) / 1e6:.0f} MB"},
+        "config": bench_config(args.blur),
+        "issue": "one caller, one context; step i is submitted (set_source + submit) before step i-1 is retired (wait)",
+        "tile_path": "tma" if sc.get_option(ssimu2.OPT_TILE_PATH) == ssimu2.TILES_TMA else "cp.async",
         "e2e": {"value": round(e2e, 1), "unit": "Mpx/s", "h2d_bytes_per_step": W * H * 9, "d2h_bytes_per_step": 8 + 864,
                 "ms_per_step": round(ms_pipe / args.steps, 4), "host_memory": "pinned (oavif_ssimu2_pinned_alloc)",
                 "h2d_gbs": round(W * H * 9 / 1e9 / (ms_pipe / args.steps / 1e3), 1),
@@ -446,14 +459,16 @@ def run_ours(args):
         "parity": "scores match the in-repo CPU oracle (SSIMULACRA2 v2.1 restatement); parity vs fssimu2 0.1.1 unpinned",
     }
     if world == 1 and not args.no_cpu:
+        from oracle import oracle as O
         threads = os.cpu_count() or 1
-        reps = 40  # ~15-25 s of CPU work in total
-        rates = [cpu_oracle_rate(threads, 8.0) for _ in range(reps)]
+        reps = 8  # ~15-25 s of CPU work in total: a full 4K pair per thread and repetition
+        rates = [cpu_oracle_rate(threads, 3.0) for _ in range(reps)]
         rate, rows, dt = float(np.mean([r[0] for r in rates])), rates[0][1], float(np.sum([r[2] for r in rates]))
-        rate1, rows1, dt1 = cpu_oracle_rate(1, 4.0)
+        rate1, rows1, dt1 = cpu_oracle_rate(1, 3.0)
         line["cpu_baseline"] = {"value": round(rate, 3), "unit": "Mpx/s", "cores": threads, "kind": "port",
-                                "sample": f"{reps} x ({threads} threads x one {W}x{rows} band of the 4K pair), {dt:.1f} s",
-                                "single_thread": {"value": round(rate1, 3), "sample": f"{W}x{rows1} band, {dt1:.1f} s"}}
+                                "sample": f"{reps} x ({threads} threads x {'the full 4K pair' if rows == H else f'one {W}x{rows} band'}: "
+                                          f"10-bit planes -> RGB8 + SSIMULACRA2), {dt:.1f} s; oracle port -O3 {O.fast_flavour()}",
+                                "single_thread": {"value": round(rate1, 3), "sample": f"{W}x{rows1}, {dt1:.1f} s"}}
     emit(line)
     dist.finalize()
 

@@ -44,6 +44,30 @@ def build(force: bool = False) -> None:
 _libs: dict[str, C.CDLL] = {}
 
 
+def _native_path() -> str | None:
+    """liboracle_fast built with -march=native ON THIS MACHINE (the timed CPU baseline should use the host's own
+    vector width; the shipped liboracle_fast.so is x86-64-v3 so that it runs anywhere).  Cached per CPU flag set
+    under oracle/_native/ (git-ignored); None when it cannot be built."""
+    import hashlib
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except (OSError, StopIteration):
+        return None
+    d = os.path.join(_HERE, "_native")
+    path = os.path.join(d, "liboracle_native_%s.so" % hashlib.sha1(flags.encode()).hexdigest()[:10])
+    srcs = [os.path.join(_HERE, f) for f in ("ssimu2_oracle.c", "yuv2rgb_oracle.c")]
+    try:
+        if not os.path.exists(path) or any(os.path.getmtime(path) < os.path.getmtime(f) for f in srcs):
+            os.makedirs(d, exist_ok=True)
+            subprocess.check_call([os.environ.get("CC", "gcc"), "-std=c11", "-fPIC", "-fno-math-errno", "-O3", "-march=native",
+                                   "-ffp-contract=off", "-shared", "-o", path + ".tmp", *srcs, "-lm"],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            os.replace(path + ".tmp", path)
+        return path
+    except (OSError, subprocess.CalledProcessError):
+        return None
+
+
 def lib(fast: bool = False) -> C.CDLL:
     name = "liboracle_fast.so" if fast else "liboracle.so"
     if name in _libs:
@@ -51,6 +75,8 @@ def lib(fast: bool = False) -> C.CDLL:
     path = os.path.join(_HERE, name)
     if not os.path.exists(path):
         build()
+    if fast and os.environ.get("OAVIF_ORACLE_NATIVE", "1") != "0":
+        path = _native_path() or path
     L = C.CDLL(path)
     u8p, f32p, f64p, ip = (C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_double),
                            C.POINTER(C.c_int))
@@ -93,6 +119,12 @@ def set_variant(flags: int, fast: bool = False, libm_cbrt: bool = False) -> None
     """Process-wide variant switches of one library (see ssimu2_oracle.h); 0 restores the default."""
     lib(fast).oracle_set_variant(flags)
     lib(fast).oracle_set_libm_cbrt(int(libm_cbrt))
+
+
+def fast_flavour() -> str:
+    """What `fast=True` loads on this machine: 'native' (-O3 -march=native, built here) or 'x86-64-v3'."""
+    lib(True)
+    return "native" if "_native" in (getattr(_libs.get("liboracle_fast.so"), "_name", "") or "") else "x86-64-v3"
 
 
 def srgb_lut() -> np.ndarray:

@@ -77,12 +77,17 @@ def main():
     res["cores_per_gpu_to_saturate_scorer"] = round(cpu_s_per_image / max(dev_s_per_image, 1e-9))
 
     if a.pinned_ab:
-        ab = {}
-        for pinned in (1, 0):
-            rr = H.corpus_synth(a.pinned_ab, w, h, n_gpus=a.gpus, workers_per_gpu=wpg, opts=o, pinned_staging=bool(pinned))
-            ab["pinned" if pinned else "pageable"] = {"mean_score_ms": round(rr["mean_score_ms"], 3),
-                                                      "encodes_per_s": round(rr["ok"] / rr["wall_s"], 3)}
-        res["decode_handoff"] = ab
+        # every call creates fresh worker contexts whose first score pays the CUDA module load: alternate the two
+        # forms and keep each form's best run, so that neither is charged for being first
+        ab = {"pinned": [], "pageable": []}
+        for rep in range(2):
+            for pinned in ((1, 0) if rep == 0 else (0, 1)):
+                rr = H.corpus_synth(a.pinned_ab, w, h, n_gpus=a.gpus, workers_per_gpu=wpg, opts=o, pinned_staging=bool(pinned))
+                ab["pinned" if pinned else "pageable"].append((rr["mean_score_ms"], rr["ok"] / rr["wall_s"]))
+        res["decode_handoff"] = {k: {"mean_score_ms_per_image": round(min(x[0] for x in v), 3),
+                                     "encodes_per_s": round(max(x[1] for x in v), 3)} for k, v in ab.items()}
+        res["decode_handoff"]["note"] = (f"{a.pinned_ab} images per run, two runs per form (alternated), best of each; score ms is "
+                                         "host wall per image (all passes) around the C-ABI call incl. the copy into staging")
 
     if a.cpu_count:
         from oracle import oracle as O

@@ -26,6 +26,8 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["unit"] == "Mpx/s" and d["higher_is_better"] is True
     assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["config"]["workload"].startswith("cfg2")
+    import bench
+    assert d["config"] == bench.bench_config("recursive")       # the same workload description as our arm's line
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "band" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -36,6 +38,8 @@ def test_our_arm_line():
     d = run_bench("--steps", "16", "--warmup", "3", "--no-cpu")
     assert BASE_KEYS | {"clocks", "roofline"} <= set(d)
     assert "impl" not in d and d["n_gpus"] == 1 and d["steps"] == 16 and d["scaling"] == "weak"
+    import bench
+    assert d["config"] == bench.bench_config("recursive")
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["vs_baseline"] is None
     assert d["gpu_launches"] == 6 * 16          # pyramid x2, rows x2 (source half, candidate half), columns, finalize per step
     assert d["value"] > 1000 and d["e2e"]["value"] > 100

@@ -693,6 +693,19 @@ def test_submit_wait_equals_the_synchronous_calls():
         sc.check_guards()
 
 
+def test_cuda_against_fssimu2_vectors():
+    """The CUDA path against vectors of the reference's own scorer, when a machine with zig has produced them
+    (scripts/pin_fssimu2.md).  Skipped — "parity unpinned" — while tests/golden/fssimu2_scores.json is absent."""
+    from test_oracle import fssimu2_vectors
+    cases = fssimu2_vectors()
+    for c in cases:
+        src = synth.synth(c["w"], c["h"], c["kind"], c["seed"])
+        dst = synth.distort(src, c["strength"], seed=c["seed"] + 100)
+        with ssimu2.Scorer(c["w"], c["h"], 1) as sc:
+            sc.set_source(src)
+            assert abs(sc.score_rgb8(dst) - c["score"]) <= 0.05, c          # north_star's bar
+
+
 # ---- several callers per GPU: one context per host thread (the corpus driver's workers-per-gpu) ------------
 def test_two_contexts_on_two_threads_score_like_one():
     """Contexts are single-owner, but several may run on one GPU at once (each on its own stream): concurrent
