@@ -780,12 +780,16 @@ template <int MODE, int STAGES, int NBUF, bool NOCOMP = false>
 inline cudaError_t iir_rows_tma_launch(const IirArgs &ar, const IirRowsTmaMaps &maps, int nr, int n, cudaStream_t st)
 {
     typedef IirRowsTmaSmem<MODE, STAGES, NBUF> Smem;
-    static bool configured = false;   // per instance; every context of the process uses the same attribute
-    if (!configured) {
+    // the attribute belongs to (kernel instance, DEVICE): the corpus driver runs contexts on several devices in one
+    // process.  Benign race between workers of one device: they store the same value.
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         const cudaError_t e = cudaFuncSetAttribute(k_iir_rows_tma<MODE, STAGES, NBUF, NOCOMP>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     k_iir_rows_tma<MODE, STAGES, NBUF, NOCOMP><<<dim3(nr, n), MODE == 2 ? 128 : MODE == 3 ? 64 : 96, sizeof(Smem), st>>>(ar, maps);
     return cudaGetLastError();

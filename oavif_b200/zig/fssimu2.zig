@@ -93,6 +93,45 @@ pub const Scorer = struct {
         return score;
     }
 
+    /// Image.toRGB8 on the device (io.zig:57-133): the loaders' native layouts, 1..4 channels, 8- or 16-bit.
+    pub fn setSourcePixels(self: *Scorer, pixels: []const u8, w: u32, h: u32, channels: u8, hbd: bool) Error!void {
+        const bps: usize = if (hbd) 2 else 1;
+        try check(c.oavif_ssimu2_set_source_pixels(self.ctx, pixels.ptr, w, h, @as(usize, w) * channels * bps, channels, if (hbd) 16 else 8));
+    }
+
+    /// Batched probing (tq_batched.zig): n decoded candidates (io.DecodedPlanes layout: same depth, strides and
+    /// matrix for all of them) against the cached source in one pass over the device.
+    pub fn scoreBatchYuv444(self: *Scorer, cands: anytype, scores: []f64) Error!void {
+        const n = cands.len;
+        if (n == 0 or n > self.max_batch or n > 16 or scores.len < n) return Error.InvalidArgument;
+        var y: [16]?*const anyopaque = undefined;
+        var u: [16]?*const anyopaque = undefined;
+        var v: [16]?*const anyopaque = undefined;
+        for (cands, 0..) |p, i| {
+            y[i] = p.planes[0];
+            u[i] = p.planes[1];
+            v[i] = p.planes[2];
+        }
+        const p0 = cands[0];
+        try check(c.oavif_ssimu2_score_batch_yuv444(self.ctx, @intCast(n), &y, &u, &v, p0.row_bytes[0], p0.row_bytes[1], p0.row_bytes[2], @intCast(p0.depth), @intCast(p0.matrix_coefficients), @intFromBool(p0.has_alpha), scores.ptr));
+    }
+
+    /// Pipelined form: submit returns at once (the upload runs on the context's copy stream under the previous
+    /// submission's kernels), wait retires the oldest submission.  Up to two in flight; planes must stay valid
+    /// until the matching wait.
+    pub fn submitYuv444(self: *Scorer, planes: [3][*]const u8, row_bytes: [3]u32, depth: u32, matrix_coefficients: u16, rgba_path: bool) Error!void {
+        const y: [1]?*const anyopaque = .{planes[0]};
+        const u: [1]?*const anyopaque = .{planes[1]};
+        const v: [1]?*const anyopaque = .{planes[2]};
+        try check(c.oavif_ssimu2_submit_yuv444(self.ctx, 1, &y, &u, &v, row_bytes[0], row_bytes[1], row_bytes[2], @intCast(depth), @intCast(matrix_coefficients), @intFromBool(rgba_path)));
+    }
+
+    pub fn wait(self: *Scorer) Error!f64 {
+        var score: f64 = 0;
+        try check(c.oavif_ssimu2_wait(self.ctx, &score));
+        return score;
+    }
+
     /// Batched probing (new in tq.zig): n candidate decodes of one image in one pass over the device.
     pub fn scoreBatchRgb8(self: *Scorer, dists: []const [*]const u8, w: u32, scores: []f64) Error!void {
         if (dists.len == 0 or dists.len > self.max_batch or scores.len < dists.len) return Error.InvalidArgument;

@@ -693,6 +693,23 @@ def test_submit_wait_equals_the_synchronous_calls():
         sc.check_guards()
 
 
+def test_every_visible_device_scores_the_same():
+    """The corpus driver runs contexts on several devices from one process: kernel attributes are per device."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one visible GPU")
+    src = synth.synth(640, 360, "mixture", 2)
+    dist = synth.distort(src, 0.4)
+    got = []
+    for dev in range(n):
+        for mode in (ssimu2.BLUR_RECURSIVE, ssimu2.BLUR_FIR):
+            with ssimu2.Scorer(640, 360, 1, device=dev, blur=mode) as sc:
+                sc.set_source(src)
+                got.append((mode, sc.score_rgb8(dist)))
+    assert len(set(got)) == 2
+
+
 def test_cuda_against_fssimu2_vectors():
     """The CUDA path against vectors of the reference's own scorer, when a machine with zig has produced them
     (scripts/pin_fssimu2.md).  Skipped — "parity unpinned" — while tests/golden/fssimu2_scores.json is absent."""
