@@ -66,10 +66,20 @@ enum { OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS = 0, OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS = 1 }
 /* How the RECURSIVE kernels move their tiles.  TMA (default): cp.async.bulk.tensor loads and stores issued by one
  * elected lane, completion on mbarriers, zero padding and edge clipping done by the hardware.  CP_ASYNC: the
  * round-1 kernels (dedicated loader / storer warps, 16-byte cp.async, one block barrier per chunk), kept for A/B
- * measurements and for drivers without a tensor-map encoder.  Same arithmetic, same bits. */
-enum { OAVIF_SSIMU2_TILES_TMA = 0, OAVIF_SSIMU2_TILES_CP_ASYNC = 1 };
+ * measurements and for drivers without a tensor-map encoder.  FUSED: ONE kernel for both passes, the maps and the
+ * pooling (ssimu2_wave.cuh): column strips run as a wavefront, the six-float state of every row chain is handed from
+ * a strip to its right neighbour through an L2-resident mailbox, and the row-filtered planes never reach HBM; the
+ * per-source cache then holds the fully blurred (mu1, sigma11) instead of the rows pass of (a, a*a).
+ * Same arithmetic, same bits in all three. */
+enum { OAVIF_SSIMU2_TILES_TMA = 0, OAVIF_SSIMU2_TILES_CP_ASYNC = 1, OAVIF_SSIMU2_TILES_FUSED = 2 };
 
-enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_WEIGHTS = 2, OAVIF_SSIMU2_OPT_TILE_PATH = 3 };
+/* When the rows pass of the source-only quantities (a, a*a) runs (RECURSIVE blur, TMA kernels).  AT_SET_SOURCE
+ * (default): a launch of its own on the source stream, enqueued by set_source — it overlaps the candidate's
+ * pyramid and rows pass, and with pipelined callers the previous image's columns pass.  WITH_FIRST_SCORE: carried by
+ * the first scoring call's rows kernel (candidate 0's CTAs), as in round 1. */
+enum { OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE = 0, OAVIF_SSIMU2_SOURCE_ROWS_WITH_FIRST_SCORE = 1 };
+
+enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_WEIGHTS = 2, OAVIF_SSIMU2_OPT_TILE_PATH = 3, OAVIF_SSIMU2_OPT_SOURCE_ROWS = 4 };
 
 typedef struct oavif_ssimu2_ctx oavif_ssimu2_ctx;
 
@@ -261,7 +271,10 @@ int oavif_ssimu2_debug_check_guards(oavif_ssimu2_ctx *ctx);
 /* Profiling aid: re-run only the RECURSIVE rows pass on the pyramids of the last score call,
  * `iters` times, and report its mean device time.  variant 0 runs both halves; bit 2 (value 4) leaves
  * out the source half (a, a*a), i.e. times what a call with a warm source cache runs; bit 3 (value 8) forces
- * the cp.async kernels whatever OAVIF_SSIMU2_OPT_TILE_PATH says. */
+ * the cp.async kernels whatever OAVIF_SSIMU2_OPT_TILE_PATH says; bits 4..6 select a TMA instance (ring depth /
+ * staging buffers, 0 = the shipped one); 128 = the source half alone; 256 = both halves issued the way the scored
+ * path issues them (source stream next to compute stream; the time is that of the pair); 512 = the COLUMNS pass alone;
+ * 1024 / 2048 = the FUSED kernel with all five quantities / with the cached source blur. */
 int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms);
 
 #ifdef __cplusplus

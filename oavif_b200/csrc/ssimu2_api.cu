@@ -27,8 +27,10 @@
 #include "ssimu2_fir.cuh"
 #include "ssimu2_iir.cuh"
 #include "ssimu2_pyramid.cuh"
+#include "ssimu2_wave.cuh"
 
 using namespace oavif;
+
 
 namespace {
 
@@ -65,11 +67,13 @@ struct Slot {
 // TMA descriptors over both.
 struct SrcSet {
     float *d_pyr = nullptr, *d_hplanes = nullptr;
-    bool rows_valid = false;               // d_hplanes holds the rows pass of the source in d_pyr
+    // d_hplanes caches what only depends on the source, in the form the selected kernels want it: the ROWS pass of
+    // (a, a*a) for the two-pass kernels, the fully blurred (mu1, sigma11) for the fused kernel
+    bool rows_valid = false, musig_valid = false;
     cudaEvent_t pyr_ready = nullptr;       // source stream: the pyramid is complete
     cudaEvent_t ready = nullptr;           // source stream: ... and so is everything else enqueued by set_source
     cudaEvent_t last_use = nullptr;        // compute stream: the last submission reading this set has finished
-    CUtensorMap in_src[kMaxScales], out_psrc[kMaxScales];
+    CUtensorMap in_src[kMaxScales], out_psrc[kMaxScales], in_musig[kMaxScales];
     int maps_w = -1, maps_h = -1;
 };
 
@@ -81,8 +85,16 @@ struct oavif_ssimu2_ctx {
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
     int weight_layout = OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS;
     int tile_path = OAVIF_SSIMU2_TILES_TMA;
+    int source_rows = OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE;
     IirRowsTmaMaps cand_maps{};    // TMA descriptors of the candidates' planes (in_dist, out_pcand, out_ab) for maps_w x maps_h
     int maps_w = -1, maps_h = -1;
+    // fused kernel (ssimu2_wave.cuh): unit list of the current geometry, ticket counter, mailbox, error flag
+    unsigned *d_units = nullptr, *d_ticket = nullptr;
+    unsigned n_units = 0, cap_units = 0, wave_epoch = 0;
+    int units_w = -1, units_h = -1;
+    unsigned long long *d_mailbox = nullptr;
+    long long cap_mailbox_words = 0;      // per candidate
+    int *h_wave_err = nullptr, *dm_wave_err = nullptr;   // pinned, mapped
 
     // capacities (computed from max_w x max_h)
     long long cap_pyr_floats = 0, cap_in_bytes = 0, cap_ctas = 0, cap_hplane_floats = 0;
@@ -426,8 +438,14 @@ long long ctas_needed(int w, int h)
 
 bool fits_capacity(const oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
 {
-    return pyr_capacity((int)w, (int)h) <= ctx->cap_pyr_floats && (long long)w * h * 8 + 3 * 256 <= ctx->cap_in_bytes &&
-           ctas_needed((int)w, (int)h) <= ctx->cap_ctas;
+    if (!(pyr_capacity((int)w, (int)h) <= ctx->cap_pyr_floats && (long long)w * h * 8 + 3 * 256 <= ctx->cap_in_bytes &&
+          ctas_needed((int)w, (int)h) <= ctx->cap_ctas))
+        return false;
+    Geom g;   // the fused kernel's unit list and mailbox
+    long long so[kMaxScales];
+    int rows[kMaxScales];
+    make_geom((int)w, (int)h, &g);
+    return wave_units(g).size() <= ctx->cap_units && wave_mailbox_words(g, 5, so, rows) <= ctx->cap_mailbox_words;
 }
 
 int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
@@ -447,7 +465,7 @@ int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
 // false selects the cp.async kernels (tile path switched off, or no descriptor encoder in this driver).
 bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
 {
-    if (ctx->tile_path != OAVIF_SSIMU2_TILES_TMA) return false;
+    if (ctx->tile_path == OAVIF_SSIMU2_TILES_CP_ASYNC) return false;
     const Geom &g = ctx->g;
     const long long P = ctx->cap_pyr_floats;
     bool ok = true;
@@ -461,6 +479,9 @@ bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
     }
     if (ok && (S.maps_w != g.w[0] || S.maps_h != g.h[0])) {
         ok = iir_rows_tma_maps_src(S.in_src, S.out_psrc, g, S.d_pyr, S.d_hplanes);
+        for (int s = 0; s < g.n_scales && ok; ++s)   // the fused kernel's view of the same buffer: (mu1, sigma11) pairs
+            ok = tma_make_4d(&S.in_musig[s], S.d_hplanes + 2 * g.off[s], 2ull * g.w[s], (uint64_t)g.h[s], 3, 1,
+                             (uint64_t)g.pitch[s] * 8, (uint64_t)g.plane[s] * 8, 0, 2 * kIirVCols, kWvB, false);
         if (ok) {
             S.maps_w = g.w[0];
             S.maps_h = g.h[0];
@@ -484,6 +505,63 @@ IirArgs iir_args_for(oavif_ssimu2_ctx *ctx, const SrcSet &S)
     a.partials = ctx->d_partials;
     a.partials_stride = ctx->cap_ctas * 6;
     return a;
+}
+
+// The fused kernel over candidates [cand0, cand0 + n): MODE 2 computes the source's quantities too and leaves
+// (mu1, sigma11) in the set's cache, MODE 1 reads them back.
+int enqueue_wave(oavif_ssimu2_ctx *ctx, SrcSet &Src, const BlurPlan &plan, int mode, uint32_t cand0, uint32_t n,
+                 const IirDebugTap *tap = nullptr)
+{
+    const Geom &g = ctx->g;
+    IirRowsTmaMaps rm;
+    if (!rows_maps_for(ctx, Src, &rm)) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "no tensor-map encoder: the fused kernel needs TMA");
+    if (ctx->units_w != g.w[0] || ctx->units_h != g.h[0]) {
+        const std::vector<unsigned> u = wave_units(g);
+        if (u.size() > ctx->cap_units) return fail(ctx, OAVIF_SSIMU2_E_STATE, "unit list exceeds capacity");
+        // pageable source: the copy has been staged when the call returns, and the stream orders it before the launch
+        CK(cudaMemcpyAsync(ctx->d_units, u.data(), u.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->n_units = (unsigned)u.size();
+        ctx->units_w = g.w[0];
+        ctx->units_h = g.h[0];
+    }
+    WaveMaps wm;
+    memcpy(wm.in_src, rm.in_src, sizeof wm.in_src);
+    memcpy(wm.in_dist, rm.in_dist, sizeof wm.in_dist);
+    memcpy(wm.in_musig, Src.in_musig, sizeof wm.in_musig);
+    WaveArgs a{};
+    a.g = g;
+    a.k = ctx->iir;
+    a.one = 1.0f;
+    a.neg_one = -1.0f;
+    a.units = ctx->d_units;
+    a.n_units = ctx->n_units;
+    a.n_cand = n;
+    a.cand0 = cand0;
+    a.ticket = ctx->d_ticket;
+    a.epoch = ++ctx->wave_epoch & 0xfffffu;
+    if (a.epoch == 0) a.epoch = ctx->wave_epoch = 1;
+    a.mailbox = ctx->d_mailbox;
+    const long long words = wave_mailbox_words(g, mode == 2 ? 5 : 3, a.mb_scale_off, a.mb_rows);
+    if (words > ctx->cap_mailbox_words) return fail(ctx, OAVIF_SSIMU2_E_STATE, "mailbox exceeds capacity");
+    a.mb_cand_stride = ctx->cap_mailbox_words;
+    a.musig = Src.d_hplanes;
+    a.partials = ctx->d_partials;
+    a.partials_stride = ctx->cap_ctas * 6;
+    for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = plan.first_cta[s];
+    for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = plan.tiles_x[s];
+    a.error_flag = ctx->dm_wave_err;
+    cudaError_t e;
+    if (tap) {
+        a.dbg_cols = tap->out;
+        a.dbg_scale = tap->scale;
+        a.dbg_channel = tap->channel;
+        a.dbg_cand = tap->cand;
+        e = mode == 2 ? wave_launch<2, true>(a, wm, ctx->stream) : wave_launch<1, true>(a, wm, ctx->stream);
+    } else {
+        e = mode == 2 ? wave_launch<2, false>(a, wm, ctx->stream) : wave_launch<1, false>(a, wm, ctx->stream);
+    }
+    if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "fused blur launch: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 // blur + maps + pooling + final score of the candidates whose pyramids were just enqueued, into slot S.
@@ -513,6 +591,24 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, SrcSet &Src, uint3
         CK(cudaGetLastError());
         CK(cudaEventRecord(S.k[2], ctx->stream));
         S.launches += 1;
+    } else if (ctx->tile_path == OAVIF_SSIMU2_TILES_FUSED) {
+        plan_iir_v(g, &plan);
+        CK(cudaStreamWaitEvent(ctx->stream, Src.ready, 0));
+        uint32_t first = 0;
+        if (!Src.musig_valid) {   // first call after set_source: candidate 0's launch carries the source's quantities
+            const int rc = enqueue_wave(ctx, Src, plan, 2, 0, 1);
+            if (rc) return rc;
+            Src.musig_valid = true;
+            Src.rows_valid = false;
+            S.launches += 1;
+            first = 1;
+        }
+        if (n > first) {
+            const int rc = enqueue_wave(ctx, Src, plan, 1, first, n - first);
+            if (rc) return rc;
+            S.launches += 1;
+        }
+        CK(cudaEventRecord(S.k[2], ctx->stream));
     } else {
         plan_iir_v(g, &plan);
         const IirArgs a = iir_args_for(ctx, Src);
@@ -524,16 +620,16 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, SrcSet &Src, uint3
             // be running next to this launch; only the columns pass has to wait for it
             e = launch_iir_rows(a, g, 1, (int)n, ctx->stream, tma ? &maps : nullptr);
             S.launches += 1;
-        } else if (tma) {   // the source was set under FIR, or before the tile path changed: build its half now
-            e = launch_iir_rows(a, g, 3, 1, ctx->stream, &maps);
-            if (e == cudaSuccess) e = launch_iir_rows(a, g, 1, (int)n, ctx->stream, &maps);
-            S.launches += 2;
+        } else if (tma) {   // the source's half rides in this launch (candidate 0's CTAs carry it), as in round 1
+            e = launch_iir_rows(a, g, 2, (int)n, ctx->stream, &maps);
+            S.launches += 1;
         } else {            // cp.async kernels: candidate 0's CTAs carry the source's half along
             e = launch_iir_rows(a, g, 2, (int)n, ctx->stream, nullptr);
             S.launches += 1;
         }
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
         Src.rows_valid = true;
+        Src.musig_valid = false;
         CK(cudaEventRecord(S.k[2], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->stream, Src.ready, 0));
         e = launch_iir_cols(a, plan.first_cta, plan.tiles_x, (int)n, ctx->stream);
@@ -628,6 +724,10 @@ int wait_common(oavif_ssimu2_ctx *ctx, double *scores)
     }
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(S.k[4]));
+    if (*ctx->h_wave_err) {
+        *ctx->h_wave_err = 0;
+        return fail(ctx, OAVIF_SSIMU2_E_CUDA, "fused blur: a strip gave up waiting for its left neighbour's row state");
+    }
     for (uint32_t i = 0; i < S.n; ++i) scores[i] = S.h_scores[i];
     float ms = 0.f;
     oavif_ssimu2_timing &t = ctx->timing;
@@ -686,6 +786,7 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
     ctx->cur ^= 1;
     SrcSet &Src = ctx->src[ctx->cur];
     Src.rows_valid = false;
+    Src.musig_valid = false;
     cudaStream_t ss = ctx->src_stream;
     CK(cudaStreamWaitEvent(ss, Src.last_use, 0));     // submissions that read this set two images ago
     const int sb = ctx->src_buf ^= 1;
@@ -703,7 +804,8 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
     CK(cudaEventRecord(ctx->src_consumed[sb], ss));
     CK(cudaEventRecord(Src.pyr_ready, ss));
     ctx->timing.launches = 1;
-    if (ctx->blur_mode == OAVIF_SSIMU2_BLUR_RECURSIVE) {
+    if (ctx->blur_mode == OAVIF_SSIMU2_BLUR_RECURSIVE && ctx->tile_path == OAVIF_SSIMU2_TILES_TMA &&
+        ctx->source_rows == OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE) {
         IirRowsTmaMaps maps;
         if (rows_maps_for(ctx, Src, &maps)) {         // rows pass of (a, a*a), once per source
             const cudaError_t e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, 3, 1, ss, &maps);
@@ -790,6 +892,10 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     cudaFree(ctx->d_dist_pyr);
     cudaFree(ctx->d_hplanes);
     cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_units);
+    cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_mailbox);
+    cudaFreeHost(ctx->h_wave_err);
     cudaFree((void *)ctx->d_tbl);
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_dbg);
@@ -855,6 +961,26 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     CKC(alloc_guarded(ctx, &ctx->d_dist_pyr, sizeof(float) * ctx->cap_pyr_floats * max_batch));
     CKC(alloc_guarded(ctx, &ctx->d_hplanes, sizeof(float) * ctx->cap_hplane_floats * max_batch));
     CKC(cudaMalloc(&ctx->d_lut, sizeof(float) * 256));
+    {   // fused kernel: unit list, ticket, mailbox (sized for the taller orientation of the capacity box), error flag
+        Geom gm;
+        long long so[kMaxScales];
+        int rows[kMaxScales];
+        make_geom(mw, mh, &gm);
+        ctx->cap_units = (unsigned)wave_units(gm).size();
+        long long words = wave_mailbox_words(gm, 5, so, rows);
+        make_geom(mh, mw, &gm);
+        ctx->cap_units = std::max<unsigned>(ctx->cap_units, (unsigned)wave_units(gm).size()) + 64;
+        words = std::max(words, wave_mailbox_words(gm, 5, so, rows));
+        ctx->cap_mailbox_words = words + 1024;
+        CKC(cudaMalloc(&ctx->d_units, sizeof(unsigned) * ctx->cap_units));
+        CKC(cudaMalloc(&ctx->d_ticket, sizeof(unsigned)));
+        CKC(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned)));
+        CKC(alloc_guarded(ctx, &ctx->d_mailbox, sizeof(unsigned long long) * ctx->cap_mailbox_words * max_batch));
+        CKC(cudaMemset(ctx->d_mailbox, 0, sizeof(unsigned long long) * ctx->cap_mailbox_words * max_batch));
+        CKC(cudaHostAlloc((void **)&ctx->h_wave_err, sizeof(int), cudaHostAllocMapped));
+        *ctx->h_wave_err = 0;
+        CKC(cudaHostGetDevicePointer((void **)&ctx->dm_wave_err, ctx->h_wave_err, 0));
+    }
     CKC(cudaMalloc((void **)&ctx->d_tbl, sizeof(void *) * 3 * (max_batch + 1) * kSlots));
     CKC(cudaHostAlloc((void **)&ctx->h_tbl, sizeof(void *) * 3 * (max_batch + 1) * kSlots, cudaHostAllocDefault));
     CKC(alloc_guarded(ctx, &ctx->d_partials, sizeof(double) * 6 * ctx->cap_ctas * max_batch));
@@ -890,8 +1016,13 @@ int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value)
         return 0;
     }
     if (option == OAVIF_SSIMU2_OPT_TILE_PATH &&
-        (value == OAVIF_SSIMU2_TILES_TMA || value == OAVIF_SSIMU2_TILES_CP_ASYNC)) {
+        (value == OAVIF_SSIMU2_TILES_TMA || value == OAVIF_SSIMU2_TILES_CP_ASYNC || value == OAVIF_SSIMU2_TILES_FUSED)) {
         ctx->tile_path = value;
+        return 0;
+    }
+    if (option == OAVIF_SSIMU2_OPT_SOURCE_ROWS &&
+        (value == OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE || value == OAVIF_SSIMU2_SOURCE_ROWS_WITH_FIRST_SCORE)) {
+        ctx->source_rows = value;
         return 0;
     }
     if (option == OAVIF_SSIMU2_OPT_WEIGHTS &&
@@ -909,6 +1040,7 @@ int oavif_ssimu2_get_option(const oavif_ssimu2_ctx *ctx, int option, int *value)
     case OAVIF_SSIMU2_OPT_BLUR: *value = ctx->blur_mode; return 0;
     case OAVIF_SSIMU2_OPT_WEIGHTS: *value = ctx->weight_layout; return 0;
     case OAVIF_SSIMU2_OPT_TILE_PATH: *value = ctx->tile_path; return 0;
+    case OAVIF_SSIMU2_OPT_SOURCE_ROWS: *value = ctx->source_rows; return 0;
     default: return OAVIF_SSIMU2_E_ARG;
     }
 }
@@ -1277,7 +1409,7 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
                                 uint32_t *w_out, uint32_t *h_out)
 {
     if (!ctx || !out || !w_out || !h_out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
-    if (!ctx->have_source || ctx->last_n == 0 || ctx->blur_mode != OAVIF_SSIMU2_BLUR_RECURSIVE || !ctx->src[ctx->cur].rows_valid ||
+    if (!ctx->have_source || ctx->last_n == 0 || ctx->blur_mode != OAVIF_SSIMU2_BLUR_RECURSIVE || !(ctx->src[ctx->cur].rows_valid || ctx->src[ctx->cur].musig_valid) ||
         scale < 0 || scale >= ctx->g.n_scales || channel < 0 || channel > 2 || candidate < 0 ||
         candidate >= (int)ctx->last_n)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such blurred plane (needs a RECURSIVE score call first)");
@@ -1298,9 +1430,14 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
     BlurPlan plan;
     plan_iir_v(g, &plan);
     const IirDebugTap tap{ctx->d_dbg, scale, channel, candidate};
-    const cudaError_t e = launch_iir_cols(iir_args_for(ctx, ctx->src[ctx->cur]), plan.first_cta, plan.tiles_x, (int)ctx->last_n,
-                                          ctx->stream, &tap);
-    if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
+    if (ctx->tile_path == OAVIF_SSIMU2_TILES_FUSED) {   // the fused kernel's own tap instance, cached-source form
+        const int rc = enqueue_wave(ctx, ctx->src[ctx->cur], plan, 1, 0, ctx->last_n, &tap);
+        if (rc) return rc;
+    } else {
+        const cudaError_t e = launch_iir_cols(iir_args_for(ctx, ctx->src[ctx->cur]), plan.first_cta, plan.tiles_x,
+                                              (int)ctx->last_n, ctx->stream, &tap);
+        if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
+    }
     CK(cudaMemcpyAsync(out, ctx->d_dbg, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     *w_out = (uint32_t)w;
@@ -1364,11 +1501,32 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
     const bool tma = !(variant & 8) && rows_maps_for(ctx, Src, &maps);
     const int which = (variant & 128) ? 3 : (variant & 4) ? 1 : 2;
     if (which == 3 && !tma) return fail(ctx, OAVIF_SSIMU2_E_ARG, "the source-only rows kernel exists in the TMA form only");
+    if ((variant & 2048) && !Src.musig_valid) return fail(ctx, OAVIF_SSIMU2_E_STATE, "no cached source blur: score in FUSED mode first");
     CK(cudaStreamSynchronize(ctx->src_stream));
     CK(cudaEventRecord(ctx->src_up0, ctx->stream));
     for (int i = 0; i < iters; ++i) {
-        const cudaError_t e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, which, 1, ctx->stream, tma ? &maps : nullptr,
-                                              (variant >> 4) & 7);
+        cudaError_t e;
+        if (variant & (1024 | 2048)) {   // the fused kernel: all five quantities / the candidate's three (cached source blur)
+            BlurPlan cp;
+            plan_iir_v(ctx->g, &cp);
+            const int rc = enqueue_wave(ctx, Src, cp, (variant & 1024) ? 2 : 1, 0, 1);
+            if (rc) return rc;
+            e = cudaSuccess;
+        } else if (variant & 256) { // the two halves as the product issues them: source stream next to compute stream
+            if (!tma) return fail(ctx, OAVIF_SSIMU2_E_ARG, "the split rows pass exists in the TMA form only");
+            CK(cudaEventRecord(ctx->ev_user, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->src_stream, ctx->ev_user, 0));
+            e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, 3, 1, ctx->src_stream, &maps);
+            if (e == cudaSuccess) e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, 1, 1, ctx->stream, &maps);
+            CK(cudaEventRecord(Src.ready, ctx->src_stream));
+            CK(cudaStreamWaitEvent(ctx->stream, Src.ready, 0));
+        } else if (variant & 512) { // the columns pass alone
+            BlurPlan cp;
+            plan_iir_v(ctx->g, &cp);
+            e = launch_iir_cols(iir_args_for(ctx, Src), cp.first_cta, cp.tiles_x, 1, ctx->stream);
+        } else {
+            e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, which, 1, ctx->stream, tma ? &maps : nullptr, (variant >> 4) & 7);
+        }
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
     }
     CK(cudaEventRecord(ctx->src_up1, ctx->stream));

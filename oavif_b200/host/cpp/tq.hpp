@@ -294,18 +294,44 @@ struct BatchedStats {
     uint32_t device_passes = 0, probes = 0, wasted = 0;
 };
 
+// score(q) is monotone and, over the range a search visits, close to linear with a slope the history reveals
+// (two probes) or that is typical of libaom at speed 9 (one probe: ~0.45 points per q step).  `expected_error`
+// is where that prior puts (score - target) of the probe the policy wants next.
+inline double expectedError(const TQSearch &s, const TQOptions &o, uint32_t want)
+{
+    const auto &h = s.history();
+    if (h.empty()) return 0.0;   // pass 0 probes predictQFromScore(target): the prior says "on target"
+    double slope = 0.45;
+    if (h.size() >= 2) {
+        const PassResult &a = h[h.size() - 2], &b = h.back();
+        if (a.q != b.q) slope = std::min(2.0, std::max(0.05, (b.score - a.score) / ((double)b.q - (double)a.q)));
+    }
+    return h.back().score + slope * ((double)want - (double)h.back().q) - o.score_tgt;
+}
+
+// The q the policy wants now, then the qs it would want NEXT under hypothetical outcomes of that probe, most
+// plausible first: outcomes are ranked by their distance from the monotone prior's expectation, so a narrow batch
+// spends its extra encodes where the search is most likely to go.
 inline std::vector<uint32_t> speculate(const TQSearch &s, const TQOptions &o, uint32_t width)
 {
     std::vector<uint32_t> qs;
     auto want = s.next();
     if (!want) return qs;
     qs.push_back(*want);
-    // Hypothetical outcomes of the wanted probe, nearest misses first, alternating sign: on the first
-    // pass the next q only depends on ceil(|err|) and the sign (tq.zig:155-164), so half-unit steps hit
-    // every bucket; on later passes they sample the interpolation densely enough around the target.
-    for (int i = 0; i < 80 && qs.size() < width; ++i) {
+    if (width <= 1) return qs;
+    // Hypothetical errors: on the first pass the next q only depends on ceil(|err|) and the sign (tq.zig:155-164),
+    // so half-unit steps hit every bucket; on later passes they sample the interpolation densely enough.  An
+    // outcome inside the tolerance ends the search and needs no candidate.
+    std::vector<double> deltas;
+    for (int i = 0; i < 80; ++i) {
         const double mag = o.tolerance + 0.25 + 0.5 * (i / 2);
-        const double dlt = (i & 1) ? -mag : mag;
+        deltas.push_back((i & 1) ? -mag : mag);
+    }
+    const double centre = expectedError(s, o, *want);
+    std::stable_sort(deltas.begin(), deltas.end(),
+                     [&](double a, double b) { return std::fabs(a - centre) < std::fabs(b - centre); });
+    for (double dlt : deltas) {
+        if (qs.size() >= width) break;
         TQSearch h = s;
         h.record(*want, o.score_tgt + dlt);
         if (auto nq = h.next())

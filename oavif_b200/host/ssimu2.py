@@ -24,8 +24,9 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "liboavif_ssimu2.so
 MAX_SCALES = 6
 BLUR_RECURSIVE, BLUR_FIR = 0, 1
 WEIGHTS_SIX_SLOTS, WEIGHTS_CONTIGUOUS = 0, 1
-TILES_TMA, TILES_CP_ASYNC = 0, 1
-OPT_BLUR, OPT_WEIGHTS, OPT_TILE_PATH = 1, 2, 3
+TILES_TMA, TILES_CP_ASYNC, TILES_FUSED = 0, 1, 2
+SOURCE_ROWS_AT_SET_SOURCE, SOURCE_ROWS_WITH_FIRST_SCORE = 0, 1
+OPT_BLUR, OPT_WEIGHTS, OPT_TILE_PATH, OPT_SOURCE_ROWS = 1, 2, 3, 4
 
 E_ARG, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 _ENAMES = {E_ARG: "InvalidArgument", E_CUDA: "CudaError", E_NOMEM: "OutOfMemory",
@@ -192,6 +193,9 @@ class Scorer:
 
     def set_tile_path(self, path: int):
         _check(self._L.oavif_ssimu2_set_option(self._ctx, OPT_TILE_PATH, path), self._ctx)
+
+    def set_option(self, option: int, value: int):
+        _check(self._L.oavif_ssimu2_set_option(self._ctx, option, value), self._ctx)
 
     def get_option(self, option: int) -> int:
         v = C.c_int()

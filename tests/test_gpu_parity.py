@@ -95,6 +95,15 @@ def tile_path(request, scorer):
     scorer.set_tile_path(ssimu2.TILES_TMA)
 
 
+@pytest.fixture(params=[ssimu2.TILES_TMA, ssimu2.TILES_CP_ASYNC, ssimu2.TILES_FUSED], ids=["tma", "cp_async", "fused"])
+def tile_path3(request, scorer):
+    """... and the fused kernel (no row-filtered planes exist there: everything but the rows tap applies)."""
+    scorer.set_tile_path(request.param)
+    yield request.param
+    assert scorer.get_option(ssimu2.OPT_TILE_PATH) == request.param
+    scorer.set_tile_path(ssimu2.TILES_TMA)
+
+
 @pytest.mark.parametrize("size", [(64, 64), (65, 63), (100, 75), (333, 257), (1027, 771)])
 def test_rows_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size, tile_path):
     """k_iir_rows_tma / k_iir_rows (packed-pair recursion, interleaved pair planes) against the oracle's horizontal
@@ -130,7 +139,7 @@ def test_rows_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size, til
 
 # ---- K4+K5, product kernel: what the columns pass hands to the error maps ----------------------------------
 @pytest.mark.parametrize("size", [(64, 64), (65, 63), (100, 75), (333, 257), (700, 300)])
-def test_cols_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size, tile_path):
+def test_cols_pass_of_the_scored_path_is_bit_identical(scorer, oracle, size, tile_path3):
     """k_iir_cols (the kernel on the scored path, not the plain debug filter): the five fully blurred values it
     feeds the SSIM / edge-diff maps — mu1, mu2, sigma11, sigma22, sigma12 — against the oracle's two-pass blur,
     bit for bit, every scale and channel, single call and second candidate of a batch."""
@@ -358,12 +367,12 @@ def test_source_rows_cache_follows_the_source_and_the_blur_mode(scorer, oracle):
 
 
 def test_tile_paths_give_the_same_bits(scorer):
-    """TMA and cp.async forms of the recursive kernels: identical pooled sums and scores, single and batch."""
+    """TMA, cp.async and fused forms of the recursive kernels: identical pooled sums and scores, single and batch."""
     src = synth.synth(1000, 700, "mixture", 14)
     cands = [synth.distort(src, s, seed=i) for i, s in enumerate((0.2, 0.5, 0.9))]
     scorer.set_blur(ssimu2.BLUR_RECURSIVE)
     res = {}
-    for path in (ssimu2.TILES_TMA, ssimu2.TILES_CP_ASYNC):
+    for path in (ssimu2.TILES_TMA, ssimu2.TILES_CP_ASYNC, ssimu2.TILES_FUSED):
         scorer.set_tile_path(path)
         scorer.set_source(src)
         single = [scorer.score_rgb8(c) for c in cands]
@@ -372,10 +381,12 @@ def test_tile_paths_give_the_same_bits(scorer):
         res[path] = (single, batch, [scorer.sums(i).copy() for i in range(3)])
         assert scorer.get_option(ssimu2.OPT_TILE_PATH) == path
     scorer.set_tile_path(ssimu2.TILES_TMA)
-    a, b = res[ssimu2.TILES_TMA], res[ssimu2.TILES_CP_ASYNC]
-    assert a[0] == b[0] == a[1] == b[1]
-    for x, y in zip(a[2], b[2]):
-        np.testing.assert_array_equal(x, y)
+    a = res[ssimu2.TILES_TMA]
+    for other in (ssimu2.TILES_CP_ASYNC, ssimu2.TILES_FUSED):
+        b = res[other]
+        assert a[0] == b[0] == a[1] == b[1], other
+        for x, y in zip(a[2], b[2]):
+            np.testing.assert_array_equal(x, y)
 
 
 def test_modes_differ_only_by_recursion_roundoff(scorer):
@@ -463,7 +474,7 @@ def test_no_kernel_writes_past_its_buffers(size):
     d1, d2 = synth.distort(src, 0.2), synth.distort(src, 0.7)
     with ssimu2.Scorer(w, h, 2) as sc:
         for mode, path in ((ssimu2.BLUR_RECURSIVE, ssimu2.TILES_TMA), (ssimu2.BLUR_RECURSIVE, ssimu2.TILES_CP_ASYNC),
-                           (ssimu2.BLUR_FIR, ssimu2.TILES_TMA)):
+                           (ssimu2.BLUR_RECURSIVE, ssimu2.TILES_FUSED), (ssimu2.BLUR_FIR, ssimu2.TILES_TMA)):
             sc.set_blur(mode)
             sc.set_tile_path(path)
             sc.set_source(src)
