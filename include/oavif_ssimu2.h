@@ -259,6 +259,11 @@ int oavif_ssimu2_debug_get_rows(oavif_ssimu2_ctx *ctx, int candidate, int quanti
 int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale, int channel, float *out,
                                 uint32_t *w_out, uint32_t *h_out);
 
+/* Timeline of one launch of the FUSED kernel over the last scored pair (mode 2: all five quantities, 1: cached source
+ * blur): per CTA, in ticket order, five 64-bit words {unit = scale | channel << 4 | strip << 8, start, end of the
+ * prologue, middle phase, end} from %globaltimer (ns).  Shows how the wavefront of strips actually advances. */
+int oavif_ssimu2_debug_wave_trace(oavif_ssimu2_ctx *ctx, int mode, uint64_t *out, uint32_t cap_units, uint32_t *n_units);
+
 /* Blur one host plane with the selected blur on the device (tests of the filter alone). */
 int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, uint32_t h,
                             float *out);

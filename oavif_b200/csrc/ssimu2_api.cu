@@ -95,6 +95,7 @@ struct oavif_ssimu2_ctx {
     unsigned long long *d_mailbox = nullptr;
     long long cap_mailbox_words = 0;      // per candidate
     int *h_wave_err = nullptr, *dm_wave_err = nullptr;   // pinned, mapped
+    unsigned long long *trace_buf = nullptr;             // oavif_ssimu2_debug_wave_trace
 
     // capacities (computed from max_w x max_h)
     long long cap_pyr_floats = 0, cap_in_bytes = 0, cap_ctas = 0, cap_hplane_floats = 0;
@@ -556,6 +557,7 @@ int enqueue_wave(oavif_ssimu2_ctx *ctx, SrcSet &Src, const BlurPlan &plan, int m
         a.dbg_scale = tap->scale;
         a.dbg_channel = tap->channel;
         a.dbg_cand = tap->cand;
+        a.dbg_trace = ctx->trace_buf;
         e = mode == 2 ? wave_launch<2, true>(a, wm, ctx->stream) : wave_launch<1, true>(a, wm, ctx->stream);
     } else {
         e = mode == 2 ? wave_launch<2, false>(a, wm, ctx->stream) : wave_launch<1, false>(a, wm, ctx->stream);
@@ -1442,6 +1444,36 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
     CK(cudaStreamSynchronize(ctx->stream));
     *w_out = (uint32_t)w;
     *h_out = (uint32_t)h;
+    return 0;
+}
+
+int oavif_ssimu2_debug_wave_trace(oavif_ssimu2_ctx *ctx, int mode, uint64_t *out, uint32_t cap_units, uint32_t *n_units)
+{
+    if (!ctx || !out || !n_units) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    if (!ctx->have_source || ctx->last_n == 0 || ctx->g.n_scales == 0 || ctx->inflight)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "needs a previous score call and nothing in flight");
+    SrcSet &Src = ctx->src[ctx->cur];
+    if (mode == 1 && !Src.musig_valid) return fail(ctx, OAVIF_SSIMU2_E_STATE, "no cached source blur: score in FUSED mode first");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->src_stream));
+    BlurPlan plan;
+    plan_iir_v(ctx->g, &plan);
+    unsigned long long *d_trace = nullptr;
+    CK(cudaMalloc(&d_trace, sizeof(unsigned long long) * 5 * (ctx->cap_units + 64)));
+    CK(cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 5 * (ctx->cap_units + 64), ctx->stream));
+    ctx->trace_buf = d_trace;
+    const IirDebugTap tap{nullptr, -1, -1, -1};
+    const int rc = enqueue_wave(ctx, Src, plan, mode == 2 ? 2 : 1, 0, 1, &tap);
+    ctx->trace_buf = nullptr;
+    if (rc) {
+        cudaFree(d_trace);
+        return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_units = ctx->n_units;
+    const uint32_t n = std::min(cap_units, ctx->n_units);
+    CK(cudaMemcpy(out, d_trace, sizeof(unsigned long long) * 5 * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_trace);
     return 0;
 }
 

@@ -65,6 +65,7 @@ struct WaveArgs {
     long long partials_stride;
     int first_cta[kMaxScales + 1], blocks[kMaxScales];   // the columns plan: where a unit's six sums go
     int *error_flag;                // set when a hand-off wait gives up
+    unsigned long long *dbg_trace;  // TAP instances: per ticket {unit, t0, t after the prologue, t at phase nphase/2, t end} (ns)
     float *dbg_cols;                // oavif_ssimu2_debug_get_cols (TAP instances only)
     int dbg_scale, dbg_channel, dbg_cand;
 };
@@ -169,6 +170,8 @@ __global__ void __launch_bounds__(WaveCfg<MODE>::THREADS, 2)
         mbar_init_fence();
     }
     __syncthreads();
+    unsigned long long t_begin = 0;
+    if (TAP && a.dbg_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     const unsigned unit = a.units[sm.ticket / a.n_cand];
     const int cand = (int)(a.cand0 + sm.ticket % a.n_cand);
     const int s = (int)(unit & 15u), c = (int)((unit >> 4) & 15u), t = (int)(unit >> 8);
@@ -211,13 +214,21 @@ __global__ void __launch_bounds__(WaveCfg<MODE>::THREADS, 2)
         issue_tile(1);
         issue_ms(0);
         __syncthreads();   // (P) chunk 0 is row-filtered
+        unsigned long long t_pro = 0, t_mid = 0, t_end = 0;
+        if (TAP && a.dbg_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_pro));
 #pragma unroll 1
         for (int q = 0; q < nphase; ++q) {
             if (!(q & 1)) issue_tile(q / 2 + 2);   // its slot held chunk q/2 - 2, dead since the barrier that ended phase q - 1
             issue_ms(q + 1);
             __syncthreads();
+            if (TAP && a.dbg_trace && q == nphase / 2) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_mid));
         }
         __syncthreads();   // final reduction
+        if (TAP && a.dbg_trace && lane == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            unsigned long long *o = a.dbg_trace + 5ull * sm.ticket;
+            o[0] = unit; o[1] = t_begin; o[2] = t_pro; o[3] = t_mid; o[4] = t_end;
+        }
         return;
     }
 

@@ -45,7 +45,7 @@ SYMBOLS = (
     "oavif_ssimu2_get_timing", "oavif_ssimu2_debug_get_xyb", "oavif_ssimu2_debug_get_rows", "oavif_ssimu2_debug_blur",
     "oavif_ssimu2_debug_time_rows", "oavif_ssimu2_debug_check_guards", "oavif_ssimu2_debug_get_cols",
     "oavif_ssimu2_set_default_device", "oavif_ssimu2_release_cached",
-    "oavif_ssimu2_get_option", "oavif_ssimu2_device_pci_bus_id", "oavif_ssimu2_submit_rgb8", "oavif_ssimu2_submit_yuv444",
+    "oavif_ssimu2_get_option", "oavif_ssimu2_device_pci_bus_id", "oavif_ssimu2_debug_wave_trace", "oavif_ssimu2_submit_rgb8", "oavif_ssimu2_submit_yuv444",
     "oavif_ssimu2_submit_rgb8_dev", "oavif_ssimu2_submit_yuv444_dev", "oavif_ssimu2_wait", "oavif_ssimu2_in_flight",
 )
 
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
     L.oavif_ssimu2_debug_get_cols.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32), C.POINTER(u32)]
     L.oavif_ssimu2_set_default_device.argtypes = [C.c_int]
     L.oavif_ssimu2_release_cached.restype = None
+    L.oavif_ssimu2_debug_wave_trace.argtypes = [vp, C.c_int, vp, u32, C.POINTER(u32)]
     L.oavif_ssimu2_debug_blur.argtypes = [vp, vp, u32, u32, vp]
     L.oavif_ssimu2_debug_check_guards.argtypes = [vp]
     L.oavif_ssimu2_debug_time_rows.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -416,6 +417,13 @@ class Scorer:
         _check(self._L.oavif_ssimu2_debug_get_cols(self._ctx, candidate, scale, channel, buf.ctypes.data,
                                                    C.byref(w), C.byref(h)), self._ctx)
         return buf[: 5 * w.value * h.value].reshape(5, h.value, w.value).copy()
+
+    def wave_trace(self, mode: int = 2) -> np.ndarray:
+        """(n_units, 5) uint64: unit, start, prologue end, middle phase, end (ns) of every CTA of one FUSED launch."""
+        buf = np.zeros((8192, 5), np.uint64)
+        n = C.c_uint32()
+        _check(self._L.oavif_ssimu2_debug_wave_trace(self._ctx, mode, buf.ctypes.data, 8192, C.byref(n)), self._ctx)
+        return buf[: min(n.value, 8192)].copy()
 
     def check_guards(self):
         """Raises if any kernel wrote past one of the context's device buffers."""
