@@ -240,8 +240,8 @@ def run_ours(args):
     # candidate side.  Every timed loop below ends with a host-synchronous call, so the torch events recorded on
     # the (otherwise idle) current stream bracket the work exactly.
     sc = ssimu2.Scorer(W, H, 1, device=local, blur=mode)
-    if args.source_rows == "first-score":
-        sc.set_option(ssimu2.OPT_SOURCE_ROWS, ssimu2.SOURCE_ROWS_WITH_FIRST_SCORE)
+    sc.set_option(ssimu2.OPT_SOURCE_ROWS, ssimu2.SOURCE_ROWS_WITH_FIRST_SCORE if args.source_rows == "first-score"
+                  else ssimu2.SOURCE_ROWS_AT_SET_SOURCE)
     stream = torch.cuda.current_stream()
 
     dev_ptrs = [(s.data_ptr(), [[y.data_ptr(), u.data_ptr(), v.data_ptr()]]) for s, (y, u, v) in dev]
@@ -307,7 +307,9 @@ def run_ours(args):
         ktimes["a"].append(t.blur_a_ms)
         ktimes["b"].append(t.blur_b_ms)
         ktimes["fin"].append(t.finalize_ms)
-        ktimes["launches"] = t.launches + 2   # per step; + set_source: the source's pyramid and its rows pass
+        # per step: the submission's launches + what set_source enqueued (the source's pyramid; its rows pass too when
+        # OAVIF_SSIMU2_OPT_SOURCE_ROWS puts it there)
+        ktimes["launches"] = t.launches + (1 if args.source_rows == "first-score" else 2)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -418,9 +420,9 @@ def run_ours(args):
         dom, dom_ms, alg = "k_fir_fused", float(np.mean(ktimes["a"])), ALG_BYTES_KERNEL["fir"]
     else:
         # the rows pass = its two halves as issued (source stream next to compute stream); the columns pass alone
-        a_ms = iso.get("k_iir_rows(both halves, two streams)", iso["k_iir_rows(both halves, one launch)"])
-        if args.source_rows == "first-score":
-            a_ms = iso["k_iir_rows(both halves, one launch)"]
+        a_ms = iso["k_iir_rows(both halves, one launch)"]
+        if args.source_rows == "set-source":
+            a_ms = iso.get("k_iir_rows(both halves, two streams)", a_ms)
         b_ms = iso["k_iir_cols"]
         if b_ms >= a_ms:
             dom, dom_ms, alg = "k_iir_cols", b_ms, ALG_BYTES_KERNEL["cols"]
@@ -437,7 +439,8 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(args.blur),
-        "issue": "one caller, one context; step i is submitted (set_source + submit) before step i-1 is retired (wait)",
+        "issue": "one caller, one context; step i is submitted (set_source + submit) before step i-1 is retired (wait): two "
+                 "submissions in flight, each on its own compute stream",
         "tile_path": "tma" if sc.get_option(ssimu2.OPT_TILE_PATH) == ssimu2.TILES_TMA else "cp.async",
         "e2e": {"value": round(e2e, 1), "unit": "Mpx/s", "h2d_bytes_per_step": W * H * 9, "d2h_bytes_per_step": 8 + 864,
                 "ms_per_step": round(ms_pipe / args.steps, 4), "host_memory": "pinned (oavif_ssimu2_pinned_alloc)",
@@ -453,6 +456,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
                      "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": "profiles/traffic.json <- ncu --set full capture of this kernel (profiles/r2_final_ncu_*.txt)",
+                     "kernel_ms_source": "that kernel alone, 100 launches between two CUDA events on its stream, in this run",
                      "alg_bytes_per_px": round(alg, 2), "kernel_ms": round(dom_ms, 4),
                      "whole_step": {"alg_bytes_per_px": round(ALG_BYTES_FULL, 2),
                                     "achieved": round(ALG_BYTES_FULL * W * H / (step_ms / 1e3) / 1e9, 1),
@@ -462,8 +467,8 @@ def run_ours(args):
                                   ("k_fir_fused" if mode == ssimu2.BLUR_FIR else "k_iir_rows(candidate half)"): round(float(np.mean(ktimes["a"])), 4),
                                   **({} if mode == ssimu2.BLUR_FIR else {"k_iir_cols": round(float(np.mean(ktimes["b"])), 4)}),
                                   "k_finalize": round(float(np.mean(ktimes["fin"])), 4),
-                                  "note": "events on the compute stream inside the timed steps; the source's pyramid and rows pass "
-                                          "run on the source stream next to the first two"},
+                                  "note": "events on the submission's compute stream inside the timed steps, where the other "
+                                          "submission in flight and the source stream share the device: not kernel durations"},
                       "alone": {k: round(v, 4) for k, v in iso.items()}},
         "sync_calls": {"value": round(world * MPX * args.steps / (ms_dev_sync / 1e3), 1), "unit": "Mpx/s",
                        "ms_per_step": round(ms_dev_sync / args.steps, 4),
@@ -520,7 +525,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blur", default="recursive", choices=["recursive", "fir"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--source-rows", default="set-source", choices=["set-source", "first-score"],
+    ap.add_argument("--source-rows", default="first-score", choices=["set-source", "first-score"],
                     help="OAVIF_SSIMU2_OPT_SOURCE_ROWS (A/B): where the rows pass of the source's quantities runs")
     ap.add_argument("--ref-seconds", type=float, default=0.0,
                     help="--impl reference: seconds of CPU work per step (default: scaled to --steps)")

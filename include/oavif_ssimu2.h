@@ -73,10 +73,12 @@ enum { OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS = 0, OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS = 1 }
  * Same arithmetic, same bits in all three. */
 enum { OAVIF_SSIMU2_TILES_TMA = 0, OAVIF_SSIMU2_TILES_CP_ASYNC = 1, OAVIF_SSIMU2_TILES_FUSED = 2 };
 
-/* When the rows pass of the source-only quantities (a, a*a) runs (RECURSIVE blur, TMA kernels).  AT_SET_SOURCE
- * (default): a launch of its own on the source stream, enqueued by set_source — it overlaps the candidate's
- * pyramid and rows pass, and with pipelined callers the previous image's columns pass.  WITH_FIRST_SCORE: carried by
- * the first scoring call's rows kernel (candidate 0's CTAs), as in round 1. */
+/* When the rows pass of the source-only quantities (a, a*a) runs (RECURSIVE blur, TMA kernels).  WITH_FIRST_SCORE
+ * (default): carried by the first scoring call's rows kernel (candidate 0's CTAs run a second pair warp), cached
+ * for every later candidate of the source.  AT_SET_SOURCE: a launch of its own on the source stream, enqueued by
+ * set_source next to the source's pyramid.  Measured equal for pipelined callers (0.518 ms per 4K evaluation either
+ * way) and 5 % slower for synchronous ones (the lone source half is bound by its one recursion warp per CTA), hence
+ * not the default; useful when set_source happens long before the first score. */
 enum { OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE = 0, OAVIF_SSIMU2_SOURCE_ROWS_WITH_FIRST_SCORE = 1 };
 
 enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_WEIGHTS = 2, OAVIF_SSIMU2_OPT_TILE_PATH = 3, OAVIF_SSIMU2_OPT_SOURCE_ROWS = 4 };
@@ -135,11 +137,11 @@ void oavif_ssimu2_pinned_free(void *p);
 
 /* ---- source side: once per image (main.zig:86) ------------------------------------------ */
 
-/* rgb: interleaved 8-bit RGB, `stride` bytes per row (>= 3*w).  Uploads, builds and caches the source side
- * on the device: the six-scale XYB pyramid and, for the RECURSIVE blur, the rows pass of the two source-only
- * quantities (a, a*a).  Both kernels run on the context's SOURCE stream, next to whatever the compute stream is
- * doing (the candidate's pyramid and rows pass of the same evaluation, or the previous image's submissions):
- * the source side exists twice, so a new source never waits for submissions that still read the old one.
+/* rgb: interleaved 8-bit RGB, `stride` bytes per row (>= 3*w).  Uploads the source and builds its six-scale XYB
+ * pyramid on the context's SOURCE stream, next to whatever the compute streams are doing (the candidate's pyramid of
+ * the same evaluation, or the previous image's submissions): the source side exists twice, so a new source never
+ * waits for submissions that still read the old one.  For the RECURSIVE blur the rows pass of the two source-only
+ * quantities (a, a*a) is computed once per source and cached (see OAVIF_SSIMU2_OPT_SOURCE_ROWS for when).
  * Returns once the caller's pixels have been read. */
 int oavif_ssimu2_set_source_rgb8(oavif_ssimu2_ctx *ctx, const uint8_t *rgb, uint32_t w,
                                  uint32_t h, size_t stride);
@@ -184,10 +186,12 @@ int oavif_ssimu2_score_batch_yuv444(oavif_ssimu2_ctx *ctx, uint32_t n, const voi
  * submit_* enqueues the upload (on the context's copy stream) and the kernels (on its compute stream) of
  * n candidates and returns at once; wait retires the OLDEST submission and stores its n scores.  Up to
  * two submissions may be in flight, and set_source_* may be called while one is: the upload of image
- * i+1 then runs under the kernels of image i, which is what one caller needs to keep the PCIe link busy
+ * i+1 then runs under the kernels of image i, which is what one caller needs to keep the PCIe link busy,
+ * and the two submissions' kernels run on two compute streams with candidate-side buffers of their own,
+ * so the rows pass of one fills the tails of the other's columns pass
  * (the synchronous score_* calls are submit + wait).  Caller memory passed to submit_* must stay valid
- * and unmodified until the matching wait returns.  The staging buffer of the second slot is allocated
- * by the first submit that finds another one in flight.  get_detail / get_timing describe the
+ * and unmodified until the matching wait returns.  The second slot's buffers (staging, pyramid, row-filtered
+ * planes: about as much again as the context itself) are allocated by the first submit that needs them.  get_detail / get_timing describe the
  * submission retired last. */
 int oavif_ssimu2_submit_rgb8(oavif_ssimu2_ctx *ctx, uint32_t n, const uint8_t *const *dists,
                              size_t stride);

@@ -49,9 +49,26 @@ int g_default_device = 0;
 
 constexpr int kSlots = 2;   // submissions that may be in flight at once (oavif_ssimu2_submit_* / _wait)
 
-// One submission: its staged candidates, its result buffers and its events.  Everything else (pyramids,
-// row-filtered planes, partial sums) is shared: the compute stream runs submissions in order.
+// Everything on the candidate side of an evaluation.  Each of the two submission slots owns one, with a compute
+// stream of its own: the kernels of two submissions in flight overlap (the rows pass of one fills the tails of the
+// other's columns pass), which is what two callers on two contexts got in round 1.
+struct CandSide {
+    cudaStream_t own_stream = nullptr, stream = nullptr;   // stream: own, or the caller's (set_stream)
+    float *d_dist_pyr = nullptr, *d_hplanes = nullptr;
+    double *d_partials = nullptr;
+    IirRowsTmaMaps cand_maps{};    // TMA descriptors of the candidates' planes (in_dist, out_pcand, out_ab) for maps_w x maps_h
+    int maps_w = -1, maps_h = -1;
+    // fused kernel (ssimu2_wave.cuh): unit list of the current geometry, ticket counter, mailbox
+    unsigned *d_units = nullptr, *d_ticket = nullptr;
+    unsigned n_units = 0;
+    int units_w = -1, units_h = -1;
+    unsigned long long *d_mailbox = nullptr;
+    bool allocated = false;
+};
+
+// One submission: its staged candidates, its candidate-side buffers, its result buffers and its events.
 struct Slot {
+    CandSide cs;
     uint8_t *d_in_dist = nullptr;                       // staged candidate pixels (slot 1: allocated on first use)
     double *h_sums = nullptr, *h_scores = nullptr;      // pinned, mapped: k_finalize writes them directly
     double *dm_sums = nullptr, *dm_scores = nullptr;    // device views of the two
@@ -72,7 +89,8 @@ struct SrcSet {
     bool rows_valid = false, musig_valid = false;
     cudaEvent_t pyr_ready = nullptr;       // source stream: the pyramid is complete
     cudaEvent_t ready = nullptr;           // source stream: ... and so is everything else enqueued by set_source
-    cudaEvent_t last_use = nullptr;        // compute stream: the last submission reading this set has finished
+    cudaEvent_t last_use[2] = {nullptr, nullptr};   // per slot: its last submission reading this set has finished
+    cudaEvent_t cache_done = nullptr;      // the launch that filled d_hplanes (whichever slot's stream it ran on)
     CUtensorMap in_src[kMaxScales], out_psrc[kMaxScales], in_musig[kMaxScales];
     int maps_w = -1, maps_h = -1;
 };
@@ -80,19 +98,14 @@ struct SrcSet {
 struct oavif_ssimu2_ctx {
     int device = 0;
     uint32_t max_w = 0, max_h = 0, max_batch = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;   // compute stream (own or the caller's)
+    cudaStream_t user_stream = nullptr;                    // set_stream: every submission's kernels go there instead
+    CandSide *cs = nullptr;                                // candidate side of the submission being enqueued / retired last
     cudaStream_t copy_stream = nullptr;                    // host -> device uploads: run under the previous submission's kernels
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
     int weight_layout = OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS;
     int tile_path = OAVIF_SSIMU2_TILES_TMA;
-    int source_rows = OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE;
-    IirRowsTmaMaps cand_maps{};    // TMA descriptors of the candidates' planes (in_dist, out_pcand, out_ab) for maps_w x maps_h
-    int maps_w = -1, maps_h = -1;
-    // fused kernel (ssimu2_wave.cuh): unit list of the current geometry, ticket counter, mailbox, error flag
-    unsigned *d_units = nullptr, *d_ticket = nullptr;
-    unsigned n_units = 0, cap_units = 0, wave_epoch = 0;
-    int units_w = -1, units_h = -1;
-    unsigned long long *d_mailbox = nullptr;
+    int source_rows = OAVIF_SSIMU2_SOURCE_ROWS_WITH_FIRST_SCORE;
+    unsigned cap_units = 0, wave_epoch = 0;               // fused kernel: capacities, launch counter (mailbox tags)
     long long cap_mailbox_words = 0;      // per candidate
     int *h_wave_err = nullptr, *dm_wave_err = nullptr;   // pinned, mapped
     unsigned long long *trace_buf = nullptr;             // oavif_ssimu2_debug_wave_trace
@@ -118,9 +131,8 @@ struct oavif_ssimu2_ctx {
     int cur = 0;
     cudaStream_t src_stream = nullptr;
     cudaEvent_t ev_user = nullptr;         // orders the source stream behind a caller-owned compute stream
-    float *d_dist_pyr = nullptr, *d_hplanes = nullptr, *d_lut = nullptr;
+    float *d_lut = nullptr;
     const void **d_tbl = nullptr, **h_tbl = nullptr;   // [slot][3 * (max_batch + 1)]
-    double *d_partials = nullptr;
     float *d_dbg = nullptr;
     long long dbg_floats = 0;
     uint8_t *d_conv = nullptr;     // oavif_ssimu2_yuv444_to_rgb8's output, grown on demand
@@ -462,6 +474,28 @@ int check_size(oavif_ssimu2_ctx *ctx, uint32_t w, uint32_t h)
     return 0;
 }
 
+// The candidate side of a slot: buffers sized like the context, a compute stream of its own.  Slot 0 at ctx_create;
+// slot 1 the first time a submission arrives while another is in flight.
+cudaError_t alloc_cand_side(oavif_ssimu2_ctx *ctx, CandSide &c)
+{
+    if (c.allocated) return cudaSuccess;
+    cudaError_t e;
+#define TRY(x) if ((e = (x)) != cudaSuccess) return e
+    TRY(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = ctx->user_stream ? ctx->user_stream : c.own_stream;
+    TRY(alloc_guarded(ctx, &c.d_dist_pyr, sizeof(float) * ctx->cap_pyr_floats * ctx->max_batch));
+    TRY(alloc_guarded(ctx, &c.d_hplanes, sizeof(float) * ctx->cap_hplane_floats * ctx->max_batch));
+    TRY(alloc_guarded(ctx, &c.d_partials, sizeof(double) * 6 * ctx->cap_ctas * ctx->max_batch));
+    TRY(cudaMalloc(&c.d_units, sizeof(unsigned) * ctx->cap_units));
+    TRY(cudaMalloc(&c.d_ticket, sizeof(unsigned)));
+    TRY(cudaMemset(c.d_ticket, 0, sizeof(unsigned)));
+    TRY(alloc_guarded(ctx, &c.d_mailbox, sizeof(unsigned long long) * ctx->cap_mailbox_words * ctx->max_batch));
+    TRY(cudaMemset(c.d_mailbox, 0, sizeof(unsigned long long) * ctx->cap_mailbox_words * ctx->max_batch));
+#undef TRY
+    c.allocated = true;
+    return cudaSuccess;
+}
+
 // TMA descriptors follow the geometry.  Fills `out` with the candidates' descriptors and those of source set `S`;
 // false selects the cp.async kernels (tile path switched off, or no descriptor encoder in this driver).
 bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
@@ -470,12 +504,12 @@ bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
     const Geom &g = ctx->g;
     const long long P = ctx->cap_pyr_floats;
     bool ok = true;
-    if (ctx->maps_w != g.w[0] || ctx->maps_h != g.h[0]) {
-        ok = iir_rows_tma_maps_cand(&ctx->cand_maps, g, ctx->d_dist_pyr, P, ctx->d_hplanes, ctx->d_hplanes + 2 * P, 3 * P,
+    if (ctx->cs->maps_w != g.w[0] || ctx->cs->maps_h != g.h[0]) {
+        ok = iir_rows_tma_maps_cand(&ctx->cs->cand_maps, g, ctx->cs->d_dist_pyr, P, ctx->cs->d_hplanes, ctx->cs->d_hplanes + 2 * P, 3 * P,
                                     (int)ctx->max_batch);
         if (ok) {
-            ctx->maps_w = g.w[0];
-            ctx->maps_h = g.h[0];
+            ctx->cs->maps_w = g.w[0];
+            ctx->cs->maps_h = g.h[0];
         }
     }
     if (ok && (S.maps_w != g.w[0] || S.maps_h != g.h[0])) {
@@ -492,7 +526,7 @@ bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
         ctx->tile_path = OAVIF_SSIMU2_TILES_CP_ASYNC;
         return false;
     }
-    *out = ctx->cand_maps;
+    *out = ctx->cs->cand_maps;
     memcpy(out->in_src, S.in_src, sizeof S.in_src);
     memcpy(out->out_psrc, S.out_psrc, sizeof S.out_psrc);
     return true;
@@ -501,9 +535,9 @@ bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
 IirArgs iir_args_for(oavif_ssimu2_ctx *ctx, const SrcSet &S)
 {
     IirArgs a{};
-    const IirBuffers B{S.d_hplanes, ctx->d_hplanes, ctx->cap_pyr_floats};
-    iir_fill_common(a, ctx->g, ctx->iir, S.d_pyr, ctx->d_dist_pyr, ctx->cap_pyr_floats, B);
-    a.partials = ctx->d_partials;
+    const IirBuffers B{S.d_hplanes, ctx->cs->d_hplanes, ctx->cap_pyr_floats};
+    iir_fill_common(a, ctx->g, ctx->iir, S.d_pyr, ctx->cs->d_dist_pyr, ctx->cap_pyr_floats, B);
+    a.partials = ctx->cs->d_partials;
     a.partials_stride = ctx->cap_ctas * 6;
     return a;
 }
@@ -516,14 +550,14 @@ int enqueue_wave(oavif_ssimu2_ctx *ctx, SrcSet &Src, const BlurPlan &plan, int m
     const Geom &g = ctx->g;
     IirRowsTmaMaps rm;
     if (!rows_maps_for(ctx, Src, &rm)) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "no tensor-map encoder: the fused kernel needs TMA");
-    if (ctx->units_w != g.w[0] || ctx->units_h != g.h[0]) {
+    if (ctx->cs->units_w != g.w[0] || ctx->cs->units_h != g.h[0]) {
         const std::vector<unsigned> u = wave_units(g);
         if (u.size() > ctx->cap_units) return fail(ctx, OAVIF_SSIMU2_E_STATE, "unit list exceeds capacity");
         // pageable source: the copy has been staged when the call returns, and the stream orders it before the launch
-        CK(cudaMemcpyAsync(ctx->d_units, u.data(), u.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-        ctx->n_units = (unsigned)u.size();
-        ctx->units_w = g.w[0];
-        ctx->units_h = g.h[0];
+        CK(cudaMemcpyAsync(ctx->cs->d_units, u.data(), u.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->cs->stream));
+        ctx->cs->n_units = (unsigned)u.size();
+        ctx->cs->units_w = g.w[0];
+        ctx->cs->units_h = g.h[0];
     }
     WaveMaps wm;
     memcpy(wm.in_src, rm.in_src, sizeof wm.in_src);
@@ -534,19 +568,19 @@ int enqueue_wave(oavif_ssimu2_ctx *ctx, SrcSet &Src, const BlurPlan &plan, int m
     a.k = ctx->iir;
     a.one = 1.0f;
     a.neg_one = -1.0f;
-    a.units = ctx->d_units;
-    a.n_units = ctx->n_units;
+    a.units = ctx->cs->d_units;
+    a.n_units = ctx->cs->n_units;
     a.n_cand = n;
     a.cand0 = cand0;
-    a.ticket = ctx->d_ticket;
+    a.ticket = ctx->cs->d_ticket;
     a.epoch = ++ctx->wave_epoch & 0xfffffu;
     if (a.epoch == 0) a.epoch = ctx->wave_epoch = 1;
-    a.mailbox = ctx->d_mailbox;
+    a.mailbox = ctx->cs->d_mailbox;
     const long long words = wave_mailbox_words(g, mode == 2 ? 5 : 3, a.mb_scale_off, a.mb_rows);
     if (words > ctx->cap_mailbox_words) return fail(ctx, OAVIF_SSIMU2_E_STATE, "mailbox exceeds capacity");
     a.mb_cand_stride = ctx->cap_mailbox_words;
     a.musig = Src.d_hplanes;
-    a.partials = ctx->d_partials;
+    a.partials = ctx->cs->d_partials;
     a.partials_stride = ctx->cap_ctas * 6;
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = plan.first_cta[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = plan.tiles_x[s];
@@ -558,9 +592,9 @@ int enqueue_wave(oavif_ssimu2_ctx *ctx, SrcSet &Src, const BlurPlan &plan, int m
         a.dbg_channel = tap->channel;
         a.dbg_cand = tap->cand;
         a.dbg_trace = ctx->trace_buf;
-        e = mode == 2 ? wave_launch<2, true>(a, wm, ctx->stream) : wave_launch<1, true>(a, wm, ctx->stream);
+        e = mode == 2 ? wave_launch<2, true>(a, wm, ctx->cs->stream) : wave_launch<1, true>(a, wm, ctx->cs->stream);
     } else {
-        e = mode == 2 ? wave_launch<2, false>(a, wm, ctx->stream) : wave_launch<1, false>(a, wm, ctx->stream);
+        e = mode == 2 ? wave_launch<2, false>(a, wm, ctx->cs->stream) : wave_launch<1, false>(a, wm, ctx->cs->stream);
     }
     if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "fused blur launch: %s", cudaGetErrorString(e));
     return 0;
@@ -577,9 +611,9 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, SrcSet &Src, uint3
         BlurArgs b{};
         b.g = g;
         b.src = Src.d_pyr;
-        b.dist = ctx->d_dist_pyr;
+        b.dist = ctx->cs->d_dist_pyr;
         b.dist_stride = ctx->cap_pyr_floats;
-        b.partials = ctx->d_partials;
+        b.partials = ctx->cs->d_partials;
         b.partials_stride = ctx->cap_ctas * 6;
         for (int s = 0; s <= kMaxScales; ++s) b.first_cta[s] = plan.first_cta[s];
         for (int s = 0; s < kMaxScales; ++s) {
@@ -589,56 +623,59 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, SrcSet &Src, uint3
         memcpy(b.taps, ctx->taps, sizeof b.taps);
         b.one = 1.0f;
         b.neg_one = -1.0f;
-        k_fir_fused<<<dim3(plan.total, n), kFirThreads, kFirSmemBytes, ctx->stream>>>(b);
+        k_fir_fused<<<dim3(plan.total, n), kFirThreads, kFirSmemBytes, ctx->cs->stream>>>(b);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(S.k[2], ctx->stream));
+        CK(cudaEventRecord(S.k[2], ctx->cs->stream));
         S.launches += 1;
     } else if (ctx->tile_path == OAVIF_SSIMU2_TILES_FUSED) {
         plan_iir_v(g, &plan);
-        CK(cudaStreamWaitEvent(ctx->stream, Src.ready, 0));
+        CK(cudaStreamWaitEvent(ctx->cs->stream, Src.ready, 0));
         uint32_t first = 0;
         if (!Src.musig_valid) {   // first call after set_source: candidate 0's launch carries the source's quantities
             const int rc = enqueue_wave(ctx, Src, plan, 2, 0, 1);
             if (rc) return rc;
+            CK(cudaEventRecord(Src.cache_done, ctx->cs->stream));
             Src.musig_valid = true;
             Src.rows_valid = false;
             S.launches += 1;
             first = 1;
         }
         if (n > first) {
+            CK(cudaStreamWaitEvent(ctx->cs->stream, Src.cache_done, 0));   // filled by another slot's stream, perhaps
             const int rc = enqueue_wave(ctx, Src, plan, 1, first, n - first);
             if (rc) return rc;
             S.launches += 1;
         }
-        CK(cudaEventRecord(S.k[2], ctx->stream));
+        CK(cudaEventRecord(S.k[2], ctx->cs->stream));
     } else {
         plan_iir_v(g, &plan);
         const IirArgs a = iir_args_for(ctx, Src);
         IirRowsTmaMaps maps;
         const bool tma = rows_maps_for(ctx, Src, &maps);
         cudaError_t e;
+        bool filled_cache = false;
         if (Src.rows_valid) {
-            // the usual case: the source's half was enqueued by set_source on the source stream and may still
-            // be running next to this launch; only the columns pass has to wait for it
-            e = launch_iir_rows(a, g, 1, (int)n, ctx->stream, tma ? &maps : nullptr);
+            // the source's half is cached (or was enqueued by set_source on the source stream and may still be
+            // running next to this launch): only the columns pass has to wait for it
+            e = launch_iir_rows(a, g, 1, (int)n, ctx->cs->stream, tma ? &maps : nullptr);
             S.launches += 1;
-        } else if (tma) {   // the source's half rides in this launch (candidate 0's CTAs carry it), as in round 1
-            e = launch_iir_rows(a, g, 2, (int)n, ctx->stream, &maps);
+        } else {            // the source's half rides in this launch (candidate 0's CTAs carry it along)
+            e = launch_iir_rows(a, g, 2, (int)n, ctx->cs->stream, tma ? &maps : nullptr);
             S.launches += 1;
-        } else {            // cp.async kernels: candidate 0's CTAs carry the source's half along
-            e = launch_iir_rows(a, g, 2, (int)n, ctx->stream, nullptr);
-            S.launches += 1;
+            filled_cache = true;
         }
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
+        if (filled_cache) CK(cudaEventRecord(Src.cache_done, ctx->cs->stream));
         Src.rows_valid = true;
         Src.musig_valid = false;
-        CK(cudaEventRecord(S.k[2], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->stream, Src.ready, 0));
-        e = launch_iir_cols(a, plan.first_cta, plan.tiles_x, (int)n, ctx->stream);
+        CK(cudaEventRecord(S.k[2], ctx->cs->stream));
+        CK(cudaStreamWaitEvent(ctx->cs->stream, Src.ready, 0));
+        CK(cudaStreamWaitEvent(ctx->cs->stream, Src.cache_done, 0));
+        e = launch_iir_cols(a, plan.first_cta, plan.tiles_x, (int)n, ctx->cs->stream);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
         S.launches += 1;
     }
-    CK(cudaEventRecord(S.k[3], ctx->stream));
+    CK(cudaEventRecord(S.k[3], ctx->cs->stream));
 
     FinalArgs f{};
     f.n_scales = g.n_scales;
@@ -648,16 +685,16 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, SrcSet &Src, uint3
         f.ctas_per_channel[s] = plan.per_channel[s];
     }
     for (int s = 0; s <= kMaxScales; ++s) f.first_cta[s] = plan.first_cta[s];
-    f.partials = ctx->d_partials;
+    f.partials = ctx->cs->d_partials;
     f.partials_stride = ctx->cap_ctas * 6;
     f.sums = S.dm_sums;
     f.scores = S.dm_scores;
     f.contiguous_weights = ctx->weight_layout == OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS;
-    k_finalize<<<n, 1024, 0, ctx->stream>>>(f);
+    k_finalize<<<n, 1024, 0, ctx->cs->stream>>>(f);
     CK(cudaGetLastError());
     S.launches += 1;
-    CK(cudaEventRecord(S.k[4], ctx->stream));
-    CK(cudaEventRecord(Src.last_use, ctx->stream));
+    CK(cudaEventRecord(S.k[4], ctx->cs->stream));
+    CK(cudaEventRecord(Src.last_use[&S - ctx->slot], ctx->cs->stream));
     return 0;
 }
 
@@ -679,8 +716,11 @@ int submit_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const H
         if (d.stride[p] < row_bytes(d, w)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "stride smaller than a row");
     CK(cudaSetDevice(ctx->device));
     Slot &S = ctx->slot[ctx->head];
-    if (!S.d_in_dist && !d.on_device && ctx->g.n_scales)   // the second staging slot exists only once submissions overlap
+    if (!S.d_in_dist && !d.on_device && ctx->g.n_scales)   // the second slot's buffers exist only once submissions overlap
         CK(alloc_guarded(ctx, &S.d_in_dist, (size_t)ctx->cap_in_bytes * ctx->max_batch));
+    CK(alloc_cand_side(ctx, S.cs));
+    S.cs.stream = ctx->user_stream ? ctx->user_stream : S.cs.own_stream;
+    ctx->cs = &S.cs;
     S.n = n;
     S.launches = 0;
     S.host_input = !d.on_device;
@@ -694,12 +734,12 @@ int submit_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const H
     if (!S.degenerate) {
         const int tbl0 = ctx->head * 3 * (int)(ctx->max_batch + 1) + 3;   // row 0 of each table is the source's
         SrcSet &Src = ctx->src[ctx->cur];
-        int rc = build_pyramids(ctx, ctx->stream, d, n, imgs, S.d_in_dist, tbl0, S.up0, S.up1, S.k[0], ctx->d_dist_pyr,
+        int rc = build_pyramids(ctx, ctx->cs->stream, d, n, imgs, S.d_in_dist, tbl0, S.up0, S.up1, S.k[0], ctx->cs->d_dist_pyr,
                                 ctx->cap_pyr_floats);
         if (rc) return rc;
         S.launches += 1;
-        CK(cudaEventRecord(S.k[1], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->stream, Src.pyr_ready, 0));   // the candidate's pyramid did not need the source's
+        CK(cudaEventRecord(S.k[1], ctx->cs->stream));
+        CK(cudaStreamWaitEvent(ctx->cs->stream, Src.pyr_ready, 0));   // the candidate's pyramid did not need the source's
         rc = enqueue_blur_and_finalize(ctx, S, Src, n);
         if (rc) return rc;
     }
@@ -790,11 +830,11 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
     Src.rows_valid = false;
     Src.musig_valid = false;
     cudaStream_t ss = ctx->src_stream;
-    CK(cudaStreamWaitEvent(ss, Src.last_use, 0));     // submissions that read this set two images ago
+    for (cudaEvent_t e : Src.last_use) CK(cudaStreamWaitEvent(ss, e, 0));   // submissions that read this set two images ago
     const int sb = ctx->src_buf ^= 1;
     if (on_device) {
-        if (ctx->stream != ctx->own_stream) {         // caller-owned compute stream: its earlier work produced the pixels
-            CK(cudaEventRecord(ctx->ev_user, ctx->stream));
+        if (ctx->user_stream != nullptr) {         // caller-owned compute stream: its earlier work produced the pixels
+            CK(cudaEventRecord(ctx->ev_user, ctx->cs->stream));
             CK(cudaStreamWaitEvent(ss, ctx->ev_user, 0));
         }
     } else {
@@ -816,6 +856,7 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
             ctx->timing.launches = 2;
         }
     }
+    CK(cudaEventRecord(Src.cache_done, ss));
     CK(cudaEventRecord(Src.ready, ss));
     // Return as soon as the caller's pixels have been consumed (host input: after the upload; device
     // input: at once): the kernels keep running behind the calls that follow.
@@ -872,7 +913,8 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->src_stream) cudaStreamSynchronize(ctx->src_stream);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &S : ctx->slot)
+        if (S.cs.own_stream) cudaStreamSynchronize(S.cs.own_stream);
     for (auto &p : ctx->d_in_src) cudaFree(p);
     for (auto &S : ctx->slot) {
         cudaFree(S.d_in_dist);
@@ -886,24 +928,27 @@ void oavif_ssimu2_ctx_destroy(oavif_ssimu2_ctx *ctx)
     for (auto &S : ctx->src) {
         cudaFree(S.d_pyr);
         cudaFree(S.d_hplanes);
-        for (cudaEvent_t e : {S.pyr_ready, S.ready, S.last_use})
+        for (cudaEvent_t e : {S.pyr_ready, S.ready, S.last_use[0], S.last_use[1], S.cache_done})
             if (e) cudaEventDestroy(e);
     }
     if (ctx->ev_user) cudaEventDestroy(ctx->ev_user);
     if (ctx->src_stream) cudaStreamDestroy(ctx->src_stream);
-    cudaFree(ctx->d_dist_pyr);
-    cudaFree(ctx->d_hplanes);
     cudaFree(ctx->d_lut);
-    cudaFree(ctx->d_units);
-    cudaFree(ctx->d_ticket);
-    cudaFree(ctx->d_mailbox);
     cudaFreeHost(ctx->h_wave_err);
     cudaFree((void *)ctx->d_tbl);
-    cudaFree(ctx->d_partials);
     cudaFree(ctx->d_dbg);
     cudaFree(ctx->d_conv);
     cudaFreeHost((void *)ctx->h_tbl);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    for (auto &S : ctx->slot) {
+        CandSide &c = S.cs;
+        cudaFree(c.d_dist_pyr);
+        cudaFree(c.d_hplanes);
+        cudaFree(c.d_partials);
+        cudaFree(c.d_units);
+        cudaFree(c.d_ticket);
+        cudaFree(c.d_mailbox);
+        if (c.own_stream) cudaStreamDestroy(c.own_stream);
+    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
@@ -917,6 +962,7 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
         return fail(nullptr, OAVIF_SSIMU2_E_ARG, "bad context capacity %ux%ux%u", max_w, max_h, max_batch);
     oavif_ssimu2_ctx *ctx = new (std::nothrow) oavif_ssimu2_ctx();
     if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_NOMEM, "out of host memory");
+    ctx->cs = &ctx->slot[0].cs;
     ctx->device = device;
     ctx->max_w = max_w;
     ctx->max_h = max_h;
@@ -932,13 +978,12 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
         }                                                                                          \
     } while (0)
     CKC(cudaSetDevice(device));
-    CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-    ctx->stream = ctx->own_stream;
     CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->src_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming));
     for (auto &S : ctx->src)
-        for (cudaEvent_t *e : {&S.pyr_ready, &S.ready, &S.last_use}) CKC(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t *e : {&S.pyr_ready, &S.ready, &S.last_use[0], &S.last_use[1], &S.cache_done})
+            CKC(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (auto &S : ctx->slot) {
         CKC(cudaEventCreate(&S.up0));
         CKC(cudaEventCreate(&S.up1));
@@ -960,8 +1005,6 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
         CKC(alloc_guarded(ctx, &S.d_pyr, sizeof(float) * ctx->cap_pyr_floats));
         CKC(alloc_guarded(ctx, &S.d_hplanes, sizeof(float) * 2 * ctx->cap_pyr_floats));
     }
-    CKC(alloc_guarded(ctx, &ctx->d_dist_pyr, sizeof(float) * ctx->cap_pyr_floats * max_batch));
-    CKC(alloc_guarded(ctx, &ctx->d_hplanes, sizeof(float) * ctx->cap_hplane_floats * max_batch));
     CKC(cudaMalloc(&ctx->d_lut, sizeof(float) * 256));
     {   // fused kernel: unit list, ticket, mailbox (sized for the taller orientation of the capacity box), error flag
         Geom gm;
@@ -974,18 +1017,13 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
         ctx->cap_units = std::max<unsigned>(ctx->cap_units, (unsigned)wave_units(gm).size()) + 64;
         words = std::max(words, wave_mailbox_words(gm, 5, so, rows));
         ctx->cap_mailbox_words = words + 1024;
-        CKC(cudaMalloc(&ctx->d_units, sizeof(unsigned) * ctx->cap_units));
-        CKC(cudaMalloc(&ctx->d_ticket, sizeof(unsigned)));
-        CKC(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned)));
-        CKC(alloc_guarded(ctx, &ctx->d_mailbox, sizeof(unsigned long long) * ctx->cap_mailbox_words * max_batch));
-        CKC(cudaMemset(ctx->d_mailbox, 0, sizeof(unsigned long long) * ctx->cap_mailbox_words * max_batch));
         CKC(cudaHostAlloc((void **)&ctx->h_wave_err, sizeof(int), cudaHostAllocMapped));
         *ctx->h_wave_err = 0;
         CKC(cudaHostGetDevicePointer((void **)&ctx->dm_wave_err, ctx->h_wave_err, 0));
     }
     CKC(cudaMalloc((void **)&ctx->d_tbl, sizeof(void *) * 3 * (max_batch + 1) * kSlots));
     CKC(cudaHostAlloc((void **)&ctx->h_tbl, sizeof(void *) * 3 * (max_batch + 1) * kSlots, cudaHostAllocDefault));
-    CKC(alloc_guarded(ctx, &ctx->d_partials, sizeof(double) * 6 * ctx->cap_ctas * max_batch));
+    CKC(alloc_cand_side(ctx, ctx->slot[0].cs));   // needs cap_pyr_floats, cap_hplane_floats, cap_ctas, cap_units, cap_mailbox_words
     for (auto &S : ctx->slot) {
         CKC(cudaHostAlloc((void **)&S.h_sums, sizeof(double) * kMaxScales * 18 * max_batch, cudaHostAllocMapped));
         CKC(cudaHostAlloc((void **)&S.h_scores, sizeof(double) * max_batch, cudaHostAllocMapped));
@@ -1050,7 +1088,9 @@ int oavif_ssimu2_get_option(const oavif_ssimu2_ctx *ctx, int option, int *value)
 int oavif_ssimu2_set_stream(oavif_ssimu2_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (ctx->inflight) return fail(ctx, OAVIF_SSIMU2_E_STATE, "a submission is in flight: retire it first");
+    ctx->user_stream = (cudaStream_t)cuda_stream;
+    for (auto &S : ctx->slot) S.cs.stream = ctx->user_stream ? ctx->user_stream : S.cs.own_stream;
     return 0;
 }
 
@@ -1296,7 +1336,7 @@ int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void
     const void *src[3] = {y, u, v};
     const size_t st[3] = {ys, us, vs};
     for (int p = 0; p < 3; ++p)
-        CK(cudaMemcpy2DAsync(base + p * plane_bytes, rb, src[p], st[p], rb, h, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpy2DAsync(base + p * plane_bytes, rb, src[p], st[p], rb, h, cudaMemcpyHostToDevice, ctx->cs->stream));
     a.y = base;
     a.u = base + plane_bytes;
     a.v = base + 2 * plane_bytes;
@@ -1314,12 +1354,12 @@ int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void
     }
     a.out = ctx->d_conv;
     const dim3 grid(cdiv((int)w, 256), h);
-    if (kind == IN_YUV8) k_yuv_to_rgb8<IN_YUV8><<<grid, 256, 0, ctx->stream>>>(a);
-    else if (kind == IN_YUV10_RGB) k_yuv_to_rgb8<IN_YUV10_RGB><<<grid, 256, 0, ctx->stream>>>(a);
-    else k_yuv_to_rgb8<IN_YUV10_RGBA><<<grid, 256, 0, ctx->stream>>>(a);
+    if (kind == IN_YUV8) k_yuv_to_rgb8<IN_YUV8><<<grid, 256, 0, ctx->cs->stream>>>(a);
+    else if (kind == IN_YUV10_RGB) k_yuv_to_rgb8<IN_YUV10_RGB><<<grid, 256, 0, ctx->cs->stream>>>(a);
+    else k_yuv_to_rgb8<IN_YUV10_RGBA><<<grid, 256, 0, ctx->cs->stream>>>(a);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(rgb_out, a.out, (size_t)w * h * 3, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(rgb_out, a.out, (size_t)w * h * 3, cudaMemcpyDeviceToHost, ctx->cs->stream));
+    CK(cudaStreamSynchronize(ctx->cs->stream));
     return 0;
 }
 
@@ -1355,9 +1395,9 @@ int oavif_ssimu2_debug_get_xyb(oavif_ssimu2_ctx *ctx, int which, int scale, int 
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such plane");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->src_stream));  // the source pyramid may still be in flight
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->cs->stream));
     const Geom &g = ctx->g;
-    const float *base = which == 0 ? ctx->src[ctx->cur].d_pyr : ctx->d_dist_pyr + (long long)(which - 1) * ctx->cap_pyr_floats;
+    const float *base = which == 0 ? ctx->src[ctx->cur].d_pyr : ctx->cs->d_dist_pyr + (long long)(which - 1) * ctx->cap_pyr_floats;
     const float *p = base + g.off[scale] + (long long)channel * g.plane[scale];
     CK(cudaMemcpy2D(out, sizeof(float) * g.w[scale], p, sizeof(float) * g.pitch[scale], sizeof(float) * g.w[scale],
                     g.h[scale], cudaMemcpyDeviceToHost));
@@ -1375,7 +1415,7 @@ int oavif_ssimu2_debug_get_rows(oavif_ssimu2_ctx *ctx, int candidate, int quanti
         candidate < 0 || candidate >= (int)ctx->last_n)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "no such row-filtered plane (needs a RECURSIVE score call first)");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->cs->stream));
     const Geom &g = ctx->g;
     const long long P = ctx->cap_pyr_floats;
     const long long poff = g.off[scale] + (long long)channel * g.plane[scale];
@@ -1384,11 +1424,11 @@ int oavif_ssimu2_debug_get_rows(oavif_ssimu2_ctx *ctx, int candidate, int quanti
     const float *p;
     size_t spitch, elem;
     if (quantity == 4) {
-        p = ctx->d_hplanes + (long long)candidate * 3 * P + 2 * P + poff;
+        p = ctx->cs->d_hplanes + (long long)candidate * 3 * P + 2 * P + poff;
         spitch = sizeof(float) * pitch;
         elem = sizeof(float);
     } else {
-        const float *base = (quantity & 1) ? ctx->d_hplanes + (long long)candidate * 3 * P : ctx->src[ctx->cur].d_hplanes;
+        const float *base = (quantity & 1) ? ctx->cs->d_hplanes + (long long)candidate * 3 * P : ctx->src[ctx->cur].d_hplanes;
         p = base + 2 * poff + (quantity >> 1);
         spitch = sizeof(float) * 2 * pitch;
         elem = 2 * sizeof(float);
@@ -1437,11 +1477,11 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
         if (rc) return rc;
     } else {
         const cudaError_t e = launch_iir_cols(iir_args_for(ctx, ctx->src[ctx->cur]), plan.first_cta, plan.tiles_x,
-                                              (int)ctx->last_n, ctx->stream, &tap);
+                                              (int)ctx->last_n, ctx->cs->stream, &tap);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
     }
-    CK(cudaMemcpyAsync(out, ctx->d_dbg, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->d_dbg, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->cs->stream));
+    CK(cudaStreamSynchronize(ctx->cs->stream));
     *w_out = (uint32_t)w;
     *h_out = (uint32_t)h;
     return 0;
@@ -1460,7 +1500,7 @@ int oavif_ssimu2_debug_wave_trace(oavif_ssimu2_ctx *ctx, int mode, uint64_t *out
     plan_iir_v(ctx->g, &plan);
     unsigned long long *d_trace = nullptr;
     CK(cudaMalloc(&d_trace, sizeof(unsigned long long) * 5 * (ctx->cap_units + 64)));
-    CK(cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 5 * (ctx->cap_units + 64), ctx->stream));
+    CK(cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 5 * (ctx->cap_units + 64), ctx->cs->stream));
     ctx->trace_buf = d_trace;
     const IirDebugTap tap{nullptr, -1, -1, -1};
     const int rc = enqueue_wave(ctx, Src, plan, mode == 2 ? 2 : 1, 0, 1, &tap);
@@ -1469,9 +1509,9 @@ int oavif_ssimu2_debug_wave_trace(oavif_ssimu2_ctx *ctx, int mode, uint64_t *out
         cudaFree(d_trace);
         return rc;
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    *n_units = ctx->n_units;
-    const uint32_t n = std::min(cap_units, ctx->n_units);
+    CK(cudaStreamSynchronize(ctx->cs->stream));
+    *n_units = ctx->cs->n_units;
+    const uint32_t n = std::min(cap_units, ctx->cs->n_units);
     CK(cudaMemcpy(out, d_trace, sizeof(unsigned long long) * 5 * n, cudaMemcpyDeviceToHost));
     cudaFree(d_trace);
     return 0;
@@ -1492,13 +1532,13 @@ int oavif_ssimu2_debug_blur(oavif_ssimu2_ctx *ctx, const float *in, uint32_t w, 
     }
     float *d_in = ctx->d_dbg, *d_tmp = d_in + (long long)pitch * h, *d_out = d_tmp + (long long)pitch * h;
     CK(cudaMemcpy2DAsync(d_in, sizeof(float) * pitch, in, sizeof(float) * w, sizeof(float) * w, h,
-                         cudaMemcpyHostToDevice, ctx->stream));
+                         cudaMemcpyHostToDevice, ctx->cs->stream));
     const cudaError_t e = launch_debug_blur(ctx->blur_mode == OAVIF_SSIMU2_BLUR_FIR, ctx->taps, ctx->iir, d_in,
-                                            d_tmp, d_out, (int)w, (int)h, pitch, ctx->stream);
+                                            d_tmp, d_out, (int)w, (int)h, pitch, ctx->cs->stream);
     if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "debug blur launch: %s", cudaGetErrorString(e));
     CK(cudaMemcpy2DAsync(out, sizeof(float) * w, d_out, sizeof(float) * pitch, sizeof(float) * w, h,
-                         cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+                         cudaMemcpyDeviceToHost, ctx->cs->stream));
+    CK(cudaStreamSynchronize(ctx->cs->stream));
     return 0;
 }
 
@@ -1535,7 +1575,7 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
     if (which == 3 && !tma) return fail(ctx, OAVIF_SSIMU2_E_ARG, "the source-only rows kernel exists in the TMA form only");
     if ((variant & 2048) && !Src.musig_valid) return fail(ctx, OAVIF_SSIMU2_E_STATE, "no cached source blur: score in FUSED mode first");
     CK(cudaStreamSynchronize(ctx->src_stream));
-    CK(cudaEventRecord(ctx->src_up0, ctx->stream));
+    CK(cudaEventRecord(ctx->src_up0, ctx->cs->stream));
     for (int i = 0; i < iters; ++i) {
         cudaError_t e;
         if (variant & (1024 | 2048)) {   // the fused kernel: all five quantities / the candidate's three (cached source blur)
@@ -1546,23 +1586,23 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
             e = cudaSuccess;
         } else if (variant & 256) { // the two halves as the product issues them: source stream next to compute stream
             if (!tma) return fail(ctx, OAVIF_SSIMU2_E_ARG, "the split rows pass exists in the TMA form only");
-            CK(cudaEventRecord(ctx->ev_user, ctx->stream));
+            CK(cudaEventRecord(ctx->ev_user, ctx->cs->stream));
             CK(cudaStreamWaitEvent(ctx->src_stream, ctx->ev_user, 0));
             e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, 3, 1, ctx->src_stream, &maps);
-            if (e == cudaSuccess) e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, 1, 1, ctx->stream, &maps);
+            if (e == cudaSuccess) e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, 1, 1, ctx->cs->stream, &maps);
             CK(cudaEventRecord(Src.ready, ctx->src_stream));
-            CK(cudaStreamWaitEvent(ctx->stream, Src.ready, 0));
+            CK(cudaStreamWaitEvent(ctx->cs->stream, Src.ready, 0));
         } else if (variant & 512) { // the columns pass alone
             BlurPlan cp;
             plan_iir_v(ctx->g, &cp);
-            e = launch_iir_cols(iir_args_for(ctx, Src), cp.first_cta, cp.tiles_x, 1, ctx->stream);
+            e = launch_iir_cols(iir_args_for(ctx, Src), cp.first_cta, cp.tiles_x, 1, ctx->cs->stream);
         } else {
-            e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, which, 1, ctx->stream, tma ? &maps : nullptr, (variant >> 4) & 7);
+            e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, which, 1, ctx->cs->stream, tma ? &maps : nullptr, (variant >> 4) & 7);
         }
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "rows launch: %s", cudaGetErrorString(e));
     }
-    CK(cudaEventRecord(ctx->src_up1, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->src_up1, ctx->cs->stream));
+    CK(cudaStreamSynchronize(ctx->cs->stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->src_up0, ctx->src_up1));
     *mean_ms = ms / iters;

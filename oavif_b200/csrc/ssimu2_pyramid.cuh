@@ -155,7 +155,10 @@ __device__ __forceinline__ void decode4(const PyrArgs &a, const uint32_t *raw, i
 template <int KIND>
 __global__ void __launch_bounds__(256, 3) k_pyramid(const __grid_constant__ PyrArgs a)
 {
-    __shared__ float s_lut[256];
+    // The sRGB table once per LANE: entry v of lane l lives at [v][l], so a warp's 32 gathers hit 32 different banks
+    // whatever the pixel values are (a single 256-entry copy made 44 % of the kernel's shared-memory wavefronts
+    // bank conflicts, profiles/r1_final_ncu_recursive.txt).
+    __shared__ float s_lut[256][32];
     __shared__ float s_l2[3][16][17];  // scale-2 linear RGB of this tile
     __shared__ float s_l3[3][8][9];
     __shared__ float s_l4[3][4][5];
@@ -177,7 +180,12 @@ __global__ void __launch_bounds__(256, 3) k_pyramid(const __grid_constant__ PyrA
     uint32_t raw[4][PyrRaw<KIND>::N];
 #pragma unroll
     for (int j = 0; j < 4; ++j) fetch4<KIND>(a, p0, p1, p2, x0, min(y0 + j, g.h[0] - 1), raw[j]);
-    s_lut[tid] = a.lut[tid];
+    {
+        const int lane = tid & 31, v0 = tid & ~31;       // warp w fills entries 32 w .. 32 w + 31
+        const float mine = a.lut[tid];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s_lut[v0 + i][lane] = __shfl_sync(0xffffffffu, mine, i);
+    }
     __syncthreads();
     float lin[4][4][3];
 #pragma unroll
@@ -186,9 +194,9 @@ __global__ void __launch_bounds__(256, 3) k_pyramid(const __grid_constant__ PyrA
         decode4<KIND>(a, raw[j], rgb);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            lin[j][i][0] = s_lut[rgb[i][0]];
-            lin[j][i][1] = s_lut[rgb[i][1]];
-            lin[j][i][2] = s_lut[rgb[i][2]];
+            lin[j][i][0] = s_lut[rgb[i][0]][tid & 31];
+            lin[j][i][1] = s_lut[rgb[i][1]][tid & 31];
+            lin[j][i][2] = s_lut[rgb[i][2]][tid & 31];
         }
     }
     {

@@ -41,7 +41,7 @@ def test_our_arm_line():
     import bench
     assert d["config"] == bench.bench_config("recursive")
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["vs_baseline"] is None
-    assert d["gpu_launches"] == 6 * 16          # pyramid x2, rows x2 (source half, candidate half), columns, finalize per step
+    assert d["gpu_launches"] == 5 * 16          # pyramid x2, rows, columns, finalize per step
     assert d["value"] > 1000 and d["e2e"]["value"] > 100
     assert d["e2e"]["h2d_bytes_per_step"] == 3840 * 2160 * 9 and d["e2e"]["d2h_bytes_per_step"] > 0
     rf = d["roofline"]
