@@ -715,6 +715,7 @@ int submit_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const H
     for (int p = 0; p < np; ++p)
         if (d.stride[p] < row_bytes(d, w)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "stride smaller than a row");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->inflight == 0) ctx->head = ctx->tail = 0;   // nothing to overlap with: a caller that never overlaps never pays for slot 1
     Slot &S = ctx->slot[ctx->head];
     if (!S.d_in_dist && !d.on_device && ctx->g.n_scales)   // the second slot's buffers exist only once submissions overlap
         CK(alloc_guarded(ctx, &S.d_in_dist, (size_t)ctx->cap_in_bytes * ctx->max_batch));

@@ -24,6 +24,8 @@
 // 20 B + 8 B.  No tensor cores (nothing here is a contraction).
 #pragma once
 
+#include <type_traits>
+
 #include "ssimu2_common.cuh"
 #include "ssimu2_tma.cuh"
 
@@ -1016,35 +1018,45 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             const float *ex = &sm.ex[b & 1][0][2 * first_pair][lane];
             const float *ab = abw + ((b * B) & 31) * kIirVCols;   // B divides 32: a batch never wraps inside the ring
             const bool whole = (b + 1) * B <= h;       // every row of the batch is inside the image
+            // one packed evaluation of rows n, n + 1 of this warp's columns.  ODD: the pair's second row lies below an
+            // odd-height image and pools as zeros — a separate instance, so that the common path carries none of the
+            // fourteen predicated moves that zeroing costs
+            auto eval_pair = [&](int g, int n, auto odd) {
+                f32x2 in[7];
+                in[0] = pk2(ab[(2 * g) * kIirVCols], ab[(2 * g + 1) * kIirVCols]);
+                in[1] = pk2(ab[kAbPlane + (2 * g) * kIirVCols], ab[kAbPlane + (2 * g + 1) * kIirVCols]);
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const int n = b * B + 2 * (first_pair + g);   // rows n, n + 1
-                if (g < npairs && (whole || n < h)) {
-                    f32x2 in[7];
-                    in[0] = pk2(ab[(2 * g) * kIirVCols], ab[(2 * g + 1) * kIirVCols]);
-                    in[1] = pk2(ab[kAbPlane + (2 * g) * kIirVCols], ab[kAbPlane + (2 * g + 1) * kIirVCols]);
+                for (int q = 0; q < 5; ++q)
+                    in[2 + q] = pk2(ex[(q * B + 2 * g) * kIirVCols], ex[(q * B + 2 * g + 1) * kIirVCols]);
+                if (TAP && dbg && cb * kIirVCols + lane < w) {   // test hook: what the maps are about to consume
 #pragma unroll
-                    for (int q = 0; q < 5; ++q)
-                        in[2 + q] = pk2(ex[(q * B + 2 * g) * kIirVCols], ex[(q * B + 2 * g + 1) * kIirVCols]);
-                    if (TAP && dbg && cb * kIirVCols + lane < w) {   // test hook: what the maps are about to consume
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) {
-                            float lo, hi;
-                            unpk2(in[2 + q], lo, hi);
-                            float *o = a.dbg_cols + ((long long)q * h + n) * w + cb * kIirVCols + lane;
-                            o[0] = lo;
-                            if (n + 1 < h) o[w] = hi;
-                        }
+                    for (int q = 0; q < 5; ++q) {
+                        float lo, hi;
+                        unpk2(in[2 + q], lo, hi);
+                        float *o = a.dbg_cols + ((long long)q * h + n) * w + cb * kIirVCols + lane;
+                        o[0] = lo;
+                        if (n + 1 < h) o[w] = hi;
                     }
-                    if (!whole && n + 1 >= h) {   // odd height: the pair's second row is outside
+                }
+                if (decltype(odd)::value) {
 #pragma unroll
-                        for (int i = 0; i < 7; ++i) {
-                            float lo, hi;
-                            unpk2(in[i], lo, hi);
-                            in[i] = pk2(lo, 0.0f);
-                        }
+                    for (int i = 0; i < 7; ++i) {
+                        float lo, hi;
+                        unpk2(in[i], lo, hi);
+                        in[i] = pk2(lo, 0.0f);
                     }
-                    error_maps2(u, in[0], in[1], in[2], in[3], in[4], in[5], in[6], acc);
+                }
+                error_maps2(u, in[0], in[1], in[2], in[3], in[4], in[5], in[6], acc);
+            };
+            if (whole) {
+#pragma unroll
+                for (int g = 0; g < npairs; ++g) eval_pair(g, b * B + 2 * (first_pair + g), std::false_type{});
+            } else {
+#pragma unroll
+                for (int g = 0; g < npairs; ++g) {
+                    const int n = b * B + 2 * (first_pair + g);   // rows n, n + 1
+                    if (n + 1 < h) eval_pair(g, n, std::false_type{});
+                    else if (n < h) eval_pair(g, n, std::true_type{});
                 }
             }
             if (b & 1) {   // binary32 over at most 4 pixels per accumulator (32 image rows), binary64 from there on

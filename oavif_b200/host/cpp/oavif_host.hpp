@@ -88,9 +88,12 @@ struct ScorerIface {
 class GpuScorer : public ScorerIface {  // include/oavif_ssimu2.h
   public:
     // pinned_staging: copy the decoder's planes into a per-scorer pinned ring (oavif_ssimu2_pinned_alloc — the
-    // "pinned host staging in src/io.zig" of the north star) and upload from there by DMA; off: hand libavif's
-    // pageable planes to the library, which then stages them itself inside cudaMemcpy2DAsync.
-    GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode, bool pinned_staging = true);
+    // "pinned host staging in src/io.zig" of the north star) and upload from there by DMA; off (default): hand
+    // libavif's pageable planes to the library, whose cudaMemcpy2DAsync stages them through the driver's own pinned
+    // buffers.  Measured on the config-5 corpus with 16 workers (profiles/r2_decode_handoff.json): the explicit
+    // copy costs 10.1 ms of scoring wall time per image against 5.6 ms, 25.0 against 26.2 encodes/s — the extra pass
+    // over the planes on a busy host is dearer than what the DMA saves, so it is an option, not the default.
+    GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode, bool pinned_staging = false);
     ~GpuScorer() override;
     void set_source(const uint8_t *rgb, uint32_t w, uint32_t h) override;
     std::vector<double> score(const std::vector<const Decoded *> &cands) override;
@@ -138,7 +141,7 @@ struct CorpusSpec {
     int first_gpu = 0, n_gpus = 1;
     uint32_t workers_per_gpu = 1, batch_width = 1;
     int blur_mode = 0;
-    bool pinned_staging = true;
+    bool pinned_staging = false;   // see GpuScorer
     // The CPU-scored arm: when set, every worker scores through this factory instead of the CUDA library (tests and
     // bench tooling inject the CPU oracle here; the product never does).  n_gpus * workers_per_gpu workers still.
     std::function<std::unique_ptr<ScorerIface>(int worker)> scorer_factory;
