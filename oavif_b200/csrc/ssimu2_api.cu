@@ -57,6 +57,7 @@ struct CandSide {
     float *d_dist_pyr = nullptr, *d_hplanes = nullptr;
     double *d_partials = nullptr;
     IirRowsTmaMaps cand_maps{};    // TMA descriptors of the candidates' planes (in_dist, out_pcand, out_ab) for maps_w x maps_h
+    IirColsTmaMaps cols_maps{};    // ... and the columns pass's view of the row-filtered planes (pcand, ab)
     int maps_w = -1, maps_h = -1;
     // fused kernel (ssimu2_wave.cuh): unit list of the current geometry, ticket counter, mailbox
     unsigned *d_units = nullptr, *d_ticket = nullptr;
@@ -91,7 +92,7 @@ struct SrcSet {
     cudaEvent_t ready = nullptr;           // source stream: ... and so is everything else enqueued by set_source
     cudaEvent_t last_use[2] = {nullptr, nullptr};   // per slot: its last submission reading this set has finished
     cudaEvent_t cache_done = nullptr;      // the launch that filled d_hplanes (whichever slot's stream it ran on)
-    CUtensorMap in_src[kMaxScales], out_psrc[kMaxScales], in_musig[kMaxScales];
+    CUtensorMap in_src[kMaxScales], out_psrc[kMaxScales], in_musig[kMaxScales], cols_psrc[kMaxScales];
     int maps_w = -1, maps_h = -1;
 };
 
@@ -506,14 +507,15 @@ bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
     bool ok = true;
     if (ctx->cs->maps_w != g.w[0] || ctx->cs->maps_h != g.h[0]) {
         ok = iir_rows_tma_maps_cand(&ctx->cs->cand_maps, g, ctx->cs->d_dist_pyr, P, ctx->cs->d_hplanes, ctx->cs->d_hplanes + 2 * P, 3 * P,
-                                    (int)ctx->max_batch);
+                                    (int)ctx->max_batch) &&
+             iir_cols_tma_maps_cand(&ctx->cs->cols_maps, g, ctx->cs->d_hplanes, ctx->cs->d_hplanes + 2 * P, 3 * P, (int)ctx->max_batch);
         if (ok) {
             ctx->cs->maps_w = g.w[0];
             ctx->cs->maps_h = g.h[0];
         }
     }
     if (ok && (S.maps_w != g.w[0] || S.maps_h != g.h[0])) {
-        ok = iir_rows_tma_maps_src(S.in_src, S.out_psrc, g, S.d_pyr, S.d_hplanes);
+        ok = iir_rows_tma_maps_src(S.in_src, S.out_psrc, g, S.d_pyr, S.d_hplanes) && iir_cols_tma_maps_src(S.cols_psrc, g, S.d_hplanes);
         for (int s = 0; s < g.n_scales && ok; ++s)   // the fused kernel's view of the same buffer: (mu1, sigma11) pairs
             ok = tma_make_4d(&S.in_musig[s], S.d_hplanes + 2 * g.off[s], 2ull * g.w[s], (uint64_t)g.h[s], 3, 1,
                              (uint64_t)g.pitch[s] * 8, (uint64_t)g.plane[s] * 8, 0, 2 * kIirVCols, kWvB, false);
@@ -530,6 +532,16 @@ bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
     memcpy(out->in_src, S.in_src, sizeof S.in_src);
     memcpy(out->out_psrc, S.out_psrc, sizeof S.out_psrc);
     return true;
+}
+
+// the columns pass's descriptors (nullptr: the cp.async loader)
+const IirColsTmaMaps *cols_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirColsTmaMaps *tmp)
+{
+    IirRowsTmaMaps rows;
+    if (!rows_maps_for(ctx, S, &rows)) return nullptr;   // also brings both sets of descriptors up to date
+    *tmp = ctx->cs->cols_maps;
+    memcpy(tmp->psrc, S.cols_psrc, sizeof tmp->psrc);
+    return tmp;
 }
 
 IirArgs iir_args_for(oavif_ssimu2_ctx *ctx, const SrcSet &S)
@@ -671,7 +683,8 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, SrcSet &Src, uint3
         CK(cudaEventRecord(S.k[2], ctx->cs->stream));
         CK(cudaStreamWaitEvent(ctx->cs->stream, Src.ready, 0));
         CK(cudaStreamWaitEvent(ctx->cs->stream, Src.cache_done, 0));
-        e = launch_iir_cols(a, plan.first_cta, plan.tiles_x, (int)n, ctx->cs->stream);
+        IirColsTmaMaps cmaps;
+        e = launch_iir_cols(a, plan.first_cta, plan.tiles_x, (int)n, ctx->cs->stream, nullptr, cols_maps_for(ctx, Src, &cmaps));
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
         S.launches += 1;
     }
@@ -1477,8 +1490,9 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
         const int rc = enqueue_wave(ctx, ctx->src[ctx->cur], plan, 1, 0, ctx->last_n, &tap);
         if (rc) return rc;
     } else {
+        IirColsTmaMaps cmaps;
         const cudaError_t e = launch_iir_cols(iir_args_for(ctx, ctx->src[ctx->cur]), plan.first_cta, plan.tiles_x,
-                                              (int)ctx->last_n, ctx->cs->stream, &tap);
+                                              (int)ctx->last_n, ctx->cs->stream, &tap, cols_maps_for(ctx, ctx->src[ctx->cur], &cmaps));
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
     }
     CK(cudaMemcpyAsync(out, ctx->d_dbg, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->cs->stream));
@@ -1596,7 +1610,9 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
         } else if (variant & 512) { // the columns pass alone
             BlurPlan cp;
             plan_iir_v(ctx->g, &cp);
-            e = launch_iir_cols(iir_args_for(ctx, Src), cp.first_cta, cp.tiles_x, 1, ctx->cs->stream);
+            IirColsTmaMaps cmaps;
+            e = launch_iir_cols(iir_args_for(ctx, Src), cp.first_cta, cp.tiles_x, 1, ctx->cs->stream, nullptr,
+                                (variant & 8) ? nullptr : cols_maps_for(ctx, Src, &cmaps));
         } else {
             e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, which, 1, ctx->cs->stream, tma ? &maps : nullptr, (variant >> 4) & 7);
         }

@@ -829,17 +829,25 @@ struct IirColsSmem {
     float ab[2][32][kIirVCols];                // consumer rows of the two XYB planes
     float ex[2][5][B][kIirVCols];              // filtered values, double-buffered
     double red[4][6];
+    uint64_t land[2];                          // TMA form: "the rows requested during batch b have landed", by parity of b
+};
+
+// TMA descriptors of the columns pass: 4-row boxes of the interleaved pair planes (64 floats wide) and of a*b (32)
+struct IirColsTmaMaps {
+    CUtensorMap psrc[kMaxScales], pcand[kMaxScales], ab[kMaxScales];
 };
 
 // B rows per exchange batch: the per-batch overhead (barrier, copy issue, address set-up) is paid once
 // per B rows by each of the eight warps.  RCAP = rows of a producer ring.
 // TAP: the test hook of oavif_ssimu2_debug_get_cols, compiled into a second instance so that the scored path's
 // kernel carries none of it (with the hook inline the kernel went from 70 to 128 registers).
-template <int RCAP, int B, bool TAP>
-__global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a)
+// TMA: the loader warp's 16-byte cp.async traffic (about 200 instructions per batch, a tenth of the CTA's) becomes
+// twelve cp.async.bulk.tensor issues by one lane; rows below the image and columns right of it arrive as zeros.
+template <int RCAP, int B, bool TAP, bool TMA>
+__global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a, const __grid_constant__ IirColsTmaMaps tm)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    IirColsSmem<RCAP, B> &sm = *reinterpret_cast<IirColsSmem<RCAP, B> *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_cols[];
+    IirColsSmem<RCAP, B> &sm = *reinterpret_cast<IirColsSmem<RCAP, B> *>(smem_cols);
     constexpr int D = ((RCAP - B - 10) / B) * B;   // rows of look-ahead: D + B + 10 <= RCAP, D % B == 0
     constexpr int DA = 16;                         // consumer look-ahead (ring of 32 rows)
     static_assert(D >= B && DA % B == 0 && DA + B <= 32 && B % 8 == 0 && RCAP % B == 0, "ring geometry");
@@ -856,7 +864,48 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     // bytes of this lane's 16-byte column group that lie inside the image: the rest is zero-filled
     const int cbytes = max(0, min(16, (w - (cb * kIirVCols + ccol)) * 4));
 
-    if (warp == 7) {
+    if (TMA && warp == 7) {
+        // ---------------- loader, TMA form: one lane, 4-row boxes (a box never wraps around the 64-row ring) ----------------
+        // Requests of a batch complete on land[parity of the batch]; the loader arrives at the barrier that ends batch
+        // b only when the rows requested during batch b - 1 (everything batch b + 1 reads) have landed.
+        constexpr unsigned kGroupBytes = 4 * (2 * 2 * kIirVCols + kIirVCols) * 4;   // 4 rows of two pair planes and a*b
+        const int x0 = cb * kIirVCols;
+        auto issue_rows4 = [&](int r0, uint64_t *bar) {
+            tma_load_4d(&sm.pring[0][r0 & (RCAP - 1)][0], &tm.psrc[s], 2 * x0, r0, c, 0, bar);
+            tma_load_4d(&sm.pring[1][r0 & (RCAP - 1)][0], &tm.pcand[s], 2 * x0, r0, c, cand, bar);
+            tma_load_4d(&sm.sring[r0 & (RCAP - 1)][0], &tm.ab[s], x0, r0, c, cand, bar);
+        };
+#pragma unroll
+        for (int j = 1; j <= 6; ++j) {   // rows -6..-1 are padding
+            sm.pring[0][RCAP - j][lane] = sm.pring[0][RCAP - j][lane + 32] = 0.0f;
+            sm.pring[1][RCAP - j][lane] = sm.pring[1][RCAP - j][lane + 32] = 0.0f;
+            sm.sring[RCAP - j][lane] = 0.0f;
+        }
+        fence_async_smem();   // these slots are rewritten by TMA once real rows wrap around to them
+        if (lane == 0) {
+            mbar_init(&sm.land[0], 1);
+            mbar_init(&sm.land[1], 1);
+            mbar_init_fence();
+            // group 0 = everything before the first batch's request (rows 0 .. 3 + D), on land[0]
+            mbar_arrive_expect_tx(&sm.land[0], (4 + D) / 4 * kGroupBytes);
+            for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0, &sm.land[0]);
+            mbar_wait(&sm.land[0], 0);
+        }
+        __syncthreads();      // (S) rows 0 .. 3+D are in the rings
+#pragma unroll 1
+        for (int b = 0; b < nbatch; ++b) {
+            if (lane == 0) {
+                const int g = b + 1;                 // group of this batch's requests
+                mbar_arrive_expect_tx(&sm.land[g & 1], B / 4 * kGroupBytes);
+#pragma unroll
+                for (int j = 0; j < B; j += 4) issue_rows4(b * B + 4 + D + j, &sm.land[g & 1]);
+                mbar_wait(&sm.land[b & 1], (unsigned)(b >> 1) & 1u);   // group b: requested during batch b - 1
+            }
+            __syncthreads();              // (b)
+        }
+        __syncthreads();      // consumers' last batch
+        __syncthreads();      // final reduction
+    } else if (warp == 7) {
         // ---------------- loader: feeds the three producer rings ----------------
         // Batch b (rows n0 = 16b ..) reads ring rows n0-6 .. n0+B+3.  The loader requests rows n0+4+D .. n0+3+D+B
         // while batch b runs (their slots held rows n0-28 .. n0-13, dead by then) and arrives at the barrier
@@ -1172,6 +1221,29 @@ inline bool iir_rows_tma_maps_src(CUtensorMap in_src[kMaxScales], CUtensorMap ou
     return ok;
 }
 
+inline bool iir_cols_tma_maps_src(CUtensorMap psrc[kMaxScales], const Geom &g, const float *hpair_src)
+{
+    bool ok = true;
+    for (int s = 0; s < g.n_scales && ok; ++s)
+        ok = tma_make_4d(&psrc[s], hpair_src + 2 * g.off[s], 2ull * g.w[s], (uint64_t)g.h[s], 3, 1, (uint64_t)g.pitch[s] * 8,
+                         (uint64_t)g.plane[s] * 8, 0, 2 * kIirVCols, 4, false);
+    return ok;
+}
+
+inline bool iir_cols_tma_maps_cand(IirColsTmaMaps *m, const Geom &g, const float *hpair_cand, const float *hab,
+                                   long long hcand_stride, int n_images)
+{
+    bool ok = true;
+    for (int s = 0; s < g.n_scales && ok; ++s) {
+        const uint64_t w = (uint64_t)g.w[s], h = (uint64_t)g.h[s], rowb = (uint64_t)g.pitch[s] * 4, planeb = (uint64_t)g.plane[s] * 4;
+        ok = ok && tma_make_4d(&m->pcand[s], hpair_cand + 2 * g.off[s], 2 * w, h, 3, (uint64_t)n_images, 2 * rowb, 2 * planeb,
+                               (uint64_t)hcand_stride * 4, 2 * kIirVCols, 4, false);
+        ok = ok && tma_make_4d(&m->ab[s], hab + g.off[s], w, h, 3, (uint64_t)n_images, rowb, planeb,
+                               (uint64_t)hcand_stride * 4, kIirVCols, 4, false);
+    }
+    return ok;
+}
+
 inline bool iir_rows_tma_maps_cand(IirRowsTmaMaps *m, const Geom &g, const float *dist, long long pyr_stride,
                                    float *hpair_cand, float *hab, long long hcand_stride, int n_images)
 {
@@ -1191,10 +1263,16 @@ inline bool iir_rows_tma_maps_cand(IirRowsTmaMaps *m, const Geom &g, const float
 inline cudaError_t iir_configure()
 {
 
-    cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_iir_cols<64, 16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(IirColsDeep));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_iir_cols<64, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(k_iir_cols<64, 16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(IirColsDeep));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_iir_cols<64, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(IirColsDeep));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_iir_cols<64, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(IirColsDeep));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_iir_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<1>));
@@ -1269,8 +1347,9 @@ inline cudaError_t launch_iir_rows(const IirArgs &base, const Geom &g, int which
 
 // Columns pass with the maps and the pooling.
 inline cudaError_t launch_iir_cols(const IirArgs &base, const int *first_cta_cols, const int *col_blocks, int n,
-                                   cudaStream_t st, const IirDebugTap *tap = nullptr)
+                                   cudaStream_t st, const IirDebugTap *tap = nullptr, const IirColsTmaMaps *maps = nullptr)
 {
+    static const IirColsTmaMaps no_maps{};
     IirArgs a = base;
     for (int s = 0; s <= kMaxScales; ++s) a.first_cta[s] = first_cta_cols[s];
     for (int s = 0; s < kMaxScales; ++s) a.blocks[s] = col_blocks[s];
@@ -1280,9 +1359,11 @@ inline cudaError_t launch_iir_cols(const IirArgs &base, const int *first_cta_col
         a.dbg_scale = tap->scale;
         a.dbg_channel = tap->channel;
         a.dbg_cand = tap->cand;
-        k_iir_cols<64, 16, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
+        if (maps) k_iir_cols<64, 16, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        else k_iir_cols<64, 16, true, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, no_maps);
     } else {
-        k_iir_cols<64, 16, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a);
+        if (maps) k_iir_cols<64, 16, false, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        else k_iir_cols<64, 16, false, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, no_maps);
     }
     return cudaGetLastError();
 }
