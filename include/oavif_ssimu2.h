@@ -232,6 +232,18 @@ int oavif_ssimu2_compute_rgb8(const uint8_t *ref, const uint8_t *dist, uint32_t 
 int oavif_ssimu2_set_default_device(int device);
 void oavif_ssimu2_release_cached(void);
 
+/* The encoder-side depth conversions of encodeAvifToBuffer (src/io.zig:562-609), on the device, from the pixels the
+ * last oavif_ssimu2_set_source_* call staged: the array avifImageRGBToYUV is handed,
+ *     8-bit source,  out_depth 10:  (v * 1023 + 127) / 255      io.zig:566-572
+ *     16-bit source, out_depth 10:  v >> 6                        io.zig:581-587
+ *     16-bit source, out_depth 8:   v >> 8                        io.zig:596-602
+ * with every channel kept (alpha rides along to the encoder, io.zig:564) and tight rows: `out` receives
+ * w * h * channels samples, uint16_t for depth 10 and uint8_t for depth 8.  The reference runs these scalar loops in
+ * EVERY search pass; a caller runs this once per image and hands the same array to every encode.  An 8-bit source
+ * at depth 8 needs no conversion (io.zig:611-613) -> E_UNSUPPORTED.  Call it between set_source_* and the next
+ * set_source_* (device sources: while the caller's buffer is alive); images below 8x8 are not staged -> E_STATE. */
+int oavif_ssimu2_source_samples(oavif_ssimu2_ctx *ctx, int out_depth, void *out, size_t out_bytes);
+
 /* decodeAvifToRgb's pixel work (io.zig:470-478, 654-663) alone: planes -> tight RGB8.  Uses the candidate
  * staging buffer and an output buffer of its own; the cached source is untouched, so it may be called in the
  * middle of a search. */

@@ -138,6 +138,10 @@ struct oavif_ssimu2_ctx {
     long long dbg_floats = 0;
     uint8_t *d_conv = nullptr;     // oavif_ssimu2_yuv444_to_rgb8's output, grown on demand
     size_t conv_bytes = 0;
+    // the pixels the last set_source_* call consumed, for oavif_ssimu2_source_samples: staged copy or caller's device pointer
+    const void *src_pix = nullptr;
+    size_t src_pix_stride = 0;
+    int src_pix_channels = 0, src_pix_bits = 0;
     oavif_ssimu2_timing timing{};
     float taps[9] = {};
     IirCoef iir{};
@@ -821,6 +825,7 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
     if (stride < (size_t)w * channels * (bits / 8)) return fail(ctx, OAVIF_SSIMU2_E_ARG, "source stride smaller than a row");
     CK(cudaSetDevice(ctx->device));
     ctx->have_source = false;
+    ctx->src_pix = nullptr;
     make_geom((int)w, (int)h, &ctx->g);
     if (ctx->g.n_scales == 0) {  // geometry still needed for argument checks in score_*
         ctx->g.w[0] = (int)w;
@@ -859,6 +864,10 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
     if (rc) return rc;
     CK(cudaEventRecord(ctx->src_consumed[sb], ss));
     CK(cudaEventRecord(Src.pyr_ready, ss));
+    ctx->src_pix = on_device ? rgb : ctx->d_in_src[sb];
+    ctx->src_pix_stride = on_device ? stride : row_bytes(d, (int)w);
+    ctx->src_pix_channels = channels;
+    ctx->src_pix_bits = bits;
     ctx->timing.launches = 1;
     if (ctx->blur_mode == OAVIF_SSIMU2_BLUR_RECURSIVE && ctx->tile_path == OAVIF_SSIMU2_TILES_TMA &&
         ctx->source_rows == OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE) {
@@ -1019,7 +1028,7 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
         CKC(alloc_guarded(ctx, &S.d_pyr, sizeof(float) * ctx->cap_pyr_floats));
         CKC(alloc_guarded(ctx, &S.d_hplanes, sizeof(float) * 2 * ctx->cap_pyr_floats));
     }
-    CKC(cudaMalloc(&ctx->d_lut, sizeof(float) * 256));
+    CKC(cudaMalloc(&ctx->d_lut, sizeof(float) * 256 * 32));
     {   // fused kernel: unit list, ticket, mailbox (sized for the taller orientation of the capacity box), error flag
         Geom gm;
         long long so[kMaxScales];
@@ -1046,12 +1055,15 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
     }
 
     // sRGB -> linear table (v2.1 §1): double evaluation, one rounding to binary32
-    float lut[256];
+    // Stored once per LANE (entry v, lane l at [32 v + l]): the pyramid kernel copies it to shared memory as is,
+    // where a warp's 32 gathers then hit 32 different banks.
+    std::vector<float> lut(256 * 32);
     for (int i = 0; i < 256; ++i) {
         const double v = (double)i / 255.0;
-        lut[i] = (float)((v <= 0.04045) ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4));
+        const float e = (float)((v <= 0.04045) ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4));
+        for (int l = 0; l < 32; ++l) lut[32 * i + l] = e;
     }
-    CKC(cudaMemcpy(ctx->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(ctx->d_lut, lut.data(), sizeof(float) * lut.size(), cudaMemcpyHostToDevice));
     solve_gaussian(1.5, ctx->taps, &ctx->iir);
 
     CKC(cudaFuncSetAttribute(k_fir_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirSmemBytes));
@@ -1374,6 +1386,48 @@ int oavif_ssimu2_yuv444_to_rgb8(oavif_ssimu2_ctx *ctx, const void *y, const void
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rgb_out, a.out, (size_t)w * h * 3, cudaMemcpyDeviceToHost, ctx->cs->stream));
     CK(cudaStreamSynchronize(ctx->cs->stream));
+    return 0;
+}
+
+int oavif_ssimu2_source_samples(oavif_ssimu2_ctx *ctx, int out_depth, void *out, size_t out_bytes)
+{
+    if (!ctx) return fail(nullptr, OAVIF_SSIMU2_E_ARG, "null context");
+    if (!out) return fail(ctx, OAVIF_SSIMU2_E_ARG, "null argument");
+    if (!ctx->have_source || !ctx->src_pix)
+        return fail(ctx, OAVIF_SSIMU2_E_STATE, "no source pixels on the device (set_source_* first; images below 8x8 are not staged)");
+    const int bits = ctx->src_pix_bits;
+    int mode;
+    if (bits == 8 && out_depth == 10) mode = 0;
+    else if (bits == 16 && out_depth == 10) mode = 1;
+    else if (bits == 16 && out_depth == 8) mode = 2;
+    else   // 8 -> 8: the reference hands src.data through untouched (io.zig:611-613)
+        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "no conversion from %d-bit source samples to depth %d", bits, out_depth);
+    const int w = ctx->g.w[0], h = ctx->g.h[0];
+    SamplesArgs a{};
+    a.row_samples = w * ctx->src_pix_channels;
+    a.h = h;
+    const size_t need = (size_t)a.row_samples * h * (out_depth > 8 ? 2 : 1);
+    if (out_bytes < need) return fail(ctx, OAVIF_SSIMU2_E_ARG, "output holds %zu bytes, %zu needed", out_bytes, need);
+    CK(cudaSetDevice(ctx->device));
+    if (need > ctx->conv_bytes) {
+        cudaFree(ctx->d_conv);
+        ctx->d_conv = nullptr;
+        ctx->conv_bytes = 0;
+        CK(cudaMalloc(&ctx->d_conv, need));
+        ctx->conv_bytes = need;
+    }
+    a.in = ctx->src_pix;
+    a.out = ctx->d_conv;
+    a.stride = (long long)ctx->src_pix_stride;
+    // on the source stream, behind the upload and the pyramid kernel that read the same staged pixels
+    cudaStream_t ss = ctx->src_stream;
+    const dim3 grid(cdiv(cdiv(a.row_samples, 4), 256), h);
+    if (mode == 0) k_source_samples<0><<<grid, 256, 0, ss>>>(a);
+    else if (mode == 1) k_source_samples<1><<<grid, 256, 0, ss>>>(a);
+    else k_source_samples<2><<<grid, 256, 0, ss>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_conv, need, cudaMemcpyDeviceToHost, ss));
+    CK(cudaStreamSynchronize(ss));
     return 0;
 }
 

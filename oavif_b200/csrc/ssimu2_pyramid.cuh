@@ -22,7 +22,7 @@ struct PyrArgs {
     long long stride[3];        // bytes per input row
     float *out;                 // pyramid of image 0
     long long out_stride;       // floats between consecutive images' pyramids
-    const float *lut;           // 256-entry sRGB->linear table
+    const float *lut;           // sRGB->linear table, each of the 256 entries repeated 32 times (one copy per lane)
     YuvK k;
     int channels, hbd;          // IN_PIXELS only: 1..4 interleaved channels, 16-bit samples if hbd
     float one, neg_one;         // 1.0f / -1.0f as run-time values (Unit2, ssimu2_common.cuh)
@@ -153,12 +153,12 @@ __device__ __forceinline__ void decode4(const PyrArgs &a, const uint32_t *raw, i
 
 // grid = (tiles_x, tiles_y, n_images), block = 256 (16x16 threads, 4x4 scale-0 pixels each).
 template <int KIND>
-__global__ void __launch_bounds__(256, 3) k_pyramid(const __grid_constant__ PyrArgs a)
+__global__ void __launch_bounds__(256, 4) k_pyramid(const __grid_constant__ PyrArgs a)
 {
     // The sRGB table once per LANE: entry v of lane l lives at [v][l], so a warp's 32 gathers hit 32 different banks
     // whatever the pixel values are (a single 256-entry copy made 44 % of the kernel's shared-memory wavefronts
     // bank conflicts, profiles/r1_final_ncu_recursive.txt).
-    __shared__ float s_lut[256][32];
+    __shared__ __align__(16) float s_lut[256][32];
     __shared__ float s_l2[3][16][17];  // scale-2 linear RGB of this tile
     __shared__ float s_l3[3][8][9];
     __shared__ float s_l4[3][4][5];
@@ -180,11 +180,14 @@ __global__ void __launch_bounds__(256, 3) k_pyramid(const __grid_constant__ PyrA
     uint32_t raw[4][PyrRaw<KIND>::N];
 #pragma unroll
     for (int j = 0; j < 4; ++j) fetch4<KIND>(a, p0, p1, p2, x0, min(y0 + j, g.h[0] - 1), raw[j]);
-    {
-        const int lane = tid & 31, v0 = tid & ~31;       // warp w fills entries 32 w .. 32 w + 31
-        const float mine = a.lut[tid];
+    {   // the table arrives already laid out per lane (32 KB, L2-resident): eight 16-byte copies per thread
+        const float4 *src = reinterpret_cast<const float4 *>(a.lut);
+        float4 *dst = reinterpret_cast<float4 *>(&s_lut[0][0]);
+        float4 t[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s_lut[v0 + i][lane] = __shfl_sync(0xffffffffu, mine, i);
+        for (int i = 0; i < 8; ++i) t[i] = __ldg(src + tid + 256 * i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[tid + 256 * i] = t[i];
     }
     __syncthreads();
     float lin[4][4][3];
@@ -365,6 +368,34 @@ __global__ void __launch_bounds__(256) k_yuv_to_rgb8(const __grid_constant__ Yuv
     o[0] = (uint8_t)r;
     o[1] = (uint8_t)g;
     o[2] = (uint8_t)b;
+}
+
+// The sample array encodeAvifToBuffer builds for avifImageRGBToYUV (io.zig:562-609), from the staged source pixels:
+// MODE 0: 8-bit -> 10-bit, (v * 1023 + 127) / 255 (io.zig:572); MODE 1: 16-bit -> 10-bit, v >> 6 (io.zig:587);
+// MODE 2: 16-bit -> 8-bit, v >> 8 (io.zig:602).  Every channel is kept; input rows `stride` bytes apart, output tight.
+struct SamplesArgs {
+    const void *in;
+    void *out;
+    long long stride;      // input bytes per row
+    int row_samples, h;    // w * channels
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_source_samples(const __grid_constant__ SamplesArgs a)
+{
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;   // four samples per thread
+    const int y = blockIdx.y;
+    if (x >= a.row_samples) return;
+    const int n = min(4, a.row_samples - x);
+    const uint8_t *row = (const uint8_t *)a.in + (long long)y * a.stride;
+    const long long o = (long long)y * a.row_samples + x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i >= n) break;
+        if (MODE == 0) ((uint16_t *)a.out)[o + i] = (uint16_t)(((uint32_t)row[x + i] * 1023u + 127u) / 255u);
+        else if (MODE == 1) ((uint16_t *)a.out)[o + i] = (uint16_t)(((const uint16_t *)row)[x + i] >> 6);
+        else ((uint8_t *)a.out)[o + i] = (uint8_t)(((const uint16_t *)row)[x + i] >> 8);
+    }
 }
 
 }  // namespace oavif

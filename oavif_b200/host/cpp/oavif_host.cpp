@@ -189,7 +189,8 @@ Decoded::~Decoded()
     if (decoder && lib) lib->avifDecoderDestroy(decoder);
 }
 
-std::vector<uint8_t> Codec::encode(const HostImage &src, uint32_t q, const EncOptions &o) const
+std::vector<uint8_t> Codec::encode(const HostImage &src, uint32_t q, const EncOptions &o,
+                                   const std::vector<uint16_t> *samples10) const
 {
     const uint32_t depth = o.tenbit ? 10 : 8;  // io.zig:546 with an 8-bit source
     void *image = L.avifImageCreate(src.w, src.h, depth, 1 /* AVIF_PIXEL_FORMAT_YUV444 */);
@@ -209,9 +210,13 @@ std::vector<uint8_t> Codec::encode(const HostImage &src, uint32_t q, const EncOp
     rgb.format = src.channels == 4 ? 1 : 0;
     std::vector<uint16_t> scaled;
     if (depth == 10) {  // io.zig:566-579
-        scaled.resize(src.data.size());
-        for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = (uint16_t)(((size_t)src.data[i] * 1023 + 127) / 255);
-        rgb.pixels = reinterpret_cast<uint8_t *>(scaled.data());
+        if (samples10 && samples10->size() == src.data.size()) {   // converted once per image on the device
+            rgb.pixels = reinterpret_cast<uint8_t *>(const_cast<uint16_t *>(samples10->data()));
+        } else {
+            scaled.resize(src.data.size());
+            for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = (uint16_t)(((size_t)src.data[i] * 1023 + 127) / 255);
+            rgb.pixels = reinterpret_cast<uint8_t *>(scaled.data());
+        }
         rgb.rowBytes = src.w * src.channels * 2;
         rgb.depth = 10;
     } else {  // io.zig:611-617
@@ -311,8 +316,27 @@ GpuScorer::~GpuScorer()
 
 void GpuScorer::set_source(const uint8_t *rgb, uint32_t w, uint32_t h)
 {
+    src_samples_ = 0;
     if (oavif_ssimu2_set_source_rgb8(ctx_, rgb, w, h, (size_t)w * 3) != 0)
         throw std::runtime_error(std::string("set_source: ") + oavif_ssimu2_last_error(ctx_));
+}
+
+void GpuScorer::set_source_image(const HostImage &img)
+{
+    if (oavif_ssimu2_set_source_pixels(ctx_, img.data.data(), img.w, img.h, (size_t)img.w * img.channels, (int)img.channels, 8) != 0)
+        throw std::runtime_error(std::string("set_source_pixels: ") + oavif_ssimu2_last_error(ctx_));
+    src_samples_ = img.data.size();
+}
+
+bool GpuScorer::source_samples10(std::vector<uint16_t> &out)
+{
+    if (src_samples_ == 0) return false;
+    out.resize(src_samples_);
+    if (oavif_ssimu2_source_samples(ctx_, 10, out.data(), out.size() * sizeof(uint16_t)) != 0) {
+        out.clear();   // e.g. an image below 8x8, which the library does not stage: the host loop converts it
+        return false;
+    }
+    return true;
 }
 
 std::vector<double> GpuScorer::score(const std::vector<const Decoded *> &cands)
@@ -384,8 +408,10 @@ SearchResult search_image(const Codec &codec, ScorerIface &scorer, const HostIma
         return R;
     }
     R.log += fmt("Searching [tgt %g±%.1f, speed %u, %u-bit]\n", o.score_tgt, o.tolerance, o.speed, R.out_depth);
-    const std::vector<uint8_t> rgb = to_rgb8(img);
-    scorer.set_source(rgb.data(), img.w, img.h);
+    scorer.set_source_image(img);
+    // io.zig:566-579 converts the source to 10 bits in every pass; a scorer that staged the pixels does it once
+    std::vector<uint16_t> samples10;
+    const std::vector<uint16_t> *s10 = (o.tenbit && scorer.source_samples10(samples10)) ? &samples10 : nullptr;
 
     TQOptions topt;
     topt.score_tgt = o.score_tgt;
@@ -406,7 +432,7 @@ SearchResult search_image(const Codec &codec, ScorerIface &scorer, const HostIma
         auto work = [&](size_t i) {
             try {
                 const double t0 = now_ms();
-                bytes[i] = codec.encode(img, qs[i], o);
+                bytes[i] = codec.encode(img, qs[i], o, s10);
                 const double t1 = now_ms();
                 dec[i] = codec.decode(bytes[i]);
                 const double t2 = now_ms();
@@ -474,7 +500,7 @@ SearchResult search_image(const Codec &codec, ScorerIface &scorer, const HostIma
                     R.avif = p.second;
                     have = true;
                 }
-        if (!have) R.avif = codec.encode(img, R.tq.q, o);
+        if (!have) R.avif = codec.encode(img, R.tq.q, o, s10);
         R.size = R.avif.size();
         R.reencoded = true;
     }

@@ -71,7 +71,9 @@ struct Decoded {  // a decoder kept alive so that its planes can be handed to th
 class Codec {
   public:
     explicit Codec(const LibAvif &lib) : L(lib) {}
-    std::vector<uint8_t> encode(const HostImage &img, uint32_t q, const EncOptions &o) const;  // io.zig:544-636
+    // io.zig:544-636.  samples10: the source already converted to 10 bits (ScorerIface::source_samples10), or null
+    std::vector<uint8_t> encode(const HostImage &img, uint32_t q, const EncOptions &o,
+                                const std::vector<uint16_t> *samples10 = nullptr) const;
     Decoded decode(const std::vector<uint8_t> &avif) const;                                       // io.zig:452-466
     std::vector<uint8_t> decode_to_rgb8(const std::vector<uint8_t> &avif) const;                 // io.zig:638-666
     const LibAvif &L;
@@ -82,7 +84,23 @@ class Codec {
 struct ScorerIface {
     virtual ~ScorerIface() = default;
     virtual void set_source(const uint8_t *rgb, uint32_t w, uint32_t h) = 0;
+    // The source as loaded (main.zig:86-87).  Default: Image.toRGB8 on the host, kept alive for the search.
+    virtual void set_source_image(const HostImage &img)
+    {
+        rgb_keep_ = to_rgb8(img);
+        set_source(rgb_keep_.data(), img.w, img.h);
+    }
+    // The 10-bit sample array encodeAvifToBuffer rebuilds from the source in EVERY pass (io.zig:566-579), made once
+    // per image from the pixels the scorer staged.  false: this scorer keeps no device copy, and Codec::encode runs
+    // the reference's loop on the host in each pass.
+    virtual bool source_samples10(std::vector<uint16_t> &out)
+    {
+        (void)out;
+        return false;
+    }
     virtual std::vector<double> score(const std::vector<const Decoded *> &cands) = 0;
+  protected:
+    std::vector<uint8_t> rgb_keep_;
 };
 
 class GpuScorer : public ScorerIface {  // include/oavif_ssimu2.h
@@ -96,6 +114,8 @@ class GpuScorer : public ScorerIface {  // include/oavif_ssimu2.h
     GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode, bool pinned_staging = false);
     ~GpuScorer() override;
     void set_source(const uint8_t *rgb, uint32_t w, uint32_t h) override;
+    void set_source_image(const HostImage &img) override;      // oavif_ssimu2_set_source_pixels: toRGB8 on the device
+    bool source_samples10(std::vector<uint16_t> &out) override; // oavif_ssimu2_source_samples
     std::vector<double> score(const std::vector<const Decoded *> &cands) override;
     double device_ms = 0.0;  // accumulated total_ms of the calls
   private:
@@ -104,6 +124,7 @@ class GpuScorer : public ScorerIface {  // include/oavif_ssimu2.h
     bool pinned_;
     uint8_t *stage_ = nullptr;   // pinned: max_batch x 3 planes
     size_t stage_bytes_ = 0, plane_cap_ = 0;
+    size_t src_samples_ = 0;     // w * h * channels of the staged source
 };
 
 struct SearchResult {

@@ -47,6 +47,7 @@ SYMBOLS = (
     "oavif_ssimu2_set_default_device", "oavif_ssimu2_release_cached",
     "oavif_ssimu2_get_option", "oavif_ssimu2_device_pci_bus_id", "oavif_ssimu2_debug_wave_trace", "oavif_ssimu2_submit_rgb8", "oavif_ssimu2_submit_yuv444",
     "oavif_ssimu2_submit_rgb8_dev", "oavif_ssimu2_submit_yuv444_dev", "oavif_ssimu2_wait", "oavif_ssimu2_in_flight",
+    "oavif_ssimu2_source_samples",
 )
 
 
@@ -113,6 +114,7 @@ def load() -> C.CDLL:
     L.oavif_ssimu2_compute_rgb8.argtypes = [u8p, u8p, u32, u32, u32, dp]
     L.oavif_ssimu2_yuv444_to_rgb8.argtypes = [vp, vp, vp, vp, szt, szt, szt, u32, u32, C.c_int, C.c_int,
                                               C.c_int, u8p]
+    L.oavif_ssimu2_source_samples.argtypes = [vp, C.c_int, vp, szt]
     L.oavif_ssimu2_get_detail.argtypes = [vp, u32, C.POINTER(Detail)]
     L.oavif_ssimu2_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.oavif_ssimu2_debug_get_xyb.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32), C.POINTER(u32)]
@@ -378,6 +380,14 @@ class Scorer:
         _check(self._L.oavif_ssimu2_yuv444_to_rgb8(self._ctx, y.ctypes.data, u.ctypes.data, v.ctypes.data,
                                                    y.strides[0], u.strides[0], v.strides[0], w, h, depth, matrix,
                                                    int(rgba_path), out.ctypes.data), self._ctx)
+        return out
+
+    def source_samples(self, out_depth: int) -> np.ndarray:
+        """encodeAvifToBuffer's per-pass depth conversion of the source (io.zig:562-609), once, on the GPU: HxWxC samples
+        at `out_depth` (uint16 for 10, uint8 for 8) from the pixels the last set_source / set_source_pixels staged."""
+        a = self._src_keep
+        out = np.empty(a.shape, np.uint16 if out_depth > 8 else np.uint8)
+        _check(self._L.oavif_ssimu2_source_samples(self._ctx, out_depth, out.ctypes.data, out.nbytes), self._ctx)
         return out
 
     # ---- introspection ----------------------------------------------------------------------------------

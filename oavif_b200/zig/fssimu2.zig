@@ -99,6 +99,13 @@ pub const Scorer = struct {
         try check(c.oavif_ssimu2_set_source_pixels(self.ctx, pixels.ptr, w, h, @as(usize, w) * channels * bps, channels, if (hbd) 16 else 8));
     }
 
+    /// The sample array encodeAvifToBuffer rebuilds from the source in every pass (io.zig:566-609: 8 -> 10 bit
+    /// (v*1023+127)/255, 16 -> 10 bit v >> 6, 16 -> 8 bit v >> 8), made ONCE from the pixels setSourcePixels staged.
+    /// `out` holds w*h*channels samples: u16 for depth 10, u8 for depth 8 (pass it as bytes).
+    pub fn sourceSamples(self: *Scorer, out_depth: u8, out: []u8) Error!void {
+        try check(c.oavif_ssimu2_source_samples(self.ctx, out_depth, out.ptr, out.len));
+    }
+
     /// Batched probing (tq_batched.zig): n decoded candidates (io.DecodedPlanes layout: same depth, strides and
     /// matrix for all of them) against the cached source in one pass over the device.
     pub fn scoreBatchYuv444(self: *Scorer, cands: anytype, scores: []f64) Error!void {

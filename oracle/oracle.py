@@ -103,6 +103,8 @@ def lib(fast: bool = False) -> C.CDLL:
     L.oracle_yuv444_to_rgb8.restype = C.c_int
     L.oracle_to_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
     L.oracle_to_rgb8.restype = C.c_int
+    L.oracle_source_samples.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    L.oracle_source_samples.restype = C.c_int
     _libs[name] = L
     return L
 
@@ -212,4 +214,14 @@ def to_rgb8(data: np.ndarray, channels: int, hbd: bool) -> np.ndarray:
     rc = lib().oracle_to_rgb8(data.ctypes.data, w, h, channels, int(hbd), _u8(out))
     if rc != 0:
         raise RuntimeError(f"oracle_to_rgb8 failed: {rc}")
+    return out
+
+
+def source_samples(data: np.ndarray, out_depth: int) -> np.ndarray:
+    """encodeAvifToBuffer's depth conversion of the source samples (io.zig:562-609); uint8 or uint16 input."""
+    data = np.ascontiguousarray(data)
+    out = np.empty(data.shape, np.uint16 if out_depth > 8 else np.uint8)
+    rc = lib().oracle_source_samples(data.ctypes.data, data.size, int(data.dtype == np.uint16), out_depth, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"oracle_source_samples: no conversion from {data.dtype} to depth {out_depth}")
     return out

@@ -23,6 +23,7 @@
 #ifndef SSIMU2_ORACLE_H
 #define SSIMU2_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -115,6 +116,10 @@ int oracle_yuv444_to_rgb8(const void *y, const void *u, const void *v,
 
 /* Image.toRGB8 (src/io.zig:57-133): channels 1..4, 8- or 16-bit (native endian) -> RGB8. */
 int oracle_to_rgb8(const void *data, int w, int h, int channels, int hbd, uint8_t *out);
+
+/* encodeAvifToBuffer's per-pass sample conversions (src/io.zig:562-609) over n samples: 8 -> 10 bit
+ * (v*1023+127)/255, 16 -> 10 bit v >> 6, 16 -> 8 bit v >> 8.  Returns 0, or -1 for 8 -> 8 (no conversion). */
+int oracle_source_samples(const void *data, size_t n, int hbd, int out_depth, void *out);
 
 #ifdef __cplusplus
 }

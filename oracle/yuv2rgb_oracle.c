@@ -110,3 +110,24 @@ int oracle_to_rgb8(const void *data, int w, int h, int channels, int hbd, uint8_
     }
     return 0;
 }
+
+/* encodeAvifToBuffer's sample conversions, /root/reference/src/io.zig:562-609, over n = w*h*channels samples:
+ * 8-bit source at depth 10: (v*1023 + 127)/255 in usize (io.zig:572); 16-bit source at depth 10: v >> 6
+ * (io.zig:587); 16-bit source at depth 8: v >> 8 (io.zig:602).  An 8-bit source at depth 8 is passed through
+ * (io.zig:611-613): not a conversion, -1 here.  out: uint16_t for depth 10, uint8_t for depth 8.          */
+int oracle_source_samples(const void *data, size_t n, int hbd, int out_depth, void *out)
+{
+    if (!data || !out) return -1;
+    const uint8_t *s8 = (const uint8_t *)data;
+    const uint16_t *s16 = (const uint16_t *)data;
+    if (!hbd && out_depth == 10) {
+        for (size_t i = 0; i < n; ++i) ((uint16_t *)out)[i] = (uint16_t)(((size_t)s8[i] * 1023 + 127) / 255);
+    } else if (hbd && out_depth == 10) {
+        for (size_t i = 0; i < n; ++i) ((uint16_t *)out)[i] = (uint16_t)(s16[i] >> 6);
+    } else if (hbd && out_depth == 8) {
+        for (size_t i = 0; i < n; ++i) ((uint8_t *)out)[i] = (uint8_t)(s16[i] >> 8);
+    } else {
+        return -1;
+    }
+    return 0;
+}

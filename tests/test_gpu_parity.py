@@ -219,6 +219,42 @@ def test_loader_native_layouts_follow_toRGB8(scorer, oracle):
     assert e.value.code == ssimu2.E_UNSUPPORTED
 
 
+def test_source_samples_bit_exact(scorer, oracle):
+    """the encoder-side depth conversions (io.zig:566-609) from the staged source, every channel kept."""
+    rng = np.random.default_rng(11)
+    for (w, h) in ((64, 64), (131, 77), (257, 9)):
+        for ch in (1, 2, 3, 4):
+            p8 = rng.integers(0, 256, (h, w, ch)).astype(np.uint8)
+            p8.reshape(-1)[:256] = np.arange(256, dtype=np.uint8)[: min(256, p8.size)]     # every sample value once
+            p16 = rng.integers(0, 65536, (h, w, ch)).astype(np.uint16)
+            scorer.set_source_pixels(p8)
+            got = scorer.source_samples(10)
+            assert got.dtype == np.uint16 and got.shape == p8.shape
+            np.testing.assert_array_equal(got, oracle.source_samples(p8, 10))
+            with pytest.raises(ssimu2.Ssimu2Error) as e:
+                scorer.source_samples(8)
+            assert e.value.code == ssimu2.E_UNSUPPORTED
+            scorer.set_source_pixels(p16)
+            np.testing.assert_array_equal(scorer.source_samples(10), oracle.source_samples(p16, 10))
+            np.testing.assert_array_equal(scorer.source_samples(8), oracle.source_samples(p16, 8))
+            scorer.check_guards()
+    # strided RGB8 through set_source_rgb8: the staged copy is tight
+    base = synth.synth(150, 90, "mixture", 2)
+    pad = np.zeros((90, 161, 3), np.uint8)
+    pad[:, :150] = base
+    scorer.set_source(pad[:, :150])
+    np.testing.assert_array_equal(scorer.source_samples(10), oracle.source_samples(base, 10))
+    # the cached source is untouched by the call
+    dist = synth.distort(base, 0.3)
+    a = scorer.score_rgb8(dist)
+    scorer.source_samples(10)
+    assert scorer.score_rgb8(dist) == a
+    scorer.set_source(synth.synth(7, 7, "noise", 0))      # below 8x8 nothing is staged
+    with pytest.raises(ssimu2.Ssimu2Error) as e:
+        scorer.source_samples(10)
+    assert e.value.code == ssimu2.E_STATE
+
+
 # ---- K4: the filter alone ----------------------------------------------------------------------------
 @pytest.mark.parametrize("mode,omode,name", MODES)
 @pytest.mark.parametrize("size", [(9, 9), (40, 33), (131, 97), (640, 360)])

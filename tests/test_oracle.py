@@ -183,6 +183,22 @@ def test_to_rgb8_semantics(oracle):
     np.testing.assert_array_equal(oracle.to_rgb8(rgb16, 3, True), (rgb16 >> 8).astype(np.uint8))
 
 
+def test_source_samples_are_the_reference_formulas(oracle):
+    """encodeAvifToBuffer's loops (io.zig:566-609): exhaustive over the sample values."""
+    v8 = np.arange(256, dtype=np.uint8).reshape(16, 16, 1)
+    want = [(int(v) * 1023 + 127) // 255 for v in range(256)]
+    got = oracle.source_samples(v8, 10)
+    assert got.dtype == np.uint16 and got.reshape(-1).tolist() == want
+    assert got.min() == 0 and got.max() == 1023
+    v16 = np.arange(65536, dtype=np.uint16).reshape(256, 64, 4)
+    np.testing.assert_array_equal(oracle.source_samples(v16, 10), v16 >> 6)
+    out8 = oracle.source_samples(v16, 8)
+    assert out8.dtype == np.uint8
+    np.testing.assert_array_equal(out8, (v16 >> 8).astype(np.uint8))
+    with pytest.raises(RuntimeError):
+        oracle.source_samples(v8, 8)          # passed through by the reference (io.zig:611-613)
+
+
 # ---- fssimu2 golden vectors (scripts/pin_fssimu2.md) ---------------------------------------------------------------
 FSSIMU2_VECTORS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fssimu2_scores.json")
 
