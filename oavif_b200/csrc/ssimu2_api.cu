@@ -92,7 +92,7 @@ struct SrcSet {
     cudaEvent_t ready = nullptr;           // source stream: ... and so is everything else enqueued by set_source
     cudaEvent_t last_use[2] = {nullptr, nullptr};   // per slot: its last submission reading this set has finished
     cudaEvent_t cache_done = nullptr;      // the launch that filled d_hplanes (whichever slot's stream it ran on)
-    CUtensorMap in_src[kMaxScales], out_psrc[kMaxScales], in_musig[kMaxScales], cols_psrc[kMaxScales];
+    CUtensorMap in_src[kMaxScales], out_psrc[kMaxScales], in_musig[kMaxScales], cols_psrc[kMaxScales], cols_xa[kMaxScales];
     int maps_w = -1, maps_h = -1;
 };
 
@@ -512,14 +512,15 @@ bool rows_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirRowsTmaMaps *out)
     if (ctx->cs->maps_w != g.w[0] || ctx->cs->maps_h != g.h[0]) {
         ok = iir_rows_tma_maps_cand(&ctx->cs->cand_maps, g, ctx->cs->d_dist_pyr, P, ctx->cs->d_hplanes, ctx->cs->d_hplanes + 2 * P, 3 * P,
                                     (int)ctx->max_batch) &&
-             iir_cols_tma_maps_cand(&ctx->cs->cols_maps, g, ctx->cs->d_hplanes, ctx->cs->d_hplanes + 2 * P, 3 * P, (int)ctx->max_batch);
+             iir_cols_tma_maps_cand(&ctx->cs->cols_maps, g, ctx->cs->d_hplanes, ctx->cs->d_hplanes + 2 * P, 3 * P, ctx->cs->d_dist_pyr, P,
+                                    (int)ctx->max_batch);
         if (ok) {
             ctx->cs->maps_w = g.w[0];
             ctx->cs->maps_h = g.h[0];
         }
     }
     if (ok && (S.maps_w != g.w[0] || S.maps_h != g.h[0])) {
-        ok = iir_rows_tma_maps_src(S.in_src, S.out_psrc, g, S.d_pyr, S.d_hplanes) && iir_cols_tma_maps_src(S.cols_psrc, g, S.d_hplanes);
+        ok = iir_rows_tma_maps_src(S.in_src, S.out_psrc, g, S.d_pyr, S.d_hplanes) && iir_cols_tma_maps_src(S.cols_psrc, S.cols_xa, g, S.d_hplanes, S.d_pyr);
         for (int s = 0; s < g.n_scales && ok; ++s)   // the fused kernel's view of the same buffer: (mu1, sigma11) pairs
             ok = tma_make_4d(&S.in_musig[s], S.d_hplanes + 2 * g.off[s], 2ull * g.w[s], (uint64_t)g.h[s], 3, 1,
                              (uint64_t)g.pitch[s] * 8, (uint64_t)g.plane[s] * 8, 0, 2 * kIirVCols, kWvB, false);
@@ -545,6 +546,7 @@ const IirColsTmaMaps *cols_maps_for(oavif_ssimu2_ctx *ctx, SrcSet &S, IirColsTma
     if (!rows_maps_for(ctx, S, &rows)) return nullptr;   // also brings both sets of descriptors up to date
     *tmp = ctx->cs->cols_maps;
     memcpy(tmp->psrc, S.cols_psrc, sizeof tmp->psrc);
+    memcpy(tmp->xa, S.cols_xa, sizeof tmp->xa);
     return tmp;
 }
 

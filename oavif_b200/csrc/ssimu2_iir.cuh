@@ -822,19 +822,23 @@ inline cudaError_t iir_rows_tma_dispatch(int shape, const IirArgs &ar, const Iir
 // of a column as one packed pair.  One block barrier per 16 rows.
 constexpr int kIirVThreads = 256;   // 3 producer warps + 4 consumer warps + 1 loader warp
 
+constexpr int kAbRows = 48;
+
 template <int RCAP, int B>
 struct IirColsSmem {
     float pring[2][RCAP][2 * kIirVCols];       // producer input rows of the pairs (a, a*a), (b, b*b), row r at [r & (RCAP-1)]
     float sring[RCAP][kIirVCols];              // ... and of a*b
-    float ab[2][32][kIirVCols];                // consumer rows of the two XYB planes
+    float ab[2][kAbRows][kIirVCols];           // consumer rows of the two XYB planes: cp.async form rows r at [r & 31];
+                                               // TMA form three 16-row batches, batch b at [16 * (b % 3)]
     float ex[2][5][B][kIirVCols];              // filtered values, double-buffered
     double red[4][6];
     uint64_t land[2];                          // TMA form: "the rows requested during batch b have landed", by parity of b
 };
 
-// TMA descriptors of the columns pass: 4-row boxes of the interleaved pair planes (64 floats wide) and of a*b (32)
+// TMA descriptors of the columns pass: 4-row boxes of the interleaved pair planes (64 floats wide) and of a*b (32),
+// 16-row boxes of the two XYB pyramids (xa: source, xb: candidates) for the consumers
 struct IirColsTmaMaps {
-    CUtensorMap psrc[kMaxScales], pcand[kMaxScales], ab[kMaxScales];
+    CUtensorMap psrc[kMaxScales], pcand[kMaxScales], ab[kMaxScales], xa[kMaxScales], xb[kMaxScales];
 };
 
 // B rows per exchange batch: the per-batch overhead (barrier, copy issue, address set-up) is paid once
@@ -869,11 +873,19 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         // Requests of a batch complete on land[parity of the batch]; the loader arrives at the barrier that ends batch
         // b only when the rows requested during batch b - 1 (everything batch b + 1 reads) have landed.
         constexpr unsigned kGroupBytes = 4 * (2 * 2 * kIirVCols + kIirVCols) * 4;   // 4 rows of two pair planes and a*b
+        constexpr unsigned kXybBytes = 2 * B * kIirVCols * 4;                       // a batch of both XYB planes
         const int x0 = cb * kIirVCols;
         auto issue_rows4 = [&](int r0, uint64_t *bar) {
             tma_load_4d(&sm.pring[0][r0 & (RCAP - 1)][0], &tm.psrc[s], 2 * x0, r0, c, 0, bar);
             tma_load_4d(&sm.pring[1][r0 & (RCAP - 1)][0], &tm.pcand[s], 2 * x0, r0, c, cand, bar);
             tma_load_4d(&sm.sring[r0 & (RCAP - 1)][0], &tm.ab[s], x0, r0, c, cand, bar);
+        };
+        // The consumers' XYB rows of batch nb go to third nb % 3 of their ring.  They are requested while batch
+        // nb - 1 is being produced: the consumers are then reading batch nb - 2's third and will read batch nb - 1's
+        // next, so the third being refilled is the one of batch nb - 3, which nobody touches any more.
+        auto issue_xyb = [&](int nb, int third, uint64_t *bar) {
+            tma_load_4d(&sm.ab[0][third * B][0], &tm.xa[s], x0, nb * B, c, 0, bar);
+            tma_load_4d(&sm.ab[1][third * B][0], &tm.xb[s], x0, nb * B, c, cand, bar);
         };
 #pragma unroll
         for (int j = 1; j <= 6; ++j) {   // rows -6..-1 are padding
@@ -886,23 +898,30 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             mbar_init(&sm.land[0], 1);
             mbar_init(&sm.land[1], 1);
             mbar_init_fence();
-            // group 0 = everything before the first batch's request (rows 0 .. 3 + D), on land[0]
-            mbar_arrive_expect_tx(&sm.land[0], (4 + D) / 4 * kGroupBytes);
+            // group 0 = everything before the first batch's request (rows 0 .. 3 + D, XYB rows of batch 0), on land[0]
+            mbar_arrive_expect_tx(&sm.land[0], (4 + D) / 4 * kGroupBytes + kXybBytes);
             for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0, &sm.land[0]);
+            issue_xyb(0, 0, &sm.land[0]);
             mbar_wait(&sm.land[0], 0);
         }
         __syncthreads();      // (S) rows 0 .. 3+D are in the rings
+        int third = 1;        // (b + 1) % 3
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             if (lane == 0) {
                 const int g = b + 1;                 // group of this batch's requests
-                mbar_arrive_expect_tx(&sm.land[g & 1], B / 4 * kGroupBytes);
+                mbar_arrive_expect_tx(&sm.land[g & 1], B / 4 * kGroupBytes + kXybBytes);
 #pragma unroll
                 for (int j = 0; j < B; j += 4) issue_rows4(b * B + 4 + D + j, &sm.land[g & 1]);
+                issue_xyb(b + 1, third, &sm.land[g & 1]);
                 mbar_wait(&sm.land[b & 1], (unsigned)(b >> 1) & 1u);   // group b: requested during batch b - 1
             }
+            third = third == 2 ? 0 : third + 1;
             __syncthreads();              // (b)
         }
+        // the last group's rows lie below the image (zeros), but they still land in this CTA's shared memory: they
+        // must have done so before the CTA gives it up
+        if (lane == 0) mbar_wait(&sm.land[nbatch & 1], (unsigned)(nbatch >> 1) & 1u);
         __syncthreads();      // consumers' last batch
         __syncthreads();      // final reduction
     } else if (warp == 7) {
@@ -1046,9 +1065,11 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
             }
         };
         static_assert(B == 16 && DA == 16, "the pair assignment is written for 16-row batches");
-        issue_ab(0);
-        cp_async_commit();
-        cp_async_wait<0>();   // the in-loop wait only covers groups committed inside the loop
+        if (!TMA) {           // TMA form: the loader warp brings the XYB rows in with everything else
+            issue_ab(0);
+            cp_async_commit();
+            cp_async_wait<0>();   // the in-loop wait only covers groups committed inside the loop
+        }
         __syncthreads();      // (S)
         const Unit2 u = unit2(a.one, a.neg_one);
         const f32x2 zero = splat2(0.0f);
@@ -1057,15 +1078,20 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
 #pragma unroll
         for (int j = 0; j < 6; ++j) acc[j] = zero;
         const float *abw = &sm.ab[0][2 * first_pair][lane];   // this warp's first row pair in ring rows 0..15
-        constexpr int kAbPlane = 32 * kIirVCols;               // floats between the two staged planes
+        constexpr int kAbPlane = kAbRows * kIirVCols;          // floats between the two staged planes
+        int third = 0;                                         // b % 3
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
-            issue_ab(b * B + DA);
-            cp_async_commit();
-            cp_async_wait<DA / B>();                   // the rows of batch b staged by this warp have landed
+            if (!TMA) {
+                issue_ab(b * B + DA);
+                cp_async_commit();
+                cp_async_wait<DA / B>();               // the rows of batch b staged by this warp have landed
+            }
             __syncthreads();                           // batch b is in ex[b & 1]; staged samples are visible
             const float *ex = &sm.ex[b & 1][0][2 * first_pair][lane];
-            const float *ab = abw + ((b * B) & 31) * kIirVCols;   // B divides 32: a batch never wraps inside the ring
+            // B divides 32 (and the thirds are B rows): a batch never wraps inside the ring
+            const float *ab = abw + (TMA ? third * B : (b * B) & 31) * kIirVCols;
+            third = third == 2 ? 0 : third + 1;
             const bool whole = (b + 1) * B <= h;       // every row of the batch is inside the image
             // one packed evaluation of rows n, n + 1 of this warp's columns.  ODD: the pair's second row lies below an
             // odd-height image and pools as zeros — a separate instance, so that the common path carries none of the
@@ -1221,17 +1247,21 @@ inline bool iir_rows_tma_maps_src(CUtensorMap in_src[kMaxScales], CUtensorMap ou
     return ok;
 }
 
-inline bool iir_cols_tma_maps_src(CUtensorMap psrc[kMaxScales], const Geom &g, const float *hpair_src)
+inline bool iir_cols_tma_maps_src(CUtensorMap psrc[kMaxScales], CUtensorMap xa[kMaxScales], const Geom &g, const float *hpair_src,
+                                  const float *src)
 {
     bool ok = true;
-    for (int s = 0; s < g.n_scales && ok; ++s)
+    for (int s = 0; s < g.n_scales && ok; ++s) {
         ok = tma_make_4d(&psrc[s], hpair_src + 2 * g.off[s], 2ull * g.w[s], (uint64_t)g.h[s], 3, 1, (uint64_t)g.pitch[s] * 8,
                          (uint64_t)g.plane[s] * 8, 0, 2 * kIirVCols, 4, false);
+        ok = ok && tma_make_4d(&xa[s], src + g.off[s], (uint64_t)g.w[s], (uint64_t)g.h[s], 3, 1, (uint64_t)g.pitch[s] * 4,
+                               (uint64_t)g.plane[s] * 4, 0, kIirVCols, 16, false);
+    }
     return ok;
 }
 
 inline bool iir_cols_tma_maps_cand(IirColsTmaMaps *m, const Geom &g, const float *hpair_cand, const float *hab,
-                                   long long hcand_stride, int n_images)
+                                   long long hcand_stride, const float *dist, long long dist_stride, int n_images)
 {
     bool ok = true;
     for (int s = 0; s < g.n_scales && ok; ++s) {
@@ -1240,6 +1270,8 @@ inline bool iir_cols_tma_maps_cand(IirColsTmaMaps *m, const Geom &g, const float
                                (uint64_t)hcand_stride * 4, 2 * kIirVCols, 4, false);
         ok = ok && tma_make_4d(&m->ab[s], hab + g.off[s], w, h, 3, (uint64_t)n_images, rowb, planeb,
                                (uint64_t)hcand_stride * 4, kIirVCols, 4, false);
+        ok = ok && tma_make_4d(&m->xb[s], dist + g.off[s], w, h, 3, (uint64_t)n_images, rowb, planeb,
+                               (uint64_t)dist_stride * 4, kIirVCols, 16, false);
     }
     return ok;
 }
