@@ -10,6 +10,7 @@
 #pragma once
 
 #include "ssimu2_common.cuh"
+#include "ssimu2_tma.cuh"
 
 namespace oavif {
 
@@ -157,9 +158,12 @@ __global__ void __launch_bounds__(256, 4) k_pyramid(const __grid_constant__ PyrA
 {
     // The sRGB table once per LANE: entry v of lane l lives at [v][l], so a warp's 32 gathers hit 32 different banks
     // whatever the pixel values are (a single 256-entry copy made 44 % of the kernel's shared-memory wavefronts
-    // bank conflicts, profiles/r1_final_ncu_recursive.txt).
-    __shared__ __align__(16) float s_lut[256][32];
-    __shared__ float s_l2[3][16][17];  // scale-2 linear RGB of this tile
+    // bank conflicts, profiles/r1_final_ncu_recursive.txt).  It arrives as one 32 KB bulk copy (no thread moves it).
+    __shared__ __align__(128) float s_lut[256][32];
+    __shared__ uint64_t s_lut_bar;
+    // scale-2 linear RGB of this tile, rows of 16: thread t stores word t (no conflict), and the scale-3 step reads
+    // it as 8-byte pairs with even and odd rows split between the two half-warps (see there)
+    __shared__ __align__(8) float s_l2[3][16][16];
     __shared__ float s_l3[3][8][9];
     __shared__ float s_l4[3][4][5];
 
@@ -180,16 +184,16 @@ __global__ void __launch_bounds__(256, 4) k_pyramid(const __grid_constant__ PyrA
     uint32_t raw[4][PyrRaw<KIND>::N];
 #pragma unroll
     for (int j = 0; j < 4; ++j) fetch4<KIND>(a, p0, p1, p2, x0, min(y0 + j, g.h[0] - 1), raw[j]);
-    {   // the table arrives already laid out per lane (32 KB, L2-resident): eight 16-byte copies per thread
-        const float4 *src = reinterpret_cast<const float4 *>(a.lut);
-        float4 *dst = reinterpret_cast<float4 *>(&s_lut[0][0]);
-        float4 t[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = __ldg(src + tid + 256 * i);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dst[tid + 256 * i] = t[i];
+    if (tid == 0) {
+        mbar_init(&s_lut_bar, 1);
+        mbar_init_fence();
     }
     __syncthreads();
+    if (tid == 0) {   // the table is already laid out per lane in global memory (32 KB, L2-resident)
+        mbar_arrive_expect_tx(&s_lut_bar, sizeof s_lut);
+        bulk_load(&s_lut[0][0], a.lut, sizeof s_lut, &s_lut_bar);
+    }
+    mbar_wait(&s_lut_bar, 0);
     float lin[4][4][3];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -277,14 +281,22 @@ __global__ void __launch_bounds__(256, 4) k_pyramid(const __grid_constant__ PyrA
     __syncthreads();
 
     // ---- scale 3: 8x8 per tile, from shared memory; clamp to the tile-local last valid ---
+    // A cell reads its two scale-2 rows as 8-byte pairs.  Rows of 16 words put even rows in banks 0..15 and odd rows
+    // in 16..31, so within a half-warp (two cell rows cy, eight cx each) the cells of even cy read their upper row
+    // first and those of odd cy their lower row first: every access covers all 32 banks once.
     if (tid < 64) {
         const int cx = tid & 7, cy = tid >> 3;
-        const int lx = max(min(2 * cx + 1, g.w[2] - 1 - bx * 16), 0);
+        const bool two_x = 2 * cx + 1 <= g.w[2] - 1 - bx * 16;      // else the cell's right column is clamped onto its left
         const int ly = max(min(2 * cy + 1, g.h[2] - 1 - by * 16), 0);
+        const bool swap = cy & 1;
+        const int ra = swap ? ly : 2 * cy, rb = swap ? 2 * cy : ly;
         float l3[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            l3[c] = box4(s_l2[c][2 * cy][2 * cx], s_l2[c][2 * cy][lx], s_l2[c][ly][2 * cx], s_l2[c][ly][lx]);
+            const float2 va = *reinterpret_cast<const float2 *>(&s_l2[c][ra][2 * cx]);
+            const float2 vb = *reinterpret_cast<const float2 *>(&s_l2[c][rb][2 * cx]);
+            const float2 top = swap ? vb : va, bot = swap ? va : vb;
+            l3[c] = box4(top.x, two_x ? top.y : top.x, bot.x, two_x ? bot.y : bot.x);
             s_l3[c][cy][cx] = l3[c];
         }
         float vx, vy, vb;

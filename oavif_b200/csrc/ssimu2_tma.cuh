@@ -61,6 +61,13 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
         : "memory");
 }
+// global -> shared, a plain run of bytes (16-byte aligned, a multiple of 16 long); completion counted on `bar`
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 // shared -> global tile (bulk async-group completion); elements outside the tensor are not written
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3, const void *smem_src)
 {
