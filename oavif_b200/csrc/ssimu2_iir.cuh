@@ -823,6 +823,12 @@ inline cudaError_t iir_rows_tma_dispatch(int shape, const IirArgs &ar, const Iir
 constexpr int kIirVThreads = 256;   // 3 producer warps + 4 consumer warps + 1 loader warp
 
 constexpr int kAbRows = 48;
+// TMA form of the columns pass: the warps of a CTA meet at no CTA-wide barrier inside the batch loop.  Each hand-over
+// is an mbarrier of its own — rows landed (loader -> producers, consumers), batch produced (3 producer warps ->
+// consumers, loader), batch consumed (4 consumer warps -> producers, loader) — so a warp waits only for what it reads.
+// Four barriers per kind although the data is double-buffered: a waiter tests a phase PARITY, and with four the next
+// phase of the same parity cannot complete before every waiter of this one has passed (argued at each wait below).
+constexpr bool kColsDecoupled = true;
 
 template <int RCAP, int B>
 struct IirColsSmem {
@@ -832,7 +838,8 @@ struct IirColsSmem {
                                                // TMA form three 16-row batches, batch b at [16 * (b % 3)]
     float ex[2][5][B][kIirVCols];              // filtered values, double-buffered
     double red[4][6];
-    uint64_t land[2];                          // TMA form: "the rows requested during batch b have landed", by parity of b
+    uint64_t land[4];                          // TMA form: "request group g has landed", g & 3
+    uint64_t full[4], empty[4];                // TMA form: batch b is in ex[b & 1] (3 producers) / has been consumed (4 consumers), b & 3
 };
 
 // TMA descriptors of the columns pass: 4-row boxes of the interleaved pair planes (64 floats wide) and of a*b (32),
@@ -867,6 +874,14 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     const int nbatch = (h + B - 1) / B;
     // bytes of this lane's 16-byte column group that lie inside the image: the rest is zero-filled
     const int cbytes = max(0, min(16, (w - (cb * kIirVCols + ccol)) * 4));
+    constexpr bool DEC = TMA && kColsDecoupled;
+    auto wait_land = [&](int g) { mbar_wait(&sm.land[g & 3], (unsigned)(g >> 2) & 1u); };
+    auto wait_full = [&](int b) { mbar_wait(&sm.full[b & 3], (unsigned)(b >> 2) & 1u); };
+    auto wait_empty = [&](int b) { mbar_wait(&sm.empty[b & 3], (unsigned)(b >> 2) & 1u); };
+    auto warp_arrive = [&](uint64_t *bar) {   // the whole warp's shared-memory accesses precede the arrival
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+    };
 
     if (TMA && warp == 7) {
         // ---------------- loader, TMA form: one lane, 4-row boxes (a box never wraps around the 64-row ring) ----------------
@@ -895,33 +910,46 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         }
         fence_async_smem();   // these slots are rewritten by TMA once real rows wrap around to them
         if (lane == 0) {
-            mbar_init(&sm.land[0], 1);
-            mbar_init(&sm.land[1], 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                mbar_init(&sm.land[i], 1);
+                mbar_init(&sm.full[i], 3);
+                mbar_init(&sm.empty[i], 4);
+            }
             mbar_init_fence();
             // group 0 = everything before the first batch's request (rows 0 .. 3 + D, XYB rows of batch 0), on land[0]
             mbar_arrive_expect_tx(&sm.land[0], (4 + D) / 4 * kGroupBytes + kXybBytes);
             for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0, &sm.land[0]);
             issue_xyb(0, 0, &sm.land[0]);
-            mbar_wait(&sm.land[0], 0);
+            if (!DEC) mbar_wait(&sm.land[0], 0);
         }
-        __syncthreads();      // (S) rows 0 .. 3+D are in the rings
+        __syncthreads();      // (S) barriers initialised (and, !DEC, rows 0 .. 3+D in the rings)
         int third = 1;        // (b + 1) % 3
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             if (lane == 0) {
                 const int g = b + 1;                 // group of this batch's requests
-                mbar_arrive_expect_tx(&sm.land[g & 1], B / 4 * kGroupBytes + kXybBytes);
+                if (DEC) {
+                    // The rows of group g replace rows (b-2)B+4 .. (b-1)B+3, last read by the producers' batch b - 1;
+                    // the XYB third replaces batch b - 2's.  Parity: the next same-parity phase of full[(b-1)&3] is
+                    // batch b + 3, whose rows THIS lane requests two iterations from now; that of empty[(b-2)&3] is
+                    // batch b + 2, produced only from the rows requested right below.
+                    if (b >= 1) wait_full(b - 1);
+                    if (b >= 2) wait_empty(b - 2);
+                }
+                mbar_arrive_expect_tx(&sm.land[g & 3], B / 4 * kGroupBytes + kXybBytes);
 #pragma unroll
-                for (int j = 0; j < B; j += 4) issue_rows4(b * B + 4 + D + j, &sm.land[g & 1]);
-                issue_xyb(b + 1, third, &sm.land[g & 1]);
-                mbar_wait(&sm.land[b & 1], (unsigned)(b >> 1) & 1u);   // group b: requested during batch b - 1
+                for (int j = 0; j < B; j += 4) issue_rows4(b * B + 4 + D + j, &sm.land[g & 3]);
+                issue_xyb(b + 1, third, &sm.land[g & 3]);
+                if (!DEC) wait_land(b);              // group b: requested during batch b - 1
             }
             third = third == 2 ? 0 : third + 1;
-            __syncthreads();              // (b)
+            if (DEC) __syncwarp();
+            else __syncthreads();         // (b)
         }
         // the last group's rows lie below the image (zeros), but they still land in this CTA's shared memory: they
         // must have done so before the CTA gives it up
-        if (lane == 0) mbar_wait(&sm.land[nbatch & 1], (unsigned)(nbatch >> 1) & 1u);
+        if (lane == 0) wait_land(nbatch);
         __syncthreads();      // consumers' last batch
         __syncthreads();      // final reduction
     } else if (warp == 7) {
@@ -978,12 +1006,21 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         const float *col = &sm.pring[warp][0][2 * lane];
         constexpr int kRow = 2 * kIirVCols;
         __syncthreads();      // (S)
+        if (DEC) wait_land(0);
         // n = -4..-1: right taps are rows 0..3, left taps are padding, nothing emitted
 #pragma unroll
         for (int n = -4; n < 0; ++n) (void)iir_step2(k, st, splat2(0.0f), lds2(col + (n + 4) * kRow));
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
+            if (DEC) {
+                // batch b reads rows up to bB + 19: group b - 1 (group 0 holds rows 0 .. 35).  land[(b-1)&3]'s next
+                // same-parity phase is group b + 3, requested only after this warp has finished batch b + 1.
+                if (b >= 1) wait_land(b - 1);
+                // ex[b & 1] held batch b - 2.  empty[(b-2)&3]'s next same-parity phase is batch b + 2, which this
+                // warp itself must produce first.
+                if (b >= 2) wait_empty(b - 2);
+            }
             const int n0 = b * B;
             // n0 is a multiple of B and so is RCAP: the left taps (rows n0-6+j) can only wrap at j = 6, the
             // right taps (rows n0+4+j) only at j = B-4 -> two bases each, static offsets otherwise
@@ -1002,7 +1039,8 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
                 const f32x2 o = (j + 1 < B) ? pipe2_step(k, P, sum[j + 1]) : pipe2_end(k, P, st);
                 unpk2(o, ex0[j * kIirVCols], ex1[j * kIirVCols]);
             }
-            __syncthreads();  // (b) batch b published; the consumers are done with the other buffer
+            if (DEC) warp_arrive(&sm.full[b & 3]);
+            else __syncthreads();  // (b) batch b published; the consumers are done with the other buffer
         }
         __syncthreads();      // consumers' last batch
         __syncthreads();      // final reduction
@@ -1015,11 +1053,16 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
         const float *col = &sm.sring[0][lane];
         __syncthreads();      // (S)
+        if (DEC) wait_land(0);
 #pragma unroll
         for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, col[(n + 4) * kIirVCols]);
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
+            if (DEC) {            // as in the pair producers
+                if (b >= 1) wait_land(b - 1);
+                if (b >= 2) wait_empty(b - 2);
+            }
             const int n0 = b * B;
             float sum[B];
             const float *l0 = col + ((n0 - 6) & (RCAP - 1)) * kIirVCols, *l1 = col + (n0 & (RCAP - 1)) * kIirVCols;
@@ -1034,7 +1077,8 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
 #pragma unroll
             for (int j = 0; j < B; ++j)
                 ex[j * kIirVCols] = (j + 1 < B) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
-            __syncthreads();  // (b)
+            if (DEC) warp_arrive(&sm.full[b & 3]);
+            else __syncthreads();  // (b)
         }
         __syncthreads();
         __syncthreads();
@@ -1087,7 +1131,14 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
                 cp_async_commit();
                 cp_async_wait<DA / B>();               // the rows of batch b staged by this warp have landed
             }
-            __syncthreads();                           // batch b is in ex[b & 1]; staged samples are visible
+            if (DEC) {
+                // full[b&3]'s next same-parity phase is batch b + 4, which needs this warp's empty(b + 2);
+                // land[b&3]'s is group b + 4, requested only after the producers' batch b + 2, which needs empty(b).
+                wait_full(b);
+                wait_land(b);                          // this batch's XYB rows ride in group b
+            } else {
+                __syncthreads();                       // batch b is in ex[b & 1]; staged samples are visible
+            }
             const float *ex = &sm.ex[b & 1][0][2 * first_pair][lane];
             // B divides 32 (and the thirds are B rows): a batch never wraps inside the ring
             const float *ab = abw + (TMA ? third * B : (b * B) & 31) * kIirVCols;
@@ -1134,6 +1185,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
                     else if (n < h) eval_pair(g, n, std::true_type{});
                 }
             }
+            if (DEC) warp_arrive(&sm.empty[b & 3]);   // ex[b & 1] and this batch's XYB third may be refilled
             if (b & 1) {   // binary32 over at most 4 pixels per accumulator (32 image rows), binary64 from there on
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
