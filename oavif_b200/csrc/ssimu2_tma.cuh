@@ -16,6 +16,8 @@
 namespace oavif {
 
 // ---- device side ------------------------------------------------------------------------------------------
+constexpr uint32_t kMbarSuspendNs = 1000000u;   // upper bound of one parked wait, ns
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -35,19 +37,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
-// blocks until the barrier's phase with the given parity has completed (try_wait suspends in hardware)
+// Blocks until the barrier's phase with the given parity has completed.  try_wait parks the warp in hardware until
+// the phase completes or a time limit passes; with the default limit a waiting warp came back every few hundred
+// cycles and re-issued the test (SYNCS + BRA were a quarter of the columns kernel's executed instructions,
+// profiles/r2_final_ncu_cols_hot.txt).  The explicit limit is far above any wait seen here, so a waiting warp costs
+// no issue slots; completion still wakes it at once.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
 }
 
