@@ -823,12 +823,17 @@ inline cudaError_t iir_rows_tma_dispatch(int shape, const IirArgs &ar, const Iir
 constexpr int kIirVThreads = 256;   // 3 producer warps + 4 consumer warps + 1 loader warp
 
 constexpr int kAbRows = 48;
-// TMA form of the columns pass: the warps of a CTA meet at no CTA-wide barrier inside the batch loop.  Each hand-over
-// is an mbarrier of its own — rows landed (loader -> producers, consumers), batch produced (3 producer warps ->
-// consumers, loader), batch consumed (4 consumer warps -> producers, loader) — so a warp waits only for what it reads.
-// Four barriers per kind although the data is double-buffered: a waiter tests a phase PARITY, and with four the next
-// phase of the same parity cannot complete before every waiter of this one has passed (argued at each wait below).
-constexpr bool kColsDecoupled = true;
+// TMA form of the columns pass, decoupled variant: the warps of a CTA meet at no CTA-wide barrier inside the batch
+// loop.  Each hand-over is an mbarrier of its own — group landed (loader -> everyone, passed on once through ready[]),
+// batch produced (3 producer warps -> consumers, loader), batch consumed (4 consumer warps -> producers, loader) — so
+// a warp waits only for what it reads.  Four barriers per kind although the data is double-buffered: a waiter tests a
+// phase PARITY, and with four the next phase of the same parity cannot complete before every waiter of this one has
+// passed (argued at each wait below).
+// Measured (profiles/r2_cols_sync_forms.txt): 0.184 ms against 0.184 ms for the one-__syncthreads-per-batch form on
+// the same box, with or without parked waits — the barrier samples of the rendezvous form were warps waiting for
+// work that is limited elsewhere, not time lost at the barrier.  Both forms are bit-identical and pass the same
+// tests; the shipped default is the rendezvous form (fewer executed instructions, one barrier to reason about).
+constexpr bool kColsDecoupled = false;
 
 template <int RCAP, int B>
 struct IirColsSmem {
@@ -840,6 +845,7 @@ struct IirColsSmem {
     double red[4][6];
     uint64_t land[4];                          // TMA form: "request group g has landed", g & 3
     uint64_t full[4], empty[4];                // TMA form: batch b is in ex[b & 1] (3 producers) / has been consumed (4 consumers), b & 3
+    uint64_t ready[4];                         // TMA form: the loader's "group g has landed", told to the other warps once
 };
 
 // TMA descriptors of the columns pass: 4-row boxes of the interleaved pair planes (64 floats wide) and of a*b (32),
@@ -876,6 +882,9 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     const int cbytes = max(0, min(16, (w - (cb * kIirVCols + ccol)) * 4));
     constexpr bool DEC = TMA && kColsDecoupled;
     auto wait_land = [&](int g) { mbar_wait(&sm.land[g & 3], (unsigned)(g >> 2) & 1u); };
+    // Every completed copy of a group wakes the warps parked on land[]; only the loader's lane parks there and passes
+    // the completed group on through ready[] (one arrival), so that seven warps wake once per group, not thirteen times.
+    auto wait_ready = [&](int g) { mbar_wait(&sm.ready[g & 3], (unsigned)(g >> 2) & 1u); };
     auto wait_full = [&](int b) { mbar_wait(&sm.full[b & 3], (unsigned)(b >> 2) & 1u); };
     auto wait_empty = [&](int b) { mbar_wait(&sm.empty[b & 3], (unsigned)(b >> 2) & 1u); };
     auto warp_arrive = [&](uint64_t *bar) {   // the whole warp's shared-memory accesses precede the arrival
@@ -915,15 +924,17 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
                 mbar_init(&sm.land[i], 1);
                 mbar_init(&sm.full[i], 3);
                 mbar_init(&sm.empty[i], 4);
+                mbar_init(&sm.ready[i], 1);
             }
             mbar_init_fence();
             // group 0 = everything before the first batch's request (rows 0 .. 3 + D, XYB rows of batch 0), on land[0]
             mbar_arrive_expect_tx(&sm.land[0], (4 + D) / 4 * kGroupBytes + kXybBytes);
             for (int r0 = 0; r0 < 4 + D; r0 += 4) issue_rows4(r0, &sm.land[0]);
             issue_xyb(0, 0, &sm.land[0]);
-            if (!DEC) mbar_wait(&sm.land[0], 0);
+            mbar_wait(&sm.land[0], 0);
+            if (DEC) mbar_arrive(&sm.ready[0]);   // nobody waits for group 0, but ready[0]'s phases must count from it
         }
-        __syncthreads();      // (S) barriers initialised (and, !DEC, rows 0 .. 3+D in the rings)
+        __syncthreads();      // (S) barriers initialised, rows 0 .. 3+D (all that batches 0 and 1 read) in the rings
         int third = 1;        // (b + 1) % 3
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
@@ -941,7 +952,12 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
 #pragma unroll
                 for (int j = 0; j < B; j += 4) issue_rows4(b * B + 4 + D + j, &sm.land[g & 3]);
                 issue_xyb(b + 1, third, &sm.land[g & 3]);
-                if (!DEC) wait_land(b);              // group b: requested during batch b - 1
+                if (b >= 1) {
+                    wait_land(b);                    // group b: requested during batch b - 1
+                    // ready[b&3]'s next same-parity phase is group b + 4, passed on only after full(b + 3): by then
+                    // every producer has started batch b + 1 and (empty(b + 1)) every consumer has finished batch b
+                    if (DEC) mbar_arrive(&sm.ready[b & 3]);
+                }
             }
             third = third == 2 ? 0 : third + 1;
             if (DEC) __syncwarp();
@@ -1006,7 +1022,6 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         const float *col = &sm.pring[warp][0][2 * lane];
         constexpr int kRow = 2 * kIirVCols;
         __syncthreads();      // (S)
-        if (DEC) wait_land(0);
         // n = -4..-1: right taps are rows 0..3, left taps are padding, nothing emitted
 #pragma unroll
         for (int n = -4; n < 0; ++n) (void)iir_step2(k, st, splat2(0.0f), lds2(col + (n + 4) * kRow));
@@ -1014,9 +1029,8 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             if (DEC) {
-                // batch b reads rows up to bB + 19: group b - 1 (group 0 holds rows 0 .. 35).  land[(b-1)&3]'s next
-                // same-parity phase is group b + 3, requested only after this warp has finished batch b + 1.
-                if (b >= 1) wait_land(b - 1);
+                // batch b reads rows up to bB + 19: group b - 1 (group 0, rows 0 .. 35, landed before (S))
+                if (b >= 2) wait_ready(b - 1);
                 // ex[b & 1] held batch b - 2.  empty[(b-2)&3]'s next same-parity phase is batch b + 2, which this
                 // warp itself must produce first.
                 if (b >= 2) wait_empty(b - 2);
@@ -1053,15 +1067,16 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         for (int i = 0; i < 3; ++i) st.p[i] = st.p2[i] = 0.0f;
         const float *col = &sm.sring[0][lane];
         __syncthreads();      // (S)
-        if (DEC) wait_land(0);
 #pragma unroll
         for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, col[(n + 4) * kIirVCols]);
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
             if (DEC) {            // as in the pair producers
-                if (b >= 1) wait_land(b - 1);
-                if (b >= 2) wait_empty(b - 2);
+                if (b >= 2) {
+                    wait_ready(b - 1);
+                    wait_empty(b - 2);
+                }
             }
             const int n0 = b * B;
             float sum[B];
@@ -1132,10 +1147,9 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
                 cp_async_wait<DA / B>();               // the rows of batch b staged by this warp have landed
             }
             if (DEC) {
-                // full[b&3]'s next same-parity phase is batch b + 4, which needs this warp's empty(b + 2);
-                // land[b&3]'s is group b + 4, requested only after the producers' batch b + 2, which needs empty(b).
+                // full[b&3]'s next same-parity phase is batch b + 4, which needs this warp's empty(b + 2)
                 wait_full(b);
-                wait_land(b);                          // this batch's XYB rows ride in group b
+                if (b >= 1) wait_ready(b);             // this batch's XYB rows ride in group b
             } else {
                 __syncthreads();                       // batch b is in ex[b & 1]; staged samples are visible
             }

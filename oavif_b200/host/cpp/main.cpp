@@ -59,7 +59,7 @@ int main(int argc, char **argv)
     fprintf(stderr, "\x1b[31moavif\x1b[0m | b200 host harness\n");
     EncOptions o;
     std::string in, out, corpus;
-    long v = 0, batch = 1, gpus = 1, workers = 1, device = 0, blur = 0, pinned = 0;
+    long v = 0, batch = 1, gpus = 1, workers = 1, device = 0, blur = 0, pinned = 1;
     double d = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];

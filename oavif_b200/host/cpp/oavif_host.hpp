@@ -105,13 +105,15 @@ struct ScorerIface {
 
 class GpuScorer : public ScorerIface {  // include/oavif_ssimu2.h
   public:
-    // pinned_staging: copy the decoder's planes into a per-scorer pinned ring (oavif_ssimu2_pinned_alloc — the
-    // "pinned host staging in src/io.zig" of the north star) and upload from there by DMA; off (default): hand
-    // libavif's pageable planes to the library, whose cudaMemcpy2DAsync stages them through the driver's own pinned
-    // buffers.  Measured on the config-5 corpus with 16 workers (profiles/r2_decode_handoff.json): the explicit
-    // copy costs 10.1 ms of scoring wall time per image against 5.6 ms, 25.0 against 26.2 encodes/s — the extra pass
-    // over the planes on a busy host is dearer than what the DMA saves, so it is an option, not the default.
-    GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode, bool pinned_staging = false);
+    // pinned_staging (default): copy the decoder's planes into a per-scorer pinned ring (oavif_ssimu2_pinned_alloc —
+    // the "pinned host staging in src/io.zig" of the north star) and upload from there by DMA; off: hand libavif's
+    // pageable planes to the library, whose cudaMemcpy2DAsync stages them through the driver's own pinned buffers.
+    // Measured four times on the config-5 corpus with 16 workers (profiles/r2_decode_handoff.json), each on a fresh
+    // box: scoring wall time per image 10.1 / 4.6 / 4.5 / 3.2 ms pinned against 5.6 / 7.2 / 17.0 / 14.4 ms pageable,
+    // 25.0 / 26.2 / 26.0 / 27.0 against 26.2 / 26.7 / 24.9 / 26.3 encodes/s.  Throughput is the same within the
+    // run-to-run spread (scoring is ~1 % of a search); the pinned form's scoring time is the lower and steadier one
+    // in three runs of four, so it is the default.
+    GpuScorer(int device, uint32_t max_w, uint32_t max_h, uint32_t max_batch, int blur_mode, bool pinned_staging = true);
     ~GpuScorer() override;
     void set_source(const uint8_t *rgb, uint32_t w, uint32_t h) override;
     void set_source_image(const HostImage &img) override;      // oavif_ssimu2_set_source_pixels: toRGB8 on the device
@@ -162,7 +164,7 @@ struct CorpusSpec {
     int first_gpu = 0, n_gpus = 1;
     uint32_t workers_per_gpu = 1, batch_width = 1;
     int blur_mode = 0;
-    bool pinned_staging = false;   // see GpuScorer
+    bool pinned_staging = true;    // see GpuScorer
     // The CPU-scored arm: when set, every worker scores through this factory instead of the CUDA library (tests and
     // bench tooling inject the CPU oracle here; the product never does).  n_gpus * workers_per_gpu workers still.
     std::function<std::unique_ptr<ScorerIface>(int worker)> scorer_factory;

@@ -205,7 +205,7 @@ def tq_margins(history, tgt=80.0, tol=2.0, max_pass=6, limit=4.0):
 
 def corpus_synth(count: int, w: int, h: int, n_gpus: int = 1, first_gpu: int = 0, workers_per_gpu: int = 1,
                  batch_width: int = 1, blur_mode: int = 0, opts: Opts | None = None, csv_path: str | None = None,
-                 libavif: str | None = None, pinned_staging: bool = False, score_pair=None):
+                 libavif: str | None = None, pinned_staging: bool = True, score_pair=None):
     """The corpus sweep.  score_pair=None: the CUDA scorer.  Otherwise the CPU-scored arm: a callable
     (src_rgb HxWx3, y, u, v, depth, matrix, rgba) -> score that worker threads call concurrently (test / bench
     tooling passes the CPU oracle; ctypes releases the GIL inside its C calls)."""

@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick GPU regression: the fast parity tests, then one bench line (summary printed)
 timeout 900 python -m pytest tests -m "gpu and not slow" -q 2>&1 | tail -6
-python bench.py --steps 300 --warmup 5 --no-cpu "$@" > gpurun_out/r2_bench_check.json 2> gpurun_out/r2_bench_check.err
+timeout 300 python bench.py --steps 300 --warmup 5 --no-cpu "$@" > gpurun_out/r2_bench_check.json 2> gpurun_out/r2_bench_check.err
 python - <<PY
 import json
 d=json.load(open("gpurun_out/r2_bench_check.json"))
