@@ -70,8 +70,11 @@ enum { OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS = 0, OAVIF_SSIMU2_WEIGHTS_CONTIGUOUS = 1 }
  * pooling (ssimu2_wave.cuh): column strips run as a wavefront, the six-float state of every row chain is handed from
  * a strip to its right neighbour through an L2-resident mailbox, and the row-filtered planes never reach HBM; the
  * per-source cache then holds the fully blurred (mu1, sigma11) instead of the rows pass of (a, a*a).
- * Same arithmetic, same bits in all three. */
-enum { OAVIF_SSIMU2_TILES_TMA = 0, OAVIF_SSIMU2_TILES_CP_ASYNC = 1, OAVIF_SSIMU2_TILES_FUSED = 2 };
+ * TMA_DECOUPLED: TMA, with the columns kernel's per-batch block barrier replaced by one mbarrier per hand-over
+ * (rows landed / batch produced / batch consumed); measured equal to TMA, kept for A/B (profiles/r2_cols_sync_forms.txt).
+ * Same arithmetic, same bits in all four. */
+enum { OAVIF_SSIMU2_TILES_TMA = 0, OAVIF_SSIMU2_TILES_CP_ASYNC = 1, OAVIF_SSIMU2_TILES_FUSED = 2,
+       OAVIF_SSIMU2_TILES_TMA_DECOUPLED = 3 };
 
 /* When the rows pass of the source-only quantities (a, a*a) runs (RECURSIVE blur, TMA kernels).  WITH_FIRST_SCORE
  * (default): carried by the first scoring call's rows kernel (candidate 0's CTAs run a second pair warp), cached
@@ -294,7 +297,8 @@ int oavif_ssimu2_debug_check_guards(oavif_ssimu2_ctx *ctx);
  * out the source half (a, a*a), i.e. times what a call with a warm source cache runs; bit 3 (value 8) forces
  * the cp.async kernels whatever OAVIF_SSIMU2_OPT_TILE_PATH says; bits 4..6 select a TMA instance (ring depth /
  * staging buffers, 0 = the shipped one); 128 = the source half alone; 256 = both halves issued the way the scored
- * path issues them (source stream next to compute stream; the time is that of the pair); 512 = the COLUMNS pass alone;
+ * path issues them (source stream next to compute stream; the time is that of the pair); 512 = the COLUMNS pass alone
+ * (| 8: its cp.async loader, | 4096: its instance without the per-batch block barrier);
  * 1024 / 2048 = the FUSED kernel with all five quantities / with the cached source blur. */
 int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms);
 

@@ -690,7 +690,8 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, SrcSet &Src, uint3
         CK(cudaStreamWaitEvent(ctx->cs->stream, Src.ready, 0));
         CK(cudaStreamWaitEvent(ctx->cs->stream, Src.cache_done, 0));
         IirColsTmaMaps cmaps;
-        e = launch_iir_cols(a, plan.first_cta, plan.tiles_x, (int)n, ctx->cs->stream, nullptr, cols_maps_for(ctx, Src, &cmaps));
+        e = launch_iir_cols(a, plan.first_cta, plan.tiles_x, (int)n, ctx->cs->stream, nullptr, cols_maps_for(ctx, Src, &cmaps),
+                            ctx->tile_path == OAVIF_SSIMU2_TILES_TMA_DECOUPLED);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
         S.launches += 1;
     }
@@ -871,7 +872,8 @@ int set_source_common(oavif_ssimu2_ctx *ctx, const void *rgb, uint32_t w, uint32
     ctx->src_pix_channels = channels;
     ctx->src_pix_bits = bits;
     ctx->timing.launches = 1;
-    if (ctx->blur_mode == OAVIF_SSIMU2_BLUR_RECURSIVE && ctx->tile_path == OAVIF_SSIMU2_TILES_TMA &&
+    if (ctx->blur_mode == OAVIF_SSIMU2_BLUR_RECURSIVE &&
+        (ctx->tile_path == OAVIF_SSIMU2_TILES_TMA || ctx->tile_path == OAVIF_SSIMU2_TILES_TMA_DECOUPLED) &&
         ctx->source_rows == OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE) {
         IirRowsTmaMaps maps;
         if (rows_maps_for(ctx, Src, &maps)) {         // rows pass of (a, a*a), once per source
@@ -1084,7 +1086,8 @@ int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value)
         return 0;
     }
     if (option == OAVIF_SSIMU2_OPT_TILE_PATH &&
-        (value == OAVIF_SSIMU2_TILES_TMA || value == OAVIF_SSIMU2_TILES_CP_ASYNC || value == OAVIF_SSIMU2_TILES_FUSED)) {
+        (value == OAVIF_SSIMU2_TILES_TMA || value == OAVIF_SSIMU2_TILES_CP_ASYNC || value == OAVIF_SSIMU2_TILES_FUSED ||
+         value == OAVIF_SSIMU2_TILES_TMA_DECOUPLED)) {
         ctx->tile_path = value;
         return 0;
     }
@@ -1548,7 +1551,8 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
     } else {
         IirColsTmaMaps cmaps;
         const cudaError_t e = launch_iir_cols(iir_args_for(ctx, ctx->src[ctx->cur]), plan.first_cta, plan.tiles_x,
-                                              (int)ctx->last_n, ctx->cs->stream, &tap, cols_maps_for(ctx, ctx->src[ctx->cur], &cmaps));
+                                              (int)ctx->last_n, ctx->cs->stream, &tap, cols_maps_for(ctx, ctx->src[ctx->cur], &cmaps),
+                                              ctx->tile_path == OAVIF_SSIMU2_TILES_TMA_DECOUPLED);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
     }
     CK(cudaMemcpyAsync(out, ctx->d_dbg, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->cs->stream));
@@ -1668,7 +1672,7 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
             plan_iir_v(ctx->g, &cp);
             IirColsTmaMaps cmaps;
             e = launch_iir_cols(iir_args_for(ctx, Src), cp.first_cta, cp.tiles_x, 1, ctx->cs->stream, nullptr,
-                                (variant & 8) ? nullptr : cols_maps_for(ctx, Src, &cmaps));
+                                (variant & 8) ? nullptr : cols_maps_for(ctx, Src, &cmaps), (variant & 4096) != 0);
         } else {
             e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, which, 1, ctx->cs->stream, tma ? &maps : nullptr, (variant >> 4) & 7);
         }

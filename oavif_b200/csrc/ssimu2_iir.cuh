@@ -823,17 +823,16 @@ inline cudaError_t iir_rows_tma_dispatch(int shape, const IirArgs &ar, const Iir
 constexpr int kIirVThreads = 256;   // 3 producer warps + 4 consumer warps + 1 loader warp
 
 constexpr int kAbRows = 48;
-// TMA form of the columns pass, decoupled variant: the warps of a CTA meet at no CTA-wide barrier inside the batch
-// loop.  Each hand-over is an mbarrier of its own — group landed (loader -> everyone, passed on once through ready[]),
-// batch produced (3 producer warps -> consumers, loader), batch consumed (4 consumer warps -> producers, loader) — so
-// a warp waits only for what it reads.  Four barriers per kind although the data is double-buffered: a waiter tests a
-// phase PARITY, and with four the next phase of the same parity cannot complete before every waiter of this one has
-// passed (argued at each wait below).
-// Measured (profiles/r2_cols_sync_forms.txt): 0.184 ms against 0.184 ms for the one-__syncthreads-per-batch form on
-// the same box, with or without parked waits — the barrier samples of the rendezvous form were warps waiting for
-// work that is limited elsewhere, not time lost at the barrier.  Both forms are bit-identical and pass the same
-// tests; the shipped default is the rendezvous form (fewer executed instructions, one barrier to reason about).
-constexpr bool kColsDecoupled = false;
+// TMA form of the columns pass, DECOUPLED instance (OAVIF_SSIMU2_TILES_TMA_DECOUPLED): the warps of a CTA meet at no
+// CTA-wide barrier inside the batch loop.  Each hand-over is an mbarrier of its own — group landed (loader ->
+// everyone, passed on once through ready[]), batch produced (3 producer warps -> consumers, loader), batch consumed
+// (4 consumer warps -> producers, loader) — so a warp waits only for what it reads.  Four barriers per kind although
+// the data is double-buffered: a waiter tests a phase PARITY, and with four the next phase of the same parity cannot
+// complete before every waiter of this one has passed (argued at each wait below).
+// Measured (profiles/r2_cols_sync_forms.txt): the same duration as the one-__syncthreads-per-batch instance to 1 % —
+// the barrier samples of the rendezvous form were warps waiting for work that is limited elsewhere, not time lost at
+// the barrier.  Both are bit-identical and run under the same tests; the default tile path uses the rendezvous
+// instance (fewer executed instructions, one barrier to reason about).
 
 template <int RCAP, int B>
 struct IirColsSmem {
@@ -860,7 +859,7 @@ struct IirColsTmaMaps {
 // kernel carries none of it (with the hook inline the kernel went from 70 to 128 registers).
 // TMA: the loader warp's 16-byte cp.async traffic (about 200 instructions per batch, a tenth of the CTA's) becomes
 // twelve cp.async.bulk.tensor issues by one lane; rows below the image and columns right of it arrive as zeros.
-template <int RCAP, int B, bool TAP, bool TMA>
+template <int RCAP, int B, bool TAP, bool TMA, bool DECOUPLED = false>
 __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a, const __grid_constant__ IirColsTmaMaps tm)
 {
     extern __shared__ __align__(128) unsigned char smem_cols[];
@@ -880,7 +879,7 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
     const int nbatch = (h + B - 1) / B;
     // bytes of this lane's 16-byte column group that lie inside the image: the rest is zero-filled
     const int cbytes = max(0, min(16, (w - (cb * kIirVCols + ccol)) * 4));
-    constexpr bool DEC = TMA && kColsDecoupled;
+    constexpr bool DEC = TMA && DECOUPLED;
     auto wait_land = [&](int g) { mbar_wait(&sm.land[g & 3], (unsigned)(g >> 2) & 1u); };
     // Every completed copy of a group wakes the warps parked on land[]; only the loader's lane parks there and passes
     // the completed group on through ready[] (one arrival), so that seven warps wake once per group, not thirteen times.
@@ -1373,6 +1372,12 @@ inline cudaError_t iir_configure()
     e = cudaFuncSetAttribute(k_iir_cols<64, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(IirColsDeep));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_iir_cols<64, 16, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(IirColsDeep));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_iir_cols<64, 16, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(IirColsDeep));
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_iir_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<1>));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_iir_rows<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<2>));
@@ -1445,7 +1450,8 @@ inline cudaError_t launch_iir_rows(const IirArgs &base, const Geom &g, int which
 
 // Columns pass with the maps and the pooling.
 inline cudaError_t launch_iir_cols(const IirArgs &base, const int *first_cta_cols, const int *col_blocks, int n,
-                                   cudaStream_t st, const IirDebugTap *tap = nullptr, const IirColsTmaMaps *maps = nullptr)
+                                   cudaStream_t st, const IirDebugTap *tap = nullptr, const IirColsTmaMaps *maps = nullptr,
+                                   bool decoupled = false)
 {
     static const IirColsTmaMaps no_maps{};
     IirArgs a = base;
@@ -1457,10 +1463,12 @@ inline cudaError_t launch_iir_cols(const IirArgs &base, const int *first_cta_col
         a.dbg_scale = tap->scale;
         a.dbg_channel = tap->channel;
         a.dbg_cand = tap->cand;
-        if (maps) k_iir_cols<64, 16, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        if (maps && decoupled) k_iir_cols<64, 16, true, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        else if (maps) k_iir_cols<64, 16, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
         else k_iir_cols<64, 16, true, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, no_maps);
     } else {
-        if (maps) k_iir_cols<64, 16, false, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        if (maps && decoupled) k_iir_cols<64, 16, false, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        else if (maps) k_iir_cols<64, 16, false, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
         else k_iir_cols<64, 16, false, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, no_maps);
     }
     return cudaGetLastError();

@@ -24,7 +24,7 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "liboavif_ssimu2.so
 MAX_SCALES = 6
 BLUR_RECURSIVE, BLUR_FIR = 0, 1
 WEIGHTS_SIX_SLOTS, WEIGHTS_CONTIGUOUS = 0, 1
-TILES_TMA, TILES_CP_ASYNC, TILES_FUSED = 0, 1, 2
+TILES_TMA, TILES_CP_ASYNC, TILES_FUSED, TILES_TMA_DECOUPLED = 0, 1, 2, 3
 SOURCE_ROWS_AT_SET_SOURCE, SOURCE_ROWS_WITH_FIRST_SCORE = 0, 1
 OPT_BLUR, OPT_WEIGHTS, OPT_TILE_PATH, OPT_SOURCE_ROWS = 1, 2, 3, 4
 

@@ -95,9 +95,11 @@ def tile_path(request, scorer):
     scorer.set_tile_path(ssimu2.TILES_TMA)
 
 
-@pytest.fixture(params=[ssimu2.TILES_TMA, ssimu2.TILES_CP_ASYNC, ssimu2.TILES_FUSED], ids=["tma", "cp_async", "fused"])
+@pytest.fixture(params=[ssimu2.TILES_TMA, ssimu2.TILES_CP_ASYNC, ssimu2.TILES_FUSED, ssimu2.TILES_TMA_DECOUPLED],
+                ids=["tma", "cp_async", "fused", "tma_decoupled"])
 def tile_path3(request, scorer):
-    """... and the fused kernel (no row-filtered planes exist there: everything but the rows tap applies)."""
+    """... the fused kernel (no row-filtered planes exist there: everything but the rows tap applies) and the columns
+    kernel without its per-batch block barrier."""
     scorer.set_tile_path(request.param)
     yield request.param
     assert scorer.get_option(ssimu2.OPT_TILE_PATH) == request.param
@@ -403,12 +405,13 @@ def test_source_rows_cache_follows_the_source_and_the_blur_mode(scorer, oracle):
 
 
 def test_tile_paths_give_the_same_bits(scorer):
-    """TMA, cp.async and fused forms of the recursive kernels: identical pooled sums and scores, single and batch."""
+    """TMA, cp.async, fused and barrier-free-columns forms of the recursive kernels: identical pooled sums and scores,
+    single and batch."""
     src = synth.synth(1000, 700, "mixture", 14)
     cands = [synth.distort(src, s, seed=i) for i, s in enumerate((0.2, 0.5, 0.9))]
     scorer.set_blur(ssimu2.BLUR_RECURSIVE)
     res = {}
-    for path in (ssimu2.TILES_TMA, ssimu2.TILES_CP_ASYNC, ssimu2.TILES_FUSED):
+    for path in (ssimu2.TILES_TMA, ssimu2.TILES_CP_ASYNC, ssimu2.TILES_FUSED, ssimu2.TILES_TMA_DECOUPLED):
         scorer.set_tile_path(path)
         scorer.set_source(src)
         single = [scorer.score_rgb8(c) for c in cands]
@@ -418,7 +421,7 @@ def test_tile_paths_give_the_same_bits(scorer):
         assert scorer.get_option(ssimu2.OPT_TILE_PATH) == path
     scorer.set_tile_path(ssimu2.TILES_TMA)
     a = res[ssimu2.TILES_TMA]
-    for other in (ssimu2.TILES_CP_ASYNC, ssimu2.TILES_FUSED):
+    for other in (ssimu2.TILES_CP_ASYNC, ssimu2.TILES_FUSED, ssimu2.TILES_TMA_DECOUPLED):
         b = res[other]
         assert a[0] == b[0] == a[1] == b[1], other
         for x, y in zip(a[2], b[2]):
@@ -510,7 +513,8 @@ def test_no_kernel_writes_past_its_buffers(size):
     d1, d2 = synth.distort(src, 0.2), synth.distort(src, 0.7)
     with ssimu2.Scorer(w, h, 2) as sc:
         for mode, path in ((ssimu2.BLUR_RECURSIVE, ssimu2.TILES_TMA), (ssimu2.BLUR_RECURSIVE, ssimu2.TILES_CP_ASYNC),
-                           (ssimu2.BLUR_RECURSIVE, ssimu2.TILES_FUSED), (ssimu2.BLUR_FIR, ssimu2.TILES_TMA)):
+                           (ssimu2.BLUR_RECURSIVE, ssimu2.TILES_FUSED), (ssimu2.BLUR_RECURSIVE, ssimu2.TILES_TMA_DECOUPLED),
+                           (ssimu2.BLUR_FIR, ssimu2.TILES_TMA)):
             sc.set_blur(mode)
             sc.set_tile_path(path)
             sc.set_source(src)
