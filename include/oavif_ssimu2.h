@@ -298,7 +298,8 @@ int oavif_ssimu2_debug_check_guards(oavif_ssimu2_ctx *ctx);
  * the cp.async kernels whatever OAVIF_SSIMU2_OPT_TILE_PATH says; bits 4..6 select a TMA instance (ring depth /
  * staging buffers, 0 = the shipped one); 128 = the source half alone; 256 = both halves issued the way the scored
  * path issues them (source stream next to compute stream; the time is that of the pair); 512 = the COLUMNS pass alone
- * (| 8: its cp.async loader, | 4096: its instance without the per-batch block barrier);
+ * (| 8: its cp.async loader, | 4096: its instance without the per-batch block barrier, | 8192: 40 KB of unused
+ * shared memory on top, i.e. two CTAs per SM instead of three);
  * 1024 / 2048 = the FUSED kernel with all five quantities / with the cached source blur. */
 int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms);
 

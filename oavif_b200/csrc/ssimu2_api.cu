@@ -1672,7 +1672,8 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
             plan_iir_v(ctx->g, &cp);
             IirColsTmaMaps cmaps;
             e = launch_iir_cols(iir_args_for(ctx, Src), cp.first_cta, cp.tiles_x, 1, ctx->cs->stream, nullptr,
-                                (variant & 8) ? nullptr : cols_maps_for(ctx, Src, &cmaps), (variant & 4096) != 0);
+                                (variant & 8) ? nullptr : cols_maps_for(ctx, Src, &cmaps), (variant & 4096) != 0,
+                                (variant & 8192) ? 40 * 1024 : 0);
         } else {
             e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, which, 1, ctx->cs->stream, tma ? &maps : nullptr, (variant >> 4) & 7);
         }

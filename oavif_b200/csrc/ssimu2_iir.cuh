@@ -1367,7 +1367,7 @@ inline cudaError_t iir_configure()
                              (int)sizeof(IirColsDeep));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_iir_cols<64, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(IirColsDeep));
+                             (int)sizeof(IirColsDeep) + 40 * 1024);   // head room for the occupancy experiment (pad_smem)
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_iir_cols<64, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(IirColsDeep));
@@ -1451,7 +1451,7 @@ inline cudaError_t launch_iir_rows(const IirArgs &base, const Geom &g, int which
 // Columns pass with the maps and the pooling.
 inline cudaError_t launch_iir_cols(const IirArgs &base, const int *first_cta_cols, const int *col_blocks, int n,
                                    cudaStream_t st, const IirDebugTap *tap = nullptr, const IirColsTmaMaps *maps = nullptr,
-                                   bool decoupled = false)
+                                   bool decoupled = false, size_t pad_smem = 0)
 {
     static const IirColsTmaMaps no_maps{};
     IirArgs a = base;
@@ -1467,8 +1467,9 @@ inline cudaError_t launch_iir_cols(const IirArgs &base, const int *first_cta_col
         else if (maps) k_iir_cols<64, 16, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
         else k_iir_cols<64, 16, true, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, no_maps);
     } else {
+        // pad_smem (profiling only): a larger shared-memory request lowers the CTAs resident per SM
         if (maps && decoupled) k_iir_cols<64, 16, false, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
-        else if (maps) k_iir_cols<64, 16, false, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        else if (maps) k_iir_cols<64, 16, false, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep) + pad_smem, st>>>(a, *maps);
         else k_iir_cols<64, 16, false, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, no_maps);
     }
     return cudaGetLastError();

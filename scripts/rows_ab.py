@@ -27,6 +27,7 @@ with ssimu2.Scorer(W, H, 1) as sc:
         ms = [sc.time_rows(8 | cand_only, 50) for _ in range(3)]
         print(f"cp.async {'':14s}{'cand only' if cand_only else 'both     '}", " ".join(f"{m:.4f}" for m in ms))
     for name, bits in (("columns pass, TMA loader", 512), ("columns pass, TMA, no block barrier", 512 | 4096),
+                       ("columns pass, TMA, 2 CTAs per SM", 512 | 8192),
                        ("columns pass, cp.async loader", 512 | 8)):
         print(f"{name:38s}", " ".join(f"{sc.time_rows(bits, 50):.4f}" for _ in range(3)))
     sc.set_tile_path(ssimu2.TILES_CP_ASYNC)
