@@ -17,6 +17,7 @@ namespace oavif {
 
 // ---- device side ------------------------------------------------------------------------------------------
 constexpr uint32_t kMbarSuspendNs = 1000000u;   // upper bound of one parked wait, ns
+constexpr uint32_t kMbarMaxTries = 1u << 24;    // failed attempts before a wait gives up (__trap)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -42,19 +43,28 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 // cycles and re-issued the test (SYNCS + BRA were a quarter of the columns kernel's executed instructions,
 // profiles/r2_final_ncu_cols_hot.txt).  The explicit limit is far above any wait seen here, so a waiting warp costs
 // no issue slots; completion still wakes it at once.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
+    uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(kMbarSuspendNs)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
+    return done != 0;
+}
+// A wait that can never be satisfied (a protocol error, a copy that faulted) must not hang the device: after
+// kMbarMaxTries failed attempts — seconds at the very least, every attempt parks first — the kernel traps and the
+// host sees a launch failure instead of a stuck GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t tries = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++tries > kMbarMaxTries) __trap();
 }
 
 // global -> shared tile; completion is counted in bytes on `bar`.  Coordinates are element indices, innermost
