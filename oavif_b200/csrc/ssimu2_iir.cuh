@@ -4,21 +4,23 @@
 // from n = -N+1, because the recursion's round-off is not negligible at the metric's C2 = 9e-4
 // scale and is therefore part of the published result.
 //
-// Both passes are instruction-issue problems before they are bandwidth problems (a recursion step
-// is 12 floating-point operations on a 4-byte sample), so both run the recursion on PACKED pairs
-// (FFMA2 / FADD2 / FMUL2: two IEEE binary32 operations per issued instruction, same bits as scalar):
+// Both passes run the recursion on PACKED pairs (FFMA2 / FADD2 / FMUL2: two IEEE binary32 operations per issued
+// instruction, same bits as scalar) and move their tiles with TMA (cp.async.bulk.tensor + mbarrier, ssimu2_tma.cuh):
 //
-//   k_iir_rows  : rows.  One CTA = 32 rows of one channel; lane = row.  The pair is two QUANTITIES of
-//                 the same pixel: (a, a*a) on the source side, (b, b*b) on the candidate side, with
-//                 a*b in a scalar recursion warp.  Loader and storer warps do all global memory traffic
-//                 (16-byte cp.async tile ring in, whole 128-byte lines out), so a recursion warp's
-//                 critical path is shared-memory loads, arithmetic, shared-memory stores.  The pairs
-//                 are written to HBM interleaved (one float2 per pixel), exactly as they are computed.
+//   k_iir_rows_tma : rows (default).  One CTA = 32 rows of one channel; lane = row.  The pair is two QUANTITIES of
+//                 the same pixel: (a, a*a) on the source side, (b, b*b) on the candidate side, with a*b in a scalar
+//                 recursion warp.  One elected lane requests 44 x 32 boxes into a four-slot ring (out-of-bounds =
+//                 the filter's zero padding); each recursion warp waits on the slot's mbarrier, runs its chain, stages
+//                 the finished 32 x 32 chunk in swizzled shared memory and sends it off with a TMA store of its own.
+//                 The pairs are written to HBM interleaved (one float2 per pixel), exactly as they are computed.
+//   k_iir_rows  : the round-1 form (loader and storer warps, 16-byte cp.async ring, one block barrier per chunk):
+//                 OAVIF_SSIMU2_TILES_CP_ASYNC.
 //   k_iir_cols  : columns + error maps + pooling.  One CTA = 32 columns of one channel; lane = column.
 //                 Two producer warps run the packed recursions of (a, a*a) and (b, b*b) straight from the
-//                 interleaved planes, one the scalar recursion of a*b; a loader warp feeds their
-//                 shared-memory rings; five consumer warps evaluate the SSIM / edge-diff maps on packed
-//                 pairs of ROWS, one batch behind — blurred planes are never written to HBM.
+//                 interleaved planes, one the scalar recursion of a*b; one lane of the loader warp feeds their
+//                 shared-memory rings and the consumers' XYB rows by TMA (TMA = false: the whole warp, by cp.async);
+//                 four consumer warps evaluate the SSIM / edge-diff maps on packed pairs of ROWS, one batch
+//                 behind — blurred planes are never written to HBM.
 //
 // HBM traffic per scale pixel and channel: rows pass reads 8 B, writes 20 B; columns pass reads
 // 20 B + 8 B.  No tensor cores (nothing here is a contraction).
@@ -814,12 +816,14 @@ inline cudaError_t iir_rows_tma_dispatch(int shape, const IirArgs &ar, const Iir
 // One CTA owns 32 columns of one channel; lane = column in the arithmetic, so the recursions of a warp
 // are 32 independent columns.  Warps 0..2 (producers) run the column recursions out of shared-memory
 // rings: warp 0 the packed pair (a, a*a), warp 1 the packed pair (b, b*b) — each reads one float2 per
-// tap from its interleaved plane —, warp 2 a*b alone.  Warp 7 (loader) feeds the three rings with
-// 16-byte cp.async, 32 rows ahead of use, zero-filling rows and columns beyond the image; both taps of
-// the recursion are read back from the ring (no register delay line).  Each producer drops its filtered
-// values into a double-buffered 16-row batch.  Warps 3..6 (consumers), one batch behind, stage the pixel's
-// own XYB samples themselves and evaluate the SSIM / edge-diff maps and the six pooled sums, two rows
-// of a column as one packed pair.  One block barrier per 16 rows.
+// tap from its interleaved plane —, warp 2 a*b alone.  Warp 7 (loader) feeds the three rings 32 rows ahead
+// of use — TMA form: one lane, 4-row cp.async.bulk.tensor boxes counted on an mbarrier per request group, the
+// hardware zero-filling rows and columns beyond the image; cp.async form: the whole warp, 16 bytes per lane —;
+// both taps of the recursion are read back from the ring (no register delay line).  Each producer drops its
+// filtered values into a double-buffered 16-row batch.  Warps 3..6 (consumers), one batch behind, evaluate the
+// SSIM / edge-diff maps and the six pooled sums, two rows of a column as one packed pair, from the batch and the
+// pixel's own XYB samples (TMA form: brought in by the loader with everything else; cp.async form: staged by each
+// consumer).  One block barrier per 16 rows (DECOUPLED instance: per-hand-over mbarriers instead).
 constexpr int kIirVThreads = 256;   // 3 producer warps + 4 consumer warps + 1 loader warp
 
 constexpr int kAbRows = 48;
