@@ -215,6 +215,7 @@ class Scorer:
     def set_source(self, rgb):
         a = _rgb8(rgb)
         self._src_keep = a
+        self._src_shape = a.shape
         self.h, self.w = a.shape[:2]
         _check(self._L.oavif_ssimu2_set_source_rgb8(self._ctx, a.ctypes.data, self.w, self.h, a.strides[0]),
                self._ctx)
@@ -232,6 +233,7 @@ class Scorer:
         """Loader-native layouts (io.zig's Image): HxWxC, C in 1..4, uint8 or uint16 -> Image.toRGB8 on the GPU."""
         a = self._pixels(pixels)
         self._src_keep = a
+        self._src_shape = a.shape
         self.h, self.w = a.shape[:2]
         _check(self._L.oavif_ssimu2_set_source_pixels(self._ctx, a.ctypes.data, self.w, self.h, a.strides[0],
                                                       a.shape[2], 8 * a.itemsize), self._ctx)
@@ -245,6 +247,7 @@ class Scorer:
 
     def set_source_dev(self, dptr: int, w: int, h: int, stride: int):
         self.w, self.h = w, h
+        self._src_shape = (h, w, 3)
         _check(self._L.oavif_ssimu2_set_source_rgb8_dev(self._ctx, C.c_void_p(dptr), w, h, stride), self._ctx)
 
     # ---- candidates ----------------------------------------------------------------------------
@@ -385,8 +388,7 @@ class Scorer:
     def source_samples(self, out_depth: int) -> np.ndarray:
         """encodeAvifToBuffer's per-pass depth conversion of the source (io.zig:562-609), once, on the GPU: HxWxC samples
         at `out_depth` (uint16 for 10, uint8 for 8) from the pixels the last set_source / set_source_pixels staged."""
-        a = self._src_keep
-        out = np.empty(a.shape, np.uint16 if out_depth > 8 else np.uint8)
+        out = np.empty(self._src_shape, np.uint16 if out_depth > 8 else np.uint8)
         _check(self._L.oavif_ssimu2_source_samples(self._ctx, out_depth, out.ctypes.data, out.nbytes), self._ctx)
         return out
 

@@ -501,6 +501,8 @@ def test_device_resident_inputs_and_external_stream(oracle):
         assert a == [host, host]
         b = sc.score_batch_dev("rgb8", [[drgb.data_ptr()]], [3 * w])
         assert abs(b[0] - oracle.ssimu2_rgb8(src, dist)) <= SCORE_TOL
+        # the encoder-side samples of a DEVICE source come straight from the caller's buffer (still alive here)
+        np.testing.assert_array_equal(sc.source_samples(10), oracle.source_samples(src, 10))
         sc.set_stream(None)
 
 
