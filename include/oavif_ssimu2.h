@@ -299,7 +299,8 @@ int oavif_ssimu2_debug_check_guards(oavif_ssimu2_ctx *ctx);
  * staging buffers, 0 = the shipped one); 128 = the source half alone; 256 = both halves issued the way the scored
  * path issues them (source stream next to compute stream; the time is that of the pair); 512 = the COLUMNS pass alone
  * (| 8: its cp.async loader, | 4096: its instance without the per-batch block barrier, | 8192: 40 KB of unused
- * shared memory on top, i.e. two CTAs per SM instead of three);
+ * shared memory on top, i.e. two CTAs per SM instead of three, | 16384: descriptors that read strip-major — durations
+ * only, the data is wrong —, | 32768: 256-byte L2 promotion on the pair planes' descriptors);
  * 1024 / 2048 = the FUSED kernel with all five quantities / with the cached source blur. */
 int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, float *mean_ms);
 

@@ -1671,8 +1671,16 @@ int oavif_ssimu2_debug_time_rows(oavif_ssimu2_ctx *ctx, int variant, int iters, 
             BlurPlan cp;
             plan_iir_v(ctx->g, &cp);
             IirColsTmaMaps cmaps;
-            e = launch_iir_cols(iir_args_for(ctx, Src), cp.first_cta, cp.tiles_x, 1, ctx->cs->stream, nullptr,
-                                (variant & 8) ? nullptr : cols_maps_for(ctx, Src, &cmaps), (variant & 4096) != 0,
+            IirArgs ca = iir_args_for(ctx, Src);
+            const IirColsTmaMaps *cm = (variant & 8) ? nullptr : cols_maps_for(ctx, Src, &cmaps);
+            if (cm && (variant & (16384 | 32768))) {   // layout / promotion experiment: durations only
+                const long long P = ctx->cap_pyr_floats;
+                if (!iir_cols_tma_maps_experiment(&cmaps, ctx->g, Src.d_hplanes, Src.d_pyr, ctx->cs->d_hplanes, ctx->cs->d_hplanes + 2 * P,
+                                                  ctx->cs->d_dist_pyr, (variant & 16384) != 0, (variant & 32768) != 0))
+                    return fail(ctx, OAVIF_SSIMU2_E_CUDA, "experiment descriptors");
+                ca.dbg_strip_major = (variant & 16384) ? 1 : 0;
+            }
+            e = launch_iir_cols(ca, cp.first_cta, cp.tiles_x, 1, ctx->cs->stream, nullptr, cm, (variant & 4096) != 0,
                                 (variant & 8192) ? 40 * 1024 : 0);
         } else {
             e = launch_iir_rows(iir_args_for(ctx, Src), ctx->g, which, 1, ctx->cs->stream, tma ? &maps : nullptr, (variant >> 4) & 7);

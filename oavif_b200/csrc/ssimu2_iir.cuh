@@ -126,6 +126,8 @@ struct IirArgs {
     // the five blurred values it hands to the maps — mu1, mu2, s11, s22, s12 — to dbg_cols[q][h][w] (tight)
     float *dbg_cols;
     int dbg_scale, dbg_channel, dbg_cand;
+    int dbg_strip_major;   // timing experiment only (debug_time_rows | 16384): the columns pass addresses its descriptors
+                           // as {strip row, image row, strip, channel} — see oavif_ssimu2_debug_time_rows
     int first_cta[kMaxScales + 1];  // CTA ranges per scale
     int blocks[kMaxScales];     // tasks per channel and scale
 };
@@ -902,17 +904,18 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         constexpr unsigned kGroupBytes = 4 * (2 * 2 * kIirVCols + kIirVCols) * 4;   // 4 rows of two pair planes and a*b
         constexpr unsigned kXybBytes = 2 * B * kIirVCols * 4;                       // a batch of both XYB planes
         const int x0 = cb * kIirVCols;
+        const bool sm_maj = a.dbg_strip_major != 0;   // (timing experiment: same byte counts, contiguous strips)
         auto issue_rows4 = [&](int r0, uint64_t *bar) {
-            tma_load_4d(&sm.pring[0][r0 & (RCAP - 1)][0], &tm.psrc[s], 2 * x0, r0, c, 0, bar);
-            tma_load_4d(&sm.pring[1][r0 & (RCAP - 1)][0], &tm.pcand[s], 2 * x0, r0, c, cand, bar);
-            tma_load_4d(&sm.sring[r0 & (RCAP - 1)][0], &tm.ab[s], x0, r0, c, cand, bar);
+            tma_load_4d(&sm.pring[0][r0 & (RCAP - 1)][0], &tm.psrc[s], sm_maj ? 0 : 2 * x0, r0, sm_maj ? cb : c, sm_maj ? c : 0, bar);
+            tma_load_4d(&sm.pring[1][r0 & (RCAP - 1)][0], &tm.pcand[s], sm_maj ? 0 : 2 * x0, r0, sm_maj ? cb : c, sm_maj ? c : cand, bar);
+            tma_load_4d(&sm.sring[r0 & (RCAP - 1)][0], &tm.ab[s], sm_maj ? 0 : x0, r0, sm_maj ? cb : c, sm_maj ? c : cand, bar);
         };
         // The consumers' XYB rows of batch nb go to third nb % 3 of their ring.  They are requested while batch
         // nb - 1 is being produced: the consumers are then reading batch nb - 2's third and will read batch nb - 1's
         // next, so the third being refilled is the one of batch nb - 3, which nobody touches any more.
         auto issue_xyb = [&](int nb, int third, uint64_t *bar) {
-            tma_load_4d(&sm.ab[0][third * B][0], &tm.xa[s], x0, nb * B, c, 0, bar);
-            tma_load_4d(&sm.ab[1][third * B][0], &tm.xb[s], x0, nb * B, c, cand, bar);
+            tma_load_4d(&sm.ab[0][third * B][0], &tm.xa[s], sm_maj ? 0 : x0, nb * B, sm_maj ? cb : c, sm_maj ? c : 0, bar);
+            tma_load_4d(&sm.ab[1][third * B][0], &tm.xb[s], sm_maj ? 0 : x0, nb * B, sm_maj ? cb : c, sm_maj ? c : cand, bar);
         };
 #pragma unroll
         for (int j = 1; j <= 6; ++j) {   // rows -6..-1 are padding
@@ -1325,6 +1328,35 @@ inline bool iir_cols_tma_maps_src(CUtensorMap psrc[kMaxScales], CUtensorMap xa[k
                          (uint64_t)g.plane[s] * 8, 0, 2 * kIirVCols, 4, false);
         ok = ok && tma_make_4d(&xa[s], src + g.off[s], (uint64_t)g.w[s], (uint64_t)g.h[s], 3, 1, (uint64_t)g.pitch[s] * 4,
                                (uint64_t)g.plane[s] * 4, 0, kIirVCols, 16, false);
+    }
+    return ok;
+}
+
+// Timing experiment (debug_time_rows | 16384, | 32768): descriptors that walk the SAME buffers strip by strip — a
+// strip's rows adjacent in memory, as a strip-major layout of the row-filtered planes would have them — or that ask
+// for 256-byte L2 promotion on the pair planes.  Strip-major descriptors read the right number of bytes from the
+// wrong places: durations only, the sums are garbage.
+inline bool iir_cols_tma_maps_experiment(IirColsTmaMaps *m, const Geom &g, const float *hpair_src, const float *src,
+                                         const float *hpair_cand, const float *hab, const float *dist, bool strip_major,
+                                         bool promote256)
+{
+    bool ok = true;
+    for (int s = 0; s < g.n_scales && ok; ++s) {
+        const uint64_t w = (uint64_t)g.w[s], h = (uint64_t)g.h[s], rowb = (uint64_t)g.pitch[s] * 4, planeb = (uint64_t)g.plane[s] * 4;
+        const uint64_t strips = (w + kIirVCols - 1) / kIirVCols;
+        if (strip_major) {
+            ok = ok && tma_make_4d(&m->psrc[s], hpair_src + 2 * g.off[s], 2 * kIirVCols, h, strips, 3, 8 * kIirVCols, h * 8 * kIirVCols, 2 * planeb, 2 * kIirVCols, 4, false, promote256);
+            ok = ok && tma_make_4d(&m->pcand[s], hpair_cand + 2 * g.off[s], 2 * kIirVCols, h, strips, 3, 8 * kIirVCols, h * 8 * kIirVCols, 2 * planeb, 2 * kIirVCols, 4, false, promote256);
+            ok = ok && tma_make_4d(&m->ab[s], hab + g.off[s], kIirVCols, h, strips, 3, 4 * kIirVCols, h * 4 * kIirVCols, planeb, kIirVCols, 4, false);
+            ok = ok && tma_make_4d(&m->xa[s], src + g.off[s], kIirVCols, h, strips, 3, 4 * kIirVCols, h * 4 * kIirVCols, planeb, kIirVCols, 16, false);
+            ok = ok && tma_make_4d(&m->xb[s], dist + g.off[s], kIirVCols, h, strips, 3, 4 * kIirVCols, h * 4 * kIirVCols, planeb, kIirVCols, 16, false);
+        } else {
+            ok = ok && tma_make_4d(&m->psrc[s], hpair_src + 2 * g.off[s], 2 * w, h, 3, 1, 2 * rowb, 2 * planeb, 0, 2 * kIirVCols, 4, false, promote256);
+            ok = ok && tma_make_4d(&m->pcand[s], hpair_cand + 2 * g.off[s], 2 * w, h, 3, 1, 2 * rowb, 2 * planeb, 0, 2 * kIirVCols, 4, false, promote256);
+            ok = ok && tma_make_4d(&m->ab[s], hab + g.off[s], w, h, 3, 1, rowb, planeb, 0, kIirVCols, 4, false);
+            ok = ok && tma_make_4d(&m->xa[s], src + g.off[s], w, h, 3, 1, rowb, planeb, 0, kIirVCols, 16, false);
+            ok = ok && tma_make_4d(&m->xb[s], dist + g.off[s], w, h, 3, 1, rowb, planeb, 0, kIirVCols, 16, false);
+        }
     }
     return ok;
 }

@@ -132,7 +132,7 @@ inline EncodeTiledFn tma_encoder()
 // A 4-D f32 tensor {inner, rows, planes, images} with byte strides for dimensions 1..3 and a {box0, box1, 1, 1} box.
 inline bool tma_make_4d(CUtensorMap *out, const float *base, uint64_t inner, uint64_t rows, uint64_t planes, uint64_t images,
                         uint64_t row_bytes, uint64_t plane_bytes, uint64_t image_bytes, uint32_t box0, uint32_t box1,
-                        bool swizzle128)
+                        bool swizzle128, bool promote256 = false)
 {
     EncodeTiledFn enc = tma_encoder();
     if (!enc) return false;
@@ -144,7 +144,8 @@ inline bool tma_make_4d(CUtensorMap *out, const float *base, uint64_t inner, uin
     const cuuint32_t es[4] = {1, 1, 1, 1};
     return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dim, str, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               promote256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace oavif
