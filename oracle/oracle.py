@@ -225,3 +225,42 @@ def source_samples(data: np.ndarray, out_depth: int) -> np.ndarray:
     if rc != 0:
         raise RuntimeError(f"oracle_source_samples: no conversion from {data.dtype} to depth {out_depth}")
     return out
+
+
+_contracted = None
+
+
+def ssimu2_rgb8_contracted(ref: np.ndarray, dist: np.ndarray, blur: int = BLUR_IIR) -> float | None:
+    """The same source compiled the way a C or LLVM tool chain contracts by default on an FMA machine
+    (-O3 -march=native -ffp-contract=fast: every a*b + c the compiler sees becomes one fused operation) — one more
+    reading of "the same algorithm" for scripts/variant_envelope.py.  None where it cannot be built or the CPU has no
+    FMA.  Built under oracle/_native/ (git-ignored)."""
+    global _contracted
+    if _contracted is None:
+        try:
+            if " fma " not in next(l for l in open("/proc/cpuinfo") if l.startswith("flags")) + " ":
+                return None
+            d = os.path.join(_HERE, "_native")
+            os.makedirs(d, exist_ok=True)
+            path = os.path.join(d, "liboracle_contracted.so")
+            srcs = [os.path.join(_HERE, f) for f in ("ssimu2_oracle.c", "yuv2rgb_oracle.c")]
+            if not os.path.exists(path) or any(os.path.getmtime(path) < os.path.getmtime(f) for f in srcs):
+                subprocess.check_call([os.environ.get("CC", "gcc"), "-std=c11", "-fPIC", "-fno-math-errno", "-O3", "-march=native",
+                                       "-ffp-contract=fast", "-shared", "-o", path + ".tmp", *srcs, "-lm"],
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                os.replace(path + ".tmp", path)
+            L = C.CDLL(path)
+            L.oracle_ssimu2_rgb8.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.POINTER(C.c_double), C.POINTER(Detail)]
+            L.oracle_ssimu2_rgb8.restype = C.c_int
+            _contracted = L
+        except (OSError, StopIteration, subprocess.CalledProcessError):
+            return None
+    ref = np.ascontiguousarray(ref, np.uint8)
+    dist = np.ascontiguousarray(dist, np.uint8)
+    h, w, _ = ref.shape
+    score = C.c_double()
+    d = Detail()
+    if _contracted.oracle_ssimu2_rgb8(_u8(ref), 3 * w, _u8(dist), 3 * w, w, h, blur, C.byref(score), C.byref(d)) != 0:
+        raise RuntimeError("oracle_ssimu2_rgb8 (contracted build) failed")
+    return score.value

@@ -13,6 +13,8 @@ libavif itself.  Every pair is scored by the CPU oracle (TEST INFRASTRUCTURE, or
                      VerticalBlock as recalled) instead of the horizontal pass's sequence
   libm_cbrt          libm cbrtf instead of the fixed binary32 sequence
   fir                the exactly equivalent 9-tap FIR instead of the recursion (what a non-recursive blur gives)
+  contracted         the same source compiled with -ffp-contract=fast -march=native: every a*b + c the compiler sees
+                     is fused (what a tool chain that contracts by default makes of the same code)
   contiguous_weights the running weight index over the scales present (only differs below six scales: measured on
                      128x96 crops)
 
@@ -46,6 +48,7 @@ def main():
     variants = {"vertical_order": dict(flags=O.VARIANT_VERTICAL_ORDER), "libm_cbrt": dict(flags=0, libm=True),
                 "fir": dict(flags=0, blur=O.BLUR_FIR)}
     deltas = {k: [] for k in variants}
+    deltas["contracted"] = []
     deltas["contiguous_weights_small_images"] = []
     rows = []
     for seed in range(a.images):
@@ -61,6 +64,10 @@ def main():
                 O.set_variant(0, fast=True)
                 row[name] = s
                 deltas[name].append(s - base)
+            sc = O.ssimu2_rgb8_contracted(src, dec)
+            if sc is not None:
+                row["contracted"] = sc
+                deltas["contracted"].append(sc - base)
             # fewer than six scales: a crop (the weight layout is the only thing that changes)
             cs, cd = np.ascontiguousarray(src[:96, :128]), np.ascontiguousarray(dec[:96, :128])
             b2 = O.ssimu2_rgb8(cs, cd, O.BLUR_IIR, fast=True)
@@ -78,7 +85,7 @@ def main():
                 "share_above_0.05": float((d > 0.05).mean())}
 
     out = {"pairs": len(rows), "size": [w, h], "what": __doc__.split("\n\n")[2].strip(),
-           "envelope": {k: stats(v) for k, v in deltas.items()}, "rows": rows}
+           "envelope": {k: stats(v) for k, v in deltas.items() if v}, "rows": rows}
     text = json.dumps(out, indent=1)
     with open(os.path.join(ROOT, a.out), "w") as f:
         f.write(text + "\n")
