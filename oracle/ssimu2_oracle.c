@@ -421,6 +421,42 @@ static void edge_diff_map(const float *i1, const float *m1, const float *i2, con
     sums[3] = s3;
 }
 
+/* ORACLE_VARIANT_F32_MAPS: both maps of one channel with binary32 values and per-row binary32 accumulators. */
+static void maps_f32(const float *i1, const float *m1, const float *i2, const float *m2, const float *s11,
+                     const float *s22, const float *s12, int w, int h, double ss[2], double ed[4])
+{
+    const float kC2 = 0.0009f;
+    double tot[6] = {0, 0, 0, 0, 0, 0};
+    for (int y = 0; y < h; ++y) {
+        float acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int x = 0; x < w; ++x) {
+            const size_t i = (size_t)y * w + x;
+            const float mu1 = m1[i], mu2 = m2[i];
+            const float mu11 = mu1 * mu1, mu22 = mu2 * mu2, mu12 = mu1 * mu2;
+            const float dm = (mu1 - mu2) * (mu1 - mu2);
+            const float num_m = 1.0f - dm;
+            const float num_s = 2.0f * (s12[i] - mu12) + kC2;
+            const float denom_s = (s11[i] - mu11) + (s22[i] - mu22) + kC2;
+            float d = 1.0f - num_m * num_s / denom_s;
+            d = d > 0.0f ? d : 0.0f;
+            acc[0] += d;
+            d *= d;
+            acc[1] += d * d;
+            const float d1 = (1.0f + fabsf(i2[i] - m2[i])) / (1.0f + fabsf(i1[i] - m1[i])) - 1.0f;
+            float art = d1 > 0.0f ? d1 : 0.0f, det = d1 < 0.0f ? -d1 : 0.0f;
+            acc[2] += art;
+            art *= art;
+            acc[3] += art * art;
+            acc[4] += det;
+            det *= det;
+            acc[5] += det * det;
+        }
+        for (int k = 0; k < 6; ++k) tot[k] += (double)acc[k];
+    }
+    ss[0] = tot[0]; ss[1] = tot[1];
+    ed[0] = tot[2]; ed[1] = tot[3]; ed[2] = tot[4]; ed[3] = tot[5];
+}
+
 /* v2.1 §7 — Msssim::Score().                                                             */
 double oracle_final_score(int n_scales, const double avg_ssim[][6], const double avg_edgediff[][12])
 {
@@ -509,8 +545,12 @@ int oracle_ssimu2_rgb8(const uint8_t *ref, int ref_stride, const uint8_t *dist, 
             oracle_blur(a, cw, ch, blur_mode, tmp, mu1);
             oracle_blur(b, cw, ch, blur_mode, tmp, mu2);
             double ss[2], ed[4];
-            ssim_map(mu1, mu2, s11, s22, s12, n, ss);
-            edge_diff_map(a, mu1, b, mu2, n, ed);
+            if (g_variant & ORACLE_VARIANT_F32_MAPS) {
+                maps_f32(a, mu1, b, mu2, s11, s22, s12, cw, ch, ss, ed);
+            } else {
+                ssim_map(mu1, mu2, s11, s22, s12, n, ss);
+                edge_diff_map(a, mu1, b, mu2, n, ed);
+            }
             const double opp = 1.0 / (double)n;
             D->sums[scale][c * 6 + 0] = ss[0];
             D->sums[scale][c * 6 + 1] = ss[1];

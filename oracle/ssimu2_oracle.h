@@ -68,7 +68,10 @@ void oracle_set_libm_cbrt(int on);
  * GPU path is held to bit for bit). */
 enum {
     ORACLE_VARIANT_CONTIGUOUS_WEIGHTS = 1, /* final sum: running weight index over the scales present     */
-    ORACLE_VARIANT_VERTICAL_ORDER = 2      /* vertical recursion: fma(n2, sum, fma(-d1, y1, -y2)) per step */
+    ORACLE_VARIANT_VERTICAL_ORDER = 2,     /* vertical recursion: fma(n2, sum, fma(-d1, y1, -y2)) per step */
+    ORACLE_VARIANT_F32_MAPS = 4            /* error maps and their powers in binary32, one binary32 accumulator per
+                                              image ROW folded into a binary64 total (what a vectorised f32 scorer
+                                              plausibly does) instead of binary64 per pixel                    */
 };
 void oracle_set_variant(int flags);
 int oracle_get_variant(void);
