@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 MAX_SCALES = 6
 BLUR_IIR, BLUR_FIR, BLUR_FIR64 = 0, 1, 2
-VARIANT_CONTIGUOUS_WEIGHTS, VARIANT_VERTICAL_ORDER, VARIANT_F32_MAPS = 1, 2, 4
+VARIANT_CONTIGUOUS_WEIGHTS, VARIANT_VERTICAL_ORDER, VARIANT_F32_MAPS, VARIANT_F32_TRANSFER = 1, 2, 4, 8
 
 
 class Detail(C.Structure):

@@ -45,8 +45,16 @@ const double *oracle_weights(void) { return kWeights; }
 
 /* ------------------------------------------------------------------------------------ */
 /* v2.1 §1 — sRGB transfer function on v = u8/255.                                       */
+int oracle_get_variant(void);
 void oracle_srgb_lut(float lut[256])
 {
+    if (oracle_get_variant() & ORACLE_VARIANT_F32_TRANSFER) {   /* the transfer function evaluated in binary32 */
+        for (int i = 0; i < 256; ++i) {
+            const float v = (float)i / 255.0f;
+            lut[i] = (v <= 0.04045f) ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f);
+        }
+        return;
+    }
     for (int i = 0; i < 256; ++i) {
         double v = (double)i / 255.0;
         double l = (v <= 0.04045) ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4);

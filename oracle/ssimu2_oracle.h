@@ -69,6 +69,7 @@ void oracle_set_libm_cbrt(int on);
 enum {
     ORACLE_VARIANT_CONTIGUOUS_WEIGHTS = 1, /* final sum: running weight index over the scales present     */
     ORACLE_VARIANT_VERTICAL_ORDER = 2,     /* vertical recursion: fma(n2, sum, fma(-d1, y1, -y2)) per step */
+    ORACLE_VARIANT_F32_TRANSFER = 8,       /* sRGB transfer function evaluated in binary32 (powf) instead of binary64 */
     ORACLE_VARIANT_F32_MAPS = 4            /* error maps and their powers in binary32, one binary32 accumulator per
                                               image ROW folded into a binary64 total (what a vectorised f32 scorer
                                               plausibly does) instead of binary64 per pixel                    */

@@ -12,6 +12,7 @@ libavif itself.  Every pair is scored by the CPU oracle (TEST INFRASTRUCTURE, or
   vertical_order     the vertical recursion step as fma(n2, sum, fma(-d1, y1, -y2)) (lib/jxl gauss_blur.cc
                      VerticalBlock as recalled) instead of the horizontal pass's sequence
   libm_cbrt          libm cbrtf instead of the fixed binary32 sequence
+  f32_transfer       the sRGB transfer function evaluated in binary32 (powf) instead of binary64 rounded once
   f32_maps           the SSIM / edge-diff maps and their fourth powers in binary32 with one binary32 accumulator per
                      image row (a vectorised f32 scorer) instead of binary64 per pixel
   fir                the exactly equivalent 9-tap FIR instead of the recursion (what a non-recursive blur gives)
@@ -48,7 +49,7 @@ def main():
     O.build()
     opts = H.default_opts(tenbit=0, speed=9)
     variants = {"vertical_order": dict(flags=O.VARIANT_VERTICAL_ORDER), "libm_cbrt": dict(flags=0, libm=True),
-                "f32_maps": dict(flags=O.VARIANT_F32_MAPS),
+                "f32_maps": dict(flags=O.VARIANT_F32_MAPS), "f32_transfer": dict(flags=O.VARIANT_F32_TRANSFER),
                 "fir": dict(flags=0, blur=O.BLUR_FIR)}
     deltas = {k: [] for k in variants}
     deltas["contracted"] = []
