@@ -212,6 +212,32 @@ def fssimu2_vectors():
         return json.load(f)
 
 
+def test_which_variant_identifies_the_generating_reading(oracle):
+    """scripts/pin_fssimu2/which_variant.py: vectors made under a non-default combination of the variant switches
+    rank exactly that combination first, at zero distance — the tool a maintainer with zig runs when pinned vectors
+    disagree with the default reading."""
+    import importlib.util
+    from oavif_b200.host import synth
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("which_variant", os.path.join(here, "..", "scripts", "pin_fssimu2", "which_variant.py"))
+    W = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(W)
+    recs = []
+    try:
+        for i, (w, h) in enumerate(((96, 80), (150, 130))):
+            src = synth.synth(w, h, i % 4, i)
+            dst = synth.distort(src, 0.4 + 0.3 * i, seed=i + 100)
+            oracle.set_variant(oracle.VARIANT_VERTICAL_ORDER | oracle.VARIANT_F32_TRANSFER, fast=True)
+            recs.append({"w": w, "h": h, "kind": i % 4, "seed": i, "strength": 0.4 + 0.3 * i,
+                         "score": oracle.ssimu2_rgb8(src, dst, oracle.BLUR_IIR, fast=True)})
+    finally:
+        oracle.set_variant(0, fast=True)
+    ranked = W.rank(recs)
+    assert ranked[0][0] == 0.0 and ranked[0][2] == "recursive + vertical_order + f32_transfer", ranked[:3]
+    assert ranked[1][0] > 0.0
+    assert oracle.lib(True).oracle_get_variant() == 0 if hasattr(oracle.lib(True), "oracle_get_variant") else True
+
+
 def test_oracle_against_fssimu2_vectors(oracle):
     from oavif_b200.host import synth
     for c in fssimu2_vectors():
