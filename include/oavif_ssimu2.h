@@ -84,7 +84,15 @@ enum { OAVIF_SSIMU2_TILES_TMA = 0, OAVIF_SSIMU2_TILES_CP_ASYNC = 1, OAVIF_SSIMU2
  * not the default; useful when set_source happens long before the first score. */
 enum { OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE = 0, OAVIF_SSIMU2_SOURCE_ROWS_WITH_FIRST_SCORE = 1 };
 
-enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_WEIGHTS = 2, OAVIF_SSIMU2_OPT_TILE_PATH = 3, OAVIF_SSIMU2_OPT_SOURCE_ROWS = 4 };
+/* How the 256-entry sRGB -> linear table is made.  F64 (default): the transfer function in binary64, rounded once to
+ * binary32.  F32: evaluated in binary32 (powf) — a few entries differ in their last bit, which moves scores by up to
+ * 0.05 (profiles/r2_variant_envelope.json); which one fssimu2 0.1.1 uses is not known here, so
+ * both exist, each bit-identical to the oracle's matching variant.  Setting it (nothing may be in flight) drops the
+ * cached source: call set_source_* again. */
+enum { OAVIF_SSIMU2_TRANSFER_F64 = 0, OAVIF_SSIMU2_TRANSFER_F32 = 1 };
+
+enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_WEIGHTS = 2, OAVIF_SSIMU2_OPT_TILE_PATH = 3, OAVIF_SSIMU2_OPT_SOURCE_ROWS = 4,
+       OAVIF_SSIMU2_OPT_TRANSFER = 5 };
 
 typedef struct oavif_ssimu2_ctx oavif_ssimu2_ctx;
 

@@ -104,6 +104,7 @@ struct oavif_ssimu2_ctx {
     cudaStream_t copy_stream = nullptr;                    // host -> device uploads: run under the previous submission's kernels
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
     int weight_layout = OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS;
+    int transfer = OAVIF_SSIMU2_TRANSFER_F64;
     int tile_path = OAVIF_SSIMU2_TILES_TMA;
     int source_rows = OAVIF_SSIMU2_SOURCE_ROWS_WITH_FIRST_SCORE;
     unsigned cap_units = 0, wave_epoch = 0;               // fused kernel: capacities, launch counter (mailbox tags)
@@ -439,6 +440,26 @@ int build_pyramids(oavif_ssimu2_ctx *ctx, cudaStream_t st, const InputDesc &d, u
     launch_pyramid(d.kind, a, (int)n, st);
     CK(cudaGetLastError());
     return 0;
+}
+
+// sRGB -> linear table (v2.1 section 1), stored once per LANE (entry v, lane l at [32 v + l]): the pyramid kernel copies
+// it to shared memory as is, where a warp's 32 gathers then hit 32 different banks.  TRANSFER_F64: binary64
+// evaluation, one rounding to binary32; TRANSFER_F32: binary32 throughout (the oracle's ORACLE_VARIANT_F32_TRANSFER).
+cudaError_t upload_srgb_table(oavif_ssimu2_ctx *ctx)
+{
+    std::vector<float> lut(256 * 32);
+    for (int i = 0; i < 256; ++i) {
+        float e;
+        if (ctx->transfer == OAVIF_SSIMU2_TRANSFER_F32) {
+            const float v = (float)i / 255.0f;
+            e = (v <= 0.04045f) ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f);
+        } else {
+            const double v = (double)i / 255.0;
+            e = (float)((v <= 0.04045) ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4));
+        }
+        for (int l = 0; l < 32; ++l) lut[32 * i + l] = e;
+    }
+    return cudaMemcpy(ctx->d_lut, lut.data(), sizeof(float) * lut.size(), cudaMemcpyHostToDevice);
 }
 
 // Everything a w x h image needs against what the context allocated: pyramid floats, staged input bytes and
@@ -1058,16 +1079,7 @@ int oavif_ssimu2_ctx_create(int device, uint32_t max_w, uint32_t max_h, uint32_t
         CKC(cudaHostGetDevicePointer((void **)&S.dm_scores, S.h_scores, 0));
     }
 
-    // sRGB -> linear table (v2.1 §1): double evaluation, one rounding to binary32
-    // Stored once per LANE (entry v, lane l at [32 v + l]): the pyramid kernel copies it to shared memory as is,
-    // where a warp's 32 gathers then hit 32 different banks.
-    std::vector<float> lut(256 * 32);
-    for (int i = 0; i < 256; ++i) {
-        const double v = (double)i / 255.0;
-        const float e = (float)((v <= 0.04045) ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4));
-        for (int l = 0; l < 32; ++l) lut[32 * i + l] = e;
-    }
-    CKC(cudaMemcpy(ctx->d_lut, lut.data(), sizeof(float) * lut.size(), cudaMemcpyHostToDevice));
+    CKC(upload_srgb_table(ctx));
     solve_gaussian(1.5, ctx->taps, &ctx->iir);
 
     CKC(cudaFuncSetAttribute(k_fir_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirSmemBytes));
@@ -1101,6 +1113,16 @@ int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value)
         ctx->weight_layout = value;
         return 0;
     }
+    if (option == OAVIF_SSIMU2_OPT_TRANSFER && (value == OAVIF_SSIMU2_TRANSFER_F64 || value == OAVIF_SSIMU2_TRANSFER_F32)) {
+        if (ctx->inflight) return fail(ctx, OAVIF_SSIMU2_E_STATE, "a submission is in flight: retire it first");
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaDeviceSynchronize());   // pyramid kernels of earlier calls read the table
+        ctx->transfer = value;
+        CK(upload_srgb_table(ctx));
+        ctx->have_source = false;      // the cached source pyramid was built from the other table
+        ctx->src_pix = nullptr;
+        return 0;
+    }
     return fail(ctx, OAVIF_SSIMU2_E_ARG, "unknown option %d / value %d", option, value);
 }
 
@@ -1112,6 +1134,7 @@ int oavif_ssimu2_get_option(const oavif_ssimu2_ctx *ctx, int option, int *value)
     case OAVIF_SSIMU2_OPT_WEIGHTS: *value = ctx->weight_layout; return 0;
     case OAVIF_SSIMU2_OPT_TILE_PATH: *value = ctx->tile_path; return 0;
     case OAVIF_SSIMU2_OPT_SOURCE_ROWS: *value = ctx->source_rows; return 0;
+    case OAVIF_SSIMU2_OPT_TRANSFER: *value = ctx->transfer; return 0;
     default: return OAVIF_SSIMU2_E_ARG;
     }
 }

@@ -691,6 +691,36 @@ def test_weight_layout_option_matches_the_oracle_variant(scorer, oracle):
         assert (six == contiguous) == (scorer.detail().n_scales == 6)
 
 
+def test_transfer_table_option_matches_the_oracle_variant(scorer, oracle):
+    """OAVIF_SSIMU2_OPT_TRANSFER: the sRGB table from binary32 powf against the oracle's F32_TRANSFER variant — XYB bit
+    for bit, the score to the usual tolerance — and back; switching drops the cached source."""
+    w, h = 333, 257
+    src = synth.synth(w, h, "mixture", 21)
+    dist = synth.distort(src, 0.5)
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    scorer.set_source(src)
+    f64 = scorer.score_rgb8(dist)
+    try:
+        scorer.set_option(ssimu2.OPT_TRANSFER, ssimu2.TRANSFER_F32)
+        assert scorer.get_option(ssimu2.OPT_TRANSFER) == ssimu2.TRANSFER_F32
+        with pytest.raises(ssimu2.Ssimu2Error) as e:
+            scorer.score_rgb8(dist)                       # the cached pyramid came from the other table
+        assert e.value.code == ssimu2.E_STATE
+        oracle.set_variant(oracle.VARIANT_F32_TRANSFER)
+        scorer.set_source(src)
+        f32 = scorer.score_rgb8(dist)
+        assert abs(f32 - oracle.ssimu2_rgb8(src, dist)) <= SCORE_TOL
+        want = oracle.xyb_at_scale(src, 0)
+        for c in range(3):
+            np.testing.assert_array_equal(bits(scorer.xyb(0, 0, c)), bits(want[c]))
+    finally:
+        oracle.set_variant(0)
+        scorer.set_option(ssimu2.OPT_TRANSFER, ssimu2.TRANSFER_F64)
+    scorer.set_source(src)
+    assert scorer.score_rgb8(dist) == f64 and f32 != f64
+    assert abs(f64 - oracle.ssimu2_rgb8(src, dist)) <= SCORE_TOL
+
+
 def test_conversion_call_leaves_the_cached_source_alone(scorer):
     src = synth.synth(200, 120, "mixture", 3)
     dist = synth.distort(src, 0.3)
