@@ -91,8 +91,16 @@ enum { OAVIF_SSIMU2_SOURCE_ROWS_AT_SET_SOURCE = 0, OAVIF_SSIMU2_SOURCE_ROWS_WITH
  * cached source: call set_source_* again. */
 enum { OAVIF_SSIMU2_TRANSFER_F64 = 0, OAVIF_SSIMU2_TRANSFER_F32 = 1 };
 
+/* Operation order of the recursion step in the VERTICAL pass (RECURSIVE blur).  AS_HORIZONTAL (default): the same
+ * sequence as the horizontal pass, (n2 * sum - y[n-2]) then fma(-d1, y[n-1], .).  FUSED_OUTER: fma(n2, sum,
+ * fma(-d1, y[n-1], -y[n-2])), the vertical block of lib/jxl/gauss_blur.cc as recalled — the oracle's
+ * ORACLE_VARIANT_VERTICAL_ORDER, up to 0.058 away in the score (profiles/r2_variant_envelope.json).  Which one fssimu2
+ * 0.1.1 follows is not known here; both are bit-identical to the oracle's matching variant.  FUSED_OUTER exists for
+ * the default tile path only (score_* return E_UNSUPPORTED under CP_ASYNC, FUSED and TMA_DECOUPLED). */
+enum { OAVIF_SSIMU2_VERTICAL_AS_HORIZONTAL = 0, OAVIF_SSIMU2_VERTICAL_FUSED_OUTER = 1 };
+
 enum { OAVIF_SSIMU2_OPT_BLUR = 1, OAVIF_SSIMU2_OPT_WEIGHTS = 2, OAVIF_SSIMU2_OPT_TILE_PATH = 3, OAVIF_SSIMU2_OPT_SOURCE_ROWS = 4,
-       OAVIF_SSIMU2_OPT_TRANSFER = 5 };
+       OAVIF_SSIMU2_OPT_TRANSFER = 5, OAVIF_SSIMU2_OPT_VERTICAL_ORDER = 6 };
 
 typedef struct oavif_ssimu2_ctx oavif_ssimu2_ctx;
 

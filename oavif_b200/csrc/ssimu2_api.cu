@@ -105,6 +105,7 @@ struct oavif_ssimu2_ctx {
     int blur_mode = OAVIF_SSIMU2_BLUR_RECURSIVE;
     int weight_layout = OAVIF_SSIMU2_WEIGHTS_SIX_SLOTS;
     int transfer = OAVIF_SSIMU2_TRANSFER_F64;
+    int vertical_order = OAVIF_SSIMU2_VERTICAL_AS_HORIZONTAL;
     int tile_path = OAVIF_SSIMU2_TILES_TMA;
     int source_rows = OAVIF_SSIMU2_SOURCE_ROWS_WITH_FIRST_SCORE;
     unsigned cap_units = 0, wave_epoch = 0;               // fused kernel: capacities, launch counter (mailbox tags)
@@ -712,7 +713,8 @@ int enqueue_blur_and_finalize(oavif_ssimu2_ctx *ctx, Slot &S, SrcSet &Src, uint3
         CK(cudaStreamWaitEvent(ctx->cs->stream, Src.cache_done, 0));
         IirColsTmaMaps cmaps;
         e = launch_iir_cols(a, plan.first_cta, plan.tiles_x, (int)n, ctx->cs->stream, nullptr, cols_maps_for(ctx, Src, &cmaps),
-                            ctx->tile_path == OAVIF_SSIMU2_TILES_TMA_DECOUPLED);
+                            ctx->tile_path == OAVIF_SSIMU2_TILES_TMA_DECOUPLED, 0,
+                            ctx->vertical_order == OAVIF_SSIMU2_VERTICAL_FUSED_OUTER);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
         S.launches += 1;
     }
@@ -748,6 +750,9 @@ int submit_common(oavif_ssimu2_ctx *ctx, const InputDesc &d, uint32_t n, const H
     if (n > ctx->max_batch) return fail(ctx, OAVIF_SSIMU2_E_STATE, "batch %u exceeds max_batch %u", n, ctx->max_batch);
     if (ctx->inflight == kSlots)
         return fail(ctx, OAVIF_SSIMU2_E_STATE, "%d submissions already in flight: call oavif_ssimu2_wait first", kSlots);
+    if (ctx->vertical_order != OAVIF_SSIMU2_VERTICAL_AS_HORIZONTAL && ctx->blur_mode == OAVIF_SSIMU2_BLUR_RECURSIVE &&
+        (ctx->tile_path != OAVIF_SSIMU2_TILES_TMA || !tma_encoder()))
+        return fail(ctx, OAVIF_SSIMU2_E_UNSUPPORTED, "the FUSED_OUTER vertical order exists for the default (TMA) tile path only");
     const int w = ctx->g.w[0];
     const int np = nplanes(d.kind);
     for (uint32_t i = 0; i < n; ++i)
@@ -1113,6 +1118,11 @@ int oavif_ssimu2_set_option(oavif_ssimu2_ctx *ctx, int option, int value)
         ctx->weight_layout = value;
         return 0;
     }
+    if (option == OAVIF_SSIMU2_OPT_VERTICAL_ORDER &&
+        (value == OAVIF_SSIMU2_VERTICAL_AS_HORIZONTAL || value == OAVIF_SSIMU2_VERTICAL_FUSED_OUTER)) {
+        ctx->vertical_order = value;
+        return 0;
+    }
     if (option == OAVIF_SSIMU2_OPT_TRANSFER && (value == OAVIF_SSIMU2_TRANSFER_F64 || value == OAVIF_SSIMU2_TRANSFER_F32)) {
         if (ctx->inflight) return fail(ctx, OAVIF_SSIMU2_E_STATE, "a submission is in flight: retire it first");
         CK(cudaSetDevice(ctx->device));
@@ -1135,6 +1145,7 @@ int oavif_ssimu2_get_option(const oavif_ssimu2_ctx *ctx, int option, int *value)
     case OAVIF_SSIMU2_OPT_TILE_PATH: *value = ctx->tile_path; return 0;
     case OAVIF_SSIMU2_OPT_SOURCE_ROWS: *value = ctx->source_rows; return 0;
     case OAVIF_SSIMU2_OPT_TRANSFER: *value = ctx->transfer; return 0;
+    case OAVIF_SSIMU2_OPT_VERTICAL_ORDER: *value = ctx->vertical_order; return 0;
     default: return OAVIF_SSIMU2_E_ARG;
     }
 }
@@ -1575,7 +1586,8 @@ int oavif_ssimu2_debug_get_cols(oavif_ssimu2_ctx *ctx, int candidate, int scale,
         IirColsTmaMaps cmaps;
         const cudaError_t e = launch_iir_cols(iir_args_for(ctx, ctx->src[ctx->cur]), plan.first_cta, plan.tiles_x,
                                               (int)ctx->last_n, ctx->cs->stream, &tap, cols_maps_for(ctx, ctx->src[ctx->cur], &cmaps),
-                                              ctx->tile_path == OAVIF_SSIMU2_TILES_TMA_DECOUPLED);
+                                              ctx->tile_path == OAVIF_SSIMU2_TILES_TMA_DECOUPLED, 0,
+                                              ctx->vertical_order == OAVIF_SSIMU2_VERTICAL_FUSED_OUTER);
         if (e != cudaSuccess) return fail(ctx, OAVIF_SSIMU2_E_CUDA, "columns launch: %s", cudaGetErrorString(e));
     }
     CK(cudaMemcpyAsync(out, ctx->d_dbg, sizeof(float) * need, cudaMemcpyDeviceToHost, ctx->cs->stream));

@@ -97,6 +97,35 @@ __device__ __forceinline__ f32x2 iir_step2(const IirCoef2 &k, IirState2 &s, f32x
     return add2(add2(o[0], o[1]), o[2]);
 }
 
+// The other reading of the published VERTICAL pass (lib/jxl/gauss_blur.cc VerticalBlock as recalled; the oracle's
+// ORACLE_VARIANT_VERTICAL_ORDER): out_k = fma(n2, sum, fma(-d1, y[n-1], -y[n-2])) — the product n2 * sum is not
+// rounded on its own and -d1 * y[n-1] - y[n-2] is formed first.  OAVIF_SSIMU2_OPT_VERTICAL_ORDER; columns pass only.
+__device__ __forceinline__ float iir_step_vorder(const IirCoef &k, IirState &s, float sum)
+{
+    float o[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float ok = fmaf(k.n2[i], sum, fmaf(-k.d1[i], s.p[i], -s.p2[i]));
+        s.p2[i] = s.p[i];
+        s.p[i] = ok;
+        o[i] = ok;
+    }
+    return (o[0] + o[1]) + o[2];
+}
+__device__ __forceinline__ f32x2 iir_step2_vorder(const IirCoef2 &k, IirState2 &s, f32x2 sum)
+{
+    f32x2 o[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        // -y[n-2] as y[n-2] * -1 (exact); a product in the ADDEND position cannot be contracted into anything
+        const f32x2 ok = fma2(k.n2[i], sum, fma2(k.nd1[i], s.p[i], mul2(s.p2[i], k.u.m1)));
+        s.p2[i] = s.p[i];
+        s.p[i] = ok;
+        o[i] = ok;
+    }
+    return add2(add2(o[0], o[1]), o[2]);
+}
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 
 constexpr int kIirRows = 32;     // rows per rows-pass task
@@ -865,7 +894,7 @@ struct IirColsTmaMaps {
 // kernel carries none of it (with the hook inline the kernel went from 70 to 128 registers).
 // TMA: the loader warp's 16-byte cp.async traffic (about 200 instructions per batch, a tenth of the CTA's) becomes
 // twelve cp.async.bulk.tensor issues by one lane; rows below the image and columns right of it arrive as zeros.
-template <int RCAP, int B, bool TAP, bool TMA, bool DECOUPLED = false>
+template <int RCAP, int B, bool TAP, bool TMA, bool DECOUPLED = false, bool VORDER = false>
 __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant__ IirArgs a, const __grid_constant__ IirColsTmaMaps tm)
 {
     extern __shared__ __align__(128) unsigned char smem_cols[];
@@ -1030,7 +1059,10 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         __syncthreads();      // (S)
         // n = -4..-1: right taps are rows 0..3, left taps are padding, nothing emitted
 #pragma unroll
-        for (int n = -4; n < 0; ++n) (void)iir_step2(k, st, splat2(0.0f), lds2(col + (n + 4) * kRow));
+        for (int n = -4; n < 0; ++n) {
+            if (VORDER) (void)iir_step2_vorder(k, st, add2(splat2(0.0f), lds2(col + (n + 4) * kRow)));
+            else (void)iir_step2(k, st, splat2(0.0f), lds2(col + (n + 4) * kRow));
+        }
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
@@ -1052,12 +1084,17 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
                 sum[j] = add2(lds2(j < 6 ? l0 + j * kRow : l1 + (j - 6) * kRow),
                               lds2(j < B - 4 ? r0 + j * kRow : r1 + (j - (B - 4)) * kRow));
             float *ex0 = &sm.ex[b & 1][warp][0][lane], *ex1 = &sm.ex[b & 1][warp + 2][0][lane];
-            IirPipe2 P;
-            pipe2_begin(k, P, st, sum[0]);
+            if (VORDER) {
 #pragma unroll
-            for (int j = 0; j < B; ++j) {
-                const f32x2 o = (j + 1 < B) ? pipe2_step(k, P, sum[j + 1]) : pipe2_end(k, P, st);
-                unpk2(o, ex0[j * kIirVCols], ex1[j * kIirVCols]);
+                for (int j = 0; j < B; ++j) unpk2(iir_step2_vorder(k, st, sum[j]), ex0[j * kIirVCols], ex1[j * kIirVCols]);
+            } else {
+                IirPipe2 P;
+                pipe2_begin(k, P, st, sum[0]);
+#pragma unroll
+                for (int j = 0; j < B; ++j) {
+                    const f32x2 o = (j + 1 < B) ? pipe2_step(k, P, sum[j + 1]) : pipe2_end(k, P, st);
+                    unpk2(o, ex0[j * kIirVCols], ex1[j * kIirVCols]);
+                }
             }
             if (DEC) warp_arrive(&sm.full[b & 3]);
             else __syncthreads();  // (b) batch b published; the consumers are done with the other buffer
@@ -1074,7 +1111,10 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
         const float *col = &sm.sring[0][lane];
         __syncthreads();      // (S)
 #pragma unroll
-        for (int n = -4; n < 0; ++n) (void)iir_step(k, st, 0.0f, col[(n + 4) * kIirVCols]);
+        for (int n = -4; n < 0; ++n) {
+            if (VORDER) (void)iir_step_vorder(k, st, 0.0f + col[(n + 4) * kIirVCols]);
+            else (void)iir_step(k, st, 0.0f, col[(n + 4) * kIirVCols]);
+        }
 
 #pragma unroll 1
         for (int b = 0; b < nbatch; ++b) {
@@ -1093,11 +1133,16 @@ __global__ void __launch_bounds__(kIirVThreads) k_iir_cols(const __grid_constant
                 sum[j] = (j < 6 ? l0[j * kIirVCols] : l1[(j - 6) * kIirVCols]) +
                          (j < B - 4 ? r0[j * kIirVCols] : r1[(j - (B - 4)) * kIirVCols]);
             float *ex = &sm.ex[b & 1][q][0][lane];
-            IirPipe P;
-            pipe_begin(k, P, st, sum[0]);
+            if (VORDER) {
 #pragma unroll
-            for (int j = 0; j < B; ++j)
-                ex[j * kIirVCols] = (j + 1 < B) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
+                for (int j = 0; j < B; ++j) ex[j * kIirVCols] = iir_step_vorder(k, st, sum[j]);
+            } else {
+                IirPipe P;
+                pipe_begin(k, P, st, sum[0]);
+#pragma unroll
+                for (int j = 0; j < B; ++j)
+                    ex[j * kIirVCols] = (j + 1 < B) ? pipe_step(k, P, sum[j + 1]) : pipe_end(k, P, st);
+            }
             if (DEC) warp_arrive(&sm.full[b & 3]);
             else __syncthreads();  // (b)
         }
@@ -1414,6 +1459,12 @@ inline cudaError_t iir_configure()
     e = cudaFuncSetAttribute(k_iir_cols<64, 16, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(IirColsDeep));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_iir_cols<64, 16, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(IirColsDeep));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_iir_cols<64, 16, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(IirColsDeep));
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_iir_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<1>));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_iir_rows<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IirRowsSmem<2>));
@@ -1487,7 +1538,7 @@ inline cudaError_t launch_iir_rows(const IirArgs &base, const Geom &g, int which
 // Columns pass with the maps and the pooling.
 inline cudaError_t launch_iir_cols(const IirArgs &base, const int *first_cta_cols, const int *col_blocks, int n,
                                    cudaStream_t st, const IirDebugTap *tap = nullptr, const IirColsTmaMaps *maps = nullptr,
-                                   bool decoupled = false, size_t pad_smem = 0)
+                                   bool decoupled = false, size_t pad_smem = 0, bool vorder = false)
 {
     static const IirColsTmaMaps no_maps{};
     IirArgs a = base;
@@ -1499,12 +1550,18 @@ inline cudaError_t launch_iir_cols(const IirArgs &base, const int *first_cta_col
         a.dbg_scale = tap->scale;
         a.dbg_channel = tap->channel;
         a.dbg_cand = tap->cand;
-        if (maps && decoupled) k_iir_cols<64, 16, true, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        if (vorder) {   // only the default tile path carries this instance (the API refuses the others)
+            if (!maps || decoupled) return cudaErrorNotSupported;
+            k_iir_cols<64, 16, true, true, false, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        } else if (maps && decoupled) k_iir_cols<64, 16, true, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
         else if (maps) k_iir_cols<64, 16, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
         else k_iir_cols<64, 16, true, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, no_maps);
     } else {
         // pad_smem (profiling only): a larger shared-memory request lowers the CTAs resident per SM
-        if (maps && decoupled) k_iir_cols<64, 16, false, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        if (vorder) {
+            if (!maps || decoupled) return cudaErrorNotSupported;
+            k_iir_cols<64, 16, false, true, false, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
+        } else if (maps && decoupled) k_iir_cols<64, 16, false, true, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, *maps);
         else if (maps) k_iir_cols<64, 16, false, true><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep) + pad_smem, st>>>(a, *maps);
         else k_iir_cols<64, 16, false, false><<<dim3(ctas, n), kIirVThreads, sizeof(IirColsDeep), st>>>(a, no_maps);
     }

@@ -26,8 +26,9 @@ BLUR_RECURSIVE, BLUR_FIR = 0, 1
 WEIGHTS_SIX_SLOTS, WEIGHTS_CONTIGUOUS = 0, 1
 TILES_TMA, TILES_CP_ASYNC, TILES_FUSED, TILES_TMA_DECOUPLED = 0, 1, 2, 3
 SOURCE_ROWS_AT_SET_SOURCE, SOURCE_ROWS_WITH_FIRST_SCORE = 0, 1
-OPT_BLUR, OPT_WEIGHTS, OPT_TILE_PATH, OPT_SOURCE_ROWS, OPT_TRANSFER = 1, 2, 3, 4, 5
+OPT_BLUR, OPT_WEIGHTS, OPT_TILE_PATH, OPT_SOURCE_ROWS, OPT_TRANSFER, OPT_VERTICAL_ORDER = 1, 2, 3, 4, 5, 6
 TRANSFER_F64, TRANSFER_F32 = 0, 1
+VERTICAL_AS_HORIZONTAL, VERTICAL_FUSED_OUTER = 0, 1
 
 E_ARG, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 _ENAMES = {E_ARG: "InvalidArgument", E_CUDA: "CudaError", E_NOMEM: "OutOfMemory",

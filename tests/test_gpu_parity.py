@@ -721,6 +721,39 @@ def test_transfer_table_option_matches_the_oracle_variant(scorer, oracle):
     assert abs(f64 - oracle.ssimu2_rgb8(src, dist)) <= SCORE_TOL
 
 
+@pytest.mark.parametrize("size", [(100, 75), (333, 257), (640, 360)])
+def test_vertical_order_option_matches_the_oracle_variant(scorer, oracle, size):
+    """OAVIF_SSIMU2_OPT_VERTICAL_ORDER: fma(n2, sum, fma(-d1, y1, -y2)) in the columns pass against the oracle's
+    VERTICAL_ORDER variant — the five blurred values the product kernel hands to the maps bit for bit, the score to the
+    usual tolerance; refused on the tile paths that do not carry the instance."""
+    w, h = size
+    src = synth.synth(w, h, "mixture", 33)
+    dist = synth.distort(src, 0.5)
+    scorer.set_blur(ssimu2.BLUR_RECURSIVE)
+    scorer.set_source(src)
+    default = scorer.score_rgb8(dist)
+    try:
+        scorer.set_option(ssimu2.OPT_VERTICAL_ORDER, ssimu2.VERTICAL_FUSED_OUTER)
+        oracle.set_variant(oracle.VARIANT_VERTICAL_ORDER)
+        got = scorer.score_rgb8(dist)
+        assert abs(got - oracle.ssimu2_rgb8(src, dist)) <= SCORE_TOL
+        a, b = oracle.xyb_at_scale(src, 1)[1], oracle.xyb_at_scale(dist, 1)[1]
+        want = [oracle.blur(p) for p in (a, b, a * a, b * b, a * b)]
+        cols = scorer.cols(0, 1, 1)
+        for q in range(5):
+            np.testing.assert_array_equal(bits(cols[q]), bits(want[q]), err_msg=f"quantity {q}")
+        scorer.set_tile_path(ssimu2.TILES_CP_ASYNC)
+        with pytest.raises(ssimu2.Ssimu2Error) as e:
+            scorer.score_rgb8(dist)
+        assert e.value.code == ssimu2.E_UNSUPPORTED
+    finally:
+        oracle.set_variant(0)
+        scorer.set_tile_path(ssimu2.TILES_TMA)
+        scorer.set_option(ssimu2.OPT_VERTICAL_ORDER, ssimu2.VERTICAL_AS_HORIZONTAL)
+    assert scorer.score_rgb8(dist) == default
+    assert abs(default - oracle.ssimu2_rgb8(src, dist)) <= SCORE_TOL
+
+
 def test_conversion_call_leaves_the_cached_source_alone(scorer):
     src = synth.synth(200, 120, "mixture", 3)
     dist = synth.distort(src, 0.3)
