@@ -99,6 +99,14 @@ pub const Scorer = struct {
         try check(c.oavif_ssimu2_set_source_pixels(self.ctx, pixels.ptr, w, h, @as(usize, w) * channels * bps, channels, if (hbd) 16 else 8));
     }
 
+    /// Readings of the published algorithm this library carries side by side until fssimu2 0.1.1 vectors settle them
+    /// (include/oavif_ssimu2.h: OAVIF_SSIMU2_OPT_*; scripts/pin_fssimu2/which_variant.py names the matching one).
+    pub const Option = enum(c_int) { blur = 1, weights = 2, tile_path = 3, source_rows = 4, transfer = 5, vertical_order = 6 };
+
+    pub fn setOption(self: *Scorer, option: Option, value: c_int) Error!void {
+        try check(c.oavif_ssimu2_set_option(self.ctx, @intFromEnum(option), value));
+    }
+
     /// The sample array encodeAvifToBuffer rebuilds from the source in every pass (io.zig:566-609: 8 -> 10 bit
     /// (v*1023+127)/255, 16 -> 10 bit v >> 6, 16 -> 8 bit v >> 8), made ONCE from the pixels setSourcePixels staged.
     /// `out` holds w*h*channels samples: u16 for depth 10, u8 for depth 8 (pass it as bytes).
